@@ -1,0 +1,638 @@
+// odometry.cu -- host side of the tracking path: GL-free restatement of the reference's
+// RGBDOdometry class (Core/src/Utils/RGBDOdometry.{h,cpp}) and of the cudafuncs.cuh host
+// functions, behind the C ABI of include/hrbf_b200.h.
+//
+// B200 design: all pyramid maps live in one dense HBM slab per object; each init* call is ONE
+// fused kernel; getIncrementalTransformation replays ONE CUDA graph that contains the SO3
+// pre-alignment, every ICP/RGB reduction of the three levels and the fp64 solves -- zero host
+// round trips inside the Gauss-Newton loop (the reference makes ~67 per frame).
+#include "odometry_kernels.cuh"
+#include <map>
+#include <new>
+#include <stdarg.h>
+#include <vector>
+
+namespace hrbf {
+
+std::atomic<unsigned long long> g_launches{0};
+static thread_local char t_err[512] = "";
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+
+static inline dim3 grid2d(int cols, int rows, dim3 b) { return dim3(div_up(cols, b.x), div_up(rows, b.y)); }
+static inline int reduce_blocks(int n) { int b = div_up(n, kReduceThreads * 2); return b < 1 ? 1 : (b > kMaxReduceBlocks ? kMaxReduceBlocks : b); }
+
+enum { M_VG = 0, M_NG, M_K1G, M_K2G, M_VC, M_NC, M_K1C, M_K2C, M_W, M_COUNT };
+
+}  // namespace hrbf
+
+using namespace hrbf;
+
+struct hrbf_odometry {
+    int width = 0, height = 0;
+    hrbf_camera intr{};
+    float distThres = 0.1f, angleThres = 0.f;
+    float sobelScale = 0.125f, maxDepthDeltaRGB = 0.07f, maxDepthRGB = 6.0f;
+    float minGrad[HRBF_NUM_PYRS] = { 5, 3, 1 };
+    float curvThr = 300.f;
+    int useSearch = 0, searchRadius = 2, rgbGradWeight = 0;
+
+    char* slab = nullptr;        // one allocation for everything below
+    float* maps[M_COUNT][HRBF_NUM_PYRS] = {};
+    float* vdepth_tmp = nullptr; // verticesToDepth of the last init_icp* texture
+    float* depth_tmp[HRBF_NUM_PYRS] = {};
+    float* lastDepth[HRBF_NUM_PYRS] = {}; float* nextDepth[HRBF_NUM_PYRS] = {};
+    unsigned char* lastImage[HRBF_NUM_PYRS] = {}; unsigned char* nextImage[HRBF_NUM_PYRS] = {}; unsigned char* lastNextImage[HRBF_NUM_PYRS] = {};
+    short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
+    float* cloud[HRBF_NUM_PYRS] = {};
+    hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
+    ReduceWork* work = nullptr;
+    float* pose_scratch = nullptr;   // device: [0..11] model pose (R,t), [12..23] track in, [24..35] track out
+    // pinned host mirrors
+    float* h_pose = nullptr;         // [0..11] in, [12..23] out
+    TrackState* h_state = nullptr;
+    float* h_model_pose = nullptr;   // staging ring for init_*_model poses
+    int h_model_pose_slot = 0;
+    int so3_parity = 0;
+
+    cudaStream_t cap_stream = nullptr;
+    std::map<uint64_t, std::pair<cudaGraphExec_t, int>> graphs;   // key -> (exec, kernel nodes)
+
+    int rows(int l) const { return height >> l; }
+    int cols(int l) const { return width >> l; }
+};
+
+namespace hrbf {
+
+static PyrOut pyr_out(hrbf_odometry* o, int which)
+{
+    PyrOut r;
+    for (int l = 0; l < 3; ++l) { r.p[l] = o->maps[which][l]; r.pitch[l] = o->cols(l); }
+    return r;
+}
+
+static int upload_pose(hrbf_odometry* o, const float* pose16, cudaStream_t s, float** dev_out)
+{
+    // row-major 4x4 -> R[9], t[3]; staged through a small pinned ring so the copy is truly async
+    float* h = o->h_model_pose + 12 * (o->h_model_pose_slot++ & 7);
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) h[i * 3 + j] = pose16[i * 4 + j]; h[9 + i] = pose16[i * 4 + 3]; }
+    HRBF_CUDA(cudaMemcpyAsync(o->pose_scratch, h, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    *dev_out = o->pose_scratch;
+    return HRBF_OK;
+}
+
+// Enqueue the whole tracking loop on `s` (used under stream capture).  Returns kernel count.
+static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
+                         bool so3, bool use_weight, bool host_io)
+{
+    const bool icp = !rgbOnly && icpWeight > 0;
+    const bool rgb = rgbOnly || icpWeight < 100;
+    int iters[3] = { fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0 };
+    int first_level = 0;
+    for (int l = 2; l >= 0; --l) if (iters[l] > 0) { first_level = l; break; }
+    int n = 0;
+    const dim3 b2(32, 8);
+    ReduceWork* wk = o->work;
+
+    if (host_io) cudaMemcpyAsync(o->pose_scratch + 12, o->h_pose, 12 * sizeof(float), cudaMemcpyHostToDevice, s);
+    track_begin_kernel<<<1, 32, 0, s>>>(wk, o->pose_scratch + 12, icp, rgb, rgbOnly, so3, icpWeight, first_level); ++n;
+    if (rgb)
+        for (int l = 0; l < 3; ++l) { sobel_kernel<<<grid2d(o->cols(l), o->rows(l), b2), b2, 0, s>>>(o->rows(l), o->cols(l), o->nextImage[l], o->dIdx[l], o->dIdy[l]); ++n; }
+    if (so3) {
+        for (int it = 0; it < 10; ++it) {
+            so3_reduce_kernel<<<reduce_blocks(o->rows(2) * o->cols(2)), kReduceThreads, 0, s>>>(o->lastNextImage[2], o->nextImage[2], o->rows(2), o->cols(2), wk, 1); ++n;
+        }
+        track_after_so3_kernel<<<1, 32, 0, s>>>(wk, first_level); ++n;
+    }
+    for (int l = 2; l >= 0; --l) {
+        if (iters[l] == 0) continue;
+        const int rows = o->rows(l), cols = o->cols(l), div = 1 << l;
+        const float fx = o->intr.fx / div, fy = o->intr.fy / div, cx = o->intr.cx / div, cy = o->intr.cy / div;
+        if (rgb) { project_cloud_kernel<<<grid2d(cols, rows, b2), b2, 0, s>>>(rows, cols, o->lastDepth[l], o->cloud[l], 1.0f / fx, 1.0f / fy, cx, cy); ++n; }
+        int next_lower = -1;
+        for (int q = l - 1; q >= 0; --q) if (iters[q] > 0) { next_lower = q; break; }
+        IcpArgs ia;
+        ia.vc = o->maps[M_VC][l]; ia.nc = o->maps[M_NC][l]; ia.k1c = o->maps[M_K1C][l]; ia.k2c = o->maps[M_K2C][l]; ia.cpitch = cols;
+        ia.vg = o->maps[M_VG][l]; ia.ng = o->maps[M_NG][l]; ia.k1g = o->maps[M_K1G][l]; ia.k2g = o->maps[M_K2G][l]; ia.gpitch = cols;
+        ia.w = o->maps[M_W][l]; ia.wpitch = cols;
+        ia.rows = rows; ia.cols = cols; ia.fx = fx; ia.fy = fy; ia.cx = cx; ia.cy = cy;
+        ia.dist_thres = o->distThres; ia.angle_thres = o->angleThres;
+        ia.use_search = o->useSearch; ia.radius = o->searchRadius; ia.use_weight = use_weight; ia.corres = nullptr;
+        RgbResArgs ra;
+        ra.minScale = (float)(pow((double)o->minGrad[l], 2.0) / pow((double)o->sobelScale, 2.0)); ra.maxDepthDelta = o->maxDepthDeltaRGB;
+        ra.dIdx = o->dIdx[l]; ra.dIdy = o->dIdy[l]; ra.lastDepth = o->lastDepth[l]; ra.nextDepth = o->nextDepth[l];
+        ra.lastImage = o->lastImage[l]; ra.nextImage = o->nextImage[l]; ra.corres = o->corresImg[l]; ra.rows = rows; ra.cols = cols;
+        RgbStepArgs sa;
+        sa.corres = o->corresImg[l]; sa.cloud3 = o->cloud[l]; sa.dIdx = o->dIdx[l]; sa.dIdy = o->dIdy[l];
+        sa.fx = fx; sa.fy = fy; sa.sobelScale = o->sobelScale; sa.use_grad_weight = o->rgbGradWeight; sa.rows = rows; sa.cols = cols;
+        const int nb = reduce_blocks(rows * cols);
+        for (int j = 0; j < iters[l]; ++j) {
+            const int next_level = (j + 1 < iters[l]) ? l : next_lower;
+            if (rgb) { rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, wk, 1, l, j == 0); ++n; }
+            if (icp) {
+                if (o->useSearch) icp_reduce_kernel<true><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
+                else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
+                ++n;
+            }
+            if (rgb) { rgb_step_kernel<<<nb, kReduceThreads, 0, s>>>(sa, -2.0f, wk, 1, l, next_level); ++n; }
+        }
+    }
+    track_end_kernel<<<1, 32, 0, s>>>(wk, o->pose_scratch + 24); ++n;
+    if (host_io) {
+        cudaMemcpyAsync(o->h_pose + 12, o->pose_scratch + 24, 12 * sizeof(float), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(o->h_state, &wk->st, sizeof(TrackState), cudaMemcpyDeviceToHost, s);
+    }
+    return n;
+}
+
+static int get_graph(hrbf_odometry* o, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3, bool use_weight,
+                     bool host_io, cudaGraphExec_t* exec, int* nk)
+{
+    uint32_t wbits;
+    memcpy(&wbits, &icpWeight, 4);
+    const uint64_t key = ((uint64_t)wbits << 32) | (uint64_t)(rgbOnly | pyramid << 1 | fastOdom << 2 | so3 << 3 | use_weight << 4 | host_io << 5 |
+                                                             (o->useSearch ? 1 : 0) << 6 | (o->rgbGradWeight ? 1 : 0) << 7 | (uint64_t)(o->searchRadius & 0xff) << 8 | (uint64_t)(o->so3_parity & 1) << 16);
+    auto it = o->graphs.find(key);
+    if (it == o->graphs.end()) {
+        cudaGraph_t g = nullptr;
+        HRBF_CUDA(cudaStreamBeginCapture(o->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int n = enqueue_track(o, o->cap_stream, rgbOnly, icpWeight, pyramid, fastOdom, so3, use_weight, host_io);
+        HRBF_CUDA(cudaStreamEndCapture(o->cap_stream, &g));
+        cudaGraphExec_t e = nullptr;
+        HRBF_CUDA(cudaGraphInstantiate(&e, g, 0));
+        cudaGraphDestroy(g);
+        it = o->graphs.emplace(key, std::make_pair(e, n)).first;
+    }
+    *exec = it->second.first;
+    *nk = it->second.second;
+    return HRBF_OK;
+}
+
+}  // namespace hrbf
+
+extern "C" {
+
+const char* hrbf_last_error(void) { return t_err; }
+const char* hrbf_version(void) { return "hrbf_b200 0.1 (sm_100a)"; }
+unsigned long long hrbf_launch_count(void) { return g_launches.load(); }
+size_t hrbf_reduce_workspace_bytes(void) { return sizeof(ReduceWork); }
+
+// ------------------------------------------------------------------ row 5 ---
+#define STEP_EL(step) ((int)((step) / sizeof(float)))
+
+int hrbf_copy_maps(const float* v, const float* n, float* vmap, size_t vstep, float* nmap, size_t nstep, int rows, int cols, void* stream)
+{
+    HRBF_CHECK_ARG(v && n && vmap && nmap && rows > 0 && cols > 0 && vstep >= cols * sizeof(float) && nstep >= cols * sizeof(float));
+    const dim3 b(32, 8);
+    copy_maps_kernel<<<grid2d(cols, rows, b), b, 0, (cudaStream_t)stream>>>(rows, cols, (const float4*)v, (const float4*)n, vmap, STEP_EL(vstep), nmap, STEP_EL(nstep));
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_copy_curvature_map(const float* c, float* cmap, size_t cstep, int rows, int cols, float thr, void* stream)
+{
+    HRBF_CHECK_ARG(c && cmap && rows > 0 && cols > 0 && cstep >= cols * sizeof(float));
+    const dim3 b(32, 8);
+    copy_curv_kernel<<<grid2d(cols, rows, b), b, 0, (cudaStream_t)stream>>>(rows, cols, (const float4*)c, cmap, STEP_EL(cstep), thr);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_copy_icpweight_map(const float* w, float* dst, size_t wstep, int rows, int cols, void* stream)
+{
+    HRBF_CHECK_ARG(w && dst && rows > 0 && cols > 0 && wstep >= cols * sizeof(float));
+    const dim3 b(32, 8);
+    copy_weight_kernel<<<grid2d(cols, rows, b), b, 0, (cudaStream_t)stream>>>(rows, cols, w, dst, STEP_EL(wstep));
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+}  // extern "C"
+template <int MODE>
+static int resize_any(const float* in, size_t is, float* out, size_t os, int in_rows, int in_cols, void* stream)
+{
+    HRBF_CHECK_ARG(in && out && in_rows > 1 && in_cols > 1);
+    const int drows = in_rows / 2, dcols = in_cols / 2;
+    HRBF_CHECK_ARG(is >= in_cols * sizeof(float) && os >= dcols * sizeof(float));
+    const dim3 b(32, 8);
+    resize_kernel<MODE><<<grid2d(dcols, drows, b), b, 0, (cudaStream_t)stream>>>(drows, dcols, in_rows, in, STEP_EL(is), out, STEP_EL(os));
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+extern "C" {
+int hrbf_resize_vmap(const float* in, size_t is, float* out, size_t os, int r, int c, void* s) { return resize_any<0>(in, is, out, os, r, c, s); }
+int hrbf_resize_nmap(const float* in, size_t is, float* out, size_t os, int r, int c, void* s) { return resize_any<1>(in, is, out, os, r, c, s); }
+int hrbf_resize_cmap(const float* in, size_t is, float* out, size_t os, int r, int c, void* s) { return resize_any<2>(in, is, out, os, r, c, s); }
+int hrbf_resize_icpweight_map(const float* in, size_t is, float* out, size_t os, int r, int c, void* s) { return resize_any<3>(in, is, out, os, r, c, s); }
+
+}  // extern "C"
+template <int MODE>
+static int transform_any(const float* as, size_t ass, const float* bs, size_t bss, const float* R, const float* t,
+                         float* ad, size_t ads, float* bd, size_t bds, int rows, int cols, void* stream)
+{
+    HRBF_CHECK_ARG(as && bs && R && t && ad && bd && rows > 0 && cols > 0);
+    Mat33 Rm; Vec3 tv;
+    memcpy(Rm.m, R, sizeof Rm.m);
+    tv.x = t[0]; tv.y = t[1]; tv.z = t[2];
+    const dim3 b(32, 8);
+    transform_kernel<MODE><<<grid2d(cols, rows, b), b, 0, (cudaStream_t)stream>>>(rows, cols, as, STEP_EL(ass), bs, STEP_EL(bss), Rm, tv, ad, STEP_EL(ads), bd, STEP_EL(bds));
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+extern "C" {
+int hrbf_transform_maps(const float* vs, size_t vss, const float* ns, size_t nss, const float* R, const float* t,
+                        float* vd, size_t vds, float* nd, size_t nds, int rows, int cols, void* stream)
+{ return transform_any<0>(vs, vss, ns, nss, R, t, vd, vds, nd, nds, rows, cols, stream); }
+int hrbf_transform_curv_maps(const float* k1s, size_t k1ss, const float* k2s, size_t k2ss, const float* R, const float* t,
+                             float* k1d, size_t k1ds, float* k2d, size_t k2ds, int rows, int cols, void* stream)
+{ return transform_any<1>(k1s, k1ss, k2s, k2ss, R, t, k1d, k1ds, k2d, k2ds, rows, cols, stream); }
+
+// --------------------------------------------------------------- rows 1-3 ---
+static int init_work_state(ReduceWork* wk, cudaStream_t s, const TrackState& h)
+{
+    HRBF_CUDA(cudaMemcpyAsync(&wk->st, &h, sizeof(TrackState), cudaMemcpyHostToDevice, s));
+    return HRBF_OK;
+}
+static void unpack_host_se3(const double* sums, float* A, float* b, float* residual)
+{
+    int shift = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 7; ++j) {
+            const float value = (float)sums[shift++];
+            if (j == 6) b[i] = value; else A[j * 6 + i] = A[i * 6 + j] = value;
+        }
+    if (residual) { residual[0] = (float)sums[27]; residual[1] = (float)sums[28]; }
+}
+
+int hrbf_icp_step(const float* Rcurr, const float* tcurr, const float* vc, const float* nc, const float* k1c, const float* k2c, size_t cstep,
+                  const float* Rprev_inv, const float* tprev, hrbf_camera intr,
+                  const float* vg, const float* ng, const float* k1g, const float* k2g, size_t gstep,
+                  const float* w, size_t wstep, int rows, int cols, const hrbf_icp_options* opts,
+                  int* corres, void* work, float* A, float* b, float* residual, double* sums29, void* stream)
+{
+    HRBF_CHECK_ARG(Rcurr && tcurr && vc && nc && k1c && k2c && Rprev_inv && tprev && vg && ng && k1g && k2g && opts && work && A && b && residual);
+    HRBF_CHECK_ARG(rows > 0 && cols > 0 && cstep >= cols * sizeof(float) && gstep >= cols * sizeof(float));
+    HRBF_CHECK_ARG(!opts->use_weight || (w && wstep >= cols * sizeof(float)));
+    cudaStream_t s = (cudaStream_t)stream;
+    ReduceWork* wk = (ReduceWork*)work;
+    TrackState h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.Rcurr, Rcurr, 36); memcpy(h.tcurr, tcurr, 12); memcpy(h.Rprev_inv, Rprev_inv, 36); memcpy(h.tprev, tprev, 12);
+    h.done_level = -1; h.icp = 1;
+    if (int rc = init_work_state(wk, s, h)) return rc;
+    IcpArgs ia;
+    ia.vc = vc; ia.nc = nc; ia.k1c = k1c; ia.k2c = k2c; ia.cpitch = STEP_EL(cstep);
+    ia.vg = vg; ia.ng = ng; ia.k1g = k1g; ia.k2g = k2g; ia.gpitch = STEP_EL(gstep);
+    ia.w = w; ia.wpitch = STEP_EL(wstep);
+    ia.rows = rows; ia.cols = cols; ia.fx = intr.fx; ia.fy = intr.fy; ia.cx = intr.cx; ia.cy = intr.cy;
+    ia.dist_thres = opts->dist_thres; ia.angle_thres = opts->angle_thres;
+    ia.use_search = opts->use_search; ia.radius = opts->search_radius; ia.use_weight = opts->use_weight; ia.corres = (int2*)corres;
+    const int nb = reduce_blocks(rows * cols);
+    if (opts->use_search) icp_reduce_kernel<true><<<nb, kReduceThreads, 0, s>>>(ia, wk, 0, 0, -1);
+    else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, wk, 0, 0, -1);
+    HRBF_KERNEL_CHECK();
+    double sums[32];
+    HRBF_CUDA(cudaMemcpyAsync(sums, wk->st.icp_sums, sizeof sums, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    unpack_host_se3(sums, A, b, residual);
+    if (sums29) memcpy(sums29, sums, 29 * sizeof(double));
+    return HRBF_OK;
+}
+
+int hrbf_compute_rgb_residual(float minScale, const short* dIdx, const short* dIdy, const float* lastDepth, const float* nextDepth,
+                              const unsigned char* lastImage, const unsigned char* nextImage, hrbf_dataterm* corresImg,
+                              float maxDepthDelta, const float* kt, const float* krkinv, int rows, int cols, void* work,
+                              int* sigmaSum, int* count, void* stream)
+{
+    HRBF_CHECK_ARG(dIdx && dIdy && lastDepth && nextDepth && lastImage && nextImage && corresImg && kt && krkinv && work && sigmaSum && count && rows > 0 && cols > 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    ReduceWork* wk = (ReduceWork*)work;
+    TrackState h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.krkinv, krkinv, 36); memcpy(h.kt, kt, 12);
+    h.done_level = -1;
+    if (int rc = init_work_state(wk, s, h)) return rc;
+    RgbResArgs ra;
+    ra.minScale = minScale; ra.maxDepthDelta = maxDepthDelta; ra.dIdx = dIdx; ra.dIdy = dIdy; ra.lastDepth = lastDepth; ra.nextDepth = nextDepth;
+    ra.lastImage = lastImage; ra.nextImage = nextImage; ra.corres = corresImg; ra.rows = rows; ra.cols = cols;
+    rgb_residual_kernel<<<reduce_blocks(rows * cols), 256, 0, s>>>(ra, wk, 0, 0, 1);
+    HRBF_KERNEL_CHECK();
+    int out[2];
+    HRBF_CUDA(cudaMemcpyAsync(out, &wk->st.rgb_count, sizeof out, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    *count = out[0]; *sigmaSum = out[1];
+    return HRBF_OK;
+}
+
+int hrbf_rgb_step(const hrbf_dataterm* corresImg, float sigma, const float* cloud3, float fx, float fy, const short* dIdx, const short* dIdy,
+                  int use_gradient_weight, float sobelScale, int rows, int cols, void* work, float* A, float* b, double* sums29, void* stream)
+{
+    HRBF_CHECK_ARG(corresImg && cloud3 && dIdx && dIdy && work && A && b && rows > 0 && cols > 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    ReduceWork* wk = (ReduceWork*)work;
+    TrackState h;
+    memset(&h, 0, sizeof h);
+    h.done_level = -1; h.rgb = 1;
+    if (int rc = init_work_state(wk, s, h)) return rc;
+    RgbStepArgs sa;
+    sa.corres = corresImg; sa.cloud3 = cloud3; sa.dIdx = dIdx; sa.dIdy = dIdy; sa.fx = fx; sa.fy = fy; sa.sobelScale = sobelScale;
+    sa.use_grad_weight = use_gradient_weight; sa.rows = rows; sa.cols = cols;
+    rgb_step_kernel<<<reduce_blocks(rows * cols), kReduceThreads, 0, s>>>(sa, sigma, wk, 0, 0, -1);
+    HRBF_KERNEL_CHECK();
+    double sums[32];
+    HRBF_CUDA(cudaMemcpyAsync(sums, wk->st.rgb_sums, sizeof sums, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    unpack_host_se3(sums, A, b, nullptr);
+    if (sums29) memcpy(sums29, sums, 29 * sizeof(double));
+    return HRBF_OK;
+}
+
+int hrbf_so3_step(const unsigned char* lastImage, const unsigned char* nextImage, const float* imageBasis, const float* kinv, const float* krlr,
+                  int rows, int cols, void* work, float* A, float* b, float* residual, double* sums11, void* stream)
+{
+    HRBF_CHECK_ARG(lastImage && nextImage && imageBasis && kinv && krlr && work && A && b && residual && rows > 2 && cols > 2);
+    cudaStream_t s = (cudaStream_t)stream;
+    ReduceWork* wk = (ReduceWork*)work;
+    TrackState h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.so3_basis, imageBasis, 36); memcpy(h.so3_kinv, kinv, 36); memcpy(h.so3_krlr, krlr, 36);
+    h.done_level = -1;
+    if (int rc = init_work_state(wk, s, h)) return rc;
+    so3_reduce_kernel<<<reduce_blocks(rows * cols), kReduceThreads, 0, s>>>(lastImage, nextImage, rows, cols, wk, 0);
+    HRBF_KERNEL_CHECK();
+    double sums[16];
+    HRBF_CUDA(cudaMemcpyAsync(sums, wk->st.so3_sums, sizeof sums, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    int shift = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 4; ++j) {
+            const float value = (float)sums[shift++];
+            if (j == 3) b[i] = value; else A[j * 3 + i] = A[i * 3 + j] = value;
+        }
+    residual[0] = (float)sums[9]; residual[1] = (float)sums[10];
+    if (sums11) memcpy(sums11, sums, 11 * sizeof(double));
+    return HRBF_OK;
+}
+
+// ------------------------------------------------------------------ row 4 ---
+int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, float cy, float fx, float fy, float distThresh, float angleThresh)
+{
+    HRBF_CHECK_ARG(out && width >= 32 && height >= 16 && width % 8 == 0 && height % 4 == 0);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device"); return HRBF_ERR_NO_DEVICE; }
+    hrbf_odometry* o = new (std::nothrow) hrbf_odometry();
+    HRBF_CHECK_ARG(o != nullptr);
+    o->width = width; o->height = height;
+    o->intr.fx = fx; o->intr.fy = fy; o->intr.cx = cx; o->intr.cy = cy;
+    o->distThres = distThresh; o->angleThres = angleThresh;
+    o->sobelScale = (float)(1.0 / pow(2.0, 3));
+
+    // one slab, 256-B aligned sub-buffers
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+    size_t o_maps[M_COUNT][3], o_dt[3], o_ld[3], o_nd[3], o_li[3], o_ni[3], o_lni[3], o_dx[3], o_dy[3], o_cl[3], o_ci[3];
+    for (int l = 0; l < 3; ++l) {
+        const size_t P = (size_t)o->rows(l) * o->cols(l);
+        for (int m = 0; m < M_W; ++m) o_maps[m][l] = take(4 * P * sizeof(float));
+        o_maps[M_W][l] = take(P * sizeof(float));
+        o_dt[l] = take(P * 4); o_ld[l] = take(P * 4); o_nd[l] = take(P * 4);
+        o_li[l] = take(P); o_ni[l] = take(P); o_lni[l] = take(P);
+        o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cl[l] = take(P * 12); o_ci[l] = take(P * sizeof(hrbf_dataterm));
+    }
+    const size_t o_vd = take((size_t)width * height * 4), o_work = take(sizeof(ReduceWork)), o_pose = take(64 * sizeof(float));
+    if (cudaMalloc(&o->slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); delete o; return HRBF_ERR_CUDA; }
+    cudaMemset(o->slab, 0, off);
+    for (int l = 0; l < 3; ++l) {
+        for (int m = 0; m < M_COUNT; ++m) o->maps[m][l] = (float*)(o->slab + o_maps[m][l]);
+        o->depth_tmp[l] = (float*)(o->slab + o_dt[l]); o->lastDepth[l] = (float*)(o->slab + o_ld[l]); o->nextDepth[l] = (float*)(o->slab + o_nd[l]);
+        o->lastImage[l] = (unsigned char*)(o->slab + o_li[l]); o->nextImage[l] = (unsigned char*)(o->slab + o_ni[l]); o->lastNextImage[l] = (unsigned char*)(o->slab + o_lni[l]);
+        o->dIdx[l] = (short*)(o->slab + o_dx[l]); o->dIdy[l] = (short*)(o->slab + o_dy[l]);
+        o->cloud[l] = (float*)(o->slab + o_cl[l]); o->corresImg[l] = (hrbf_dataterm*)(o->slab + o_ci[l]);
+    }
+    o->vdepth_tmp = (float*)(o->slab + o_vd);
+    o->work = (ReduceWork*)(o->slab + o_work);
+    o->pose_scratch = (float*)(o->slab + o_pose);
+    cudaMallocHost(&o->h_pose, 24 * sizeof(float));
+    cudaMallocHost(&o->h_state, sizeof(TrackState));
+    cudaMallocHost(&o->h_model_pose, 8 * 12 * sizeof(float));
+    cudaStreamCreateWithFlags(&o->cap_stream, cudaStreamNonBlocking);
+    // camera lives in the device state for the fp64 K matrices
+    TrackState h;
+    memset(&h, 0, sizeof h);
+    h.fx = fx; h.fy = fy; h.cx = cx; h.cy = cy; h.done_level = -1;
+    cudaMemcpy(&o->work->st, &h, sizeof h, cudaMemcpyHostToDevice);
+    if (cudaGetLastError() != cudaSuccess) { set_error("odometry_create: CUDA setup failed"); hrbf_odometry_destroy(o); return HRBF_ERR_CUDA; }
+    *out = o;
+    return HRBF_OK;
+}
+
+int hrbf_odometry_destroy(hrbf_odometry* o)
+{
+    if (!o) return HRBF_OK;
+    for (auto& kv : o->graphs) cudaGraphExecDestroy(kv.second.first);
+    if (o->cap_stream) cudaStreamDestroy(o->cap_stream);
+    if (o->h_pose) cudaFreeHost(o->h_pose);
+    if (o->h_state) cudaFreeHost(o->h_state);
+    if (o->h_model_pose) cudaFreeHost(o->h_model_pose);
+    if (o->slab) cudaFree(o->slab);
+    delete o;
+    return HRBF_OK;
+}
+
+int hrbf_odometry_set_params(hrbf_odometry* o, float curvThr, int useSearch, int searchRadius, int rgbGradWeight)
+{
+    HRBF_CHECK_ARG(o && searchRadius >= 0 && searchRadius <= 2);
+    o->curvThr = curvThr; o->useSearch = useSearch; o->searchRadius = searchRadius; o->rgbGradWeight = rgbGradWeight;
+    return HRBF_OK;
+}
+
+int hrbf_odometry_init_icp_depth(hrbf_odometry* o, const float* depth, float cutoff, float factor, void* stream)
+{
+    HRBF_CHECK_ARG(o && depth);
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 b(32, 8);
+    HRBF_CUDA(cudaMemcpyAsync(o->depth_tmp[0], depth, (size_t)o->width * o->height * 4, cudaMemcpyDeviceToDevice, s));
+    for (int i = 1; i < 3; ++i) {
+        pyrdown_depth_kernel<<<grid2d(o->cols(i), o->rows(i), b), b, 0, s>>>(o->rows(i - 1), o->cols(i - 1), o->depth_tmp[i - 1], o->depth_tmp[i]);
+        HRBF_KERNEL_CHECK();
+    }
+    for (int i = 0; i < 3; ++i) {
+        const int div = 1 << i;
+        create_vmap_kernel<<<grid2d(o->cols(i), o->rows(i), b), b, 0, s>>>(o->rows(i), o->cols(i), o->depth_tmp[i], o->maps[M_VC][i], o->cols(i),
+                                                                         1.f / (o->intr.fx / div), 1.f / (o->intr.fy / div), o->intr.cx / div, o->intr.cy / div, cutoff, factor);
+        HRBF_KERNEL_CHECK();
+        create_nmap_kernel<<<grid2d(o->cols(i), o->rows(i), b), b, 0, s>>>(o->rows(i), o->cols(i), o->maps[M_VC][i], o->cols(i), o->maps[M_NC][i], o->cols(i));
+        HRBF_KERNEL_CHECK();
+    }
+    return HRBF_OK;
+}
+
+static inline dim3 pyr_grid(const hrbf_odometry* o) { return dim3(div_up(o->width, 32), div_up(o->height, 8)); }
+
+int hrbf_odometry_init_icp(hrbf_odometry* o, const float* v, const float* n, float depthCutoff, void* stream)
+{
+    (void)depthCutoff;
+    HRBF_CHECK_ARG(o && v && n);
+    pyr_pair_kernel<PYR_VN><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)v, (const float4*)n, o->height, o->width, 0.f, nullptr,
+                                                                         pyr_out(o, M_VC), pyr_out(o, M_NC), o->vdepth_tmp, o->maxDepthRGB);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_odometry_init_icp_model(hrbf_odometry* o, const float* v, const float* n, float depthCutoff, const float* pose16, void* stream)
+{
+    (void)depthCutoff;
+    HRBF_CHECK_ARG(o && v && n && pose16);
+    float* dpose = nullptr;
+    if (int rc = upload_pose(o, pose16, (cudaStream_t)stream, &dpose)) return rc;
+    pyr_pair_kernel<PYR_VN><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)v, (const float4*)n, o->height, o->width, 0.f, dpose,
+                                                                         pyr_out(o, M_VG), pyr_out(o, M_NG), o->vdepth_tmp, o->maxDepthRGB);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_odometry_init_curvature(hrbf_odometry* o, const float* k1, const float* k2, void* stream)
+{
+    HRBF_CHECK_ARG(o && k1 && k2);
+    pyr_pair_kernel<PYR_K><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)k1, (const float4*)k2, o->height, o->width, o->curvThr, nullptr,
+                                                                        pyr_out(o, M_K1C), pyr_out(o, M_K2C), nullptr, 0.f);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_odometry_init_curvature_model(hrbf_odometry* o, const float* k1, const float* k2, const float* pose16, void* stream)
+{
+    HRBF_CHECK_ARG(o && k1 && k2 && pose16);
+    float* dpose = nullptr;
+    if (int rc = upload_pose(o, pose16, (cudaStream_t)stream, &dpose)) return rc;
+    pyr_pair_kernel<PYR_K><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)k1, (const float4*)k2, o->height, o->width, o->curvThr, dpose,
+                                                                        pyr_out(o, M_K1G), pyr_out(o, M_K2G), nullptr, 0.f);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_odometry_init_icp_weight(hrbf_odometry* o, const float* w, void* stream)
+{
+    HRBF_CHECK_ARG(o && w);
+    pyr_weight_kernel<<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>(w, o->height, o->width, o->maps[M_W][0], o->cols(0), o->maps[M_W][1], o->cols(1), o->maps[M_W][2], o->cols(2));
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int hrbf_odometry_fill_neutral_curvature(hrbf_odometry* o, void* stream)
+{
+    HRBF_CHECK_ARG(o);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int l = 0; l < 3; ++l) {
+        const size_t P = (size_t)o->rows(l) * o->cols(l);
+        for (int m : { M_K1G, M_K2G, M_K1C, M_K2C }) HRBF_CUDA(cudaMemsetAsync(o->maps[m][l], 0, 4 * P * sizeof(float), s));
+        std::vector<float> ones(P, 1.0f);
+        HRBF_CUDA(cudaMemcpyAsync(o->maps[M_W][l], ones.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
+        HRBF_CUDA(cudaStreamSynchronize(s));
+    }
+    return HRBF_OK;
+}
+
+static int populate_rgbd(hrbf_odometry* o, const unsigned char* rgba, float** depths, unsigned char** images, cudaStream_t s)
+{
+    const dim3 b(32, 8);
+    HRBF_CUDA(cudaMemcpyAsync(depths[0], o->vdepth_tmp, (size_t)o->width * o->height * 4, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i + 1 < 3; ++i) {
+        pyrdown_gauss_f32_kernel<<<grid2d(o->cols(i + 1), o->rows(i + 1), b), b, 0, s>>>(o->rows(i), o->cols(i), depths[i], depths[i + 1]);
+        HRBF_KERNEL_CHECK();
+    }
+    const int n = o->width * o->height;
+    rgba_to_intensity_kernel<<<div_up(n, 256), 256, 0, s>>>(n, (const uchar4*)rgba, images[0]);
+    HRBF_KERNEL_CHECK();
+    for (int i = 0; i + 1 < 3; ++i) {
+        pyrdown_gauss_u8_kernel<<<grid2d(o->cols(i + 1), o->rows(i + 1), b), b, 0, s>>>(o->rows(i), o->cols(i), images[i], images[i + 1]);
+        HRBF_KERNEL_CHECK();
+    }
+    return HRBF_OK;
+}
+int hrbf_odometry_init_rgb(hrbf_odometry* o, const unsigned char* rgba, void* stream)
+{ HRBF_CHECK_ARG(o && rgba); return populate_rgbd(o, rgba, o->nextDepth, o->nextImage, (cudaStream_t)stream); }
+int hrbf_odometry_init_rgb_model(hrbf_odometry* o, const unsigned char* rgba, void* stream)
+{ HRBF_CHECK_ARG(o && rgba); return populate_rgbd(o, rgba, o->lastDepth, o->lastImage, (cudaStream_t)stream); }
+int hrbf_odometry_init_first_rgb(hrbf_odometry* o, const unsigned char* rgba, void* stream)
+{
+    HRBF_CHECK_ARG(o && rgba);
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 b(32, 8);
+    const int n = o->width * o->height;
+    rgba_to_intensity_kernel<<<div_up(n, 256), 256, 0, s>>>(n, (const uchar4*)rgba, o->lastNextImage[0]);
+    HRBF_KERNEL_CHECK();
+    for (int i = 0; i + 1 < 3; ++i) {
+        pyrdown_gauss_u8_kernel<<<grid2d(o->cols(i + 1), o->rows(i + 1), b), b, 0, s>>>(o->rows(i), o->cols(i), o->lastNextImage[i], o->lastNextImage[i + 1]);
+        HRBF_KERNEL_CHECK();
+    }
+    return HRBF_OK;
+}
+
+static void swap_so3_images(hrbf_odometry* o)
+{   // RGBDOdometry.cpp:1239-1245 : pointer swap.  Captured graphs bake buffer addresses, so the
+    // graph key carries the swap parity (two alternating graph sets).
+    for (int i = 0; i < 3; ++i) std::swap(o->lastNextImage[i], o->nextImage[i]);
+    o->so3_parity ^= 1;
+}
+
+int hrbf_odometry_get_incremental_transformation(hrbf_odometry* o, float* trans, float* rot, int rgbOnly, float icpWeight, int pyramid,
+                                                 int fastOdom, int so3, int if_curvature_info, int index_frame, hrbf_track_stats* stats, void* stream)
+{
+    (void)index_frame;
+    HRBF_CHECK_ARG(o && trans && rot);
+    cudaStream_t s = (cudaStream_t)stream;
+    memcpy(o->h_pose, rot, 36);
+    memcpy(o->h_pose + 9, trans, 12);
+    cudaGraphExec_t exec = nullptr;
+    int nk = 0;
+    if (int rc = get_graph(o, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0, true, &exec, &nk)) return rc;
+    HRBF_CUDA(cudaGraphLaunch(exec, s));
+    count_launch(nk);
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    if (so3) swap_so3_images(o);
+    memcpy(rot, o->h_pose + 12, 36);
+    memcpy(trans, o->h_pose + 21, 12);
+    if (stats) {
+        const TrackState& h = *o->h_state;
+        stats->lastICPError = h.lastICPError; stats->lastICPCount = h.lastICPCount;
+        stats->lastRGBError = h.lastRGBError; stats->lastRGBCount = h.lastRGBCount;
+        stats->lastSO3Error = h.lastSO3Error; stats->lastSO3Count = h.lastSO3Count;
+        memcpy(stats->lastA, h.lastA, sizeof h.lastA); memcpy(stats->lastb, h.lastb, sizeof h.lastb);
+        stats->icp_iterations_run = h.icp_iterations_run;
+        stats->kernel_launches = nk;
+    }
+    return HRBF_OK;
+}
+
+int hrbf_odometry_track_async(hrbf_odometry* o, const float* prev_pose_dev, float* pose_out_dev, int rgbOnly, float icpWeight, int pyramid,
+                              int fastOdom, int so3, int if_curvature_info, void* stream)
+{
+    HRBF_CHECK_ARG(o && prev_pose_dev && pose_out_dev);
+    cudaStream_t s = (cudaStream_t)stream;
+    HRBF_CUDA(cudaMemcpyAsync(o->pose_scratch + 12, prev_pose_dev, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int nk = 0;
+    cudaGraphExec_t exec = nullptr;
+    if (int rc = get_graph(o, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0, false, &exec, &nk)) return rc;
+    HRBF_CUDA(cudaGraphLaunch(exec, s));
+    if (so3) swap_so3_images(o);
+    count_launch(nk);
+    HRBF_CUDA(cudaMemcpyAsync(pose_out_dev, o->pose_scratch + 24, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return HRBF_OK;
+}
+
+const float* hrbf_odometry_map(const hrbf_odometry* o, int which, int level, size_t* step)
+{
+    if (!o || which < 0 || which >= M_COUNT || level < 0 || level > 2) return nullptr;
+    if (step) *step = (size_t)o->cols(level) * sizeof(float);
+    return o->maps[which][level];
+}
+const unsigned char* hrbf_odometry_image(const hrbf_odometry* o, int which, int level)
+{
+    if (!o || level < 0 || level > 2) return nullptr;
+    return which == 0 ? o->lastImage[level] : which == 1 ? o->nextImage[level] : o->lastNextImage[level];
+}
+const float* hrbf_odometry_depth(const hrbf_odometry* o, int which, int level)
+{
+    if (!o || level < 0 || level > 2) return nullptr;
+    return which == 0 ? o->lastDepth[level] : o->nextDepth[level];
+}
+
+}  // extern "C"

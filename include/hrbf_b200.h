@@ -1,0 +1,202 @@
+/*
+ * hrbf_b200.h -- C ABI of the B200-native (sm_100a) HRBFFusion3D hot path.
+ *
+ * Drop-in boundary for the reference's per-frame path:
+ *   free functions of Core/src/Cuda/cudafuncs.cuh           -> hrbf_* map / step functions
+ *   class RGBDOdometry  (Core/src/Utils/RGBDOdometry.h)      -> hrbf_odometry_*
+ *   class IndexMap      (Core/src/IndexMap.h)                -> hrbf_indexmap_*
+ *   class GlobalModel   (Core/src/GlobalModel.h)             -> hrbf_model_*
+ *   HRBFFusion::processFrame / predict (Core/src/HRBFFusion.cpp:991-1260) -> hrbf_fusion_*
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `dev` pointers are CUDA device pointers,
+ *     `host` pointers are host memory.  No torch / Eigen / GL types.
+ *   - every function returns an int status (HRBF_OK == 0); nothing calls exit()
+ *     (the reference's cudaSafeCall does: Cuda/convenience.cuh:64-71).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - no allocation inside step functions: objects allocate once at create().
+ *   - layouts are the reference's:
+ *       SoA map     float[4*rows][cols], planes x,y,z,w stacked row-wise, `step` = row
+ *                   pitch in BYTES (DeviceArray2D::step(), RGBDOdometry.cpp:128-136)
+ *       AoS texture float[rows][cols][4] (RGBA32F as cudaMemcpyFromArray delivers it)
+ *       surfel      5 x float4 = 80 B (Shaders/Vertex.cpp:20-44)
+ *       A 6x6 row-major float, b 6 float, residual[2] = {sum w r^2, inliers}
+ *       sums29      JtJJtrSE3 field order (Cuda/types.cuh:100-151)
+ */
+#ifndef HRBF_B200_H_
+#define HRBF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRBF_OK                0
+#define HRBF_ERR_INVALID_ARG  -1
+#define HRBF_ERR_CUDA         -2
+#define HRBF_ERR_NO_DEVICE    -3
+#define HRBF_ERR_CAPACITY     -4
+
+#define HRBF_NUM_PYRS 3
+#define HRBF_SURFEL_FLOATS 20
+
+/* last error text of the calling thread ("" if none) */
+const char* hrbf_last_error(void);
+/* library / build identification, e.g. "hrbf_b200 0.1 sm_100a" */
+const char* hrbf_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long hrbf_launch_count(void);
+
+typedef struct { float fx, fy, cx, cy; } hrbf_camera;   /* CameraModel, Cuda/types.cuh:82-98 */
+
+/* ------------------------------------------------------------------------
+ * Row 5 : pyramid / map preparation  (replaces Cuda/cudafuncs.cuh:148-214)
+ * ---------------------------------------------------------------------- */
+/* copyMaps, cudafuncs.cu:344-403 */
+int hrbf_copy_maps(const float* v_aos_dev, const float* n_aos_dev,
+                   float* vmap_dev, size_t vstep, float* nmap_dev, size_t nstep,
+                   int rows, int cols, void* stream);
+/* copyCurvatureMap, cudafuncs.cu:405-449 */
+int hrbf_copy_curvature_map(const float* c_aos_dev, float* cmap_dev, size_t cstep,
+                            int rows, int cols, float curvatureThreshold, void* stream);
+/* copyicpWeightMap, cudafuncs.cu:452-491 */
+int hrbf_copy_icpweight_map(const float* w_src_dev, float* w_dst_dev, size_t wstep,
+                            int rows, int cols, void* stream);
+/* resizeVMap / resizeNMap, cudafuncs.cu:526-615 (in_rows/in_cols = source size) */
+int hrbf_resize_vmap(const float* in_dev, size_t in_step, float* out_dev, size_t out_step,
+                     int in_rows, int in_cols, void* stream);
+int hrbf_resize_nmap(const float* in_dev, size_t in_step, float* out_dev, size_t out_step,
+                     int in_rows, int in_cols, void* stream);
+/* resizeCMap, cudafuncs.cu:618-692 */
+int hrbf_resize_cmap(const float* in_dev, size_t in_step, float* out_dev, size_t out_step,
+                     int in_rows, int in_cols, void* stream);
+/* resizeicpWeightMap, cudafuncs.cu:694-743 */
+int hrbf_resize_icpweight_map(const float* in_dev, size_t in_step, float* out_dev, size_t out_step,
+                              int in_rows, int in_cols, void* stream);
+/* tranformMaps, cudafuncs.cu:213-277 (in place allowed); R row-major 3x3, t 3 (host) */
+int hrbf_transform_maps(const float* vsrc_dev, size_t vsstep, const float* nsrc_dev, size_t nsstep,
+                        const float* R_host, const float* t_host,
+                        float* vdst_dev, size_t vdstep, float* ndst_dev, size_t ndstep,
+                        int rows, int cols, void* stream);
+/* transformCurvMaps, cudafuncs.cu:279-342 */
+int hrbf_transform_curv_maps(const float* k1src_dev, size_t k1sstep, const float* k2src_dev, size_t k2sstep,
+                             const float* R_host, const float* t_host,
+                             float* k1dst_dev, size_t k1dstep, float* k2dst_dev, size_t k2dstep,
+                             int rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Rows 1-3 : Jacobian-product reductions  (replaces Cuda/cudafuncs.cuh:82-147)
+ * Synchronous like the reference: results are on the host when the call returns.
+ * `work_dev` : >= hrbf_reduce_workspace_bytes() of device scratch.
+ * ---------------------------------------------------------------------- */
+size_t hrbf_reduce_workspace_bytes(void);
+
+typedef struct {
+    int use_search;          /* registrationICPUseCoorespondenceSearch */
+    int search_radius;       /* registrationICPNeighborSearchRadius    */
+    int use_weight;          /* icp_if_use_weight                      */
+    float dist_thres;        /* RGBDOdometry.h:65 (0.1 m)              */
+    float angle_thres;       /* RGBDOdometry.h:66 (sin 20 deg)         */
+} hrbf_icp_options;
+
+/* icpStep, reduce.cu:580-693.  corres_dev (optional) int2[rows*cols] */
+int hrbf_icp_step(const float* Rcurr_host, const float* tcurr_host,
+                  const float* vmap_curr_dev, const float* nmap_curr_dev,
+                  const float* ck1_curr_dev, const float* ck2_curr_dev, size_t curr_step,
+                  const float* Rprev_inv_host, const float* tprev_host, hrbf_camera intr,
+                  const float* vmap_g_prev_dev, const float* nmap_g_prev_dev,
+                  const float* ck1_g_prev_dev, const float* ck2_g_prev_dev, size_t prev_step,
+                  const float* icpw_g_prev_dev, size_t icpw_step,
+                  int rows, int cols, const hrbf_icp_options* opts,
+                  int* corres_dev, void* work_dev,
+                  float* A_host, float* b_host, float* residual_host, double* sums29_host,
+                  void* stream);
+
+/* DataTerm, Cuda/types.cuh:74-80 (16 B) */
+typedef struct { short zero_x, zero_y, one_x, one_y; float diff; unsigned char valid; unsigned char pad[3]; } hrbf_dataterm;
+
+/* computeRgbResidual, reduce.cu:1088-1154 (images dense, pitch == cols) */
+int hrbf_compute_rgb_residual(float minScale, const short* dIdx_dev, const short* dIdy_dev,
+                              const float* lastDepth_dev, const float* nextDepth_dev,
+                              const unsigned char* lastImage_dev, const unsigned char* nextImage_dev,
+                              hrbf_dataterm* corresImg_dev, float maxDepthDelta,
+                              const float* kt_host, const float* krkinv_host,
+                              int rows, int cols, void* work_dev,
+                              int* sigmaSum_host, int* count_host, void* stream);
+/* rgbStep, reduce.cu:842-896 */
+int hrbf_rgb_step(const hrbf_dataterm* corresImg_dev, float sigma, const float* cloud3_dev,
+                  float fx, float fy, const short* dIdx_dev, const short* dIdy_dev,
+                  int use_gradient_weight, float sobelScale, int rows, int cols, void* work_dev,
+                  float* A_host, float* b_host, double* sums29_host, void* stream);
+/* so3Step, reduce.cu:1301-1359 */
+int hrbf_so3_step(const unsigned char* lastImage_dev, const unsigned char* nextImage_dev,
+                  const float* imageBasis_host, const float* kinv_host, const float* krlr_host,
+                  int rows, int cols, void* work_dev,
+                  float* A_host, float* b_host, float* residual_host, double* sums11_host, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Row 4 : RGBDOdometry  (Utils/RGBDOdometry.h:57-107)
+ * "Textures" are dense device buffers: RGBA32F AoS float[h][w][4], R32F float[h][w],
+ * RGBA8 uchar[h][w][4].
+ * ---------------------------------------------------------------------- */
+typedef struct hrbf_odometry hrbf_odometry;
+
+/* RGBDOdometry::RGBDOdometry, RGBDOdometry.cpp:35-154 */
+int hrbf_odometry_create(hrbf_odometry** out, int width, int height,
+                         float cx, float cy, float fx, float fy,
+                         float distThresh, float angleThresh);
+int hrbf_odometry_destroy(hrbf_odometry*);
+/* knobs read from GlobalStateParam inside the reference path */
+int hrbf_odometry_set_params(hrbf_odometry*, float curvValidThreshold, int useCorrespondenceSearch,
+                             int searchRadius, int rgbUseGradientWeight);
+/* initICP(depth) [GPUTest path], RGBDOdometry.cpp:161-181 : depth_dev = float[h][w] raw units */
+int hrbf_odometry_init_icp_depth(hrbf_odometry*, const float* depth_dev, float depthCutoff, float depthMapFactor, void* stream);
+/* initICP(vertices, normals), RGBDOdometry.cpp:183-206 */
+int hrbf_odometry_init_icp(hrbf_odometry*, const float* vert_aos_dev, const float* norm_aos_dev, float depthCutoff, void* stream);
+/* initICPModel, RGBDOdometry.cpp:208-247 : modelPose row-major 4x4 (host) */
+int hrbf_odometry_init_icp_model(hrbf_odometry*, const float* vert_aos_dev, const float* norm_aos_dev,
+                                 float depthCutoff, const float* modelPose_host, void* stream);
+/* initRGB / initRGBModel / initFirstRGB, RGBDOdometry.cpp:689-699, 777-794 */
+int hrbf_odometry_init_rgb(hrbf_odometry*, const unsigned char* rgba_dev, void* stream);
+int hrbf_odometry_init_rgb_model(hrbf_odometry*, const unsigned char* rgba_dev, void* stream);
+int hrbf_odometry_init_first_rgb(hrbf_odometry*, const unsigned char* rgba_dev, void* stream);
+/* initCurvature / initCurvatureModel, RGBDOdometry.cpp:701-759 */
+int hrbf_odometry_init_curvature(hrbf_odometry*, const float* k1_aos_dev, const float* k2_aos_dev, void* stream);
+int hrbf_odometry_init_curvature_model(hrbf_odometry*, const float* k1_aos_dev, const float* k2_aos_dev,
+                                       const float* modelPose_host, void* stream);
+/* initICPweight, RGBDOdometry.cpp:761-775 */
+int hrbf_odometry_init_icp_weight(hrbf_odometry*, const float* w_dev, void* stream);
+/* GPUTest-pair convention: curvature planes 0 (valid), weights 1 */
+int hrbf_odometry_fill_neutral_curvature(hrbf_odometry*, void* stream);
+
+typedef struct {
+    float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
+    double lastA[36], lastb[6];
+    int icp_iterations_run;
+    int kernel_launches;
+} hrbf_track_stats;
+
+/* getIncrementalTransformation, RGBDOdometry.cpp:796-1249.
+ * trans_host[3], rot_host[9] (row-major): in = previous pose, out = estimated pose.
+ * The whole coarse-to-fine Gauss-Newton loop (reductions, 6x6 LDLT in fp64, SE3 update)
+ * runs on the device without host round trips; the call returns after one sync. */
+int hrbf_odometry_get_incremental_transformation(hrbf_odometry*, float* trans_host, float* rot_host,
+                                                 int rgbOnly, float icpWeight, int pyramid, int fastOdom,
+                                                 int so3, int if_curvature_info, int index_frame,
+                                                 hrbf_track_stats* stats_host, void* stream);
+/* asynchronous variant: the pose stays on the device (pose_dev: float[12] = rot[9], trans[3]) */
+int hrbf_odometry_track_async(hrbf_odometry*, const float* prev_pose_dev, float* pose_out_dev,
+                              int rgbOnly, float icpWeight, int pyramid, int fastOdom,
+                              int so3, int if_curvature_info, void* stream);
+/* device views of the internal pyramid maps (tests, chaining):
+ * which = 0..8 -> vmap_g_prev,nmap_g_prev,ck1_g_prev,ck2_g_prev,vmap_curr,nmap_curr,ck1_curr,ck2_curr,icpWeight */
+const float* hrbf_odometry_map(const hrbf_odometry*, int which, int level, size_t* step_bytes);
+const unsigned char* hrbf_odometry_image(const hrbf_odometry*, int which, int level); /* 0 last, 1 next, 2 lastNext */
+const float* hrbf_odometry_depth(const hrbf_odometry*, int which, int level);        /* 0 last, 1 next */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRBF_B200_H_ */

@@ -1,0 +1,240 @@
+"""GPU parity tests (run on the B200): CUDA path through the C ABI vs the CPU oracle.
+SURVEY.md section 8 rows 1-5 (+ RGB / SO3)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import pair, nan_eq_planes, pose_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+# tolerances (north_star: pose <= 1e-5; the sums are fp32 products accumulated fp32-per-block /
+# fp64-across-blocks on the GPU and fp64 in the oracle)
+SUM_RTOL = 2e-5
+POSE_TOL = 1e-5
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build_both(orc, torch, W, H, kind="room", seed=0):
+    from hrbffusion3d_b200 import odometry as od
+    m0, pose0, m1, pose1, cam = pair(W, H, kind=kind, seed=seed)
+    oo = orc.Odometry(W, H, cam[2], cam[3], cam[0], cam[1])
+    go = od.RGBDOdometry(W, H, cam[2], cam[3], cam[0], cam[1])
+    for o, f in ((oo, lambda a: a), (go, lambda a: dev(torch, a))):
+        o.initFirstRGB(f(m0["rgba"]))
+        o.initICPModel(f(m0["vertex"]), f(m0["normal"]), 20.0, pose0)
+        o.initRGBModel(f(m0["rgba"]))
+        o.initCurvatureModel(f(m0["k1"]), f(m0["k2"]), pose0)
+        o.initICP(f(m1["vertex"]), f(m1["normal"]), 20.0)
+        o.initRGB(f(m1["rgba"]))
+        o.initCurvature(f(m1["k1"]), f(m1["k2"]))
+        o.initICPweight(f(m0["icpw"]))
+    return oo, go, (m0, pose0, m1, pose1, cam)
+
+
+@pytest.mark.parametrize("W,H", [(160, 120), (640, 480)])
+def test_pyramid_maps_match_oracle(orc, cuda, W, H):
+    oo, go, _ = build_both(orc, cuda, W, H)
+    for lvl in range(3):
+        rows = H >> lvl
+        for name in ("vmap_g_prev", "nmap_g_prev", "vmap_curr", "nmap_curr"):
+            nan_eq_planes(go.map(name, lvl).cpu().numpy(), oo.map(name, lvl), rows, atol=2e-6, rtol=2e-6)
+        for name in ("ck1_g_prev", "ck2_g_prev", "ck1_curr", "ck2_curr"):
+            a, b = go.map(name, lvl).cpu().numpy(), oo.map(name, lvl)
+            # curvature validity lives in plane w
+            assert np.array_equal(np.isnan(a[3 * rows:]), np.isnan(b[3 * rows:]))
+            ok = ~np.isnan(b[3 * rows:])
+            for p in range(4):
+                np.testing.assert_allclose(a[p * rows:(p + 1) * rows][ok], b[p * rows:(p + 1) * rows][ok], rtol=2e-6, atol=2e-6)
+        a, b = go.map("icpWeight", lvl).cpu().numpy(), oo.map("icpWeight", lvl)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(a[~np.isnan(b)], b[~np.isnan(b)], rtol=2e-6)
+        # RGB branch prep is integer / exact
+        for which in (0, 1, 2):
+            assert np.array_equal(go.image(which, lvl).cpu().numpy(), oo.image(which, lvl)), (which, lvl)
+        for which in (0, 1):
+            a, b = go.depth(which, lvl).cpu().numpy(), oo.depth(which, lvl)
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            np.testing.assert_allclose(a[~np.isnan(b)], b[~np.isnan(b)], rtol=1e-6)
+
+
+def test_row5_single_kernels_match_oracle(orc, cuda):
+    """The one-to-one cudafuncs.cuh replacements (pitched destination, like DeviceArray2D)."""
+    import ctypes as C
+    from hrbffusion3d_b200._lib import lib, check, ptr, stream_ptr
+    torch = cuda
+    m0, pose0, m1, pose1, cam = pair(160, 120)
+    rows, cols, pitch = 120, 160, 192          # pitch in elements (> cols)
+    v = torch.full((4 * rows, pitch), 7.0, device="cuda"); n = torch.full((4 * rows, pitch), 7.0, device="cuda")
+    check(lib().hrbf_copy_maps(ptr(dev(torch, m0["vertex"])), ptr(dev(torch, m0["normal"])), ptr(v), C.c_size_t(pitch * 4), ptr(n), C.c_size_t(pitch * 4), rows, cols, stream_ptr()))
+    ov, on = orc.copyMaps(m0["vertex"], m0["normal"])
+    np.testing.assert_array_equal(v[:, :cols].cpu().numpy(), ov)
+    np.testing.assert_array_equal(n[:, :cols].cpu().numpy(), on)
+    assert float(v[:, cols:].min()) == 7.0      # padding untouched
+    # resize (vmap / nmap) with stale-plane semantics: only plane x is written for NaN pixels
+    for mode, fn in ((0, lib().hrbf_resize_vmap), (1, lib().hrbf_resize_nmap)):
+        src = v if mode == 0 else n
+        dst = torch.full((4 * (rows // 2), 96), 3.0, device="cuda")
+        check(fn(ptr(src), C.c_size_t(pitch * 4), ptr(dst), C.c_size_t(96 * 4), rows, cols, stream_ptr()))
+        ref = orc.resizeMap(ov if mode == 0 else on, mode, init=np.full((4 * (rows // 2), cols // 2), 3.0, np.float32))
+        np.testing.assert_allclose(dst[:, :cols // 2].cpu().numpy(), ref, rtol=1e-6, atol=1e-7, equal_nan=True)
+    # curvature copy / resize, weight copy / resize
+    c = torch.zeros((4 * rows, pitch), device="cuda")
+    check(lib().hrbf_copy_curvature_map(ptr(dev(torch, m0["k1"])), ptr(c), C.c_size_t(pitch * 4), rows, cols, C.c_float(300.0), stream_ptr()))
+    oc = orc.copyCurvatureMap(m0["k1"], 300.0)
+    np.testing.assert_array_equal(c[:, :cols].cpu().numpy(), oc)
+    c1 = torch.full((4 * (rows // 2), cols // 2), np.nan, device="cuda")
+    check(lib().hrbf_resize_cmap(ptr(c), C.c_size_t(pitch * 4), ptr(c1), C.c_size_t(cols // 2 * 4), rows, cols, stream_ptr()))
+    np.testing.assert_allclose(c1.cpu().numpy(), orc.resizeCMap(oc), rtol=1e-6, equal_nan=True)
+    w = torch.zeros((rows, pitch), device="cuda")
+    check(lib().hrbf_copy_icpweight_map(ptr(dev(torch, m0["icpw"])), ptr(w), C.c_size_t(pitch * 4), rows, cols, stream_ptr()))
+    ow = orc.copyicpWeightMap(m0["icpw"])
+    np.testing.assert_array_equal(w[:, :cols].cpu().numpy(), ow)
+    w1 = torch.zeros((rows // 2, cols // 2), device="cuda")
+    check(lib().hrbf_resize_icpweight_map(ptr(w), C.c_size_t(pitch * 4), ptr(w1), C.c_size_t(cols // 2 * 4), rows, cols, stream_ptr()))
+    np.testing.assert_allclose(w1.cpu().numpy(), orc.resizeicpWeightMap(ow), rtol=1e-6, equal_nan=True)
+    # rigid transforms, in place
+    R = np.ascontiguousarray(pose0[:3, :3]); t = np.ascontiguousarray(pose0[:3, 3])
+    hp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    check(lib().hrbf_transform_maps(ptr(v), C.c_size_t(pitch * 4), ptr(n), C.c_size_t(pitch * 4), hp(R), hp(t), ptr(v), C.c_size_t(pitch * 4), ptr(n), C.c_size_t(pitch * 4), rows, cols, stream_ptr()))
+    tv, tn = orc.tranformMaps(ov, on, R, t)
+    nan_eq_planes(v[:, :cols].cpu().numpy(), tv, rows, atol=1e-6)
+    nan_eq_planes(n[:, :cols].cpu().numpy(), tn, rows, atol=1e-6)
+
+
+@pytest.mark.parametrize("W,H,use_weight", [(160, 120, 1), (640, 480, 1), (640, 480, 0), (1280, 960, 1)])
+def test_icp_step_matches_oracle(orc, cuda, W, H, use_weight):
+    from hrbffusion3d_b200 import odometry as od
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
+    Rp, tp = pose0[:3, :3], pose0[:3, 3]
+    Rpi = np.linalg.inv(Rp).astype(np.float32)
+    for lvl in range(3):
+        camL = tuple(np.float32(c) / np.float32(1 << lvl) for c in cam)
+        names = ("vmap_curr", "nmap_curr", "ck1_curr", "ck2_curr")
+        gnames = ("vmap_g_prev", "nmap_g_prev", "ck1_g_prev", "ck2_g_prev", "icpWeight")
+        A, b, res, sums, cg = od.icpStep(Rp, tp, *[go.map(k, lvl) for k in names], Rpi, tp, camL, *[go.map(k, lvl) for k in gnames],
+                                         use_weight=bool(use_weight), want_corres=True)
+        Ao, bo, reso, sumso, co = orc.icpStep(Rp, tp, *[oo.map(k, lvl) for k in names], Rpi, tp, camL, *[oo.map(k, lvl) for k in gnames],
+                                              use_weight=use_weight, want_corres=True)
+        # index work is bit-exact up to pixels whose projection sits on a rounding boundary
+        mism = np.mean(np.any(cg.cpu().numpy() != co, axis=-1))
+        assert mism < 2e-4, mism
+        assert abs(res[1] - reso[1]) <= max(2.0, 2e-4 * reso[1])
+        scale = np.abs(sumso[:27]).max()
+        np.testing.assert_allclose(sums[:27], sumso[:27], rtol=SUM_RTOL * 50, atol=SUM_RTOL * scale)
+        np.testing.assert_allclose(A, Ao, rtol=1e-3, atol=SUM_RTOL * np.abs(Ao).max())
+
+
+def test_icp_step_search_window(orc, cuda):
+    from hrbffusion3d_b200 import odometry as od
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, 160, 120)
+    Rp, tp = pose0[:3, :3], pose0[:3, 3]
+    Rpi = np.linalg.inv(Rp).astype(np.float32)
+    names = ("vmap_curr", "nmap_curr", "ck1_curr", "ck2_curr")
+    gnames = ("vmap_g_prev", "nmap_g_prev", "ck1_g_prev", "ck2_g_prev", "icpWeight")
+    A, b, res, sums, _ = od.icpStep(Rp, tp, *[go.map(k, 0) for k in names], Rpi, tp, cam, *[go.map(k, 0) for k in gnames], use_search=True, search_radius=2)
+    Ao, bo, reso, sumso, _ = orc.icpStep(Rp, tp, *[oo.map(k, 0) for k in names], Rpi, tp, cam, *[oo.map(k, 0) for k in gnames], use_search=1, radius=2)
+    assert abs(res[1] - reso[1]) <= 3
+    np.testing.assert_allclose(sums[:27], sumso[:27], rtol=5e-3, atol=1e-3 * np.abs(sumso[:27]).max())
+
+
+def test_rgb_and_so3_steps_match_oracle(orc, cuda):
+    from hrbffusion3d_b200 import odometry as od
+    torch = cuda
+    W, H = 320, 240
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
+    for lvl in range(3):
+        camL = tuple(np.float32(c) / np.float32(1 << lvl) for c in cam)
+        nextI, lastI = oo.image(1, lvl), oo.image(0, lvl)
+        dx, dy = orc.sobel(nextI)
+        Kl = np.array([[camL[0], 0, camL[2]], [0, camL[1], camL[3]], [0, 0, 1]], np.float64)
+        Rrel = np.eye(3)
+        krkinv = (Kl @ Rrel @ np.linalg.inv(Kl)).astype(np.float32)
+        kt = (Kl @ np.array([0.002, -0.001, 0.003])).astype(np.float32)
+        minScale = [5, 3, 1][lvl] ** 2 / 0.125 ** 2
+        co, sigo, cnto = orc.computeRgbResidual(minScale, dx, dy, oo.depth(0, lvl), oo.depth(1, lvl), lastI, nextI, 0.07, kt, krkinv)
+        cg, sigg, cntg = od.computeRgbResidual(minScale, dev(torch, dx), dev(torch, dy), go.depth(0, lvl), go.depth(1, lvl), go.image(0, lvl), go.image(1, lvl), 0.07, kt, krkinv)
+        assert cnto > 100
+        assert (sigg, cntg) == (sigo, cnto)                      # integer sums: bit-exact
+        assert np.array_equal(cg.cpu().numpy().view(orc.DATATERM).reshape(co.shape), co)
+        cloud = orc.projectToPointCloud(oo.depth(0, lvl), camL)
+        sigma = float(np.sqrt(cnto))
+        Ao, bo, so = orc.rgbStep(co, sigma, cloud, camL[0], camL[1], dx, dy, 0, 0.125)
+        A, b, s = od.rgbStep(cg, sigma, dev(torch, cloud), camL[0], camL[1], dev(torch, dx), dev(torch, dy), 0, 0.125)
+        np.testing.assert_allclose(s[:27], so[:27], rtol=1e-4, atol=2e-5 * np.abs(so[:27]).max())
+    # SO3 (level 2 images)
+    lvl = 2
+    camL = tuple(np.float32(c) / np.float32(1 << lvl) for c in cam)
+    Kl = np.array([[camL[0], 0, camL[2]], [0, camL[1], camL[3]], [0, 0, 1]], np.float64)
+    from hrbffusion3d_b200 import synth
+    Rr = synth.rot_xyz(0.002, -0.003, 0.001)
+    B = (Kl @ Rr @ np.linalg.inv(Kl)).astype(np.float32); kinv = np.linalg.inv(Kl).astype(np.float32); krlr = (Kl @ Rr).astype(np.float32)
+    Ao, bo, ro, so = orc.so3Step(oo.image(2, lvl), oo.image(1, lvl), B, kinv, krlr)
+    A, b, r, s = od.so3Step(go.image(2, lvl), go.image(1, lvl), B, kinv, krlr)
+    assert r[1] == ro[1]
+    np.testing.assert_allclose(s[:10], so[:10], rtol=1e-4, atol=2e-5 * np.abs(so[:10]).max())
+
+
+@pytest.mark.parametrize("W,H,kw", [
+    (640, 480, dict(icpWeight=100.0, so3=False)),                 # ICP only
+    (640, 480, dict(icpWeight=10.0, so3=True)),                   # reference default: joint RGB-D + SO3 pre-alignment
+    (640, 480, dict(icpWeight=10.0, so3=False, pyramid=False)),
+    (320, 240, dict(rgbOnly=True, so3=True)),
+    (640, 480, dict(icpWeight=100.0, so3=False, fastOdom=True, if_curvature_info=False)),
+    (1280, 960, dict(icpWeight=100.0, so3=False)),
+])
+def test_tracking_pose_matches_oracle(orc, cuda, W, H, kw):
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
+    to, Ro, sto = oo.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **kw)
+    tg, Rg, stg = go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **kw)
+    ang, dt = pose_err(Ro, to, Rg, tg)
+    assert dt <= POSE_TOL and ang <= POSE_TOL, (ang, dt)
+    np.testing.assert_allclose(np.asarray(Rg), np.asarray(Ro), atol=POSE_TOL)
+    assert stg.icp_iterations_run == sto.icp_iterations_run
+    if not kw.get("rgbOnly"):
+        assert abs(stg.lastICPCount - sto.lastICPCount) <= max(3.0, 3e-4 * sto.lastICPCount)
+    # and both actually track: closer to the true pose than the start
+    ang1, dt1 = pose_err(Rg, tg, pose1[:3, :3], pose1[:3, 3])
+    ang0, dt0 = pose_err(pose0[:3, :3], pose0[:3, 3], pose1[:3, :3], pose1[:3, 3])
+    assert dt1 < dt0 and ang1 < ang0
+
+
+def test_tracking_two_frames_so3_swap(orc, cuda):
+    """Second call exercises the lastNextImage/nextImage swap (RGBDOdometry.cpp:1239-1245)."""
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, 320, 240)
+    for _ in range(2):
+        to, Ro, _s = oo.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], icpWeight=10.0, so3=True)
+        tg, Rg, _s = go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], icpWeight=10.0, so3=True)
+        ang, dt = pose_err(Ro, to, Rg, tg)
+        assert dt <= POSE_TOL and ang <= POSE_TOL, (ang, dt)
+        for o, f in ((oo, lambda a: a), (go, lambda a: dev(cuda, a))):
+            o.initRGB(f(m1["rgba"]))
+
+
+def test_gputest_pair_golden(orc, cuda):
+    """Reference GPUTest frame pair: CUDA path vs the committed golden vector (oracle output)."""
+    g = np.load(os.path.join(GOLD, "gputest_pair.npz"))
+    from tests.gputest_pair import run_cuda
+    out = run_cuda(g)
+    for k in ("icp_only", "faithful"):
+        ang, dt = pose_err(out[k + "_rot"], out[k + "_trans"], g[k + "_rot"], g[k + "_trans"])
+        assert dt <= POSE_TOL and ang <= POSE_TOL, (k, ang, dt)
+    np.testing.assert_allclose(out["A0"], g["A0"], rtol=1e-3, atol=SUM_RTOL * np.abs(g["A0"]).max())
+    np.testing.assert_allclose(out["b0"], g["b0"], rtol=1e-3, atol=SUM_RTOL * np.abs(g["A0"]).max())
+    assert abs(out["res0"][1] - g["res0"][1]) <= 30
+
+
+def test_invalid_arguments_fail_loudly(cuda):
+    import ctypes as C
+    from hrbffusion3d_b200._lib import lib, HrbfError
+    from hrbffusion3d_b200 import odometry as od
+    with pytest.raises(HrbfError):
+        od.RGBDOdometry(641, 480, 320, 240, 528, 528)          # width not a multiple of 8
+    h = C.c_void_p()
+    assert lib().hrbf_odometry_create(None, 640, 480, C.c_float(1), C.c_float(1), C.c_float(1), C.c_float(1), C.c_float(.1), C.c_float(.3)) == -1
+    assert b"invalid argument" in lib().hrbf_last_error()
