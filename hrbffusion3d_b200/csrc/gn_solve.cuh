@@ -1,6 +1,7 @@
 // gn_solve.cuh -- device-side Gauss-Newton bookkeeping: fp64 6x6 / 3x3 LDLT, Rodrigues, SE3
 // composition.  Runs in ONE thread of the last block of a reduction kernel, so the whole
-// coarse-to-fine loop never leaves the GPU.
+// coarse-to-fine loop never leaves the GPU.  Everything on the fast path is fully unrolled with
+// compile-time indices so the small matrices live in registers (no local-memory traffic).
 //
 // Restates the host code of Utils/RGBDOdometry.cpp:825-914 (SO3), :983-992 (K R K^-1, K t),
 // :1162-1204 (normal equations, solve, pose update) and Utils/OdometryProvider.h:35-93.
@@ -10,10 +11,10 @@
 
 namespace hrbf {
 
-// A.ldlt().solve(b) stand-in: LDL^T with symmetric diagonal pivoting, fp64; a vanishing pivot
-// contributes 0 (Eigen's solve() behaviour).  N = 6 (SE3) or 3 (SO3).
+// Slow path: LDL^T with symmetric diagonal pivoting; a vanishing pivot contributes 0 (what
+// Eigen's ldlt().solve() does for a singular system, e.g. no correspondences at all).
 template <int N>
-__device__ inline void ldlt_solve(const double* Ain, const double* bin, double* x)
+__device__ __noinline__ void ldlt_solve_pivoted(const double* Ain, const double* bin, double* x)
 {
     double A[N * N], y[N];
     int perm[N];
@@ -47,22 +48,87 @@ __device__ inline void ldlt_solve(const double* Ain, const double* bin, double* 
     for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
 }
 
-// OdometryProvider.h:35-69
-__device__ inline void rodrigues(const double* w, double* R)
+// Fast path: unpivoted LDL^T in registers (the normal matrix is SPD whenever tracking has
+// support).  Returns false if a pivot is not safely positive -> caller takes the pivoted path.
+template <int N>
+__device__ __forceinline__ bool ldlt_solve_spd(const double (&A)[N * N], const double (&b)[N], double (&x)[N])
 {
-    double rx = w[0], ry = w[1], rz = w[2];
-    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
-    for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
-    if (theta >= DBL_EPSILON) {
-        const double c = cos(theta), s = sin(theta), c1 = 1. - c, it = 1. / theta;
-        rx *= it; ry *= it; rz *= it;
-        const double rrt[9] = { rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz };
-        const double rx_[9] = { 0, -rz, ry, rz, 0, -rx, -ry, rx, 0 };
-        for (int k = 0; k < 9; ++k) R[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * rx_[k];
+    double L[N][N], D[N], y[N];
+    double amax = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) amax = fmax(amax, fabs(A[i * N + i]));
+    const double tiny = amax * 1e-13;
+    bool ok = amax > 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double d = A[j * N + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+        D[j] = d;
+        ok = ok && (d > tiny);
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double s = A[i * N + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = s * inv;
+        }
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+        y[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] /= D[i];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        double s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) s -= L[k][i] * x[k];
+        x[i] = s;
+    }
+    return true;
+}
+
+template <int N>
+__device__ __forceinline__ void ldlt_solve(const double (&A)[N * N], const double (&b)[N], double (&x)[N])
+{
+    if (!ldlt_solve_spd<N>(A, b, x)) {
+        // copies keep the caller's arrays in registers (their address never escapes)
+        double Ac[N * N], bc[N], xc[N];
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) Ac[i] = A[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) bc[i] = b[i];
+        ldlt_solve_pivoted<N>(Ac, bc, xc);
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xc[i];
     }
 }
 
-__device__ inline void inv3(const double* m, double* o)
+// OdometryProvider.h:35-69
+__device__ __forceinline__ void rodrigues(const double (&w)[3], double (&R)[9])
+{
+    double rx = w[0], ry = w[1], rz = w[2];
+    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    if (theta >= DBL_EPSILON) {
+        double s, c;
+        sincos(theta, &s, &c);
+        const double c1 = 1. - c, it = 1. / theta;
+        rx *= it; ry *= it; rz *= it;
+        R[0] = c + c1 * rx * rx; R[1] = c1 * rx * ry - s * rz; R[2] = c1 * rx * rz + s * ry;
+        R[3] = c1 * rx * ry + s * rz; R[4] = c + c1 * ry * ry; R[5] = c1 * ry * rz - s * rx;
+        R[6] = c1 * rx * rz - s * ry; R[7] = c1 * ry * rz + s * rx; R[8] = c + c1 * rz * rz;
+    }
+}
+
+__device__ __forceinline__ void inv3(const double (&m)[9], double (&o)[9])
 {
     const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
     const double det = m[0] * c00 + m[1] * c01 + m[2] * c02, id = 1.0 / det;
@@ -70,7 +136,7 @@ __device__ inline void inv3(const double* m, double* o)
     o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
     o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
 }
-__device__ inline void inv3f(const float* m, float* o)
+__device__ __forceinline__ void inv3f(const float* m, float* o)
 {
     const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
     const float det = m[0] * c00 + m[1] * c01 + m[2] * c02, id = 1.0f / det;
@@ -78,16 +144,19 @@ __device__ inline void inv3f(const float* m, float* o)
     o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
     o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
 }
-__device__ inline void mul3(const double* a, const double* b, double* o)
+__device__ __forceinline__ void mul3(const double (&a)[9], const double (&b)[9], double (&o)[9])
 {
     double r[9];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) r[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+#pragma unroll
     for (int k = 0; k < 9; ++k) o[k] = r[k];
 }
 
 // K of pyramid level `level` (Cuda/types.cuh:93-97: float division by 2^level)
-__device__ inline void level_K(const TrackState* st, int level, double* K)
+__device__ __forceinline__ void level_K(const TrackState* st, int level, double (&K)[9])
 {
     const int div = 1 << level;
     const float fx = st->fx / div, fy = st->fy / div, cx = st->cx / div, cy = st->cy / div;
@@ -95,145 +164,171 @@ __device__ inline void level_K(const TrackState* st, int level, double* K)
 }
 
 // RGBDOdometry.cpp:983-992 : Rt = resultRt^-1, K R K^-1 and K t for the photometric warp
-__device__ inline void update_krk(TrackState* st, int level)
+__device__ __forceinline__ void update_krk(TrackState* st, const double (&Rt)[16], int level)
 {
     double K[9], Kinv[9], Rm[9], Rinv[9], tm[3], KR[9], KRK[9];
     level_K(st, level, K);
     inv3(K, Kinv);
+#pragma unroll
     for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) Rm[a * 3 + b] = st->resultRt[a * 4 + b];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Rm[a * 3 + b] = Rt[a * 4 + b];
     inv3(Rm, Rinv);
-    for (int a = 0; a < 3; ++a)
-        tm[a] = -(Rinv[a * 3] * st->resultRt[3] + Rinv[a * 3 + 1] * st->resultRt[7] + Rinv[a * 3 + 2] * st->resultRt[11]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) tm[a] = -(Rinv[a * 3] * Rt[3] + Rinv[a * 3 + 1] * Rt[7] + Rinv[a * 3 + 2] * Rt[11]);
     mul3(K, Rinv, KR);
     mul3(KR, Kinv, KRK);
+#pragma unroll
     for (int k = 0; k < 9; ++k) st->krkinv[k] = (float)KRK[k];
+#pragma unroll
     for (int a = 0; a < 3; ++a) st->kt[a] = (float)(K[a * 3] * tm[0] + K[a * 3 + 1] * tm[1] + K[a * 3 + 2] * tm[2]);
 }
 
 // RGBDOdometry.cpp:851-862 : homography K R K^-1, K^-1, K R for the SO3 step (level 2)
-__device__ inline void update_so3_mats(TrackState* st)
+__device__ __forceinline__ void update_so3_mats(TrackState* st, const double (&resultR)[9])
 {
     double K[9], Kinv[9], KR[9], H[9];
     level_K(st, 2, K);
     inv3(K, Kinv);
-    mul3(K, st->resultR, KR);
+    mul3(K, resultR, KR);
     mul3(KR, Kinv, H);
+#pragma unroll
     for (int k = 0; k < 9; ++k) { st->so3_basis[k] = (float)H[k]; st->so3_kinv[k] = (float)Kinv[k]; st->so3_krlr[k] = (float)KR[k]; }
 }
 
-// unpack 27 upper-triangular sums into symmetric A (6x6) and b (reduce.cu:677-689), as floats
-__device__ inline void unpack_se3(const double* s, float* A, float* b)
+// 27 upper-triangular sums -> symmetric A (6x6) and b, rounded through float like the
+// reference's download into Eigen float matrices (reduce.cu:677-689, RGBDOdometry.cpp:1163-1166)
+__device__ __forceinline__ void unpack_se3(const double* s, double (&A)[36], double (&b)[6])
 {
     int shift = 0;
+#pragma unroll
     for (int i = 0; i < 6; ++i)
+#pragma unroll
         for (int j = i; j < 7; ++j) {
-            const float value = (float)s[shift++];
-            if (j == 6) b[i] = value; else A[j * 6 + i] = A[i * 6 + j] = value;
+            const double value = (double)(float)s[shift++];
+            if (j == 6) b[i] = value; else { A[j * 6 + i] = value; A[i * 6 + j] = value; }
         }
 }
 
 // One Gauss-Newton update (RGBDOdometry.cpp:1135-1204) from the reduced sums held in the state.
-// next_level: pyramid level of the NEXT iteration (-1: none); cur_level: level just processed.
-__device__ inline void gn_update(TrackState* st, int cur_level, int next_level)
+// next_level: pyramid level of the NEXT iteration (-1: none).
+__device__ __forceinline__ void gn_update(TrackState* st, int cur_level, int next_level)
 {
-    float A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
+    (void)cur_level;
     double lastA[36], lastb[6], result[6];
-    if (st->icp) {
-        unpack_se3(st->icp_sums, A_icp, b_icp);
+    const bool icp = st->icp != 0, rgb = st->rgb != 0;
+    if (icp) {
         const float r0 = (float)st->icp_sums[27], r1 = (float)st->icp_sums[28];
         st->lastICPError = sqrtf(r0) / r1;
         st->lastICPCount = r1;
         st->icp_iterations_run++;
     }
-    if (st->rgb) unpack_se3(st->rgb_sums, A_rgb, b_rgb);
-    if (st->icp && st->rgb) {
+    if (icp && rgb) {
+        double Ai[36], bi[6];
+        unpack_se3(st->rgb_sums, lastA, lastb);
+        unpack_se3(st->icp_sums, Ai, bi);
         const double w = st->icpWeight;
-        for (int k = 0; k < 36; ++k) lastA[k] = (double)A_rgb[k] + w * w * (double)A_icp[k];
-        for (int k = 0; k < 6; ++k) lastb[k] = (double)b_rgb[k] + w * (double)b_icp[k];
-    } else if (st->icp) {
-        for (int k = 0; k < 36; ++k) lastA[k] = A_icp[k];
-        for (int k = 0; k < 6; ++k) lastb[k] = b_icp[k];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) lastA[k] = lastA[k] + w * w * Ai[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) lastb[k] = lastb[k] + w * bi[k];
+    } else if (icp) {
+        unpack_se3(st->icp_sums, lastA, lastb);
     } else {
-        for (int k = 0; k < 36; ++k) lastA[k] = A_rgb[k];
-        for (int k = 0; k < 6; ++k) lastb[k] = b_rgb[k];
+        unpack_se3(st->rgb_sums, lastA, lastb);
     }
     ldlt_solve<6>(lastA, lastb, result);
+#pragma unroll
     for (int k = 0; k < 36; ++k) st->lastA[k] = lastA[k];
+#pragma unroll
     for (int k = 0; k < 6; ++k) st->lastb[k] = lastb[k];
 
     // OdometryProvider.h:71-93 : resultRt = [exp(w) | t] * resultRt
-    double Rupd[9], Rt[16], nrt[16];
-    rodrigues(result + 3, Rupd);
-    for (int k = 0; k < 16; ++k) Rt[k] = 0.0;
-    for (int a = 0; a < 3; ++a) {
-        for (int b = 0; b < 3; ++b) Rt[a * 4 + b] = Rupd[a * 3 + b];
-        Rt[a * 4 + 3] = result[a];
-    }
-    Rt[15] = 1.0;
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-            double s = 0;
-            for (int k = 0; k < 4; ++k) s += Rt[a * 4 + k] * st->resultRt[k * 4 + b];
-            nrt[a * 4 + b] = s;
-        }
+    double Rupd[9], old[16], nrt[16];
+    const double wv[3] = { result[3], result[4], result[5] };
+    rodrigues(wv, Rupd);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) old[k] = st->resultRt[k];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            nrt[a * 4 + b] = Rupd[a * 3 + 0] * old[0 * 4 + b] + Rupd[a * 3 + 1] * old[1 * 4 + b] + Rupd[a * 3 + 2] * old[2 * 4 + b] + result[a] * old[3 * 4 + b];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) nrt[12 + b] = old[12 + b];
+#pragma unroll
     for (int k = 0; k < 16; ++k) st->resultRt[k] = nrt[k];
 
     // RGBDOdometry.cpp:1196-1204 : currentT = [Rprev|tprev] * rgbOdom^-1 in float
-    float Rf[9], tf[3], ti[3];
+    float Rf[9], tf[3], ti[3], Rp[9], tp[3];
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
-        for (int b = 0; b < 3; ++b) Rf[a * 3 + b] = (float)nrt[a * 4 + b];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) { Rf[a * 3 + b] = (float)nrt[a * 4 + b]; Rp[a * 3 + b] = st->Rprev[a * 3 + b]; }
         tf[a] = (float)nrt[a * 4 + 3];
+        tp[a] = st->tprev[a];
     }
+#pragma unroll
     for (int a = 0; a < 3; ++a) ti[a] = -(Rf[0 * 3 + a] * tf[0] + Rf[1 * 3 + a] * tf[1] + Rf[2 * 3 + a] * tf[2]);
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
-        for (int b = 0; b < 3; ++b)
-            st->Rcurr[a * 3 + b] = st->Rprev[a * 3] * Rf[b * 3] + st->Rprev[a * 3 + 1] * Rf[b * 3 + 1] + st->Rprev[a * 3 + 2] * Rf[b * 3 + 2];
-        st->tcurr[a] = st->Rprev[a * 3] * ti[0] + st->Rprev[a * 3 + 1] * ti[1] + st->Rprev[a * 3 + 2] * ti[2] + st->tprev[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) st->Rcurr[a * 3 + b] = Rp[a * 3] * Rf[b * 3] + Rp[a * 3 + 1] * Rf[b * 3 + 1] + Rp[a * 3 + 2] * Rf[b * 3 + 2];
+        st->tcurr[a] = Rp[a * 3] * ti[0] + Rp[a * 3 + 1] * ti[1] + Rp[a * 3 + 2] * ti[2] + tp[a];
     }
-    (void)cur_level;
-    if (next_level >= 0 && st->rgb) update_krk(st, next_level);
-    st->rgb_count = 0;
-    st->rgb_sigma = 0;
+    if (next_level >= 0 && rgb) update_krk(st, nrt, next_level);
 }
 
 // SO3 control flow of one iteration (RGBDOdometry.cpp:879-912) from st->so3_sums
-__device__ inline void so3_update(TrackState* st)
+__device__ __forceinline__ void so3_update(TrackState* st)
 {
     const double* s = st->so3_sums;
-    float jtj[9], jtr[3];
-    int shift = 0;
-    for (int i = 0; i < 3; ++i)
-        for (int j = i; j < 4; ++j) {
-            const float value = (float)s[shift++];
-            if (j == 3) jtr[i] = value; else jtj[j * 3 + i] = jtj[i * 3 + j] = value;
-        }
+    double Ad[9], bd[3], xd[3];
+    {
+        int shift = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 4; ++j) {
+                const double value = (double)(float)s[shift++];
+                if (j == 3) bd[i] = value; else { Ad[j * 3 + i] = value; Ad[i * 3 + j] = value; }
+            }
+    }
     const float r0 = (float)s[9], r1 = (float)s[10];
-    st->lastSO3Error = sqrtf(r0) / r1;
+    const float err = sqrtf(r0) / r1;
+    st->lastSO3Error = err;
     st->lastSO3Count = r1;
-    if (st->lastSO3Error < st->so3_lastError && st->so3_lastCount == st->lastSO3Count) { st->so3_done = 1; return; }
-    if ((double)st->lastSO3Error > (double)st->so3_lastError + 0.001) {
-        st->lastSO3Error = st->so3_lastError;
-        st->lastSO3Count = st->so3_lastCount;
+    const float lastError = st->so3_lastError, lastCount = st->so3_lastCount;
+    if (err < lastError && lastCount == r1) { st->so3_done = 1; return; }
+    if ((double)err > (double)lastError + 0.001) {
+        st->lastSO3Error = lastError;
+        st->lastSO3Count = lastCount;
+#pragma unroll
         for (int k = 0; k < 9; ++k) st->resultR[k] = st->lastResultR[k];
         st->so3_done = 1;
         return;
     }
-    st->so3_lastError = st->lastSO3Error;
-    st->so3_lastCount = st->lastSO3Count;
+    st->so3_lastError = err;
+    st->so3_lastCount = r1;
+#pragma unroll
     for (int k = 0; k < 9; ++k) st->lastResultR[k] = st->resultR[k];
-    double Ad[9], bd[3], xd[3], upd[9];
-    for (int k = 0; k < 9; ++k) Ad[k] = jtj[k];
-    for (int k = 0; k < 3; ++k) bd[k] = jtr[k];
     ldlt_solve<3>(Ad, bd, xd);
-    for (int k = 0; k < 3; ++k) xd[k] = (double)(float)xd[k];   // Eigen solves this one in float
-    rodrigues(xd, upd);
-    float nr[9];
+    const double xw[3] = { (double)(float)xd[0], (double)(float)xd[1], (double)(float)xd[2] };   // Eigen solves this one in float
+    double upd[9], nrd[9];
+    rodrigues(xw, upd);
+    float Rl[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rl[k] = st->R_lr[k];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j)
-            nr[i * 3 + j] = (float)upd[i * 3] * st->R_lr[j] + (float)upd[i * 3 + 1] * st->R_lr[3 + j] + (float)upd[i * 3 + 2] * st->R_lr[6 + j];
-    for (int k = 0; k < 9; ++k) { st->R_lr[k] = nr[k]; st->resultR[k] = nr[k]; }
-    update_so3_mats(st);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float v = (float)upd[i * 3] * Rl[j] + (float)upd[i * 3 + 1] * Rl[3 + j] + (float)upd[i * 3 + 2] * Rl[6 + j];
+            st->R_lr[i * 3 + j] = v;
+            nrd[i * 3 + j] = (double)v;
+            st->resultR[i * 3 + j] = (double)v;
+        }
+    update_so3_mats(st, nrd);
 }
 
 }  // namespace hrbf

@@ -181,6 +181,12 @@ const char* hrbf_last_error(void) { return t_err; }
 const char* hrbf_version(void) { return "hrbf_b200 0.1 (sm_100a)"; }
 unsigned long long hrbf_launch_count(void) { return g_launches.load(); }
 size_t hrbf_reduce_workspace_bytes(void) { return sizeof(ReduceWork); }
+int hrbf_copy_device(void* dst, const void* src, size_t bytes, void* stream)
+{
+    HRBF_CHECK_ARG(dst && src);
+    HRBF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HRBF_OK;
+}
 
 // ------------------------------------------------------------------ row 5 ---
 #define STEP_EL(step) ((int)((step) / sizeof(float)))

@@ -524,9 +524,19 @@ __global__ void __launch_bounds__(256) rgb_residual_kernel(RgbResArgs a, ReduceW
             hrbf_dataterm c;
             c.zero_x = c.zero_y = c.one_x = c.one_y = 0; c.diff = 0.f; c.valid = 0; c.pad[0] = c.pad[1] = c.pad[2] = 0;
             if (j0 < cols - 5 && i < rows - 1) {
-                bool valid = true;
-                for (int u = max(i - 2, 0); u < min(i + 2, rows); ++u)
-                    for (int v = max(j0 - 2, 0); v < min(j0 + 2, cols); ++v) valid = valid && (__ldg(a.nextImage + (size_t)u * cols + v) > 0);
+                // 4x4 "not an isolated pixel" test (reduce.cu:1005-1011); all loads issued up front
+                // (clamped addresses, out-of-window taps ignored) instead of a short-circuit chain
+                unsigned int zero_seen = 0;
+#pragma unroll
+                for (int du = -2; du < 2; ++du)
+#pragma unroll
+                    for (int dv = -2; dv < 2; ++dv) {
+                        const int u = i + du, v = j0 + dv;
+                        const bool in = u >= 0 && u < rows && v >= 0 && v < cols;
+                        const unsigned char px = __ldg(a.nextImage + (size_t)min(max(u, 0), rows - 1) * cols + min(max(v, 0), cols - 1));
+                        zero_seen |= (in && px == 0) ? 1u : 0u;
+                    }
+                const bool valid = zero_seen == 0;
                 if (valid) {
                     const short valx = __ldg(a.dIdx + k), valy = __ldg(a.dIdy + k);
                     const float mTwo = (float)((valx * valx) + (valy * valy));
@@ -570,6 +580,7 @@ __global__ void __launch_bounds__(256) rgb_residual_kernel(RgbResArgs a, ReduceW
         st->ticket = 0u;
         if (!level_done) {
             const int sigma = *(volatile int*)&st->rgb_sigma, rgbSize = *(volatile int*)&st->rgb_count;
+            st->rgb_sigma = 0; st->rgb_count = 0;   // consumed: re-arm for the next iteration
             float sigmaVal = sqrtf(((float)sigma / (float)rgbSize == 0.f) ? 1.f : (float)rgbSize);
             const float rgbError = sqrtf((float)sigma) / (float)(rgbSize == 0 ? 1 : rgbSize);
             const float lastErr = first_iter ? FLT_MAX : st->lastRGBError;   // RGBDOdometry.cpp:962
@@ -718,8 +729,10 @@ __global__ void track_begin_kernel(ReduceWork* wk, const float* __restrict__ pre
     st->lastICPError = 0; st->lastICPCount = 0; st->lastRGBError = FLT_MAX; st->lastRGBCount = 0; st->lastSO3Error = 0; st->lastSO3Count = 0;
     st->icp_iterations_run = 0; st->ticket = 0u;
     for (int k = 0; k < 32; ++k) { st->icp_sums[k] = 0; st->rgb_sums[k] = 0; }
-    if (so3) update_so3_mats(st);
-    else if (rgb) update_krk(st, first_level);
+    const double I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    const double I4[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    if (so3) update_so3_mats(st, I3);
+    else if (rgb) update_krk(st, I4, first_level);
 }
 // After the SO3 iterations: seed resultRt with the rotation (RGBDOdometry.cpp:926-935)
 __global__ void track_after_so3_kernel(ReduceWork* wk, int first_level)
@@ -728,7 +741,12 @@ __global__ void track_after_so3_kernel(ReduceWork* wk, int first_level)
     TrackState* st = &wk->st;
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) st->resultRt[a * 4 + b] = st->resultR[a * 3 + b];
-    if (st->rgb) update_krk(st, first_level);
+    if (st->rgb) {
+        double Rt[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) Rt[k] = st->resultRt[k];
+        update_krk(st, Rt, first_level);
+    }
 }
 // End of a tracking call: 0.3 m guard (RGBDOdometry.cpp:1232-1236), pose out
 __global__ void track_end_kernel(ReduceWork* wk, float* __restrict__ pose_out)

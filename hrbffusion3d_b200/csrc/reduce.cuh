@@ -93,9 +93,19 @@ __device__ __forceinline__ bool grid_reduce32(float (&v)[32], float (*partials)[
     __threadfence();
     // final: 8 slices x 32 values, fp64, fixed order
     {
+        // each warp sums every 8th partial; loads are batched 8 deep for memory-level parallelism,
+        // the additions stay in a fixed order
         double acc = 0.0;
-        for (unsigned int b = warp; b < gridDim.x; b += kReduceThreads / 32)
-            acc += (double)__ldcg(&partials[b][lane]);
+        constexpr int W = kReduceThreads / 32, U = 8;
+        unsigned int b = warp;
+        for (; b + (U - 1) * W < gridDim.x; b += U * W) {
+            float t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] = __ldcg(&partials[b + u * W][lane]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += (double)t[u];
+        }
+        for (; b < gridDim.x; b += W) acc += (double)__ldcg(&partials[b][lane]);
         s_d[warp][lane] = acc;
     }
     __syncthreads();

@@ -113,17 +113,8 @@ class RGBDOdometry:
         return out.view(rows, cols)
 
 
-_cudart = None
-
-
 def _memcpy_d2d(dst, src, nbytes):
-    global _cudart
-    torch.cuda.synchronize()
-    if _cudart is None:
-        _cudart = torch.cuda.cudart()
-    err = _cudart.cudaMemcpy(dst, src, nbytes, 3)  # cudaMemcpyDeviceToDevice
-    if int(err) != 0:
-        raise RuntimeError(f"cudaMemcpy failed: {err}")
+    check(lib().hrbf_copy_device(C.c_void_p(dst), C.c_void_p(src), C.c_size_t(nbytes), stream_ptr()))
 
 
 class ReduceWorkspace:

@@ -49,6 +49,9 @@ const char* hrbf_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long hrbf_launch_count(void);
 
+/* stream-ordered device-to-device copy (host mirrors use it to snapshot internal maps) */
+int hrbf_copy_device(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+
 typedef struct { float fx, fy, cx, cy; } hrbf_camera;   /* CameraModel, Cuda/types.cuh:82-98 */
 
 /* ------------------------------------------------------------------------

@@ -228,8 +228,8 @@ class Odometry:
         self.curvThr = 300.0
 
     def __del__(self):
-        if getattr(self, "o", None):
-            lib().orc_odom_destroy(C.c_void_p(self.o))
+        if getattr(self, "o", None) and _LIB is not None and C is not None:
+            _LIB.orc_odom_destroy(C.c_void_p(self.o))
             self.o = None
 
     def initICP_depth(self, depth_f32, cutoff, factor):

@@ -33,5 +33,6 @@ def nan_eq_planes(a, b, rows, atol=1e-6, rtol=1e-6):
 
 def pose_err(R0, t0, R1, t1):
     dR = np.asarray(R0, np.float64).T @ np.asarray(R1, np.float64)
-    ang = np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))
+    # arccos((tr-1)/2) loses half the digits near 0; use the skew part instead
+    ang = np.arcsin(min(1.0, np.linalg.norm(dR - dR.T) / (2.0 * np.sqrt(2.0))))
     return float(ang), float(np.linalg.norm(np.asarray(t0, np.float64) - np.asarray(t1, np.float64)))
