@@ -86,6 +86,37 @@ static int upload_pose(hrbf_odometry* o, const float* pose16, cudaStream_t s, fl
     return HRBF_OK;
 }
 
+static IcpArgs icp_args(const hrbf_odometry* o, int l, bool use_weight)
+{
+    const int rows = o->rows(l), cols = o->cols(l), div = 1 << l;
+    IcpArgs ia;
+    ia.vc = o->maps[M_VC][l]; ia.nc = o->maps[M_NC][l]; ia.k1c = o->maps[M_K1C][l]; ia.k2c = o->maps[M_K2C][l]; ia.cpitch = cols;
+    ia.vg = o->maps[M_VG][l]; ia.ng = o->maps[M_NG][l]; ia.k1g = o->maps[M_K1G][l]; ia.k2g = o->maps[M_K2G][l]; ia.gpitch = cols;
+    ia.w = o->maps[M_W][l]; ia.wpitch = cols;
+    ia.rows = rows; ia.cols = cols;
+    ia.fx = o->intr.fx / div; ia.fy = o->intr.fy / div; ia.cx = o->intr.cx / div; ia.cy = o->intr.cy / div;
+    ia.dist_thres = o->distThres; ia.angle_thres = o->angleThres;
+    ia.use_search = o->useSearch; ia.radius = o->searchRadius; ia.use_weight = use_weight; ia.corres = nullptr;
+    return ia;
+}
+static RgbResArgs rgbres_args(const hrbf_odometry* o, int l)
+{
+    RgbResArgs ra;
+    ra.minScale = (float)(pow((double)o->minGrad[l], 2.0) / pow((double)o->sobelScale, 2.0)); ra.maxDepthDelta = o->maxDepthDeltaRGB;
+    ra.dIdx = o->dIdx[l]; ra.dIdy = o->dIdy[l]; ra.lastDepth = o->lastDepth[l]; ra.nextDepth = o->nextDepth[l];
+    ra.lastImage = o->lastImage[l]; ra.nextImage = o->nextImage[l]; ra.corres = o->corresImg[l]; ra.rows = o->rows(l); ra.cols = o->cols(l);
+    return ra;
+}
+static RgbStepArgs rgbstep_args(const hrbf_odometry* o, int l)
+{
+    const int div = 1 << l;
+    RgbStepArgs sa;
+    sa.corres = o->corresImg[l]; sa.cloud3 = o->cloud[l]; sa.dIdx = o->dIdx[l]; sa.dIdy = o->dIdy[l];
+    sa.fx = o->intr.fx / div; sa.fy = o->intr.fy / div; sa.sobelScale = o->sobelScale; sa.use_grad_weight = o->rgbGradWeight;
+    sa.rows = o->rows(l); sa.cols = o->cols(l);
+    return sa;
+}
+
 // Enqueue the whole tracking loop on `s` (used under stream capture).  Returns kernel count.
 static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
                          bool so3, bool use_weight, bool host_io)
@@ -116,20 +147,9 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
         if (rgb) { project_cloud_kernel<<<grid2d(cols, rows, b2), b2, 0, s>>>(rows, cols, o->lastDepth[l], o->cloud[l], 1.0f / fx, 1.0f / fy, cx, cy); ++n; }
         int next_lower = -1;
         for (int q = l - 1; q >= 0; --q) if (iters[q] > 0) { next_lower = q; break; }
-        IcpArgs ia;
-        ia.vc = o->maps[M_VC][l]; ia.nc = o->maps[M_NC][l]; ia.k1c = o->maps[M_K1C][l]; ia.k2c = o->maps[M_K2C][l]; ia.cpitch = cols;
-        ia.vg = o->maps[M_VG][l]; ia.ng = o->maps[M_NG][l]; ia.k1g = o->maps[M_K1G][l]; ia.k2g = o->maps[M_K2G][l]; ia.gpitch = cols;
-        ia.w = o->maps[M_W][l]; ia.wpitch = cols;
-        ia.rows = rows; ia.cols = cols; ia.fx = fx; ia.fy = fy; ia.cx = cx; ia.cy = cy;
-        ia.dist_thres = o->distThres; ia.angle_thres = o->angleThres;
-        ia.use_search = o->useSearch; ia.radius = o->searchRadius; ia.use_weight = use_weight; ia.corres = nullptr;
-        RgbResArgs ra;
-        ra.minScale = (float)(pow((double)o->minGrad[l], 2.0) / pow((double)o->sobelScale, 2.0)); ra.maxDepthDelta = o->maxDepthDeltaRGB;
-        ra.dIdx = o->dIdx[l]; ra.dIdy = o->dIdy[l]; ra.lastDepth = o->lastDepth[l]; ra.nextDepth = o->nextDepth[l];
-        ra.lastImage = o->lastImage[l]; ra.nextImage = o->nextImage[l]; ra.corres = o->corresImg[l]; ra.rows = rows; ra.cols = cols;
-        RgbStepArgs sa;
-        sa.corres = o->corresImg[l]; sa.cloud3 = o->cloud[l]; sa.dIdx = o->dIdx[l]; sa.dIdy = o->dIdy[l];
-        sa.fx = fx; sa.fy = fy; sa.sobelScale = o->sobelScale; sa.use_grad_weight = o->rgbGradWeight; sa.rows = rows; sa.cols = cols;
+        const IcpArgs ia = icp_args(o, l, use_weight);
+        const RgbResArgs ra = rgbres_args(o, l);
+        const RgbStepArgs sa = rgbstep_args(o, l);
         const int nb = reduce_blocks(rows * cols);
         for (int j = 0; j < iters[l]; ++j) {
             const int next_level = (j + 1 < iters[l]) ? l : next_lower;
@@ -621,6 +641,38 @@ int hrbf_odometry_track_async(hrbf_odometry* o, const float* prev_pose_dev, floa
     if (so3) swap_so3_images(o);
     count_launch(nk);
     HRBF_CUDA(cudaMemcpyAsync(pose_out_dev, o->pose_scratch + 24, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return HRBF_OK;
+}
+
+int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_update, int reps, float* avg_us, void* stream)
+{
+    HRBF_CHECK_ARG(o && avg_us && which >= 0 && which <= 3 && level >= 0 && level <= 2 && reps > 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    HRBF_CUDA(cudaEventCreate(&e0));
+    HRBF_CUDA(cudaEventCreate(&e1));
+    const IcpArgs ia = icp_args(o, level, true);
+    const RgbResArgs ra = rgbres_args(o, level);
+    const RgbStepArgs sa = rgbstep_args(o, level);
+    const int nb = reduce_blocks(o->rows(level) * o->cols(level));
+    // one warm-up launch outside the timed region, then `reps` back-to-back launches between two events
+    for (int r = -1; r < reps; ++r) {
+        if (r == 0) HRBF_CUDA(cudaEventRecord(e0, s));
+        switch (which) {
+        case 0: icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, o->work, with_update ? 1 : 0, level, -1); break;
+        case 1: rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, o->work, 1, level, 0); break;
+        case 2: rgb_step_kernel<<<nb, kReduceThreads, 0, s>>>(sa, -2.0f, o->work, with_update ? 1 : 0, level, -1); break;
+        default: so3_reduce_kernel<<<reduce_blocks(o->rows(2) * o->cols(2)), kReduceThreads, 0, s>>>(o->lastNextImage[2], o->nextImage[2], o->rows(2), o->cols(2), o->work, 0); break;
+        }
+    }
+    HRBF_CUDA(cudaEventRecord(e1, s));
+    count_launch(reps + 1);
+    HRBF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HRBF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    HRBF_CUDA(cudaGetLastError());
+    *avg_us = ms * 1000.f / (float)reps;
     return HRBF_OK;
 }
 

@@ -396,7 +396,7 @@ __device__ __forceinline__ void icp_pixel(const IcpArgs& a, const float* Rc, con
     float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
     float weight = 1.f;
     bool found = false;
-    int bx = -1, by = -1;
+    int bx = -1, by = -1, cnt = 0;
     float3 n_g, d_g, s_g;
 
     const float3 vcurr = make_float3(ldc(a.vc, 0), ldc(a.vc, 1), ldc(a.vc, 2));
@@ -423,7 +423,7 @@ __device__ __forceinline__ void icp_pixel(const IcpArgs& a, const float* Rc, con
         } else {
             const int R = a.radius, D = 2 * R + 1;
             float DpR = -1e8f, best_p = 1e8f;
-            int cnt = 0;
+            cnt = 0;
             for (int pass = 0; pass < 2; ++pass) {
                 for (int cy = uy - D / 2; cy < uy + D / 2 + 1; ++cy)
                     for (int cx = ux - D / 2; cx < ux + D / 2 + 1; ++cx) {
@@ -443,6 +443,8 @@ __device__ __forceinline__ void icp_pixel(const IcpArgs& a, const float* Rc, con
                     }
                 if (pass == 0 && cnt == 0) break;
             }
+            // all scores NaN: undefined behaviour in the reference (uninitialised vectors, reduce.cu:404-434);
+            // defined here, as in the oracle, as "no correspondence"
             found = bx >= 0;
         }
         s_g = vg;

@@ -474,8 +474,11 @@ void orc_icpStep(int rows, int cols,
                             }
                         if (pass == 0 && cnt == 0) break;
                     }
-                    /* use_search with a NaN score selects nothing in the reference (its outputs are then
-                     * uninitialised); the oracle defines that case as "no correspondence" */
+                    /* When every candidate's score is NaN (ckmax == 0 or D_p_R == 0) nothing is selected, yet the
+                     * reference still returns if_found = true with UNINITIALISED vprev_g / nprev_g and
+                     * corres = (-1,-1) (reduce.cu:404-434): undefined behaviour.  Observed with the reference's own
+                     * kernel on a B200 (GPUTest pair, zero curvature): NaN sums in one run, zero sums in the next.
+                     * The oracle defines the case as "no correspondence". */
                     if (cx_best < 0) found = 0;
                     if (found) memcpy(s_g, vg, sizeof s_g);
                 } while (0);

@@ -44,3 +44,17 @@ pout = torch.zeros(12, device="cuda")
 for name, kw in (("icp-only", dict(icpWeight=100.0, so3=False)), ("default", dict(icpWeight=10.0, so3=True))):
     f = lambda: go.trackAsync(pin, pout, **kw)
     print("trackAsync %-10s: %.1f us" % (name, timeit(f, iters)))
+import ctypes as C
+from hrbffusion3d_b200._lib import lib, check, stream_ptr
+go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], icpWeight=10.0, so3=True)
+print("isolated kernels, back-to-back (us): which level update -> us   [GB/s algorithmic for ICP = 68 B/px]")
+for which, name in ((0, "icp"), (1, "rgbres"), (2, "rgbstep"), (3, "so3")):
+    for lvl in (0, 1, 2):
+        for upd in (0, 1):
+            if which in (1, 3) and upd: continue
+            if which == 3 and lvl != 2: continue
+            us = C.c_float()
+            check(lib().hrbf_odometry_time_kernel(go._h, which, lvl, upd, 200, C.byref(us), stream_ptr()))
+            n = (W >> lvl) * (H >> lvl)
+            extra = "  %.0f GB/s" % (68.0 * n / us.value * 1e-3) if which == 0 else ""
+            print(f"  {name:8s} L{lvl} upd={upd}: {us.value:7.2f} us{extra}")
