@@ -163,3 +163,29 @@ def circle_trajectory(n_frames, radius=0.05, yaw_deg=2.0, frames_per_rev=200):
         poses.append(make_pose(0.0, np.deg2rad(yaw_deg) * np.sin(a), 0.0,
                                (radius * np.cos(a) - radius, radius * np.sin(a), 0.0)))
     return poses
+
+
+def surfels_from_maps(maps, pose, time=1, submap=0, stride=1):
+    """Global-frame surfel records (float32 [n, 20], the reference's 80-B layout, Shaders/Vertex.cpp:20-44) from
+    camera-frame ideal maps: {pos.xyz, conf | colour24, submap, initTime, lastTime | n.xyz, radius | k1dir, k1 | k2dir, k2}.
+    Pixel order is x outer / y inner like the reference's uv VBO (GlobalModel.cpp:89-96)."""
+    V, N, K1, K2, rgba = maps["vertex"], maps["normal"], maps["k1"], maps["k2"], maps["rgba"]
+    H, W = V.shape[:2]
+    R, t = pose[:3, :3].astype(np.float32), pose[:3, 3].astype(np.float32)
+    xs, ys = np.meshgrid(np.arange(0, W, stride), np.arange(0, H, stride), indexing="ij")
+    xs, ys = xs.reshape(-1), ys.reshape(-1)
+    v, n, k1, k2, c = V[ys, xs], N[ys, xs], K1[ys, xs], K2[ys, xs], rgba[ys, xs].astype(np.int64)
+    ok = v[:, 2] > 0
+    v, n, k1, k2, c = v[ok], n[ok], k1[ok], k2[ok], c[ok]
+    s = np.zeros((v.shape[0], 20), np.float32)
+    s[:, 0:3] = v[:, :3] @ R.T + t
+    s[:, 3] = v[:, 3]
+    s[:, 4] = ((c[:, 0] << 16) + (c[:, 1] << 8) + c[:, 2]).astype(np.float32)
+    s[:, 5], s[:, 6], s[:, 7] = submap, time, time
+    s[:, 8:11] = n[:, :3] @ R.T
+    s[:, 11] = n[:, 3]
+    s[:, 12:15] = k1[:, :3] @ R.T
+    s[:, 15] = k1[:, 3]
+    s[:, 16:19] = k2[:, :3] @ R.T
+    s[:, 19] = k2[:, 3]
+    return s

@@ -204,6 +204,54 @@ const float* hrbf_odometry_map(const hrbf_odometry*, int which, int level, size_
 const unsigned char* hrbf_odometry_image(const hrbf_odometry*, int which, int level); /* 0 last, 1 next, 2 lastNext */
 const float* hrbf_odometry_depth(const hrbf_odometry*, int which, int level);        /* 0 last, 1 next */
 
+/* ------------------------------------------------------------------------
+ * Rows 6-7 : IndexMap  (Core/src/IndexMap.h:36-201)
+ * Every GPUTexture of the reference is a dense device buffer: RGBA32F -> float[h][w][4],
+ * R32UI -> uint32[h][w], RGBA8 -> uchar[h][w][4], R16UI -> uint16[h][w], R32F -> float[h][w].
+ * ---------------------------------------------------------------------- */
+typedef struct hrbf_indexmap hrbf_indexmap;
+#define HRBF_ACTIVE_KEYFRAME_DIMENSION 19200      /* IndexMap::ACTIVE_KEYFRAME_DIMENSION, IndexMap.cpp:24 */
+
+enum hrbf_indexmap_tex {                           /* accessor of IndexMap.h it replaces */
+    HRBF_TEX_INDEX = 0,        /* indexTex()      u32  */
+    HRBF_TEX_VERTCONF,         /* vertConfTex()   f32x4: camera-frame xyz, confidence */
+    HRBF_TEX_COLORTIME,        /* colorTimeTex()  f32x4 */
+    HRBF_TEX_NORMRAD,          /* normalRadTex()  f32x4 */
+    HRBF_TEX_CURVMAX,          /* curvMaxTex()    f32x4 */
+    HRBF_TEX_CURVMIN,          /* curvMinTex()    f32x4 */
+    HRBF_TEX_IMAGE_HRBF,       /* imageTexHRBF()  u8x4  */
+    HRBF_TEX_VERTEX_HRBF,      /* vertexTexHRBF() f32x4: xyz, confidence */
+    HRBF_TEX_NORMAL_HRBF,      /* normalTexHRBF() f32x4: xyz, radius */
+    HRBF_TEX_CURVK1_HRBF,      /* curvk1TexHRBF() f32x4 */
+    HRBF_TEX_CURVK2_HRBF,      /* curvk2TexHRBF() f32x4 */
+    HRBF_TEX_TIME_HRBF,        /* (timeTexture)   u16   */
+    HRBF_TEX_ICPW_HRBF,        /* icpweightTexHRBF() f32 */
+    HRBF_TEX_OLD_IMAGE_HRBF, HRBF_TEX_OLD_VERTEX_HRBF, HRBF_TEX_OLD_NORMAL_HRBF, HRBF_TEX_OLD_CURVK1_HRBF,
+    HRBF_TEX_OLD_CURVK2_HRBF, HRBF_TEX_OLD_TIME_HRBF, HRBF_TEX_OLD_ICPW_HRBF,   /* old*TexHRBF(): INACTIVE prediction */
+    HRBF_TEX_COUNT
+};
+
+/* IndexMap::IndexMap, IndexMap.cpp:25-191 (camera from the Intrinsics singleton there) */
+int hrbf_indexmap_create(hrbf_indexmap** out, int width, int height, float cx, float cy, float fx, float fy);
+int hrbf_indexmap_destroy(hrbf_indexmap*);
+/* IndexMap::lActiveKFID (IndexMap.h:199, used at IndexMap.cpp:222-237): ids of the active sub-maps */
+int hrbf_indexmap_set_active_keyframes(hrbf_indexmap*, const int* ids_host, int n, void* stream);
+/* IndexMap::predictIndices, IndexMap.cpp:193-267.  pose16_host: row-major 4x4 camera-to-world;
+ * surfels_dev: float[count][20] (the model VBO).  Writes the 6 index-map textures. */
+int hrbf_indexmap_predict_indices(hrbf_indexmap*, const float* pose16_host, int time, int maxTime,
+                                  const float* surfels_dev, unsigned int count, float depthCutoff,
+                                  int insertSubmap, int indexSubmap, void* stream);
+/* same, fully device-driven (no host pose / count): inv_pose_dev = R^T[9], -R^T t[3]; count read on the device */
+int hrbf_indexmap_predict_indices_dev(hrbf_indexmap*, const float* inv_pose_dev, const float* surfels_dev,
+                                      const unsigned int* count_dev, unsigned int count_bound, float depthCutoff, void* stream);
+/* IndexMap::predictHRBF, IndexMap.cpp:413-518 (predictionType 0 = ACTIVE, 1 = INACTIVE); the GlobalStateParam
+ * knobs the reference reads there are arguments: preictionWindowMultiplier (<= 3), preictionMinNeighbors,
+ * preictionMaxNeighbors (<= 16), preictionConfThreshold, registrationICPCurvWeightImpactControl */
+int hrbf_indexmap_predict_hrbf(hrbf_indexmap*, int predictionType, int win, int minNeighbors, int maxNeighbors,
+                               float confThreshold, float icpWeightLambda, void* stream);
+/* device pointer of one texture (enum hrbf_indexmap_tex) */
+void* hrbf_indexmap_texture(hrbf_indexmap*, int which);
+
 #ifdef __cplusplus
 }
 #endif

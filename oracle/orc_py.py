@@ -288,3 +288,33 @@ class Odometry:
         rows, cols = self.h >> level, self.w >> level
         p = lib().orc_odom_depth(C.c_void_p(self.o), which, level)
         return np.ctypeslib.as_array(p, shape=(rows * cols,)).reshape(rows, cols).copy()
+
+
+# --------------------------------------------------------------- rows 6-7 --
+def predictIndices(pose, surfels, cam, width, height, maxDepth=20.0, active_kf=None):
+    """-> dict(index u32 [h,w], vertConf, colorTime, normRad, curvMax, curvMin f32 [h,w,4])"""
+    surfels = np.ascontiguousarray(surfels, np.float32).reshape(-1, 20)
+    P = SplatParams(cam[2], cam[3], cam[0], cam[1], width, height, maxDepth)
+    if active_kf is None:
+        active_kf = np.zeros(19200, np.float32)
+        active_kf[0] = 1.0
+    out = {"index": np.zeros((height, width), np.uint32)}
+    for k in ("vertConf", "colorTime", "normRad", "curvMax", "curvMin"):
+        out[k] = np.zeros((height, width, 4), np.float32)
+    lib().orc_predictIndices(_p(_f(pose)), _p(surfels), C.c_int(surfels.shape[0]), C.byref(P), _p(_f(active_kf)), C.c_int(len(active_kf)),
+                             _p(out["index"], C.c_uint32), _p(out["vertConf"]), _p(out["colorTime"]), _p(out["normRad"]),
+                             _p(out["curvMax"]), _p(out["curvMin"]))
+    return out
+
+
+def predictHRBF(idx, cam, width, height, win=3, minNeighbors=6, maxNeighbors=10, confThreshold=3.0, icpWeightLambda=10.0):
+    """idx: dict from predictIndices -> dict(image u8 [h,w,4], vertex, normal, curvk1, curvk2 f32 [h,w,4], time u16, icpw f32)"""
+    P = PredictParams(cam[2], cam[3], cam[0], cam[1], width, height, win, minNeighbors, maxNeighbors, confThreshold, icpWeightLambda)
+    out = {"image": np.zeros((height, width, 4), np.uint8), "time": np.zeros((height, width), np.uint16),
+           "icpw": np.zeros((height, width), np.float32)}
+    for k in ("vertex", "normal", "curvk1", "curvk2"):
+        out[k] = np.zeros((height, width, 4), np.float32)
+    lib().orc_predictHRBF(C.byref(P), _p(_f(idx["vertConf"])), _p(_f(idx["colorTime"])), _p(_f(idx["normRad"])), _p(_f(idx["curvMax"])),
+                          _p(_f(idx["curvMin"])), _p(out["image"], C.c_ubyte), _p(out["vertex"]), _p(out["normal"]), _p(out["curvk1"]),
+                          _p(out["curvk2"]), _p(out["time"], C.c_ushort), _p(out["icpw"]))
+    return out
