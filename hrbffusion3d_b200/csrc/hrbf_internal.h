@@ -1,0 +1,75 @@
+// hrbf_internal.h -- library-internal declarations shared by the translation units of libhrbf_b200.so
+// (not part of the C ABI; the public surface is include/hrbf_b200.h).
+#pragma once
+#include "common.cuh"
+#include <map>
+#include <utility>
+
+namespace hrbf {
+struct ReduceWork;
+struct TrackState;
+enum { M_VG = 0, M_NG, M_K1G, M_K2G, M_VC, M_NC, M_K1C, M_K2C, M_W, M_COUNT };
+}
+
+struct hrbf_odometry {
+    int width = 0, height = 0;
+    hrbf_camera intr{};
+    float distThres = 0.1f, angleThres = 0.f;
+    float sobelScale = 0.125f, maxDepthDeltaRGB = 0.07f, maxDepthRGB = 6.0f;
+    float minGrad[HRBF_NUM_PYRS] = { 5, 3, 1 };
+    float curvThr = 300.f;
+    int useSearch = 0, searchRadius = 2, rgbGradWeight = 0;
+
+    char* slab = nullptr;        // one allocation for everything below
+    float* maps[hrbf::M_COUNT][HRBF_NUM_PYRS] = {};
+    float* vdepth_tmp = nullptr; // verticesToDepth of the last init_icp* texture
+    float* depth_tmp[HRBF_NUM_PYRS] = {};
+    float* lastDepth[HRBF_NUM_PYRS] = {}; float* nextDepth[HRBF_NUM_PYRS] = {};
+    unsigned char* lastImage[HRBF_NUM_PYRS] = {}; unsigned char* nextImage[HRBF_NUM_PYRS] = {}; unsigned char* lastNextImage[HRBF_NUM_PYRS] = {};
+    short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
+    float* cloud[HRBF_NUM_PYRS] = {};
+    hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
+    hrbf::ReduceWork* work = nullptr;
+    float* pose_scratch = nullptr;   // device: [0..11] model pose (R,t), [12..23] track in, [24..35] track out
+    // pinned host mirrors
+    float* h_pose = nullptr;         // [0..11] in, [12..23] out
+    hrbf::TrackState* h_state = nullptr;
+    float* h_model_pose = nullptr;   // staging ring for init_*_model poses
+    int h_model_pose_slot = 0;
+    int so3_parity = 0;
+
+    cudaStream_t cap_stream = nullptr;
+    std::map<uint64_t, std::pair<cudaGraphExec_t, int>> graphs;   // key -> (exec, kernel nodes)
+
+    int rows(int l) const { return height >> l; }
+    int cols(int l) const { return width >> l; }
+};
+
+
+struct hrbf_indexmap {
+    int width = 0, height = 0;
+    float cx = 0, cy = 0, fx = 0, fy = 0;
+    char* slab = nullptr;
+    unsigned long long* keys = nullptr;
+    void* tex[HRBF_TEX_COUNT] = {};
+    float* active_kf = nullptr;          // device float[HRBF_ACTIVE_KEYFRAME_DIMENSION]
+    float* inv_pose = nullptr;           // device: ring of 8 x (Ri[9], ti[3])
+    unsigned int* count_slot = nullptr;  // device ring of 8 counts (host-count API)
+    float* h_stage = nullptr;            // pinned ring: 8 x 16 floats
+    float* h_kf = nullptr;               // pinned keyframe mask
+    int slot = 0;
+};
+
+
+namespace hrbf {
+int indexmap_splat(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels, const unsigned int* count_dev, unsigned int bound,
+                   float depthCutoff, cudaStream_t s);
+// device-pose / device-select forms of the RGBDOdometry init* calls (odometry.cu), used by fusion.cu:
+// when `sel` is non-null and *sel != 0 the `_alt` textures are read instead (shouldFillIn, HRBFFusion.cpp:1069-1086)
+int odom_init_icp_model_dev(hrbf_odometry* o, const float* v, const float* n, const float* v_alt, const float* n_alt, const int* sel,
+                            const float* pose_dev, cudaStream_t s);
+int odom_init_curvature_model_dev(hrbf_odometry* o, const float* k1, const float* k2, const float* k1_alt, const float* k2_alt, const int* sel,
+                                  const float* pose_dev, cudaStream_t s);
+int odom_init_icp_weight_dev(hrbf_odometry* o, const float* w, const float* w_alt, const int* sel, cudaStream_t s);
+int odom_init_rgb_model_dev(hrbf_odometry* o, const unsigned char* rgba, const unsigned char* rgba_alt, const int* sel, cudaStream_t s);
+}

@@ -6,19 +6,7 @@
 
 using namespace hrbf;
 
-struct hrbf_indexmap {
-    int width = 0, height = 0;
-    float cx = 0, cy = 0, fx = 0, fy = 0;
-    char* slab = nullptr;
-    unsigned long long* keys = nullptr;
-    void* tex[HRBF_TEX_COUNT] = {};
-    float* active_kf = nullptr;          // device float[HRBF_ACTIVE_KEYFRAME_DIMENSION]
-    float* inv_pose = nullptr;           // device: ring of 8 x (Ri[9], ti[3])
-    unsigned int* count_slot = nullptr;  // device ring of 8 counts (host-count API)
-    float* h_stage = nullptr;            // pinned ring: 8 x 16 floats
-    float* h_kf = nullptr;               // pinned keyframe mask
-    int slot = 0;
-};
+#include "hrbf_internal.h"
 
 static size_t tex_bytes(int which, size_t P)
 {
@@ -91,8 +79,7 @@ int hrbf_indexmap_set_active_keyframes(hrbf_indexmap* m, const int* ids, int n, 
     return HRBF_OK;
 }
 
-static int splat(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels, const unsigned int* count_dev, unsigned int bound,
-                 float depthCutoff, cudaStream_t s);
+using hrbf::indexmap_splat;
 
 int hrbf_indexmap_predict_indices(hrbf_indexmap* m, const float* pose16, int time, int maxTime, const float* surfels_dev,
                                   unsigned int count, float depthCutoff, int insertSubmap, int indexSubmap, void* stream)
@@ -108,14 +95,14 @@ int hrbf_indexmap_predict_indices(hrbf_indexmap* m, const float* pose16, int tim
     memcpy(h + 12, &count, 4);
     HRBF_CUDA(cudaMemcpyAsync(m->inv_pose + 12 * k, h, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     HRBF_CUDA(cudaMemcpyAsync(m->count_slot + k, h + 12, 4, cudaMemcpyHostToDevice, s));
-    return splat(m, m->inv_pose + 12 * k, surfels_dev, m->count_slot + k, count, depthCutoff, s);
+    return indexmap_splat(m, m->inv_pose + 12 * k, surfels_dev, m->count_slot + k, count, depthCutoff, s);
 }
 
 int hrbf_indexmap_predict_indices_dev(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels_dev, const unsigned int* count_dev,
                                       unsigned int count_bound, float depthCutoff, void* stream)
 {
     HRBF_CHECK_ARG(m && inv_pose_dev && surfels_dev && count_dev);
-    return splat(m, inv_pose_dev, surfels_dev, count_dev, count_bound, depthCutoff, (cudaStream_t)stream);
+    return indexmap_splat(m, inv_pose_dev, surfels_dev, count_dev, count_bound, depthCutoff, (cudaStream_t)stream);
 }
 
 int hrbf_indexmap_predict_hrbf(hrbf_indexmap* m, int predictionType, int win, int minNeighbors, int maxNeighbors, float confThreshold,
@@ -146,8 +133,8 @@ void* hrbf_indexmap_texture(hrbf_indexmap* m, int which)
 
 }  // extern "C"
 
-static int splat(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels, const unsigned int* count_dev, unsigned int bound,
-                 float depthCutoff, cudaStream_t s)
+int hrbf::indexmap_splat(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels, const unsigned int* count_dev, unsigned int bound,
+                         float depthCutoff, cudaStream_t s)
 {
     SplatArgs a;
     a.inv_pose = inv_pose_dev;

@@ -1,0 +1,396 @@
+// model_kernels.cuh -- sm_100a kernels for SURVEY.md section 8 rows 8-9: the surfel map.
+// Replaces the GL transform-feedback passes of Core/src/GlobalModel.cpp:
+//   initialise (:214-288, init_unstableTex.vert/.geom)   -> init_flags_kernel + compacting scan
+//   fuse       (:355-549, data.vert/.geom/.frag, update.vert) -> fuse_associate_kernel (1/4 of the pixels: association,
+//              PCA normal, new-surfel record, 32-bit atomicMin "first primitive wins") + fuse_merge_kernel (in-place
+//              confidence-weighted merge of the winners only: no full-map pass, no 4596^2 update textures)
+//   clean      (:551-688, copy_unstable.vert/.geom)      -> clean_flags_kernel + block scan + clean_scatter_kernel
+//              (order-preserving stream compaction; the count never leaves the device)
+// Surfel record = 5 x float4 (80 B), the reference's VBO layout (Shaders/Vertex.cpp:20-44).
+#pragma once
+#include "prep_kernels.cuh"
+
+namespace hrbf {
+
+struct ModelArgs {
+    int cols, rows;
+    float cx, cy, fx, fy, icx, icy;
+    float maxDepth, confThreshold, radiusMultiplier, curvThr;
+    int pca, cleanWindow;
+};
+
+constexpr int kScanBlock = 256;
+constexpr unsigned int kNoWinner = 0xffffffffu;
+
+__device__ __forceinline__ float3 pose_apply(const float* P /* R[9], t[3] */, float3 v)
+{
+    return make_float3(((P[0] * v.x + P[1] * v.y) + P[2] * v.z) + P[9], ((P[3] * v.x + P[4] * v.y) + P[5] * v.z) + P[10],
+                       ((P[6] * v.x + P[7] * v.y) + P[8] * v.z) + P[11]);
+}
+__device__ __forceinline__ float3 pose_rotate(const float* P, float3 v)
+{
+    return make_float3((P[0] * v.x + P[1] * v.y) + P[2] * v.z, (P[3] * v.x + P[4] * v.y) + P[5] * v.z, (P[6] * v.x + P[7] * v.y) + P[8] * v.z);
+}
+__device__ __forceinline__ float encode_rgb8(const unsigned char* c) { return (float)((((((int)c[0]) << 8) + (int)c[1]) << 8) + (int)c[2]); }
+__device__ __forceinline__ float encode_color(float3 c)
+{
+    int rgb = (int)roundf(c.x * 255.0f);
+    rgb = (rgb << 8) + (int)roundf(c.y * 255.0f);
+    rgb = (rgb << 8) + (int)roundf(c.z * 255.0f);
+    return (float)rgb;
+}
+__device__ __forceinline__ float3 decode_color(float c)
+{
+    const int i = (int)c;
+    return make_float3((float)(i >> 16 & 0xFF) / 255.0f, (float)(i >> 8 & 0xFF) / 255.0f, (float)(i & 0xFF) / 255.0f);
+}
+
+// pose (R[9], t[3]) -> its rigid inverse, same arithmetic as the host path (R^T, -R^T t)
+__global__ void pose_inverse_kernel(const float* __restrict__ pose, float* __restrict__ inv)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float Ri[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = pose[j * 3 + i];
+    for (int k = 0; k < 9; ++k) inv[k] = Ri[k];
+    for (int i = 0; i < 3; ++i) inv[9 + i] = -(__fadd_rn(__fadd_rn(__fmul_rn(Ri[i * 3], pose[9]), __fmul_rn(Ri[i * 3 + 1], pose[10])), __fmul_rn(Ri[i * 3 + 2], pose[11])));
+}
+
+// HRBFFusion.cpp:1112-1123 : fusion weight from the inter-frame motion (|t| vs rotation angle), on the device
+__global__ void velocity_weighting_kernel(const float* __restrict__ curr, const float* __restrict__ last, float weightMultiplier, float* __restrict__ weighting)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // diff = curr^-1 * last
+    float R[9], t[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = (curr[0 * 3 + i] * last[0 * 3 + j] + curr[1 * 3 + i] * last[1 * 3 + j]) + curr[2 * 3 + i] * last[2 * 3 + j];
+        const float d0 = last[9] - curr[9], d1 = last[10] - curr[10], d2 = last[11] - curr[11];
+        t[i] = (curr[0 * 3 + i] * d0 + curr[1 * 3 + i] * d1) + curr[2 * 3 + i] * d2;
+    }
+    const double rx = (double)R[7] - (double)R[5], ry = (double)R[2] - (double)R[6], rz = (double)R[3] - (double)R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = ((double)((R[0] + R[4]) + R[8]) - 1.0) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    double theta = acos(c);
+    if (s < 1e-5 && c > 0) theta = 0.0;
+    const float tn = sqrtf((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]);
+    float w = fmaxf(tn, (float)theta);
+    const float largest = 0.01f, minWeight = 0.5f;
+    if (w > largest) w = largest;
+    weighting[0] = fmaxf(1.0f - (w / largest), minWeight) * weightMultiplier;
+}
+
+// ------------------------------------------------------------------ generic order-preserving compaction ---
+// flags (1 byte per item, written by a *_flags_kernel together with block_counts) -> block_offsets, total
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const unsigned int* __restrict__ block_counts, unsigned int* __restrict__ block_offsets,
+                                                           const unsigned int* __restrict__ n_items_dev, unsigned int n_items_add,
+                                                           unsigned int capacity, unsigned int* __restrict__ total_out, unsigned int* __restrict__ overflow)
+{
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    const unsigned int n_items = (n_items_dev ? *n_items_dev : 0u) + n_items_add;
+    const unsigned int nb = (n_items + kScanBlock - 1) / kScanBlock;
+    if (threadIdx.x == 0) s_carry = 0u;
+    __syncthreads();
+    for (unsigned int base = 0; base < nb; base += 1024) {
+        const unsigned int b = base + threadIdx.x;
+        const unsigned int v = b < nb ? block_counts[b] : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += y; }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const unsigned int incl = x + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u) + s_carry;
+        if (b < nb) block_offsets[b] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned int tot = s_carry;
+        if (tot > capacity) { tot = capacity; *overflow = 1u; }
+        *total_out = tot;
+    }
+}
+
+// exclusive position of a flagged item inside its block (ballot + warp prefix)
+__device__ __forceinline__ unsigned int block_rank(bool flag, unsigned int* s_warp /* [kScanBlock/32] */)
+{
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int off = 0;
+    for (unsigned int w = 0; w < warp; ++w) off += s_warp[w];
+    return off + __popc(bal & ((1u << lane) - 1u));
+}
+
+// ------------------------------------------------------------------ initialise ---
+struct InitArgs {
+    const float4 *vertexRaw, *normal, *curv1, *curv2; const unsigned char* rgb; const float* gradientMag;
+    const float* pose;      // device R[9], t[3]
+    int useConfEval; float epsilon;
+};
+// item i = px * rows + py (the reference's uv buffer order, GlobalModel.cpp:89-96)
+__device__ __forceinline__ bool init_record(const ModelArgs& m, const InitArgs& a, const float* P, int i, float4 (&rec)[5])
+{
+    const int px = i / m.rows, py = i - px * m.rows;
+    const size_t o = (size_t)py * m.cols + px;
+    const float4 vl = __ldg(a.vertexRaw + o), nl = __ldg(a.normal + o), k1 = __ldg(a.curv1 + o), k2 = __ldg(a.curv2 + o);
+    const float3 g = pose_apply(P, make_float3(vl.x, vl.y, vl.z));
+    const float max_dist = sqrtf(((float)m.rows * 0.5f) * ((float)m.rows * 0.5f) + ((float)m.cols * 0.5f) * ((float)m.cols * 0.5f));
+    float conf = confidence_fn(m.cx, m.cy, (float)px + 0.5f, (float)py + 0.5f, max_dist, 1.0f);
+    if (a.useConfEval > 0) conf = conf * expf(-a.epsilon / sqrtf(__ldg(a.gradientMag + o)));
+    const float3 n = pose_rotate(P, make_float3(nl.x, nl.y, nl.z));
+    rec[0] = make_float4(g.x, g.y, g.z, conf);
+    rec[1] = make_float4(encode_rgb8(a.rgb + 3 * o), 0.0f, 1.0f, 1.0f);
+    rec[2] = make_float4(n.x, n.y, n.z, nl.w);
+    rec[3] = k1; rec[4] = k2;
+    return sqrtf(n.x * n.x + n.y * n.y + n.z * n.z) > 0.5f && k1.w > -m.curvThr && k1.w < m.curvThr && k2.w > -m.curvThr && k2.w < m.curvThr;
+}
+__global__ void __launch_bounds__(kScanBlock) init_flags_kernel(ModelArgs m, InitArgs a, unsigned char* __restrict__ flags, unsigned int* __restrict__ block_counts)
+{
+    const int i = blockIdx.x * kScanBlock + threadIdx.x;
+    float P[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P[k] = __ldg(a.pose + k);
+    bool f = false;
+    if (i < m.cols * m.rows) { float4 rec[5]; f = init_record(m, a, P, i, rec); flags[i] = f ? 1 : 0; }
+    const int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(kScanBlock) init_scatter_kernel(ModelArgs m, InitArgs a, const unsigned char* __restrict__ flags,
+                                                                  const unsigned int* __restrict__ block_offsets, unsigned int capacity, float4* __restrict__ out)
+{
+    __shared__ unsigned int s_warp[kScanBlock / 32];
+    const int i = blockIdx.x * kScanBlock + threadIdx.x;
+    float P[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P[k] = __ldg(a.pose + k);
+    const bool f = i < m.cols * m.rows && flags[i];
+    const unsigned int pos = block_offsets[blockIdx.x] + block_rank(f, s_warp);
+    if (!f || pos >= capacity) return;
+    float4 rec[5];
+    init_record(m, a, P, i, rec);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) out[5 * (size_t)pos + k] = rec[k];
+}
+
+// ------------------------------------------------------------------ fuse ---
+struct FuseArgs {
+    const unsigned char* rgb; const float *depthRaw, *depthFiltered; const float4 *curv1, *curv2; const float* confidence;
+    const unsigned int* index; const float4 *vertConf, *normRad;
+    const float* pose;               // device R[9], t[3]
+    int time; float indexSubmap;
+    float4* staging;                 // [(cols/2+1)*(rows/2+1)][5] : this frame's candidate records
+    unsigned char* update_id;        // per slot: 0 none, 1 merge, 2 new
+    unsigned int* best;              // per slot: surfel to merge with
+    unsigned int* winner;            // per surfel: lowest slot that wants to update it (kNoWinner = none); self re-arming
+};
+__host__ __device__ inline int fuse_slots_x(int cols) { return (cols + 1) / 2; }
+__host__ __device__ inline int fuse_slots_y(int rows) { return (rows + 1) / 2; }
+
+// One thread per candidate pixel (x%2 == t%2 && y%2 == t%2, data.vert:113).  Slot order = uv order (x outer, y inner).
+__global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepArgs pa, FuseArgs f, const unsigned int* __restrict__ count_dev)
+{
+    const int sxn = fuse_slots_x(m.cols), syn = fuse_slots_y(m.rows);
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= sxn * syn) return;
+    const int par = f.time % 2;
+    const int px = 2 * (slot / syn) + par, py = 2 * (slot % syn) + par;
+    f.update_id[slot] = 0;
+    if (px >= m.cols || py >= m.rows) return;
+    const int W = m.cols, H = m.rows;
+    const size_t o = (size_t)py * W + px;
+    const float x = (float)px + 0.5f, y = (float)py + 0.5f;
+    const float z = __ldg(f.depthRaw + o), zf = __ldg(f.depthFiltered + o);
+    const float4 k1 = __ldg(f.curv1 + o), k2 = __ldg(f.curv2 + o);
+    if (!(z > 0.3f && z <= m.maxDepth && k1.w > -300.0f && k1.w < 300.0f && k2.w > -300.0f && k2.w < 300.0f)) return;
+    float3 n = make_float3(0.f, 0.f, 0.f);
+    if (m.pca) n = normal_pca(pa, [&](int qx, int qy) { return __ldg(f.depthFiltered + (size_t)qy * W + qx); }, px, py, zf);
+    const float nlen = norm(n);
+    if (!(nlen > 0.8f)) return;
+
+    float P[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P[k] = __ldg(f.pose + k);
+    const float3 vloc = make_float3((x - m.cx) * z * m.icx, (y - m.cy) * z * m.icy, z);
+    const float3 g = pose_apply(P, vloc), ng = pose_rotate(P, n);
+
+    const float xl = (x - m.cx) * m.icx, yl = (y - m.cy) * m.icy;
+    const float lambda = sqrtf(xl * xl + yl * yl + 1);
+    const float3 ray = make_float3(xl, yl, 1.0f);
+    const float raylen = norm(ray);
+    const unsigned int count = *count_dev;
+    int counter = 0;
+    float bestDist = 1000;
+    unsigned int best = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float ox = -1.0f + 0.5f * (float)a, oy = -1.0f + 0.5f * (float)b;
+            const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
+            const size_t q = (size_t)sy * W + sx;
+            const unsigned int current = __ldg(f.index + q);
+            if (current > 0u) {
+                const float4 vc = __ldg(f.vertConf + q);
+                if (fabsf((vc.z * lambda) - (vloc.z * lambda)) < 0.05f) {
+                    const float dist = norm(cross(ray, make_float3(vc.x, vc.y, vc.z))) / raylen;
+                    const float4 nr = __ldg(f.normRad + q);
+                    const float la = sqrtf(nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
+                    const float ang = acosf((nr.x * n.x + nr.y * n.y + nr.z * n.z) / (la * nlen));
+                    if (dist < bestDist && (fabsf(nr.z) < 0.75f || fabsf(ang) < 0.5f)) { counter++; bestDist = dist; best = current; }
+                }
+            }
+        }
+    const bool merge = counter > 0 && best < count;
+    float4* rec = f.staging + 5 * (size_t)slot;
+    rec[0] = make_float4(g.x, g.y, g.z, __ldg(f.confidence + o));
+    rec[1] = make_float4(encode_rgb8(f.rgb + 3 * o), f.indexSubmap, (float)f.time, counter > 0 ? -1.0f : -2.0f);
+    rec[2] = make_float4(ng.x, ng.y, ng.z, m.radiusMultiplier * get_radius(m.icx, m.icy, zf, n.z));
+    rec[3] = k1; rec[4] = k2;
+    f.update_id[slot] = counter > 0 ? 1 : 2;
+    f.best[slot] = best;
+    if (merge) atomicMin(f.winner + best, (unsigned int)slot);     // first primitive in uv order wins (GL_LESS at equal depth)
+}
+
+// update.vert:51-115, applied in place to the winners only
+__global__ void __launch_bounds__(128) fuse_merge_kernel(ModelArgs m, FuseArgs f, float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= fuse_slots_x(m.cols) * fuse_slots_y(m.rows)) return;
+    if (f.update_id[slot] != 1) return;
+    const unsigned int best = f.best[slot];
+    if (best >= *count_dev || f.winner[best] != (unsigned int)slot) return;
+    f.winner[best] = kNoWinner;                                     // re-arm
+    float4* s = surfels + 5 * (size_t)best;
+    const float4* nw = f.staging + 5 * (size_t)slot;
+    const float4 sp = s[0], sc = s[1], sn = s[2], sk1 = s[3], sk2 = s[4];
+    const float4 np = nw[0], nc = nw[1], nn = nw[2], nk1 = nw[3], nk2 = nw[4];
+    const float c_k = sp.w, a = np.w;
+    if (nn.w < (1.0f + 0.5f) * sn.w) {
+        const float d = c_k + a;
+        s[0] = make_float4(((c_k * sp.x) + (a * np.x)) / d, ((c_k * sp.y) + (a * np.y)) / d, ((c_k * sp.z) + (a * np.z)) / d, d);
+        const float3 oc = decode_color(sc.x), ncol = decode_color(nc.x);
+        const float3 avg = make_float3(((c_k * oc.x) + (a * ncol.x)) / d, ((c_k * oc.y) + (a * ncol.y)) / d, ((c_k * oc.z) + (a * ncol.z)) / d);
+        s[1] = make_float4(encode_color(avg), sc.y, sc.z, (float)f.time);
+        const float4 nr = make_float4(((c_k * sn.x) + (a * nn.x)) / d, ((c_k * sn.y) + (a * nn.y)) / d, ((c_k * sn.z) + (a * nn.z)) / d, ((c_k * sn.w) + (a * nn.w)) / d);
+        const float len = sqrtf(nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
+        s[2] = make_float4(nr.x / len, nr.y / len, nr.z / len, nr.w);
+        s[3] = make_float4(((c_k * sk1.x) + (a * nk1.x)) / d, ((c_k * sk1.y) + (a * nk1.y)) / d, ((c_k * sk1.z) + (a * nk1.z)) / d, ((c_k * sk1.w) + (a * nk1.w)) / d);
+        s[4] = make_float4(((c_k * sk2.x) + (a * nk2.x)) / d, ((c_k * sk2.y) + (a * nk2.y)) / d, ((c_k * sk2.z) + (a * nk2.z)) / d, ((c_k * sk2.w) + (a * nk2.w)) / d);
+    } else {
+        s[0].w = c_k + a;
+        s[1].w = (float)f.time;
+    }
+}
+
+// ------------------------------------------------------------------ clean ---
+struct CleanArgs {
+    const unsigned int* index; const float4 *vertConf, *colorTime;
+    const float* inv_pose;            // device Ri[9], ti[3]
+    const float* active_kf; int kf_dim;
+    int time;
+    const float4* staging; const unsigned char* update_id; int n_slots;
+};
+// copy_unstable.vert:62-166 on one record; rec[1].w is rewritten (-2 -> time)
+__device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& c, const float* Pi, float4 (&rec)[5])
+{
+    const int W = m.cols, H = m.rows;
+    bool test = true;
+    const float3 lp = pose_apply(Pi, make_float3(rec[0].x, rec[0].y, rec[0].z));
+    const float x = ((m.fx * lp.x) / lp.z) + m.cx, y = ((m.fy * lp.y) / lp.z) + m.cy;
+    const float3 ln = pose_rotate(Pi, make_float3(rec[2].x, rec[2].y, rec[2].z));
+    const float lnz = ln.z / norm(ln);
+    int count = 0, zCount = 0;
+    const float sub = rec[1].y;
+    const int kf = (sub >= 0.0f && sub < (float)c.kf_dim) ? (int)sub : -1;
+    const float active = kf >= 0 ? __ldg(c.active_kf + kf) : 0.0f;
+    if (lp.z < m.maxDepth && lp.z > 0 && x > 0 && y > 0 && x < (float)W && y < (float)H) {
+        const int ns = 2 * m.cleanWindow;
+        for (int a = 0; a < ns; ++a)
+            for (int b = 0; b < ns; ++b) {
+                const float ox = 0.5f * (float)(a - m.cleanWindow), oy = 0.5f * (float)(b - m.cleanWindow);
+                const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
+                const size_t q = (size_t)sy * W + sx;
+                if (__ldg(c.index + q) > 0u) {
+                    const float4 vc = __ldg(c.vertConf + q), ct = __ldg(c.colorTime + q);
+                    const float dx = vc.x - lp.x, dy = vc.y - lp.y;
+                    if (ct.z < rec[1].z && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z < 0.01f && sqrtf(dx * dx + dy * dy) < rec[2].w * 1.4f) count++;
+                    if (ct.w == (float)c.time && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z > 0.01f && fabsf(lnz) > 0.85f && active > 0.0f) zCount++;
+                }
+            }
+    }
+    if (rec[3].w < -m.curvThr || rec[3].w > m.curvThr || rec[4].w < -m.curvThr || rec[4].w > m.curvThr) test = false;
+    if (count > 8 || zCount > 4) test = false;
+    if (rec[1].w == -2.0f) rec[1].w = (float)c.time;
+    if (rec[1].w == -1.0f || (((float)c.time - rec[1].w) > 200.0f && rec[0].w < m.confThreshold)) test = false;
+    return test;
+}
+// items [0, count) = existing surfels, [count, count + n_slots) = this frame's staging slots (update_id 2 = live)
+__device__ __forceinline__ bool clean_load(const CleanArgs& c, const float4* __restrict__ surfels, unsigned int count, unsigned int i, float4 (&rec)[5])
+{
+    const float4* src;
+    if (i < count) src = surfels + 5 * (size_t)i;
+    else {
+        const unsigned int slot = i - count;
+        if (c.update_id[slot] != 2) return false;        // 0: nothing emitted; 1: merged (vColor.w == -1 -> dropped)
+        src = c.staging + 5 * (size_t)slot;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) rec[k] = src[k];
+    return true;
+}
+__global__ void __launch_bounds__(kScanBlock) clean_flags_kernel(ModelArgs m, CleanArgs c, const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
+                                                                 unsigned char* __restrict__ flags, unsigned int* __restrict__ block_counts)
+{
+    const unsigned int count = *count_dev, n = count + (unsigned int)c.n_slots;
+    float Pi[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Pi[k] = __ldg(c.inv_pose + k);
+    for (unsigned int blk = blockIdx.x; blk * kScanBlock < n; blk += gridDim.x) {
+        const unsigned int i = blk * kScanBlock + threadIdx.x;
+        bool f = false;
+        if (i < n) {
+            float4 rec[5];
+            f = clean_load(c, surfels, count, i, rec) && clean_test(m, c, Pi, rec);
+            flags[i] = f ? 1 : 0;
+        }
+        const int cnt = __syncthreads_count(f);
+        if (threadIdx.x == 0) block_counts[blk] = cnt;
+    }
+}
+__global__ void __launch_bounds__(kScanBlock) clean_scatter_kernel(CleanArgs c, const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
+                                                                   const unsigned char* __restrict__ flags, const unsigned int* __restrict__ block_offsets,
+                                                                   unsigned int capacity, float4* __restrict__ out)
+{
+    __shared__ unsigned int s_warp[kScanBlock / 32];
+    const unsigned int count = *count_dev, n = count + (unsigned int)c.n_slots;
+    for (unsigned int blk = blockIdx.x; blk * kScanBlock < n; blk += gridDim.x) {
+        const unsigned int i = blk * kScanBlock + threadIdx.x;
+        const bool f = i < n && flags[i];
+        const unsigned int pos = block_offsets[blk] + block_rank(f, s_warp);
+        if (f && pos < capacity) {
+            float4 rec[5];
+            clean_load(c, surfels, count, i, rec);
+            if (rec[1].w == -2.0f) rec[1].w = (float)c.time;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) out[5 * (size_t)pos + k] = rec[k];
+        }
+        __syncthreads();       // s_warp is reused by the next tile
+    }
+}
+
+__global__ void fill_u32_kernel(unsigned int* p, size_t n, unsigned int v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace hrbf

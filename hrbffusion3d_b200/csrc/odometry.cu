@@ -27,45 +27,12 @@ void set_error(const char* fmt, ...)
 static inline dim3 grid2d(int cols, int rows, dim3 b) { return dim3(div_up(cols, b.x), div_up(rows, b.y)); }
 static inline int reduce_blocks(int n) { int b = div_up(n, kReduceThreads * 2); return b < 1 ? 1 : (b > kMaxReduceBlocks ? kMaxReduceBlocks : b); }
 
-enum { M_VG = 0, M_NG, M_K1G, M_K2G, M_VC, M_NC, M_K1C, M_K2C, M_W, M_COUNT };
 
 }  // namespace hrbf
 
 using namespace hrbf;
 
-struct hrbf_odometry {
-    int width = 0, height = 0;
-    hrbf_camera intr{};
-    float distThres = 0.1f, angleThres = 0.f;
-    float sobelScale = 0.125f, maxDepthDeltaRGB = 0.07f, maxDepthRGB = 6.0f;
-    float minGrad[HRBF_NUM_PYRS] = { 5, 3, 1 };
-    float curvThr = 300.f;
-    int useSearch = 0, searchRadius = 2, rgbGradWeight = 0;
-
-    char* slab = nullptr;        // one allocation for everything below
-    float* maps[M_COUNT][HRBF_NUM_PYRS] = {};
-    float* vdepth_tmp = nullptr; // verticesToDepth of the last init_icp* texture
-    float* depth_tmp[HRBF_NUM_PYRS] = {};
-    float* lastDepth[HRBF_NUM_PYRS] = {}; float* nextDepth[HRBF_NUM_PYRS] = {};
-    unsigned char* lastImage[HRBF_NUM_PYRS] = {}; unsigned char* nextImage[HRBF_NUM_PYRS] = {}; unsigned char* lastNextImage[HRBF_NUM_PYRS] = {};
-    short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
-    float* cloud[HRBF_NUM_PYRS] = {};
-    hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
-    ReduceWork* work = nullptr;
-    float* pose_scratch = nullptr;   // device: [0..11] model pose (R,t), [12..23] track in, [24..35] track out
-    // pinned host mirrors
-    float* h_pose = nullptr;         // [0..11] in, [12..23] out
-    TrackState* h_state = nullptr;
-    float* h_model_pose = nullptr;   // staging ring for init_*_model poses
-    int h_model_pose_slot = 0;
-    int so3_parity = 0;
-
-    cudaStream_t cap_stream = nullptr;
-    std::map<uint64_t, std::pair<cudaGraphExec_t, int>> graphs;   // key -> (exec, kernel nodes)
-
-    int rows(int l) const { return height >> l; }
-    int cols(int l) const { return width >> l; }
-};
+#include "hrbf_internal.h"
 
 namespace hrbf {
 
@@ -502,26 +469,51 @@ int hrbf_odometry_init_icp(hrbf_odometry* o, const float* v, const float* n, flo
     (void)depthCutoff;
     HRBF_CHECK_ARG(o && v && n);
     pyr_pair_kernel<PYR_VN><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)v, (const float4*)n, o->height, o->width, 0.f, nullptr,
-                                                                         pyr_out(o, M_VC), pyr_out(o, M_NC), o->vdepth_tmp, o->maxDepthRGB);
+                                                                         pyr_out(o, M_VC), pyr_out(o, M_NC), o->vdepth_tmp, o->maxDepthRGB, nullptr, nullptr, nullptr);
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }
+}  // extern "C"
+namespace hrbf {
+// device-pose / device-select forms used by the fused frame pipeline (fusion.cu)
+int odom_init_icp_model_dev(hrbf_odometry* o, const float* v, const float* n, const float* v_alt, const float* n_alt, const int* sel,
+                            const float* pose_dev, cudaStream_t s)
+{
+    pyr_pair_kernel<PYR_VN><<<pyr_grid(o), 256, 0, s>>>((const float4*)v, (const float4*)n, o->height, o->width, 0.f, pose_dev,
+                                                      pyr_out(o, M_VG), pyr_out(o, M_NG), o->vdepth_tmp, o->maxDepthRGB,
+                                                      (const float4*)v_alt, (const float4*)n_alt, sel);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int odom_init_curvature_model_dev(hrbf_odometry* o, const float* k1, const float* k2, const float* k1_alt, const float* k2_alt, const int* sel,
+                                  const float* pose_dev, cudaStream_t s)
+{
+    pyr_pair_kernel<PYR_K><<<pyr_grid(o), 256, 0, s>>>((const float4*)k1, (const float4*)k2, o->height, o->width, o->curvThr, pose_dev,
+                                                     pyr_out(o, M_K1G), pyr_out(o, M_K2G), nullptr, 0.f, (const float4*)k1_alt, (const float4*)k2_alt, sel);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+int odom_init_icp_weight_dev(hrbf_odometry* o, const float* w, const float* w_alt, const int* sel, cudaStream_t s)
+{
+    pyr_weight_kernel<<<pyr_grid(o), 256, 0, s>>>(w, o->height, o->width, o->maps[M_W][0], o->cols(0), o->maps[M_W][1], o->cols(1), o->maps[M_W][2], o->cols(2), w_alt, sel);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
+}  // namespace hrbf
+extern "C" {
 int hrbf_odometry_init_icp_model(hrbf_odometry* o, const float* v, const float* n, float depthCutoff, const float* pose16, void* stream)
 {
     (void)depthCutoff;
     HRBF_CHECK_ARG(o && v && n && pose16);
     float* dpose = nullptr;
     if (int rc = upload_pose(o, pose16, (cudaStream_t)stream, &dpose)) return rc;
-    pyr_pair_kernel<PYR_VN><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)v, (const float4*)n, o->height, o->width, 0.f, dpose,
-                                                                         pyr_out(o, M_VG), pyr_out(o, M_NG), o->vdepth_tmp, o->maxDepthRGB);
-    HRBF_KERNEL_CHECK();
-    return HRBF_OK;
+    return odom_init_icp_model_dev(o, v, n, nullptr, nullptr, nullptr, dpose, (cudaStream_t)stream);
 }
 int hrbf_odometry_init_curvature(hrbf_odometry* o, const float* k1, const float* k2, void* stream)
 {
     HRBF_CHECK_ARG(o && k1 && k2);
     pyr_pair_kernel<PYR_K><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)k1, (const float4*)k2, o->height, o->width, o->curvThr, nullptr,
-                                                                        pyr_out(o, M_K1C), pyr_out(o, M_K2C), nullptr, 0.f);
+                                                                        pyr_out(o, M_K1C), pyr_out(o, M_K2C), nullptr, 0.f, nullptr, nullptr, nullptr);
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }
@@ -530,17 +522,12 @@ int hrbf_odometry_init_curvature_model(hrbf_odometry* o, const float* k1, const 
     HRBF_CHECK_ARG(o && k1 && k2 && pose16);
     float* dpose = nullptr;
     if (int rc = upload_pose(o, pose16, (cudaStream_t)stream, &dpose)) return rc;
-    pyr_pair_kernel<PYR_K><<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>((const float4*)k1, (const float4*)k2, o->height, o->width, o->curvThr, dpose,
-                                                                        pyr_out(o, M_K1G), pyr_out(o, M_K2G), nullptr, 0.f);
-    HRBF_KERNEL_CHECK();
-    return HRBF_OK;
+    return odom_init_curvature_model_dev(o, k1, k2, nullptr, nullptr, nullptr, dpose, (cudaStream_t)stream);
 }
 int hrbf_odometry_init_icp_weight(hrbf_odometry* o, const float* w, void* stream)
 {
     HRBF_CHECK_ARG(o && w);
-    pyr_weight_kernel<<<pyr_grid(o), 256, 0, (cudaStream_t)stream>>>(w, o->height, o->width, o->maps[M_W][0], o->cols(0), o->maps[M_W][1], o->cols(1), o->maps[M_W][2], o->cols(2));
-    HRBF_KERNEL_CHECK();
-    return HRBF_OK;
+    return odom_init_icp_weight_dev(o, w, nullptr, nullptr, (cudaStream_t)stream);
 }
 int hrbf_odometry_fill_neutral_curvature(hrbf_odometry* o, void* stream)
 {
@@ -556,7 +543,8 @@ int hrbf_odometry_fill_neutral_curvature(hrbf_odometry* o, void* stream)
     return HRBF_OK;
 }
 
-static int populate_rgbd(hrbf_odometry* o, const unsigned char* rgba, float** depths, unsigned char** images, cudaStream_t s)
+static int populate_rgbd(hrbf_odometry* o, const unsigned char* rgba, float** depths, unsigned char** images, cudaStream_t s,
+                         const unsigned char* rgba_alt = nullptr, const int* sel = nullptr)
 {
     const dim3 b(32, 8);
     HRBF_CUDA(cudaMemcpyAsync(depths[0], o->vdepth_tmp, (size_t)o->width * o->height * 4, cudaMemcpyDeviceToDevice, s));
@@ -565,7 +553,7 @@ static int populate_rgbd(hrbf_odometry* o, const unsigned char* rgba, float** de
         HRBF_KERNEL_CHECK();
     }
     const int n = o->width * o->height;
-    rgba_to_intensity_kernel<<<div_up(n, 256), 256, 0, s>>>(n, (const uchar4*)rgba, images[0]);
+    rgba_to_intensity_kernel<<<div_up(n, 256), 256, 0, s>>>(n, (const uchar4*)rgba, images[0], (const uchar4*)rgba_alt, sel);
     HRBF_KERNEL_CHECK();
     for (int i = 0; i + 1 < 3; ++i) {
         pyrdown_gauss_u8_kernel<<<grid2d(o->cols(i + 1), o->rows(i + 1), b), b, 0, s>>>(o->rows(i), o->cols(i), images[i], images[i + 1]);
@@ -577,13 +565,19 @@ int hrbf_odometry_init_rgb(hrbf_odometry* o, const unsigned char* rgba, void* st
 { HRBF_CHECK_ARG(o && rgba); return populate_rgbd(o, rgba, o->nextDepth, o->nextImage, (cudaStream_t)stream); }
 int hrbf_odometry_init_rgb_model(hrbf_odometry* o, const unsigned char* rgba, void* stream)
 { HRBF_CHECK_ARG(o && rgba); return populate_rgbd(o, rgba, o->lastDepth, o->lastImage, (cudaStream_t)stream); }
+}  // extern "C"
+namespace hrbf {
+int odom_init_rgb_model_dev(hrbf_odometry* o, const unsigned char* rgba, const unsigned char* rgba_alt, const int* sel, cudaStream_t s)
+{ return populate_rgbd(o, rgba, o->lastDepth, o->lastImage, s, rgba_alt, sel); }
+}
+extern "C" {
 int hrbf_odometry_init_first_rgb(hrbf_odometry* o, const unsigned char* rgba, void* stream)
 {
     HRBF_CHECK_ARG(o && rgba);
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 b(32, 8);
     const int n = o->width * o->height;
-    rgba_to_intensity_kernel<<<div_up(n, 256), 256, 0, s>>>(n, (const uchar4*)rgba, o->lastNextImage[0]);
+    rgba_to_intensity_kernel<<<div_up(n, 256), 256, 0, s>>>(n, (const uchar4*)rgba, o->lastNextImage[0], nullptr, nullptr);
     HRBF_KERNEL_CHECK();
     for (int i = 0; i + 1 < 3; ++i) {
         pyrdown_gauss_u8_kernel<<<grid2d(o->cols(i + 1), o->rows(i + 1), b), b, 0, s>>>(o->rows(i), o->cols(i), o->lastNextImage[i], o->lastNextImage[i + 1]);

@@ -34,11 +34,15 @@ __device__ __forceinline__ void store4(float* base, int pitch, int rows, int y, 
 // pose (device, R[9] t[3]) != nullptr : every level is moved to the global frame after the
 //                  pyramid is built (RGBDOdometry.cpp:233-244, 747-757); vertices get +t.
 // depth_out != nullptr (PYR_VN) : verticesToDepth of the raw texture (cudafuncs.cu:874-885).
+// sel != nullptr && *sel != 0 : read the alternate textures (a_alt, b_alt) instead -- the device-side form of
+//                  `shouldFillIn ? &fillIn.xTexture : indexMap.xTexHRBF()` (HRBFFusion.cpp:1073-1086), no host round trip.
 template <int KIND>
 __global__ void __launch_bounds__(256) pyr_pair_kernel(const float4* __restrict__ a_aos, const float4* __restrict__ b_aos,
                                                        int rows, int cols, float thr, const float* __restrict__ pose,
-                                                       PyrOut oa, PyrOut ob, float* __restrict__ depth_out, float depth_cutoff)
+                                                       PyrOut oa, PyrOut ob, float* __restrict__ depth_out, float depth_cutoff,
+                                                       const float4* __restrict__ a_alt, const float4* __restrict__ b_alt, const int* __restrict__ sel)
 {
+    if (sel != nullptr && *sel != 0) { a_aos = a_alt; b_aos = b_alt; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
     const int x = (blockIdx.x * 4 + (warp & 3)) * 8 + lx;
@@ -121,8 +125,10 @@ __global__ void __launch_bounds__(256) pyr_pair_kernel(const float4* __restrict_
 
 // icp weight: copy (w>0 else NaN, cudafuncs.cu:464) + 2 resize levels (:718-725)
 __global__ void __launch_bounds__(256) pyr_weight_kernel(const float* __restrict__ w_src, int rows, int cols,
-                                                         float* o0, int p0, float* o1, int p1, float* o2, int p2)
+                                                         float* o0, int p0, float* o1, int p1, float* o2, int p2,
+                                                         const float* __restrict__ w_alt, const int* __restrict__ sel)
 {
+    if (sel != nullptr && *sel != 0) w_src = w_alt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
     const int x = (blockIdx.x * 4 + (warp & 3)) * 8 + lx;
@@ -325,8 +331,10 @@ __global__ void pyrdown_gauss_u8_kernel(int srows, int scols, const unsigned cha
     const float r = sum / (float)count;
     dst[(size_t)y * dcols + x] = isnan(r) ? (unsigned char)0 : (unsigned char)(int)r;
 }
-__global__ void rgba_to_intensity_kernel(int n, const uchar4* __restrict__ rgba, unsigned char* dst)
+__global__ void rgba_to_intensity_kernel(int n, const uchar4* __restrict__ rgba, unsigned char* dst,
+                                         const uchar4* __restrict__ rgba_alt, const int* __restrict__ sel)
 {
+    if (sel != nullptr && *sel != 0) rgba = rgba_alt;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uchar4 s = __ldg(rgba + i);

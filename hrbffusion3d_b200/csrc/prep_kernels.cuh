@@ -1,0 +1,421 @@
+// prep_kernels.cuh -- sm_100a kernels for SURVEY.md section 8 row 10: the per-frame preprocessing that
+// produces the ICP "curr" maps (replaces the full-screen GLSL passes driven by
+// Core/src/HRBFFusion.cpp:1016-1021,1262-1346), plus FillIn (Shaders/FillIn.cpp) and the
+// dense-enough test (HRBFFusion.cpp:974-987, Shaders/Resize.cpp).
+//   depth_bilateral.frag + depth_metric_{raw,filtered}.frag       -> depth_filter_metric_kernel (one pass, smem tile)
+//   depth_vertex_normal_radius.frag (PCA normals, geometry.glsl)  -> vertex_normal_radius_kernel
+//   depth_curvature_gradient.frag (HRBF gradient + 3rd-derivative curvature) -> curvature_gradient_kernel
+//   depth_confidence_evaluation.frag                              -> confidence_kernel
+//   fill_{vertex,normal,curvature,rgb}.frag                       -> fill_in_kernel (4 passes fused)
+#pragma once
+#include "common.cuh"
+
+namespace hrbf {
+
+struct PrepArgs {
+    int cols, rows;
+    float cx, cy, icx, icy;          // cam = (cx, cy, 1/fx, 1/fy)
+    float depthFactor, maxD;         // metres per raw unit, globalDepthCutoff
+    float radiusMultiplier;
+    int pca, curvWin, bilateral;
+};
+
+// exp() of the bilateral weights as a fixed sequence of IEEE fp32 operations (no FMA), identical to the oracle's
+// orc_exp_bilateral: the filtered depth must be bit-reproducible because the PCA normal estimation downstream
+// amplifies 1-ulp depth differences to ~1e-3 in the normal.
+__device__ __forceinline__ float exp_bilateral(float x)
+{
+    if (!(x > -87.0f)) return 0.0f;
+    const float t = __fmul_rn(x, 1.44269504088896341f);
+    const float n = rintf(t);
+    const float f = __fsub_rn(t, n);
+    float p = 1.54035304e-4f;
+    p = __fadd_rn(__fmul_rn(p, f), 1.33335581e-3f);
+    p = __fadd_rn(__fmul_rn(p, f), 9.61812911e-3f);
+    p = __fadd_rn(__fmul_rn(p, f), 5.55041087e-2f);
+    p = __fadd_rn(__fmul_rn(p, f), 2.40226507e-1f);
+    p = __fadd_rn(__fmul_rn(p, f), 6.93147181e-1f);
+    p = __fadd_rn(__fmul_rn(p, f), 1.0f);
+    return ldexpf(p, (int)n);
+}
+
+// ---- depth_bilateral.frag + depth_metric_raw.frag + depth_metric_filtered.frag -------------------------
+constexpr int kBilR = 6, kBilTW = 32, kBilTH = 8;
+__global__ void __launch_bounds__(256) depth_filter_metric_kernel(PrepArgs a, const unsigned short* __restrict__ raw,
+                                                                  float* __restrict__ filtered, float* __restrict__ metric, float* __restrict__ metric_filtered)
+{
+    __shared__ float s_t[kBilTH + 2 * kBilR][kBilTW + 2 * kBilR];
+    const int W = a.cols, H = a.rows;
+    const float adj = 1.0f / (a.depthFactor * 1000.0f);
+    const int x0 = blockIdx.x * kBilTW - kBilR, y0 = blockIdx.y * kBilTH - kBilR;
+    for (int t = threadIdx.x; t < (kBilTH + 2 * kBilR) * (kBilTW + 2 * kBilR); t += 256) {
+        const int sy = t / (kBilTW + 2 * kBilR), sx = t - sy * (kBilTW + 2 * kBilR);
+        const int gx = x0 + sx, gy = y0 + sy;
+        s_t[sy][sx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __fdiv_rn((float)__ldg(raw + (size_t)gy * W + gx), adj) : 0.f;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = blockIdx.x * kBilTW + lx, y = blockIdx.y * kBilTH + ly;
+    if (x >= W || y >= H) return;
+    const size_t o = (size_t)y * W + x;
+    const unsigned int rv = __ldg(raw + o);
+    const float value = s_t[ly + kBilR][lx + kBilR];
+    float out = 0.f;
+    if (!(value > a.maxD * 1000.0f || value < 300.0f)) {
+        if (a.bilateral) {
+            const float ss = 0.024691358f, sc = 0.000555556f;
+            const int cx0 = max(x - kBilR, 0), cx1 = min(x + kBilR + 1, W), cy0 = max(y - kBilR, 0), cy1 = min(y + kBilR + 1, H);
+            float sum1 = 0.f, sum2 = 0.f;
+            for (int cy = cy0; cy < cy1; ++cy)
+                for (int cx = cx0; cx < cx1; ++cx) {
+                    const float tmp = s_t[cy - y0][cx - x0];
+                    const float dx = (float)x - (float)cx, dy = (float)y - (float)cy;
+                    const float space2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                    const float dc = __fsub_rn(value, tmp);
+                    const float color2 = __fmul_rn(dc, dc);
+                    const float weight = exp_bilateral(-__fadd_rn(__fmul_rn(space2, ss), __fmul_rn(color2, sc)));
+                    sum1 = __fadd_rn(sum1, __fmul_rn(tmp, weight));
+                    sum2 = __fadd_rn(sum2, weight);
+                }
+            out = __fmul_rn(__fdiv_rn(sum1, sum2), adj);
+        } else out = (float)rv;
+    }
+    if (filtered) filtered[o] = out;
+    const unsigned int hi = (unsigned int)(a.maxD / a.depthFactor), lo = (unsigned int)(0.3f / a.depthFactor);
+    metric[o] = (rv > hi || rv < lo) ? 0.f : (float)rv * a.depthFactor;
+    metric_filtered[o] = (out > a.maxD / a.depthFactor || out < 0.3f / a.depthFactor) ? 0.f : __fmul_rn(out, a.depthFactor);
+}
+
+// ---- surfels.glsl / geometry.glsl helpers -------------------------------------------------------------
+__device__ __forceinline__ float get_radius(float icx, float icy, float depth, float norm_z)
+{
+    const float meanFocal = ((1.0f / fabsf(icx)) + (1.0f / fabsf(icy))) / 2.0f;
+    const float radius = (depth / meanFocal) * 1.41421356237f;
+    const float radius_n = radius / fabsf(norm_z);
+    const float two = 2.0f * radius;
+    return two < radius_n ? two : radius_n;
+}
+__device__ __forceinline__ float confidence_fn(float cx, float cy, float x, float y, float max_dist, float weighting)
+{
+    const float dx = x - cx, dy = y - cy;
+    const float radialDist = sqrtf(dx * dx + dy * dy) / max_dist;
+    return expf((-(radialDist * radialDist) / 0.72f)) * weighting;
+}
+__device__ __forceinline__ void roots2(float b, float c, float (&r)[3])
+{
+    float d = b * b - 4.0f * c;
+    if (d < 0.0f) d = 0.0f;
+    const float sd = sqrtf(d);
+    r[0] = 0.0f; r[1] = 0.5f * (b + sd); r[2] = 0.5f * (b - sd);
+}
+// geometry.glsl:86-160 on the symmetric matrix (m00 m10 m20 / m11 m21 / m22)
+__device__ __forceinline__ void compute_roots(float m00, float m10, float m20, float m11, float m21, float m22, float (&r)[3])
+{
+    // left-to-right, uncontracted (see normal_pca)
+    const float c0 = __fsub_rn(__fsub_rn(__fsub_rn(__fadd_rn(__fmul_rn(__fmul_rn(m00, m11), m22), __fmul_rn(__fmul_rn(__fmul_rn(2.0f, m10), m20), m21)),
+                                                   __fmul_rn(__fmul_rn(m00, m21), m21)), __fmul_rn(__fmul_rn(m11, m20), m20)), __fmul_rn(__fmul_rn(m22, m10), m10));
+    const float c1 = __fsub_rn(__fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(m00, m11), __fmul_rn(m10, m10)), __fmul_rn(m00, m22)), __fmul_rn(m20, m20)),
+                                         __fmul_rn(m11, m22)), __fmul_rn(m21, m21));
+    const float c2 = __fadd_rn(__fadd_rn(m00, m11), m22);
+    if (fabsf(c0) < 0.000001f) { roots2(c2, c1, r); return; }
+    const float s_inv3 = 1.0f / 3.0f, s_sqrt3 = sqrtf(3.0f);
+    const float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    const float rho = sqrtf(-a_over_3);
+    const float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+    const float cos_theta = cosf(theta), sin_theta = sinf(theta);
+    r[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    float t;
+    if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+    if (r[1] >= r[2]) {
+        t = r[1]; r[1] = r[2]; r[2] = t;
+        if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+    }
+    if (r[0] <= 0) roots2(c2, c1, r);
+}
+
+// geometry.glsl:190-244, window 3, over the filtered metric depth.  The accumulation runs in the shader's
+// order (x outer, y inner); depth(qx,qy) is a callable so callers can serve it from shared memory.
+template <typename DepthAt>
+__device__ __forceinline__ float3 normal_pca(const PrepArgs& a, DepthAt depth_at, int px, int py, float vz)
+{
+    const int W = a.cols, H = a.rows, win = 3;
+    const int x0 = max(px - win, 0), x1 = min(px + win, W - 1), y0 = max(py - win, 0), y1 = min(py + win, H - 1);
+    const bool xcl = px - win < 0, ycl = py - win < 0;     // clamped windows start at texture coordinate 0.0: integer coords
+    // The covariance is a difference of nearly equal numbers (E[x^2] - E[x]^2 with |x| ~ 1 m and a spread of
+    // centimetres), so the normal inherits ~1e-3 of relative round-off: only a bit-identical evaluation order
+    // reproduces the oracle.  Hence explicit _rn arithmetic (no FMA contraction) for the sums and the covariance.
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+    int N = 0;
+    for (int qx = x0; qx <= x1; ++qx)
+        for (int qy = y0; qy <= y1; ++qy) {
+            const float z = depth_at(qx, qy);
+            const float fx_ = xcl ? (float)qx : (float)qx + 0.5f, fy_ = ycl ? (float)qy : (float)qy + 0.5f;
+            const float X = __fmul_rn(__fmul_rn(__fsub_rn(fx_, a.cx), z), a.icx), Y = __fmul_rn(__fmul_rn(__fsub_rn(fy_, a.cy), z), a.icy);
+            if (z > 0.3f && fabsf(__fsub_rn(z, vz)) < 0.05f) {
+                a0 = __fadd_rn(a0, __fmul_rn(X, X)); a1 = __fadd_rn(a1, __fmul_rn(X, Y)); a2 = __fadd_rn(a2, __fmul_rn(X, z));
+                a3 = __fadd_rn(a3, __fmul_rn(Y, Y)); a4 = __fadd_rn(a4, __fmul_rn(Y, z)); a5 = __fadd_rn(a5, __fmul_rn(z, z));
+                a6 = __fadd_rn(a6, X); a7 = __fadd_rn(a7, Y); a8 = __fadd_rn(a8, z);
+                ++N;
+            }
+        }
+    if (N < 8) return make_float3(0.f, 0.f, 0.f);
+    const float fn = (float)N;
+    a0 = __fdiv_rn(a0, fn); a1 = __fdiv_rn(a1, fn); a2 = __fdiv_rn(a2, fn); a3 = __fdiv_rn(a3, fn); a4 = __fdiv_rn(a4, fn);
+    a5 = __fdiv_rn(a5, fn); a6 = __fdiv_rn(a6, fn); a7 = __fdiv_rn(a7, fn); a8 = __fdiv_rn(a8, fn);
+    const float c00 = __fsub_rn(a0, __fmul_rn(a6, a6)), c10 = __fsub_rn(a1, __fmul_rn(a6, a7)), c20 = __fsub_rn(a2, __fmul_rn(a6, a8)),
+                c11 = __fsub_rn(a3, __fmul_rn(a7, a7)), c21 = __fsub_rn(a4, __fmul_rn(a7, a8)), c22 = __fsub_rn(a5, __fmul_rn(a8, a8));
+    const float scale = fmaxf(fmaxf(fmaxf(c00, c10), fmaxf(c20, c11)), fmaxf(c21, c22));
+    float ev[3];
+    compute_roots(c00, c10, c20, c11, c21, c22, ev);
+    const float eigenvalue = ev[0] * scale;
+    const float s00 = __fsub_rn(__fdiv_rn(c00, scale), eigenvalue), s10 = __fdiv_rn(c10, scale), s20 = __fdiv_rn(c20, scale),
+                s11 = __fsub_rn(__fdiv_rn(c11, scale), eigenvalue), s21 = __fdiv_rn(c21, scale), s22 = __fsub_rn(__fdiv_rn(c22, scale), eigenvalue);
+    const float3 r0 = make_float3(s00, s10, s20), r1 = make_float3(s10, s11, s21), r2 = make_float3(s20, s21, s22);
+    auto cross_rn = [](float3 p, float3 q) {
+        return make_float3(__fsub_rn(__fmul_rn(p.y, q.z), __fmul_rn(p.z, q.y)), __fsub_rn(__fmul_rn(p.z, q.x), __fmul_rn(p.x, q.z)),
+                           __fsub_rn(__fmul_rn(p.x, q.y), __fmul_rn(p.y, q.x)));
+    };
+    const float3 v1 = cross_rn(r0, r1), v2 = cross_rn(r0, r2), v3 = cross_rn(r1, r2);
+    const float l1 = norm(v1), l2 = norm(v2), l3 = norm(v3);
+    float3 n = (l1 >= l2 && l1 >= l3) ? v1 : (l2 >= l1 && l2 >= l3) ? v2 : v3;
+    if (n.z < 0) n = make_float3(-n.x, -n.y, -n.z);
+    const float len = norm(n);
+    return make_float3(n.x / len, n.y / len, n.z / len);
+}
+
+// ---- depth_vertex_normal_radius.frag:23-68 --------------------------------------------------------------
+__global__ void __launch_bounds__(256) vertex_normal_radius_kernel(PrepArgs a, const float* __restrict__ metric, const float* __restrict__ metric_filtered,
+                                                                   float4* __restrict__ vertex_raw, float4* __restrict__ vertex_filtered,
+                                                                   float4* __restrict__ normal, float* __restrict__ radius)
+{
+    constexpr int TW = 32, TH = 8, R = 3;
+    __shared__ float s_d[TH + 2 * R][TW + 2 * R];
+    const int W = a.cols, H = a.rows;
+    const int x0 = blockIdx.x * TW - R, y0 = blockIdx.y * TH - R;
+    for (int t = threadIdx.x; t < (TH + 2 * R) * (TW + 2 * R); t += 256) {
+        const int sy = t / (TW + 2 * R), sx = t - sy * (TW + 2 * R);
+        const int gx = x0 + sx, gy = y0 + sy;
+        s_d[sy][sx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(metric_filtered + (size_t)gy * W + gx) : 0.f;
+    }
+    __syncthreads();
+    const int px = blockIdx.x * TW + (threadIdx.x & 31), py = blockIdx.y * TH + (threadIdx.x >> 5);
+    if (px >= W || py >= H) return;
+    const size_t o = (size_t)py * W + px;
+    const float z = __ldg(metric + o), zf = s_d[py - y0][px - x0];
+    float3 v = make_float3(((float)px - a.cx) * z * a.icx, ((float)py - a.cy) * z * a.icy, z);
+    float3 vf = make_float3(((float)px - a.cx) * zf * a.icx, ((float)py - a.cy) * zf * a.icy, zf);
+    float3 n = make_float3(0.f, 0.f, 0.f);
+    if (a.pca) n = normal_pca(a, [&](int qx, int qy) { return s_d[qy - y0][qx - x0]; }, px, py, zf);
+    float rad = a.radiusMultiplier * get_radius(a.icx, a.icy, vf.z, n.z);
+    if (norm(n) < 0.3f || v.z < 0.3f || vf.z < 0.3f) { v = vf = n = make_float3(0.f, 0.f, 0.f); rad = 0.f; }
+    const float max_dist = sqrtf(((float)H * 0.5f) * ((float)H * 0.5f) + ((float)W * 0.5f) * ((float)W * 0.5f));
+    vertex_raw[o] = make_float4(v.x, v.y, v.z, confidence_fn(a.cx, a.cy, (float)px + 0.5f, (float)py + 0.5f, max_dist, 1.0f));
+    vertex_filtered[o] = make_float4(vf.x, vf.y, vf.z, 1.0f);
+    normal[o] = make_float4(n.x, n.y, n.z, rad);
+    if (radius) radius[o] = rad;
+}
+
+// ---- depth_curvature_gradient.frag:28-142 ------------------------------------------------------------------
+// One thread per pixel; the 7x7 neighbourhood of (filtered vertex, PCA normal + radius) is served from a
+// shared-memory halo tile; gradient (hrbfbase.glsl:147-166) and the symmetric third-derivative contraction
+// (hrbfHessianMatrix :168-195 -- only g[0,1,2,4,5,8] are accumulated there) are summed in one neighbour loop.
+__global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, const float4* __restrict__ vertex_filtered, const float4* __restrict__ normal,
+                                                                 float4* __restrict__ curv1, float4* __restrict__ curv2, float* __restrict__ gradient_mag,
+                                                                 float4* __restrict__ normal_opt)
+{
+    constexpr int TW = 16, TH = 8, R = 3;
+    __shared__ float4 s_v[TH + 2 * R][TW + 2 * R];
+    __shared__ float4 s_n[TH + 2 * R][TW + 2 * R];
+    const int W = a.cols, H = a.rows, win = a.curvWin;
+    const int x0 = blockIdx.x * TW - R, y0 = blockIdx.y * TH - R;
+    for (int t = threadIdx.x; t < (TH + 2 * R) * (TW + 2 * R); t += 128) {
+        const int sy = t / (TW + 2 * R), sx = t - sy * (TW + 2 * R);
+        const int gx = x0 + sx, gy = y0 + sy;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) { v = __ldg(vertex_filtered + (size_t)gy * W + gx); n = __ldg(normal + (size_t)gy * W + gx); }
+        s_v[sy][sx] = v; s_n[sy][sx] = n;
+    }
+    __syncthreads();
+    const int px = blockIdx.x * TW + (threadIdx.x & 15), py = blockIdx.y * TH + (threadIdx.x >> 4);
+    if (px >= W || py >= H) return;
+    const size_t o = (size_t)py * W + px;
+    const float4 vf = s_v[py - y0][px - x0], vn = s_n[py - y0][px - x0];
+    float4 kmax = make_float4(0.f, 0.f, 0.f, 1000.0f), kmin = kmax, nopt = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gm = 0.f;
+    if (vf.z > 0.3f && sqrtf(vn.x * vn.x + vn.y * vn.y + vn.z * vn.z) > 0.5f) {
+        float k1 = 1000.0f, k2 = 1000.0f;
+        float3 pmax = make_float3(0.f, 0.f, 0.f), pmin = pmax;
+        const int qx0 = max(px - win, 0), qx1 = min(px + win, W - 1), qy0 = max(py - win, 0), qy1 = min(py + win, H - 1);
+        int N = 0;
+        float gx = 0.f, gy = 0.f, gz = 0.f;                               // gradient
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f, h4 = 0.f, h5 = 0.f, h8 = 0.f;   // "Hessian" entries g[0], g[1], g[2], g[4], g[5], g[8]
+        for (int qx = qx0; qx <= qx1; ++qx)
+            for (int qy = qy0; qy <= qy1; ++qy) {
+                const float4 v = s_v[qy - y0][qx - x0], n = s_n[qy - y0][qx - x0];
+                if (!(fabsf(v.z - vf.z) < 0.10f && v.z > 0.3f && sqrtf(n.x * n.x + n.y * n.y + n.z * n.z) > 0.8f)) continue;
+                ++N;
+                const float sx = 10.0f * n.x, sy = 10.0f * n.y, sz = 10.0f * n.z;
+                const float vx = vf.x - v.x, vy = vf.y - v.y, vz = vf.z - v.z;
+                const float d2 = vx * vx + vy * vy + vz * vz;
+                const float T2 = n.w * n.w;
+                if (d2 > T2) continue;
+                if (d2 == 0.0f) {            // getWeightH: -20/T2 I ; getWeightT: 0
+                    const float h = -20.0f / T2;
+                    gx -= sx * h; gy -= sy * h; gz -= sz * h;
+                    continue;
+                }
+                const float r = sqrtf(d2 / T2);
+                const float s = 1.0f - r;
+                {   // hrbfbase.glsl:51-68
+                    const float t1 = 20.0f * (s * s) / (T2 * T2 * r), t2 = -r * s * T2;
+                    const float w0 = t1 * (3.0f * (vx * vx) + t2), w1 = t1 * 3.0f * vx * vy, w2 = t1 * 3.0f * vx * vz;
+                    const float w4 = t1 * (3.0f * (vy * vy) + t2), w5 = t1 * 3.0f * vy * vz, w8 = t1 * (3.0f * (vz * vz) + t2);
+                    gx -= sx * w0 + sy * w1 + sz * w2;
+                    gy -= sx * w1 + sy * w4 + sz * w5;
+                    gz -= sx * w2 + sy * w5 + sz * w8;
+                }
+                {   // hrbfbase.glsl:81-123, only the entries hrbfHessianMatrix consumes
+                    const float s2 = r - 2 + 1 / r;
+                    const float s3 = 60 / (T2 * T2);
+                    const float s4 = 1 / (r * r);
+                    const float prx = vx / (T2 * r), pry = vy / (T2 * r), prz = vz / (T2 * r);
+                    const float qx_ = prx - s4 * prx, qy_ = pry - s4 * pry, qz_ = prz - s4 * prz;
+                    const float Tss = T2 * s * s;
+                    const float t0 = s3 * (Tss * prx + 2 * vx * s2 + vx * vx * qx_);
+                    const float t1 = s3 * vy * (qx_ * vx + s2);
+                    const float t2 = s3 * vz * (qx_ * vx + s2);
+                    const float t3 = s3 * (Tss * pry + vx * vx * qy_);
+                    const float t4 = s3 * vx * (qy_ * vy + s2);
+                    const float t5 = s3 * vx * vz * qy_;
+                    const float t6 = s3 * (Tss * prz + vx * vx * qz_);
+                    const float t7 = s3 * vx * vy * qz_;
+                    const float t8 = s3 * vx * (qz_ * vz + s2);
+                    const float t13 = s3 * (Tss * pry + 2 * vy * s2 + vy * vy * qy_);
+                    const float t14 = s3 * vz * (qy_ * vy + s2);
+                    const float t16 = s3 * (Tss * prz + vy * vy * qz_);
+                    const float t17 = s3 * vy * (qz_ * vz + s2);
+                    const float t26 = s3 * (Tss * prz + 2 * vz * s2 + vz * vz * qz_);
+                    h0 -= sx * t0 + sy * t1 + sz * t2;
+                    h1 -= sx * t3 + sy * t4 + sz * t5;
+                    h2 -= sx * t6 + sy * t7 + sz * t8;
+                    h4 -= sx * t4 + sy * t13 + sz * t14;       // t[12] = t[4]
+                    h5 -= sx * t7 + sy * t16 + sz * t17;       // t[15] = t[7]
+                    h8 -= sx * t8 + sy * t17 + sz * t26;       // t[24] = t[8], t[25] = t[17]
+                }
+            }
+        if (N > 15) {
+            gm = fabsf(gx * vn.x + gy * vn.y + gz * vn.z);
+            const float gl = sqrtf(gx * gx + gy * gy + gz * gz);
+            nopt = make_float4(gx / gl, gy / gl, gz / gl, vn.w);
+            const float h_x = -gx / gz, h_y = -gy / gz;
+            const float gz3 = gz * gz * gz;
+            const float h_xx = (2 * gx * gz * h2 - gx * gx * h8 - gz * gz * h0) / gz3;
+            const float h_xy = (gx * gz * h5 + gy * gz * h2 - gx * gy * h8 - gz * gz * h1) / gz3;
+            const float h_yy = (2 * gy * gz * h5 - gy * gy * h8 - gz * gz * h4) / gz3;
+            const float E = 1 + h_x * h_x, F = h_x * h_y, G = 1 + h_y * h_y;
+            const float len = sqrtf(h_x * h_x + h_y * h_y + 1);
+            const float L = h_xx / len, M = h_xy / len, Nn = h_yy / len;
+            const float cg = (L * Nn - M * M) / (E * G - F * F);
+            const float cm = (E * Nn + G * L - 2 * F * M) / (2 * (E * G - F * F));
+            if (!isnan(cg) && !isnan(cm)) {
+                float delta = cm * cm - cg;
+                if (delta < 0.0f) delta = 0.0f;
+                k1 = cm + sqrtf(delta); k2 = cm - sqrtf(delta);
+                const float lmax = -(M - k1 * F) / (Nn - k1 * G), lmin = -(M - k2 * F) / (Nn - k2 * G);
+                const float3 A = make_float3(1.0f, lmax, h_x + lmax * h_y), B = make_float3(1.0f, lmin, h_x + lmin * h_y);
+                const float la = norm(A), lb = norm(B);
+                pmax = make_float3(A.x / la, A.y / la, A.z / la);
+                pmin = make_float3(B.x / lb, B.y / lb, B.z / lb);
+            }
+        }
+        kmax = make_float4(pmax.x, pmax.y, pmax.z, k1);
+        kmin = make_float4(pmin.x, pmin.y, pmin.z, k2);
+    }
+    curv1[o] = kmax; curv2[o] = kmin; gradient_mag[o] = gm; normal_opt[o] = nopt;
+}
+
+// ---- depth_confidence_evaluation.frag ; weighting is read from device memory (no host round trip) ---------
+__global__ void confidence_kernel(PrepArgs a, const float* __restrict__ gradient_mag, const float* __restrict__ weighting_dev,
+                                  int useConfEval, float epsilon, float* __restrict__ confidence)
+{
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= a.cols || py >= a.rows) return;
+    const size_t o = (size_t)py * a.cols + px;
+    const float max_dist = sqrtf(((float)a.rows * 0.5f) * ((float)a.rows * 0.5f) + ((float)a.cols * 0.5f) * ((float)a.cols * 0.5f));
+    float c = confidence_fn(a.cx, a.cy, (float)px + 0.5f, (float)py + 0.5f, max_dist, __ldg(weighting_dev));
+    if (useConfEval > 0) c = c * expf(-epsilon / sqrtf(__ldg(gradient_mag + o)));
+    confidence[o] = c;
+}
+
+// ---- fill_vertex / fill_normal / fill_curvature / fill_rgb (FillIn.cpp; every target is cleared to 0 first) ---
+struct FillArgs {
+    const float4 *eVertex, *eNormal, *eK1, *eK2; const float* eIcpW; const uchar4* eImage;      // existing = HRBF prediction
+    const float4 *vertexFiltered, *normal, *k1, *k2; const float* confidence; const unsigned char* rgb;   // raw frame (rgb: RGB8)
+    float4 *oVertex, *oNormal, *oK1, *oK2; float* oIcpW; uchar4* oImage;
+    int n, passthrough;
+    float lambda, curvThr;
+};
+__global__ void fill_in_kernel(FillArgs f)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= f.n) return;
+    const bool pass = f.passthrough == 1;
+    const float4 s = __ldg(f.eVertex + o);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float w = 0.f;
+    const float4 rk1 = __ldg(f.k1 + o), rk2 = __ldg(f.k2 + o);
+    if (s.z == 0 || pass) {
+        if (rk1.w > -f.curvThr && rk1.w < f.curvThr && rk2.w > -f.curvThr && rk2.w < f.curvThr) {
+            const float4 fv = __ldg(f.vertexFiltered + o);
+            const float vConf = __ldg(f.confidence + o);
+            const float cmax = fmaxf(fabsf(rk1.w), fabsf(rk2.w));
+            w = (1.0f / (fv.z * fv.z)) * (vConf / 256.0f + expf(-0.5f * (f.lambda * f.lambda) / (cmax * cmax)));
+            v = make_float4(fv.x, fv.y, fv.z, vConf);
+        }
+    } else { v = s; w = __ldg(f.eIcpW + o); }
+    f.oVertex[o] = v; f.oIcpW[o] = w;
+    const float4 en = __ldg(f.eNormal + o);
+    f.oNormal[o] = (sqrtf(en.x * en.x + en.y * en.y + en.z * en.z) < 0.8f || pass) ? __ldg(f.normal + o) : en;
+    const float4 ek1 = __ldg(f.eK1 + o), ek2 = __ldg(f.eK2 + o);
+    const bool rawk = ek1.w > 300 || ek2.w > 300 || pass;
+    f.oK1[o] = rawk ? rk1 : ek1; f.oK2[o] = rawk ? rk2 : ek2;
+    const uchar4 ei = __ldg(f.eImage + o);
+    f.oImage[o] = ((ei.x == 0 && ei.y == 0 && ei.z == 0) || pass) ? make_uchar4(f.rgb[3 * o], f.rgb[3 * o + 1], f.rgb[3 * o + 2], 255) : ei;
+}
+
+// ---- Resize (1/20, texel centres) + denseEnough : flag[0] = 1 when the prediction must be filled in -----------
+__global__ void should_fill_kernel(const float4* __restrict__ vertex, int rows, int cols, float thresh, int* __restrict__ flag)
+{
+    const int f = 20, w = cols / f, h = rows / f;
+    int sum = 0;
+    for (int k = threadIdx.x; k < w * h; k += blockDim.x) {
+        const int j = k / w, i = k - j * w;
+        sum += __ldg(vertex + (size_t)(f * j + f / 2) * cols + (f * i + f / 2)).z > 0 ? 1 : 0;
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    __shared__ int s_sum[32];
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_sum[k];
+        const float per = (float)tot / (float)(h * w);
+        flag[0] = per > thresh ? 0 : 1;
+    }
+}
+
+// RGB8 -> RGBA8 (the GL upload of the RGB texture, alpha = 1)
+__global__ void rgb_to_rgba_kernel(int n, const unsigned char* __restrict__ rgb, uchar4* __restrict__ rgba)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rgba[i] = make_uchar4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 255);
+}
+
+}  // namespace hrbf

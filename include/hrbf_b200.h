@@ -252,6 +252,145 @@ int hrbf_indexmap_predict_hrbf(hrbf_indexmap*, int predictionType, int win, int 
 /* device pointer of one texture (enum hrbf_indexmap_tex) */
 void* hrbf_indexmap_texture(hrbf_indexmap*, int which);
 
+/* ------------------------------------------------------------------------
+ * Row 10 : per-frame preprocessing (HRBFFusion::filterDepth / metriciseDepth / computeVertexNormalRadius /
+ * computeCurvatureGradient / updateNormalRad / VertexConfidence, Core/src/HRBFFusion.cpp:1016-1021, 1262-1346)
+ * and FillIn (Core/src/Shaders/FillIn.{h,cpp}).  A hrbf_frame owns the reference's `textures[...]` map.
+ * ---------------------------------------------------------------------- */
+typedef struct hrbf_frame hrbf_frame;
+enum hrbf_frame_tex {            /* GPUTexture:: name (GPUTexture.cpp:20-37) */
+    HRBF_FT_RGB = 0,             /* RGB               u8 x3 (as uploaded)   */
+    HRBF_FT_RGBA,                /* RGB as the GL_RGBA texture reads: u8 x4, alpha 255 */
+    HRBF_FT_DEPTH_RAW,           /* DEPTH             u16                   */
+    HRBF_FT_DEPTH_FILTERED,      /* DEPTH_FILTERED    f32 (raw units)       */
+    HRBF_FT_DEPTH_METRIC,        /* DEPTH_METRIC      f32 metres            */
+    HRBF_FT_DEPTH_METRIC_FILTERED,
+    HRBF_FT_VERTEX_RAW,          /* f32x4 xyz, radial confidence            */
+    HRBF_FT_VERTEX_FILTERED,     /* f32x4 xyz, 1                            */
+    HRBF_FT_NORMAL_PCA,          /* NORMAL before updateNormalRad: PCA normal, radius */
+    HRBF_FT_NORMAL,              /* NORMAL (= NORMAL_OPT after updateNormalRad): HRBF-gradient normal, radius */
+    HRBF_FT_PRINCIPAL_CURV1,     /* f32x4 direction, k1                     */
+    HRBF_FT_PRINCIPAL_CURV2,
+    HRBF_FT_GRADIENT_MAG,        /* f32                                     */
+    HRBF_FT_RADIUS,              /* f32                                     */
+    HRBF_FT_CONFIDENCE,          /* f32                                     */
+    HRBF_FT_COUNT
+};
+typedef struct {
+    int width, height;
+    float cx, cy, fx, fy;
+    float depthFactor;           /* metres per raw unit = 1 / DepthMapFactor (HRBFFusion.cpp:771-781), TUM: 1/5000 */
+    float depthCutoff;           /* globalDepthCutoff (3.5)                 */
+    float radiusMultiplier;      /* preprocessingInitRadiusMultiplier (4)   */
+    int normalPCA;               /* preprocessingNormalEstimationPCA (1)    */
+    int curvWindow;              /* preprocessingCurvEstimationWindow (3)   */
+    int bilateral;               /* preprocessingUsebilateralFilter (1)     */
+    int useConfEval;             /* preprocessingUseConfEval (0)            */
+    float confEvalEpsilon;       /* preprocessingConfEvalEpsilon (1000)     */
+} hrbf_frame_params;
+int hrbf_frame_create(hrbf_frame** out, const hrbf_frame_params* p);
+int hrbf_frame_destroy(hrbf_frame*);
+/* textures[DEPTH_RAW/RGB]->Upload (HRBFFusion.cpp:1006-1010); host != 0: pointers are host memory (pinned for async) */
+int hrbf_frame_upload(hrbf_frame*, const unsigned char* rgb8, const unsigned short* depth16, int host, void* stream);
+/* filterDepth + metriciseDepth + computeVertexNormalRadius + computeCurvatureGradient + updateNormalRad */
+int hrbf_frame_preprocess(hrbf_frame*, void* stream);
+/* VertexConfidence(weighting), HRBFFusion.cpp:1310-1327 */
+int hrbf_frame_vertex_confidence(hrbf_frame*, float weighting, void* stream);
+void* hrbf_frame_texture(hrbf_frame*, int which);
+
+typedef struct hrbf_fillin hrbf_fillin;
+enum hrbf_fillin_tex { HRBF_FILL_IMAGE = 0, HRBF_FILL_VERTEX, HRBF_FILL_NORMAL, HRBF_FILL_CURVK1, HRBF_FILL_CURVK2, HRBF_FILL_ICPWEIGHT, HRBF_FILL_COUNT };
+int hrbf_fillin_create(hrbf_fillin** out, int width, int height);
+int hrbf_fillin_destroy(hrbf_fillin*);
+/* FillIn::vertex + normal + curvature + image (FillIn.cpp:78-380), one fused pass.  lambda =
+ * registrationICPCurvWeightImpactControl, curvThr = preprocessingCurvValidThreshold */
+int hrbf_fillin_run(hrbf_fillin*, hrbf_indexmap* prediction, hrbf_frame* frame, int passthrough, float lambda, float curvThr, void* stream);
+void* hrbf_fillin_texture(hrbf_fillin*, int which);
+/* HRBFFusion::denseEnough(resize.vertex(...)) (HRBFFusion.cpp:974-987,1069-1070): 1 if more than `thresh` of the
+ * 1/20-subsampled vertex texture has z > 0.  Synchronous (reads one int back). */
+int hrbf_dense_enough(const float* vertex_tex_dev, int width, int height, float thresh, int* dense_host, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Rows 8-9 : GlobalModel  (Core/src/GlobalModel.h:35-150)
+ * The model "VBO" is a device array of 80-B surfels; the count lives on the device.
+ * ---------------------------------------------------------------------- */
+typedef struct hrbf_model hrbf_model;
+/* capacity in surfels (reference: TEXTURE_DIMENSION^2 = 4596^2, GlobalModel.cpp:21-22); 0 -> that default */
+int hrbf_model_create(hrbf_model** out, int width, int height, float cx, float cy, float fx, float fy, unsigned int capacity);
+int hrbf_model_destroy(hrbf_model*);
+/* GlobalStateParam knobs read inside initialise / fuse / clean */
+int hrbf_model_set_params(hrbf_model*, float radiusMultiplier, float curvValidThreshold, int normalPCA, int cleanWindow,
+                          int useConfEval, float confEvalEpsilon);
+int hrbf_model_set_active_keyframes(hrbf_model*, const int* ids_host, int n, void* stream);   /* GlobalModel::lActiveKFID */
+/* GlobalModel::initialise, GlobalModel.cpp:214-288 (colorMap: RGB8) */
+int hrbf_model_initialise(hrbf_model*, const float* vertexMap, const float* normalMap, const unsigned char* colorMap_rgb8,
+                          const float* curv1Map, const float* curv2Map, const float* gradientMagMap,
+                          const float* init_pose16_host, void* stream);
+/* GlobalModel::fuse, GlobalModel.cpp:355-549 */
+int hrbf_model_fuse(hrbf_model*, const float* pose16_host, int time, const unsigned char* rgb8,
+                    const float* depthRaw_metric, const float* depthFiltered_metric, const float* curv1, const float* curv2,
+                    const float* confidence, const unsigned int* indexMap, const float* vertConfMap, const float* colorTimeMap,
+                    const float* normRadMap, float depthCutoff, float confThreshold, float weighting,
+                    int insertSubmap, int indexSubmap, void* stream);
+/* GlobalModel::clean, GlobalModel.cpp:551-688 */
+int hrbf_model_clean(hrbf_model*, const float* pose16_host, int time, const unsigned int* indexMap, const float* vertConfMap,
+                     const float* colorTimeMap, const float* normRadMap, const float* depthMap, float confThreshold,
+                     float maxDepth, void* stream);
+/* load a surfel array (e.g. a saved map) as the current model; host != 0: `surfels` is host memory.  Synchronous. */
+int hrbf_model_set_model(hrbf_model*, const float* surfels, unsigned int count, int host, void* stream);
+/* GlobalModel::model() / lastCount(): device pointer of the current surfel array; lastCount synchronises */
+const float* hrbf_model_model(hrbf_model*);
+const unsigned int* hrbf_model_count_dev(hrbf_model*);
+int hrbf_model_last_count(hrbf_model*, unsigned int* count_host, void* stream);
+/* 1 if a compaction ever ran out of capacity (survivors beyond it were dropped) */
+int hrbf_model_overflowed(hrbf_model*, int* flag_host, void* stream);
+
+/* ------------------------------------------------------------------------
+ * The per-frame orchestrator: HRBFFusion::processFrame / predict (Core/src/HRBFFusion.cpp:991-1260)
+ * with the sparse back-end off (optimizationUseLocalBA = optimizationUseGlobalBA = false).
+ * Everything between the input upload and the pose read-back is enqueued on one stream without a host
+ * round trip: pose, fusion weight, fill-in decision and surfel count all stay on the device.
+ * ---------------------------------------------------------------------- */
+typedef struct hrbf_fusion hrbf_fusion;
+typedef struct {
+    hrbf_frame_params frame;
+    float confidenceThreshold;    /* globalConfidenceThreshold (5)           */
+    float maxDepthProcessed;      /* HRBFFusion.cpp:37 (20)                  */
+    float icpWeight;              /* registrationJointICPWeight (10)         */
+    int rgbOnly, pyramid, fastOdom, so3, weightedICP;   /* false, true, false, registrationPreAlignSO3, registrationICPUseWeightedICP */
+    int predWindow, predMinNeighbors, predMaxNeighbors; /* preictionWindowMultiplier 3, preictionMinNeighbors 6, preictionMaxNeighbors 10 */
+    float predConfThreshold;      /* preictionConfThreshold (3)              */
+    float icpWeightLambda;        /* registrationICPCurvWeightImpactControl (10) */
+    float curvValidThreshold;     /* preprocessingCurvValidThreshold (300)   */
+    float denseEnoughThresh;      /* globalDenseEnoughThresh (0.75)          */
+    int cleanWindow;              /* fusionCleanWindowMultiplier (2)         */
+    unsigned int capacity;        /* surfel capacity, 0 = reference default  */
+} hrbf_fusion_params;
+void hrbf_fusion_default_params(hrbf_fusion_params* p, int width, int height, float cx, float cy, float fx, float fy);
+int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p);
+int hrbf_fusion_destroy(hrbf_fusion*);
+/* processFrame with HOST input buffers (rgb8: h*w*3, depth16: h*w); blocks until the pose is on the host.
+ * pose16_out_host (optional): row-major 4x4 currPose */
+int hrbf_fusion_process_frame(hrbf_fusion*, const unsigned char* rgb8_host, const unsigned short* depth16_host,
+                              long long timestamp, float weightMultiplier, float* pose16_out_host, void* stream);
+/* same, inputs already on the device, nothing is read back: enqueue-only.  Use hrbf_fusion_get_pose to synchronise. */
+int hrbf_fusion_process_frame_dev(hrbf_fusion*, const unsigned char* rgb8_dev, const unsigned short* depth16_dev,
+                                  long long timestamp, float weightMultiplier, void* stream);
+int hrbf_fusion_get_pose(hrbf_fusion*, float* pose16_out_host, void* stream);
+int hrbf_fusion_tick(const hrbf_fusion*);
+/* per-frame poses since creation, device array float[frames][12] (R row-major, t): gathered by the multi-GPU bench */
+const float* hrbf_fusion_trajectory_dev(hrbf_fusion*, int* n_frames);
+/* the components (reference members frameToModel, indexMap, globalModel, textures, fillIn) */
+hrbf_odometry* hrbf_fusion_odometry(hrbf_fusion*);
+hrbf_indexmap* hrbf_fusion_indexmap(hrbf_fusion*);
+hrbf_model* hrbf_fusion_model(hrbf_fusion*);
+hrbf_frame* hrbf_fusion_frame(hrbf_fusion*);
+hrbf_fillin* hrbf_fusion_fillin(hrbf_fusion*);
+/* CUDA-event timings of the last frame in ms, the reference's Stopwatch spans (HRBFFusion.cpp:1016,1063,1196,1248):
+ * [0] Initialization [1] Registration [2] Integration [3] Prediction.  Only recorded when enabled. */
+int hrbf_fusion_enable_timings(hrbf_fusion*, int on);
+int hrbf_fusion_last_timings(hrbf_fusion*, float ms4_host[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,8 @@
  * PARITY PINNING
  *   rows 1-3 (icpStep / rgbStep / computeRgbResidual / so3Step): pinned against
  *     the reference's OWN CUDA kernels (Core/src/Cuda/reduce.cu compiled
- *     unmodified into oracle/_ref/, run on a B200; golden vectors under
- *     tests/golden/ref_reduce_*.npz, generator oracle/gen_ref_golden.py).
+ *     unmodified into oracle/_ref/, run on a B200; golden vectors in
+ *     tests/golden/ref_reduce.npz, generator oracle/gen_ref_golden.py).
  *   rows 4-10 (host GN loop, pyramid prep, GLSL passes): the reference holds no
  *     golden vectors, no tests, and its GL/Eigen/Pangolin path cannot be built
  *     here -> "parity unpinned" for those rows; the oracle's own outputs on the
@@ -194,8 +194,9 @@ typedef struct {
 /* GlobalModel.cpp:214-288 + Shaders/init_unstableTex.vert:51-89, .geom.  Returns count.
  * Pixel order = uv VBO order: x outer, y inner (GlobalModel.cpp:89-96). */
 int orc_model_initialise(const orc_model_params* p, const float pose[16],
-                         const float* vertexRaw, const float* normal, const unsigned char* rgb,
-                         const float* curv1, const float* curv2, float* surfels_out);
+                         const float* vertexRaw, const float* normal, const unsigned char* rgb /* RGB8 */,
+                         const float* curv1, const float* curv2, const float* gradientMag, int useConfEval, float epsilon,
+                         float* surfels_out);
 /* GlobalModel.cpp:355-549 + Shaders/data.vert:63-198, data.geom, data.frag, update.vert:51-115.
  * surfels_in[count] -> surfels_out[count] (ping-pong), unstable_out[<= rows*cols] ; returns n_unstable */
 int orc_model_fuse(const orc_model_params* p, const float pose[16], int time,
@@ -218,11 +219,16 @@ typedef struct {
     float maxD;             /* globalDepthCutoff */
     float radiusMultiplier; int pca; float curvWindow; int bilateral;
 } orc_prep_params;
-/* Shaders/depth_bilateral.frag */
+/* Shaders/depth_bilateral.frag ; orc_exp_bilateral: the deterministic exp() this pass is defined with */
+float orc_exp_bilateral(float x);
 void orc_filterDepth(const orc_prep_params* p, const unsigned short* raw, float* filtered);
 /* Shaders/depth_metric_raw.frag, depth_metric_filtered.frag */
 void orc_metriciseDepth(const orc_prep_params* p, const unsigned short* raw, const float* filtered,
                         float* metric, float* metric_filtered);
+/* geometry.glsl:190-244 (getNormalPCA, window 3) at pixel (px,py); surfels.glsl:19-34, 37-46 */
+void orc_getNormalPCA(const orc_prep_params* p, const float* depth, int px, int py, float vz, float n[3]);
+float orc_getRadius(float icx, float icy, float depth, float norm_z);
+float orc_confidence(float cx, float cy, float x, float y, float max_dist, float w);
 /* Shaders/depth_vertex_normal_radius.frag:23-68, geometry.glsl:190-244, surfels.glsl:19-34 */
 void orc_computeVertexNormalRadius(const orc_prep_params* p, const float* metric, const float* metric_filtered,
                                    float* vertex_raw, float* vertex_filtered, float* normal, float* radius);

@@ -318,3 +318,88 @@ def predictHRBF(idx, cam, width, height, win=3, minNeighbors=6, maxNeighbors=10,
                           _p(_f(idx["curvMin"])), _p(out["image"], C.c_ubyte), _p(out["vertex"]), _p(out["normal"]), _p(out["curvk1"]),
                           _p(out["curvk2"]), _p(out["time"], C.c_ushort), _p(out["icpw"]))
     return out
+
+
+# ----------------------------------------------------------- rows 8-10 --
+def prep_params(cam, width, height, depthFactor=1.0 / 5000.0, maxD=3.5, radiusMultiplier=4.0, pca=1, curvWindow=3.0, bilateral=1):
+    return PrepParams(cam[2], cam[3], cam[0], cam[1], width, height, depthFactor, maxD, radiusMultiplier, pca, curvWindow, bilateral)
+
+
+def model_params(cam, width, height, maxDepth=20.0, confThreshold=5.0, radiusMultiplier=4.0, curvThr=300.0, pca=1, cleanWindow=2):
+    return ModelParams(cam[2], cam[3], cam[0], cam[1], width, height, maxDepth, confThreshold, radiusMultiplier, curvThr, pca, cleanWindow)
+
+
+def preprocess(pp, depth_u16):
+    """filterDepth -> metriciseDepth -> computeVertexNormalRadius -> computeCurvatureGradient -> updateNormalRad
+    (HRBFFusion.cpp:1017-1021).  Returns the textures dict (AoS float32)."""
+    H, W = pp.rows, pp.cols
+    depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+    t = {"filtered": np.zeros((H, W), np.float32), "metric": np.zeros((H, W), np.float32), "metric_filtered": np.zeros((H, W), np.float32)}
+    for k in ("vertex_raw", "vertex_filtered", "normal_pca", "curv1", "curv2", "normal_opt"):
+        t[k] = np.zeros((H, W, 4), np.float32)
+    t["radius"] = np.zeros((H, W), np.float32)
+    t["gradient_mag"] = np.zeros((H, W), np.float32)
+    L = lib()
+    L.orc_filterDepth(C.byref(pp), _p(depth_u16, C.c_ushort), _p(t["filtered"]))
+    L.orc_metriciseDepth(C.byref(pp), _p(depth_u16, C.c_ushort), _p(t["filtered"]), _p(t["metric"]), _p(t["metric_filtered"]))
+    L.orc_computeVertexNormalRadius(C.byref(pp), _p(t["metric"]), _p(t["metric_filtered"]), _p(t["vertex_raw"]), _p(t["vertex_filtered"]),
+                                    _p(t["normal_pca"]), _p(t["radius"]))
+    L.orc_computeCurvatureGradient(C.byref(pp), _p(t["vertex_filtered"]), _p(t["normal_pca"]), _p(t["curv1"]), _p(t["curv2"]),
+                                   _p(t["gradient_mag"]), _p(t["normal_opt"]))
+    t["normal"] = t["normal_opt"]          # updateNormalRad: NORMAL <- NORMAL_OPT
+    return t
+
+
+def vertexConfidence(pp, gradient_mag, weighting, useConfEval=0, epsilon=1000.0):
+    out = np.zeros((pp.rows, pp.cols), np.float32)
+    lib().orc_vertexConfidence(C.byref(pp), _p(_f(gradient_mag)), C.c_float(weighting), int(useConfEval), C.c_float(epsilon), _p(out))
+    return out
+
+
+def fillIn(pp, pred, frame, confidence, rgb, passthrough=0, lamb=10.0, curvThr=300.0):
+    """pred: dict from predictHRBF; frame: dict from preprocess -> dict(vertex, icpw, normal, curvk1, curvk2, image)"""
+    H, W = pp.rows, pp.cols
+    o = {"vertex": np.zeros((H, W, 4), np.float32), "icpw": np.zeros((H, W), np.float32), "normal": np.zeros((H, W, 4), np.float32),
+         "curvk1": np.zeros((H, W, 4), np.float32), "curvk2": np.zeros((H, W, 4), np.float32), "image": np.zeros((H, W, 4), np.uint8)}
+    lib().orc_fillIn(C.byref(pp), int(passthrough), C.c_float(lamb), C.c_float(curvThr),
+                     _p(_f(pred["vertex"])), _p(_f(pred["icpw"])), _p(_f(pred["normal"])), _p(_f(pred["curvk1"])), _p(_f(pred["curvk2"])),
+                     _p(np.ascontiguousarray(pred["image"]), C.c_ubyte),
+                     _p(_f(frame["vertex_filtered"])), _p(_f(frame["normal"])), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])),
+                     _p(_f(confidence)), _p(np.ascontiguousarray(rgb), C.c_ubyte),
+                     _p(o["vertex"]), _p(o["icpw"]), _p(o["normal"]), _p(o["curvk1"]), _p(o["curvk2"]), _p(o["image"], C.c_ubyte))
+    return o
+
+
+def denseEnough(vertex, thresh=0.75):
+    H, W = vertex.shape[:2]
+    return bool(lib().orc_denseEnough(H, W, _p(_f(vertex)), C.c_float(thresh)))
+
+
+def modelInitialise(mp, pose, frame, rgb, useConfEval=0, epsilon=1000.0):
+    out = np.zeros((mp.cols * mp.rows, 20), np.float32)
+    n = lib().orc_model_initialise(C.byref(mp), _p(_f(pose)), _p(_f(frame["vertex_raw"])), _p(_f(frame["normal"])),
+                                   _p(np.ascontiguousarray(rgb), C.c_ubyte), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])),
+                                   _p(_f(frame["gradient_mag"])), int(useConfEval), C.c_float(epsilon), _p(out))
+    return out[:n].copy()
+
+
+def modelFuse(mp, pose, time, rgb, frame, confidence, idx, indexSubmap, surfels):
+    count = surfels.shape[0]
+    out = np.zeros((max(count, 1), 20), np.float32)
+    un = np.zeros((mp.cols * mp.rows, 20), np.float32)
+    n = lib().orc_model_fuse(C.byref(mp), _p(_f(pose)), int(time), _p(np.ascontiguousarray(rgb), C.c_ubyte), _p(_f(frame["metric"])),
+                             _p(_f(frame["metric_filtered"])), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])), _p(_f(confidence)),
+                             _p(idx["index"], C.c_uint32), _p(_f(idx["vertConf"])), _p(_f(idx["colorTime"])), _p(_f(idx["normRad"])),
+                             C.c_float(indexSubmap), _p(_f(surfels)), int(count), _p(out), _p(un))
+    return out[:count].copy(), un[:n].copy()
+
+
+def modelClean(mp, pose, time, idx, surfels, unstable, active_kf=None):
+    if active_kf is None:
+        active_kf = np.zeros(19200, np.float32)
+        active_kf[0] = 1.0
+    out = np.zeros((surfels.shape[0] + unstable.shape[0] + 1, 20), np.float32)
+    n = lib().orc_model_clean(C.byref(mp), _p(_f(pose)), int(time), _p(idx["index"], C.c_uint32), _p(_f(idx["vertConf"])),
+                              _p(_f(idx["colorTime"])), _p(_f(idx["normRad"])), _p(_f(active_kf)), int(len(active_kf)),
+                              _p(_f(surfels)), int(surfels.shape[0]), _p(_f(unstable)), int(unstable.shape[0]), _p(out))
+    return out[:n].copy()

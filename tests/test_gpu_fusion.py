@@ -1,0 +1,177 @@
+"""GPU parity tests, SURVEY.md section 8 rows 8-10 + the frame orchestrator: preprocessing, FillIn, GlobalModel
+initialise / fuse / clean and HRBFFusion::processFrame through the C ABI vs the CPU oracle.
+
+Tolerances: these passes are float32 arithmetic whose decisions (validity thresholds, nearest-neighbour picks) can
+flip for a pixel sitting within round-off of a threshold, because nvcc contracts a*b+c into FMA and the oracle does
+not.  Values are compared to ~1e-5 relative; discrete outcomes must agree on all but a tiny bounded fraction."""
+import numpy as np
+import pytest
+
+from hrbffusion3d_b200 import synth
+from tests.util import pose_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(W, H, n, kind="room", noise=True):
+    cam = synth.default_camera(W, H)
+    sc = synth.Scene(kind)
+    poses = synth.circle_trajectory(n, frames_per_rev=120)
+    out = [synth.render_depth(sc, p, W, H, cam, noise=noise, seed=i) for i, p in enumerate(poses)]
+    return cam, poses, out
+
+
+def _close(a, b, what, rtol=2e-5, atol=2e-6, max_bad=1e-4):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, what
+    bad = ~np.isclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+    frac = bad.mean()
+    assert frac <= max_bad, (what, frac, np.abs(a - b)[bad].max() if bad.any() else 0)
+
+
+@pytest.mark.parametrize("W,H", [(160, 120), (640, 480)])
+def test_preprocess_matches_oracle(orc, cuda, W, H):
+    from hrbffusion3d_b200.fusion import Frame, frame_params
+    cam, poses, fr = _frames(W, H, 1)
+    depth, rgb = fr[0]
+    depth = depth.copy(); depth[:5, :7] = 4000; depth[-3:, -3:] = 40000      # border + beyond-cutoff values
+    pp = orc.prep_params(cam, W, H)
+    ref = orc.preprocess(pp, depth)
+    f = Frame(frame_params(W, H, cam))
+    f.upload(rgb, depth)
+    f.preprocess()
+    g = lambda n: f.tex(n).cpu().numpy()
+    _close(g("DEPTH_FILTERED"), ref["filtered"], "filtered", rtol=1e-5, atol=1e-3)
+    assert np.array_equal(g("DEPTH_METRIC"), ref["metric"])
+    _close(g("DEPTH_METRIC_FILTERED"), ref["metric_filtered"], "metric_filtered", rtol=1e-5, atol=1e-6)
+    _close(g("VERTEX_RAW"), ref["vertex_raw"], "vertex_raw", max_bad=2e-4)
+    _close(g("VERTEX_FILTERED"), ref["vertex_filtered"], "vertex_filtered", rtol=1e-5, atol=1e-6, max_bad=2e-4)
+    _close(g("NORMAL_PCA"), ref["normal_pca"], "normal_pca", rtol=1e-3, atol=2e-4, max_bad=2e-3)
+    # curvature / HRBF-gradient normals: third-derivative sums amplify round-off -> compare where both are valid
+    gk1, rk1 = g("PRINCIPAL_CURV1"), ref["curv1"]
+    valid_g, valid_r = np.abs(gk1[..., 3]) < 300, np.abs(rk1[..., 3]) < 300
+    assert np.mean(valid_g != valid_r) < 2e-3
+    both = valid_g & valid_r
+    assert both.mean() > 0.3
+    _close(g("NORMAL")[both], ref["normal"][both], "normal_opt", rtol=1e-3, atol=2e-4, max_bad=2e-3)
+    _close(gk1[..., 3][both], rk1[..., 3][both], "k1", rtol=2e-2, atol=2e-2, max_bad=5e-3)
+    _close(g("PRINCIPAL_CURV2")[..., 3][both], ref["curv2"][..., 3][both], "k2", rtol=2e-2, atol=2e-2, max_bad=5e-3)
+    _close(g("GRADIENT_MAG")[both], ref["gradient_mag"][both], "gradient_mag", rtol=1e-3, atol=1e-3, max_bad=2e-3)
+    assert np.array_equal(g("RGBA")[..., :3], rgb) and np.all(g("RGBA")[..., 3] == 255)
+    f.vertexConfidence(0.8)
+    _close(g("CONFIDENCE"), orc.vertexConfidence(pp, ref["gradient_mag"], 0.8), "confidence", rtol=1e-5)
+
+
+def _oracle_two_frames(orc, W, H, cam, fr):
+    """frame 1 initialises the map; frame 2's textures + index maps are the inputs of fuse/clean"""
+    pp, mp = orc.prep_params(cam, W, H), orc.model_params(cam, W, H)
+    f0 = orc.preprocess(pp, fr[0][0])
+    pose0 = np.eye(4, dtype=np.float32)
+    surfels = orc.modelInitialise(mp, pose0, f0, fr[0][1])
+    return pp, mp, f0, pose0, surfels
+
+
+def test_model_initialise_fuse_clean_match_oracle(orc, cuda):
+    torch = cuda
+    from hrbffusion3d_b200.fusion import GlobalModel
+    from hrbffusion3d_b200.indexmap import IndexMap
+    W, H = 320, 240
+    cam, poses, fr = _frames(W, H, 3)
+    pp, mp, f0, pose0, s_ref = _oracle_two_frames(orc, W, H, cam, fr)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    gm = GlobalModel(W, H, cam, capacity=200000)
+    gm.initialise(d(f0["vertex_raw"]), d(f0["normal"]), d(fr[0][1]), d(f0["curv1"]), d(f0["curv2"]), d(f0["gradient_mag"]), pose0)
+    s_gpu, n = gm.model()
+    assert n == s_ref.shape[0] and n > 10000
+    _close(s_gpu.cpu().numpy(), s_ref, "initialise", max_bad=0)
+    # give some surfels enough confidence that clean's tests fire, and cut a hole into the map (a third of the
+    # surfels, contiguous in uv order) so that fuse also creates new unstable points there
+    s_ref = s_ref.copy(); s_ref[::3, 3] += 6.0
+    keep = np.ones(n, bool); keep[n // 3: 2 * n // 3] = False
+    s_ref = np.ascontiguousarray(s_ref[keep]); n = s_ref.shape[0]
+    gm.setModel(s_ref)
+    assert gm.lastCount() == n
+    rel = np.linalg.inv(poses[0].astype(np.float64)) @ poses[1].astype(np.float64)
+    pose1 = rel.astype(np.float32)
+    f1 = orc.preprocess(pp, fr[1][0])
+    conf = orc.vertexConfidence(pp, f1["gradient_mag"], 0.9)
+    time = 2
+    idx = orc.predictIndices(pose1, s_ref, cam, W, H)
+    fused_ref, unstable_ref = orc.modelFuse(mp, pose1, time, fr[1][1], f1, conf, idx, 0, s_ref)
+    im = IndexMap(W, H, cam[2], cam[3], cam[0], cam[1])
+    im.predictIndices(pose1, time, time, (gm.model()[0], n), 20.0)
+    assert np.array_equal(im.tex("index").cpu().numpy().view(np.uint32), idx["index"])
+    gm.fuse(pose1, time, d(fr[1][1]), d(f1["metric"]), d(f1["metric_filtered"]), d(f1["curv1"]), d(f1["curv2"]), d(conf),
+            im.tex("index"), im.tex("vertConf"), im.tex("colorTime"), im.tex("normRad"))
+    fused_gpu = gm.model()[0].cpu().numpy()
+    merged_ref = fused_ref[:, 7] == time
+    assert merged_ref.sum() > 1000
+    assert np.mean((fused_gpu[:, 7] == time) != merged_ref) < 1e-3
+    same = (fused_gpu[:, 7] == time) == merged_ref
+    _close(fused_gpu[same], fused_ref[same], "fuse", rtol=1e-4, atol=1e-5, max_bad=1e-4)
+    # clean: second splat on the fused map, then compaction (order preserving) + append of the new points
+    idx2 = orc.predictIndices(pose1, fused_ref, cam, W, H)
+    cleaned_ref = orc.modelClean(mp, pose1, time, idx2, fused_ref, unstable_ref)
+    im.predictIndices(pose1, time, time, (gm.model()[0], n), 20.0)
+    gm.clean(pose1, time, im.tex("index"), im.tex("vertConf"), im.tex("colorTime"), im.tex("normRad"))
+    c_gpu, n2 = gm.model()
+    c_gpu = c_gpu.cpu().numpy()
+    new_ref = int((unstable_ref[:, 7] == -2).sum())
+    assert new_ref > 50
+    assert abs(n2 - cleaned_ref.shape[0]) <= max(3, int(2e-3 * cleaned_ref.shape[0])), (n2, cleaned_ref.shape)
+    if n2 == cleaned_ref.shape[0]:
+        _close(c_gpu, cleaned_ref, "clean", rtol=1e-4, atol=1e-5, max_bad=2e-3)
+    assert not gm.overflowed()
+    # a clean without a preceding fuse of the same frame only compacts
+    gm.clean(pose1, time + 1, im.tex("index"), im.tex("vertConf"), im.tex("colorTime"), im.tex("normRad"))
+    assert gm.lastCount() <= n2
+
+
+def test_model_capacity_overflow_is_reported(orc, cuda):
+    torch = cuda
+    from hrbffusion3d_b200.fusion import GlobalModel
+    W, H = 160, 120
+    cam, poses, fr = _frames(W, H, 1)
+    pp, mp, f0, pose0, s_ref = _oracle_two_frames(orc, W, H, cam, fr)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    gm = GlobalModel(W, H, cam, capacity=1000)
+    gm.initialise(d(f0["vertex_raw"]), d(f0["normal"]), d(fr[0][1]), d(f0["curv1"]), d(f0["curv2"]), d(f0["gradient_mag"]), pose0)
+    assert gm.lastCount() == 1000 and gm.overflowed()
+    _close(gm.model()[0].cpu().numpy(), s_ref[:1000], "first 1000 survive in order", max_bad=0)
+
+
+@pytest.mark.parametrize("W,H,kw", [(320, 240, dict(icpWeight=100.0, so3=0)), (320, 240, {}), (640, 480, dict(icpWeight=100.0, so3=0))])
+def test_process_frame_sequence_matches_oracle(orc, cuda, W, H, kw):
+    """HRBFFusion::processFrame over a short sequence, frame by frame against the oracle pipeline."""
+    from hrbffusion3d_b200.fusion import HRBFFusion
+    from oracle import orc_pipeline as op
+    n = 6
+    cam, poses, fr = _frames(W, H, n)
+    okw = dict(kw)
+    if "so3" in okw:
+        okw["so3"] = bool(okw["so3"])
+    ref = op.HRBFFusion(W, H, cam, **okw)
+    gpu = HRBFFusion(W, H, cam, capacity=1 << 20, **kw)
+    for i, (depth, rgb) in enumerate(fr):
+        To = ref.processFrame(rgb, depth)
+        Tg = gpu.processFrame(rgb, depth)
+        ang, dt = pose_err(To[:3, :3], To[:3, 3], Tg[:3, :3], Tg[:3, 3])
+        cnt = gpu.globalModel.lastCount()
+        print(f"frame {i}: pose diff ang {ang:.2e} t {dt:.2e}; surfels gpu {cnt} oracle {ref.surfels.shape[0]}")
+        tol = 1e-5 if kw.get("icpWeight", 10.0) >= 100 else 3e-4       # ICP-only: north_star tolerance; RGB term: see test_gpu_odometry
+        tol *= (i + 1)                                                 # free-running: differences accumulate frame over frame
+        assert ang <= tol and dt <= tol, (i, ang, dt)
+        assert abs(cnt - ref.surfels.shape[0]) <= max(5, int(3e-3 * ref.surfels.shape[0]))
+        # the prediction the next frame will be tracked against
+        pv = gpu.indexMap.tex("vertexHRBF").cpu().numpy()
+        fg, fo = pv[..., 2] > 0, ref.pred["vertex"][..., 2] > 0
+        assert np.mean(fg != fo) < (5e-3 if kw.get("icpWeight", 10.0) >= 100 else 3e-2)      # RGB term: poses differ ~1e-4 (not a contraction)
+        both = fg & fo
+        if both.sum() > 100:
+            dv = pv[..., :3][both] - ref.pred["vertex"][..., :3][both]
+            rmse = float(np.sqrt((dv.astype(np.float64) ** 2).sum(-1).mean()))
+            assert rmse <= (1e-4 if kw.get("icpWeight", 10.0) >= 100 else 1e-3) * (i + 1), rmse
+    assert gpu.tick == n + 1
+    tr = gpu.trajectory().cpu().numpy()
+    assert tr.shape == (n, 12)
+    np.testing.assert_allclose(tr[-1, 9:], Tg[:3, 3], atol=1e-7)
