@@ -34,19 +34,21 @@ if ROOT not in sys.path:
 from hrbffusion3d_b200 import synth  # noqa: E402
 
 W, H = 640, 480
-RING = 8                     # distinct synthetic frames cycled through (inputs > L2, see config)
+RING = 96                    # frames of one closed camera loop, cycled (96 x 1.54 MB of inputs = 147 MB > 126 MB L2)
 ICP_BYTES_PER_PIXEL_ITER = 68.0
-TRACK_KW = dict(rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True, if_curvature_info=True)
+FUSION_KW = {}               # reference defaults: RGB+ICP (weight 10), SO3 pre-alignment, iterations 10/5/4, HRBF win 3 / K 10
 
 
-def make_frames(seed, n=RING):
-    """n consecutive views of the planar scene: per frame the textures the
-    tracking path consumes (the reference's RGBA32F vertex / normal / curvature maps, icp weight, RGBA8)."""
+def make_sequence(seed, n=RING):
+    """plane z = 1.5 m tilted 15 deg, camera on a 5 cm circle with 2 deg yaw wobble, Kinect-style
+    noise.  One closed loop of n frames (3.3 mm / 0.13 deg per frame), replayed for as many steps as asked."""
     sc = synth.Scene("plane")
     cam = synth.default_camera(W, H)
-    poses = synth.circle_trajectory(n + 1)
-    frames = [synth.ideal_maps(sc, p, W, H, cam, seed=seed * 1000 + i) for i, p in enumerate(poses)]
-    return frames, poses, cam
+    poses = synth.circle_trajectory(n, frames_per_rev=n)
+    frames = [synth.render_depth(sc, p, W, H, cam, noise=True, seed=seed * 100000 + i) for i, p in enumerate(poses)]
+    depth = np.stack([f[0] for f in frames])
+    rgb = np.stack([f[1] for f in frames])
+    return depth, rgb, poses, cam
 
 
 class ClockSampler:
@@ -89,45 +91,44 @@ def measured_peak_hbm():
 
 
 # --------------------------------------------------------------------------- CPU arm
-def run_oracle_frames(frames, poses, cam, n_frames, threads):
-    """The oracle's tracking path (prep + getIncrementalTransformation) on n_frames frames -> seconds"""
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    from oracle import orc_py as orc
-    oo = orc.Odometry(W, H, cam[2], cam[3], cam[0], cam[1])
-    oo.initFirstRGB(frames[0]["rgba"])
-    t0 = time.perf_counter()
-    for i in range(n_frames):
-        m0, m1, pose0 = frames[i % RING], frames[i % RING + 1], poses[i % RING]
-        oo.initICPModel(m0["vertex"], m0["normal"], 20.0, pose0)
-        oo.initRGBModel(m0["rgba"])
-        oo.initCurvatureModel(m0["k1"], m0["k2"], pose0)
-        oo.initICP(m1["vertex"], m1["normal"], 20.0)
-        oo.initRGB(m1["rgba"])
-        oo.initCurvature(m1["k1"], m1["k2"])
-        oo.initICPweight(m0["icpw"])
-        oo.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **TRACK_KW)
-    return time.perf_counter() - t0
+class OracleRunner:
+    """The CPU oracle's processFrame (oracle/orc_pipeline.py, a restatement of HRBFFusion::processFrame) on the same frames."""
+
+    def __init__(self, depth, rgb, cam, threads):
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        from oracle import orc_pipeline as op
+        self.f = op.HRBFFusion(W, H, cam, **FUSION_KW)
+        self.depth, self.rgb, self.i = depth, rgb, 0
+
+    def step(self):
+        t0 = time.perf_counter()
+        self.f.processFrame(self.rgb[self.i % RING], self.depth[self.i % RING])
+        self.i += 1
+        return time.perf_counter() - t0
 
 
 def config_dict(n_gpus):
-    return {"workload": "synthetic 640x480 planar scene (SURVEY 8d config 2), tracking stage: pyramid prep (7 init* calls) + "
-                        "getIncrementalTransformation, reference defaults (RGB+ICP weight 10, SO3 pre-align, iterations 10/5/4)",
-            "width": W, "height": H, "frames_in_ring": RING,
-            "l2": "inputs cycle through a ring of %d frames x 22 MB = %d MB > 126 MB L2" % (RING, RING * 22),
-            "sequences": n_gpus, "parallelism": "one independent sequence per GPU"}
+    return {"workload": "synthetic 640x480 Kinect-noise planar scene (SURVEY 8d config 2): full per-frame hot path = preprocess "
+                        "(bilateral, PCA normals, HRBF curvature) + pyramid prep + RGB-D/ICP tracking (reference defaults: icpWeight 10, "
+                        "SO3 pre-align, iterations 10/5/4) + splat/fuse/splat/clean + splat/HRBF predict (win 3, K 10) + fill-in",
+            "width": W, "height": H, "frames_in_loop": RING,
+            "l2": "inputs cycle through a closed loop of %d frames x 1.54 MB = %d MB > 126 MB L2; a frame also streams ~30 full-resolution textures" % (RING, int(RING * 1.536)),
+            "sequences": n_gpus, "parallelism": "one independent sequence per GPU, no collective inside the frame loop"}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    global RING
     cores = os.cpu_count() or 1
-    frames, poses, cam = make_frames(0)
-    run_oracle_frames(frames, poses, cam, max(1, args.warmup // 3 or 1), cores)
-    per_step = []
-    for _ in range(args.steps):
-        per_step.append(run_oracle_frames(frames, poses, cam, 1, cores))
-    t = float(np.sum(per_step))
+    n_gen = min(RING, args.steps + args.warmup)
+    RING = n_gen
+    depth, rgb, poses, cam = make_sequence(0, n_gen)
+    r = OracleRunner(depth, rgb, cam, cores)
+    for _ in range(args.warmup):
+        r.step()
+    t = sum(r.step() for _ in range(args.steps))
     v = args.steps / t
     print(json.dumps({"impl": "reference", "metric": "frames/sec HRBF+ICP 640x480", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
@@ -141,7 +142,7 @@ def reference_arm(args):
 def ours_arm(args):
     import torch
     import torch.distributed as dist
-    from hrbffusion3d_b200 import odometry as od
+    from hrbffusion3d_b200.fusion import HRBFFusion
     from hrbffusion3d_b200._lib import check, lib, stream_ptr
 
     rank = int(os.environ.get("RANK", "0"))
@@ -156,76 +157,61 @@ def ours_arm(args):
     if world > 1:
         seeds = [torch.tensor([r], dtype=torch.int64, device="cuda") for r in range(world)] if rank == 0 else None
         dist.scatter(seed_t, seeds, src=0)
-    frames, poses, cam = make_frames(int(seed_t.item()))
+    depth, rgb, poses, cam = make_sequence(int(seed_t.item()))
+    depth_pin = torch.from_numpy(depth.view(np.int16)).pin_memory()
+    rgb_pin = torch.from_numpy(rgb).pin_memory()
+    depth_dev, rgb_dev = depth_pin.cuda(), rgb_pin.cuda()
+    h2d_bytes = W * H * 2 + W * H * 3
 
-    KEYS = ("vertex", "normal", "k1", "k2", "icpw", "rgba")
-    pinned = [{k: torch.from_numpy(np.ascontiguousarray(f[k])).pin_memory() for k in KEYS} for f in frames]
-    dev = [{k: v.cuda() for k, v in f.items()} for f in pinned]
-    stage = [{k: torch.empty_like(v, device="cuda") for k, v in pinned[0].items()} for _ in range(2)]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values()) * 2      # model + current frame textures
-    go = od.RGBDOdometry(W, H, cam[2], cam[3], cam[0], cam[1])
-    go.initFirstRGB(dev[0]["rgba"])
-    traj = torch.zeros((args.steps, 12), dtype=torch.float32)
-    launches0 = lib().hrbf_launch_count()
+    def run(host_inputs):
+        """fresh pipeline: W warm-up frames (frame 1 initialises the map), then K timed frames"""
+        F = HRBFFusion(W, H, cam, capacity=1 << 22, **FUSION_KW)
+        pose = np.zeros(16, np.float32)
 
-    def step(i, host_inputs):
-        a, b = i % RING, i % RING + 1
-        if host_inputs:
-            for k in KEYS:
-                stage[0][k].copy_(pinned[a][k], non_blocking=True)
-                stage[1][k].copy_(pinned[b][k], non_blocking=True)
-            m0, m1 = stage
-        else:
-            m0, m1 = dev[a], dev[b]
-        pose0 = poses[a]
-        go.initICPModel(m0["vertex"], m0["normal"], 20.0, pose0)
-        go.initRGBModel(m0["rgba"])
-        go.initCurvatureModel(m0["k1"], m0["k2"], pose0)
-        go.initICP(m1["vertex"], m1["normal"], 20.0)
-        go.initRGB(m1["rgba"])
-        go.initCurvature(m1["k1"], m1["k2"])
-        go.initICPweight(m0["icpw"])
-        t, R, _ = go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **TRACK_KW)   # syncs; pose lands on the host
-        return t, R
-
-    def timed(host_inputs, record):
+        def step(i):
+            k = i % RING
+            if host_inputs:
+                F.processFramePinned(rgb_pin[k], depth_pin[k], pose)       # H2D of the frame + D2H of the pose inside
+            else:
+                F.processFrameDev(rgb_dev[k], depth_dev[k])                # enqueue only
         for i in range(args.warmup):
-            step(i, host_inputs)
+            step(i)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        l0 = lib().hrbf_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            t, R = step(i, host_inputs)
-            if record:
-                traj[i, :9] = torch.from_numpy(np.asarray(R).reshape(9))
-                traj[i, 9:] = torch.from_numpy(np.asarray(t))
+        for i in range(args.warmup, args.warmup + args.steps):
+            step(i)
         e1.record()
         torch.cuda.synchronize()
+        launches = lib().hrbf_launch_count() - l0
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), int(launches), F
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l_before = lib().hrbf_launch_count()
-    ms_dev = timed(False, True)
-    launches = lib().hrbf_launch_count() - l_before
-    ms_e2e = timed(True, False)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # roofline of the dominant kernel: level-0 ICP reduction, timed live with CUDA events
+    ms_dev, launches, F = run(False)
+    count = F.globalModel.lastCount()
+    traj = F.trajectory().clone()
+    # roofline of the dominant kernel: level-0 ICP reduction, timed live with CUDA events on this pipeline's maps
     us = C.c_float()
-    check(lib().hrbf_odometry_time_kernel(go._h, 0, 0, 1, 200, C.byref(us), stream_ptr()))
+    check(lib().hrbf_odometry_time_kernel(C.c_void_p(lib().hrbf_fusion_odometry(F._h)), 0, 0, 1, 200, C.byref(us), stream_ptr()))
     torch.cuda.synchronize()
+    del F
+    ms_e2e, _, F2 = run(True)
+    del F2
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        gathered = [torch.zeros_like(traj).cuda() for _ in range(world)] if rank == 0 else None
-        dist.gather(traj.cuda(), gathered, dst=0)       # trajectories back to rank 0
+        n = traj.shape[0]
+        gathered = [torch.zeros_like(traj) for _ in range(world)] if rank == 0 else None
+        dist.gather(traj, gathered, dst=0)       # per-sequence trajectories back to rank 0 (SURVEY 8e)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -235,20 +221,22 @@ def ours_arm(args):
     alg_bytes = ICP_BYTES_PER_PIXEL_ITER * W * H
     achieved = alg_bytes / (us.value * 1e-6) / 1e9
     cores = os.cpu_count() or 1
-    n_cpu = 3
-    run_oracle_frames(frames, poses, cam, 1, cores)
-    cpu_s = run_oracle_frames(frames, poses, cam, n_cpu, cores)
+    n_cpu = 6
+    r = OracleRunner(depth, rgb, cam, cores)
+    r.step()
+    cpu_s = sum(r.step() for _ in range(n_cpu))
     total_frames = args.steps * world
     out = {"metric": "frames/sec HRBF+ICP 640x480", "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
-           "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 48 + 8 * 48},
-           "gpu_launches": int(launches), "clocks": clocks,
+           "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 48},
+           "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count,
            "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false> level 0 (640x480), incl. in-kernel Gauss-Newton solve",
                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                        "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": None},
+                        "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": 20927232.0,
+                        "traffic_source": "ncu --set full, profiles/r1_icp_l0_ncu_full_summary.txt (dram__bytes_read.sum, cold cache)"},
            "cpu_baseline": {"value": n_cpu / cpu_s, "unit": "frames/s", "cores": cores, "kind": "port",
-                            "sample": "%d frames of the same ring (oracle, OpenMP over %d threads)" % (n_cpu, cores)}}
+                            "sample": "frames 2-%d of the same sequence (oracle pipeline, OpenMP over %d threads)" % (n_cpu + 1, cores)}}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -30,6 +30,10 @@ struct hrbf_odometry {
     float* cloud[HRBF_NUM_PYRS] = {};
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
     hrbf::ReduceWork* work = nullptr;
+    float* tp_partials = nullptr; int* tp_ipartials = nullptr; unsigned int* tp_barrier = nullptr;   // persistent tracker scratch
+    int num_sms = 0;
+    long long* tp_dbg = nullptr;
+    bool use_graph = false;          // true: one kernel per reduction replayed as a CUDA graph (first-generation path)
     float* pose_scratch = nullptr;   // device: [0..11] model pose (R,t), [12..23] track in, [24..35] track out
     // pinned host mirrors
     float* h_pose = nullptr;         // [0..11] in, [12..23] out

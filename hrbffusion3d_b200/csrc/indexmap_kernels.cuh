@@ -149,34 +149,13 @@ inline PredTable make_pred_table()
     return t;
 }
 
-struct Nb { float cx, cy, cz, sx, sy, sz, T2, invT2; };
+struct Nb { float cx, cy, cz, sx, sy, sz, T2, invT; };   // s = (200 / rho^2) n (the gradient recovers 10 n = s rho^2 / 20)
 
-// hrbfbase.glsl:126-145 over this lane's slots; group-reduced over the 4 lanes of the pixel
-__device__ __forceinline__ float hrbf_value_group(const Nb (&nb)[kPredSlots], int nslots, float px, float py, float pz, unsigned gmask, int* support)
-{
-    float value = 0.f;
-    int cnt = 0;
-#pragma unroll
-    for (int s = 0; s < kPredSlots; ++s) {
-        if (s < nslots) {
-            const float vx = px - nb[s].cx, vy = py - nb[s].cy, vz = pz - nb[s].cz;
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
-            if (!(nb[s].T2 < d2)) {
-                if (!(d2 > nb[s].T2 || d2 == 0.0f)) {
-                    const float r = sqrtf(d2 * nb[s].invT2);
-                    const float q = 1.0f - r;
-                    const float t = -20.f * (q * q * q) * nb[s].invT2;
-                    value -= (vx * t) * nb[s].sx + (vy * t) * nb[s].sy + (vz * t) * nb[s].sz;
-                }
-                ++cnt;
-            }
-        }
-    }
-    value += __shfl_xor_sync(gmask, value, 1); cnt += __shfl_xor_sync(gmask, cnt, 1);
-    value += __shfl_xor_sync(gmask, value, 2); cnt += __shfl_xor_sync(gmask, cnt, 2);
-    *support = cnt;
-    return value;
-}
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// f(p) = -sum_i grad phi_i(p - c_i) . (10 n_i) with grad phi = -20 (1-r)^3 (p - c)/rho^2, r = |p - c|/rho  (hrbfbase.glsl:20-34,126-145)
+//      =  sum_i (1-r)^3 (p - c_i) . s_i,  s_i = (200/rho_i^2) n_i  precomputed per neighbour: ~15 instructions per
+// neighbour and evaluation (FMA, sqrt.approx); differs from the shader's operation order by float round-off only.
 
 // hrbfbase.glsl:147-166 (+ getWeightH :37-69)
 __device__ __forceinline__ float3 hrbf_gradient_group(const Nb (&nb)[kPredSlots], int nslots, float px, float py, float pz, unsigned gmask)
@@ -191,7 +170,7 @@ __device__ __forceinline__ float3 hrbf_gradient_group(const Nb (&nb)[kPredSlots]
             if (d2 > T2) continue;
             if (d2 == 0.0f) {
                 const float h = -20.0f / T2;
-                gx -= nb[s].sx * h; gy -= nb[s].sy * h; gz -= nb[s].sz * h;
+                gx -= (nb[s].sx * (0.05f * T2)) * h; gy -= (nb[s].sy * (0.05f * T2)) * h; gz -= (nb[s].sz * (0.05f * T2)) * h;
                 continue;
             }
             const float r = sqrtf(d2 / T2);
@@ -200,9 +179,9 @@ __device__ __forceinline__ float3 hrbf_gradient_group(const Nb (&nb)[kPredSlots]
             const float t2 = -r * q * T2;
             const float h0 = t1 * (3.0f * vx * vx + t2), h1 = t1 * 3.0f * vx * vy, h2 = t1 * 3.0f * vx * vz;
             const float h4 = t1 * (3.0f * vy * vy + t2), h5 = t1 * 3.0f * vy * vz, h8 = t1 * (3.0f * vz * vz + t2);
-            gx -= nb[s].sx * h0 + nb[s].sy * h1 + nb[s].sz * h2;
-            gy -= nb[s].sx * h1 + nb[s].sy * h4 + nb[s].sz * h5;
-            gz -= nb[s].sx * h2 + nb[s].sy * h5 + nb[s].sz * h8;
+            gx -= (nb[s].sx * (0.05f * T2)) * h0 + (nb[s].sy * (0.05f * T2)) * h1 + (nb[s].sz * (0.05f * T2)) * h2;
+            gy -= (nb[s].sx * (0.05f * T2)) * h1 + (nb[s].sy * (0.05f * T2)) * h4 + (nb[s].sz * (0.05f * T2)) * h5;
+            gz -= (nb[s].sx * (0.05f * T2)) * h2 + (nb[s].sy * (0.05f * T2)) * h5 + (nb[s].sz * (0.05f * T2)) * h8;
         }
     }
     gx += __shfl_xor_sync(gmask, gx, 1); gy += __shfl_xor_sync(gmask, gy, 1); gz += __shfl_xor_sync(gmask, gz, 1);
@@ -212,7 +191,7 @@ __device__ __forceinline__ float3 hrbf_gradient_group(const Nb (&nb)[kPredSlots]
 
 // 256 threads = 64 pixels (16 x 4 tile) x 4 lanes.  The (16+6) x (4+6) halo tile of the two maps the
 // ray march needs (position+confidence, normal+radius) is staged in shared memory once per CTA.
-__global__ void __launch_bounds__(256) predict_hrbf_kernel(PredictArgs a)
+__global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
 {
     __shared__ float4 s_v[kPredSH][kPredSW];
     __shared__ float4 s_n[kPredSH][kPredSW];
@@ -233,8 +212,10 @@ __global__ void __launch_bounds__(256) predict_hrbf_kernel(PredictArgs a)
 
     const int lane = threadIdx.x & 31, sub = lane & 3;
     const unsigned gmask = 0xFu << (lane & ~3);
-    const int grp = threadIdx.x >> 2;                   // pixel within the tile
-    const int lx = grp & (kPredTileW - 1), ly = grp >> 4;
+    const int grp = threadIdx.x >> 2;                   // pixel slot of this 4-lane group (also its s_sel row)
+    // a warp's 8 pixels form a compact 4 x 2 patch (similar surfaces -> similar trip counts of the ray march)
+    const int wrp = threadIdx.x >> 5, gin = (threadIdx.x >> 2) & 7;
+    const int lx = 4 * (wrp & 3) + (gin & 3), ly = 2 * (wrp >> 2) + (gin >> 2);
     const int px = tx0 + lx, py = ty0 + ly;
     const bool inside = px < a.cols && py < a.rows;     // uniform within the 4-lane group
 
@@ -246,8 +227,8 @@ __global__ void __launch_bounds__(256) predict_hrbf_kernel(PredictArgs a)
         if (qx < 0 || qx >= a.cols || qy < 0 || qy >= a.rows) continue;
         const float4 v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
         const float4 n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
-        const float nl = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z)));
-        if (v.z < 0.1f || nl < 0.1f || v.w < a.confThr || n.z < 0.0f) continue;
+        const float nl2 = __fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z));     // length < 0.1 <=> length^2 < 0.01
+        if (v.z < 0.1f || nl2 < 0.01f || v.w < a.confThr || n.z < 0.0f) continue;
         valid |= 1ull << c;
     }
     valid |= __shfl_xor_sync(gmask, valid, 1);
@@ -273,15 +254,16 @@ __global__ void __launch_bounds__(256) predict_hrbf_kernel(PredictArgs a)
     const int nslots = (N - sub + kPredLanes - 1) / kPredLanes;       // slots s with s*4+sub < N
 #pragma unroll
     for (int s = 0; s < kPredSlots; ++s) {
-        nb[s].cx = nb[s].cy = nb[s].cz = nb[s].sx = nb[s].sy = nb[s].sz = 0.f; nb[s].T2 = -1.f; nb[s].invT2 = 0.f;
+        nb[s].cx = nb[s].cy = nb[s].cz = nb[s].sx = nb[s].sy = nb[s].sz = 0.f; nb[s].T2 = -1.f; nb[s].invT = 0.f;
         if (s < nslots) {
             const int c = s_sel[grp][s * kPredLanes + sub];
             const float4 v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
             const float4 n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
             nb[s].cx = v.x; nb[s].cy = v.y; nb[s].cz = v.z;
-            nb[s].sx = 10.0f * n.x; nb[s].sy = 10.0f * n.y; nb[s].sz = 10.0f * n.z;
             nb[s].T2 = __fmul_rn(n.w, n.w);
-            nb[s].invT2 = __fdiv_rn(1.0f, nb[s].T2);
+            nb[s].invT = 1.0f / n.w;
+            const float k = 200.0f / nb[s].T2;
+            nb[s].sx = k * n.x; nb[s].sy = k * n.y; nb[s].sz = k * n.z;
         }
     }
 
@@ -302,57 +284,74 @@ __global__ void __launch_bounds__(256) predict_hrbf_kernel(PredictArgs a)
     projmin = fminf(projmin, __shfl_xor_sync(gmask, projmin, 2));
     const float c0x = projmin * rx, c0y = projmin * ry, c0z = projmin * rz;
 
-    // ---- interval search (:152-230) ----
-    bool find_interval = false;
-    float sx_ = 0.f, sy_ = 0.f, sz_ = 0.f, ex_ = 0.f, ey_ = 0.f, ez_ = 0.f;   // starting / ending point
-    int sup = 0;
-    if (inside && N > a.minN) {
-        const float v0 = hrbf_value_group(nb, nslots, c0x, c0y, c0z, gmask, &sup);
-        if (sup > a.minN) {
-            const float dir = v0 > 0.f ? -1.0f : 1.0f;           // v0 > 0: search backward for f < 0; else forward for f > 0
-            float ax = c0x, ay = c0y, az = c0z;                   // anchor of the coarse march
-            bool coarse = false;
-            float bx = 0.f, by = 0.f, bz = 0.f;
-            for (int i = 0; i < 25; ++i) {
-                const float tt = 0.004f * (float)i * dir;
-                const float qx = ax + tt * rx, qy = ay + tt * ry, qz = az + tt * rz;
-                int dummy;
-                const float v1 = hrbf_value_group(nb, nslots, qx, qy, qz, gmask, &dummy);
-                if (v0 > 0.f ? (v1 < 0.f) : (v1 > 0.f)) { bx = qx; by = qy; bz = qz; coarse = true; break; }
-            }
-            if (coarse) {
-                for (int i = 1; i < 11; ++i) {
-                    const float tt = -0.0004f * (float)i * dir;
-                    const float qx = bx + tt * rx, qy = by + tt * ry, qz = bz + tt * rz;
-                    int dummy;
-                    const float v2 = hrbf_value_group(nb, nslots, qx, qy, qz, gmask, &dummy);
-                    if (v0 > 0.f ? (v2 > 0.f) : (v2 < 0.f)) {
-                        if (v0 > 0.f) { sx_ = bx; sy_ = by; sz_ = bz; ex_ = qx; ey_ = qy; ez_ = qz; }
-                        else { ex_ = bx; ey_ = by; ez_ = bz; sx_ = qx; sy_ = qy; sz_ = qz; }
-                        find_interval = true;
-                        break;
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- bisection (:234-270) ----
+    // ---- interval search + bisection (:152-270) as ONE warp-convergent state machine ----
+    // The shader runs three data-dependent loops in sequence (coarse march of 4 mm steps, fine march of 0.4 mm steps
+    // back, bisection); run as written, a warp pays the SUM of its pixels' worst trip counts with ~60 % of the lanes
+    // idle.  Here every lane evaluates f once per iteration at the point its pixel's state asks for, so a warp pays
+    // the MAXIMUM of its pixels' total evaluation counts and the evaluation itself is executed convergently.
+    enum { ST_FIRST = 0, ST_COARSE, ST_FINE, ST_BISECT, ST_DONE };
+    int nmax = nslots;                                   // warp-uniform slot bound
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, m));
+    int state = (inside && N > a.minN) ? ST_FIRST : ST_DONE;
+    int step = 1, bis = 0;
+    float v0 = 0.f, dir = 1.f;
+    float bx = 0.f, by = 0.f, bz = 0.f;                  // anchor of the fine march
+    float sx_ = 0.f, sy_ = 0.f, sz_ = 0.f, ex_ = 0.f, ey_ = 0.f, ez_ = 0.f;   // starting / ending point of the bisection
+    float tx = 0.f, ty = 0.f, tz = 0.f;                  // p_temp
     bool found = false;
-    float tx = 0.f, ty = 0.f, tz = 0.f;                 // p_temp
-    float3 g = make_float3(0.f, 0.f, 0.f);
-    if (find_interval) {
-        for (int j = 0; j < 10; ++j) {
+    while (__any_sync(0xffffffffu, state != ST_DONE)) {
+        // 1. the sample point this pixel's state asks for
+        float qx = c0x, qy = c0y, qz = c0z;
+        if (state == ST_COARSE) { const float tt = 0.004f * (float)step * dir; qx = c0x + tt * rx; qy = c0y + tt * ry; qz = c0z + tt * rz; }
+        else if (state == ST_FINE) { const float tt = -0.0004f * (float)step * dir; qx = bx + tt * rx; qy = by + tt * ry; qz = bz + tt * rz; }
+        else if (state == ST_BISECT) {
             const float dx = ex_ - sx_, dy = ey_ - sy_, dz = ez_ - sz_;
-            if (sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))) < 0.00001f) { found = true; break; }
-            tx = sx_ + 0.5f * dx; ty = sy_ + 0.5f * dy; tz = sz_ + 0.5f * dz;
-            int dummy;
-            const float f = hrbf_value_group(nb, nslots, tx, ty, tz, gmask, &dummy);
-            if (fabsf(f) < 0.00001f) { found = true; break; }
-            if (f < 0.f) { sx_ = tx; sy_ = ty; sz_ = tz; } else { ex_ = tx; ey_ = ty; ez_ = tz; }
+            if (sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))) < 0.00001f) { found = true; state = ST_DONE; }
+            else { tx = sx_ + 0.5f * dx; ty = sy_ + 0.5f * dy; tz = sz_ + 0.5f * dz; qx = tx; qy = ty; qz = tz; }
         }
-        if (found) g = hrbf_gradient_group(nb, nslots, tx, ty, tz, gmask);
+        // 2. f(q) = sum over this lane's neighbours, reduced over the 4 lanes of the pixel (hrbfbase.glsl:126-145)
+        float value = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int s = 0; s < kPredSlots; ++s) {
+            if (s < nmax) {                              // warp-uniform; empty slots have T2 = -1 and contribute 0
+                const float vx = qx - nb[s].cx, vy = qy - nb[s].cy, vz = qz - nb[s].cz;
+                const float d2 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+                const bool in = !(nb[s].T2 < d2);
+                const float q = 1.0f - sqrt_approx(d2) * nb[s].invT;
+                const float w = in ? q * q * q : 0.f;
+                value = fmaf(w, fmaf(vz, nb[s].sz, fmaf(vy, nb[s].sy, vx * nb[s].sx)), value);
+                cnt += in ? 1 : 0;
+            }
+        }
+        value += __shfl_xor_sync(0xffffffffu, value, 1); cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        value += __shfl_xor_sync(0xffffffffu, value, 2); cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        // 3. state transition
+        if (state == ST_FIRST) {
+            v0 = value;
+            dir = v0 > 0.f ? -1.0f : 1.0f;               // v0 > 0: search backward for f < 0; else forward for f > 0
+            state = (cnt > a.minN) ? ST_COARSE : ST_DONE; // i = 0 of the coarse march re-evaluates this point: never a sign change
+            step = 1;
+        } else if (state == ST_COARSE) {
+            if (v0 > 0.f ? (value < 0.f) : (value > 0.f)) { bx = qx; by = qy; bz = qz; state = ST_FINE; step = 1; }
+            else if (++step >= 25) state = ST_DONE;
+        } else if (state == ST_FINE) {
+            if (v0 > 0.f ? (value > 0.f) : (value < 0.f)) {
+                if (v0 > 0.f) { sx_ = bx; sy_ = by; sz_ = bz; ex_ = qx; ey_ = qy; ez_ = qz; }
+                else { ex_ = bx; ey_ = by; ez_ = bz; sx_ = qx; sy_ = qy; sz_ = qz; }
+                state = ST_BISECT; bis = 0;
+            } else if (++step >= 11) state = ST_DONE;
+        } else if (state == ST_BISECT) {
+            if (fabsf(value) < 0.00001f) { found = true; state = ST_DONE; }
+            else {
+                if (value < 0.f) { sx_ = tx; sy_ = ty; sz_ = tz; } else { ex_ = tx; ey_ = ty; ez_ = tz; }
+                if (++bis >= 10) state = ST_DONE;
+            }
+        }
     }
+    float3 g = make_float3(0.f, 0.f, 0.f);
+    if (found) g = hrbf_gradient_group(nb, nslots, tx, ty, tz, gmask);
 
     // ---- attributes of the nearest neighbour (:273-303) ----
     float best = 1000000.f;

@@ -6,7 +6,7 @@
 // fused kernel; getIncrementalTransformation replays ONE CUDA graph that contains the SO3
 // pre-alignment, every ICP/RGB reduction of the three levels and the fp64 solves -- zero host
 // round trips inside the Gauss-Newton loop (the reference makes ~67 per frame).
-#include "odometry_kernels.cuh"
+#include "track_persistent.cuh"
 #include <map>
 #include <new>
 #include <stdarg.h>
@@ -135,6 +135,34 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
         cudaMemcpyAsync(o->h_state, &wk->st, sizeof(TrackState), cudaMemcpyDeviceToHost, s);
     }
     return n;
+}
+
+// The whole tracking loop as one cooperative persistent kernel (track_persistent.cuh).
+static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
+                                   bool so3, bool use_weight, const float* prev_pose_dev, float* pose_out_dev)
+{
+    TrackParams p;
+    const int iters[3] = { fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0 };
+    for (int l = 0; l < 3; ++l) {
+        p.lvl[l].icp = icp_args(o, l, use_weight);
+        p.lvl[l].res = rgbres_args(o, l);
+        p.lvl[l].step = rgbstep_args(o, l);
+        p.lvl[l].cloud = o->cloud[l];
+        p.lvl[l].iters = iters[l];
+    }
+    p.so3_last = o->lastNextImage[2]; p.so3_next = o->nextImage[2];
+    p.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
+    p.rgb = (rgbOnly || icpWeight < 100) ? 1 : 0;
+    p.rgbOnly = rgbOnly; p.so3 = so3; p.icpWeight = icpWeight;
+    p.prev_pose = prev_pose_dev; p.pose_out = pose_out_dev;
+    p.st_global = &o->work->st;
+    p.partials = o->tp_partials; p.ipartials = o->tp_ipartials; p.barrier = o->tp_barrier;
+    p.dbg = o->tp_dbg;
+    HRBF_CUDA(cudaMemsetAsync(o->tp_barrier, 0, sizeof(unsigned int), s));
+    void* args[] = { (void*)&p };
+    HRBF_CUDA(cudaLaunchCooperativeKernel((const void*)track_persistent_kernel, dim3(o->num_sms), dim3(kTrackThreads), args, 0, s));
+    count_launch();
+    return HRBF_OK;
 }
 
 static int get_graph(hrbf_odometry* o, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3, bool use_weight,
@@ -395,6 +423,10 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
         o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cl[l] = take(P * 12); o_ci[l] = take(P * sizeof(hrbf_dataterm));
     }
     const size_t o_vd = take((size_t)width * height * 4), o_work = take(sizeof(ReduceWork)), o_pose = take(64 * sizeof(float));
+    cudaDeviceGetAttribute(&o->num_sms, cudaDevAttrMultiProcessorCount, 0);
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&o->num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    if (o->num_sms <= 0) o->num_sms = kNumSMs;
+    const size_t o_tpp = take((size_t)2 * o->num_sms * 64 * sizeof(float)), o_tpi = take((size_t)2 * o->num_sms * 2 * sizeof(int)), o_tpb = take(256);
     if (cudaMalloc(&o->slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); delete o; return HRBF_ERR_CUDA; }
     cudaMemset(o->slab, 0, off);
     for (int l = 0; l < 3; ++l) {
@@ -407,6 +439,7 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
     o->vdepth_tmp = (float*)(o->slab + o_vd);
     o->work = (ReduceWork*)(o->slab + o_work);
     o->pose_scratch = (float*)(o->slab + o_pose);
+    o->tp_partials = (float*)(o->slab + o_tpp); o->tp_ipartials = (int*)(o->slab + o_tpi); o->tp_barrier = (unsigned int*)(o->slab + o_tpb);
     cudaMallocHost(&o->h_pose, 24 * sizeof(float));
     cudaMallocHost(&o->h_state, sizeof(TrackState));
     cudaMallocHost(&o->h_model_pose, 8 * 12 * sizeof(float));
@@ -430,10 +463,25 @@ int hrbf_odometry_destroy(hrbf_odometry* o)
     if (o->h_state) cudaFreeHost(o->h_state);
     if (o->h_model_pose) cudaFreeHost(o->h_model_pose);
     if (o->slab) cudaFree(o->slab);
+    if (o->tp_dbg) cudaFree(o->tp_dbg);
     delete o;
     return HRBF_OK;
 }
 
+int hrbf_odometry_debug_stamps(hrbf_odometry* o, long long* out_host, int n)
+{   // development aid: (slot << 56 | globaltimer ns) stamps written by CTA 0 of the last persistent tracking call
+    HRBF_CHECK_ARG(o && out_host && n > 0 && n <= 512);
+    if (!o->tp_dbg) { HRBF_CUDA(cudaMalloc(&o->tp_dbg, 512 * sizeof(long long))); HRBF_CUDA(cudaMemset(o->tp_dbg, 0, 512 * sizeof(long long))); return HRBF_OK; }
+    HRBF_CUDA(cudaMemcpy(out_host, o->tp_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    HRBF_CUDA(cudaMemset(o->tp_dbg, 0, 512 * sizeof(long long)));
+    return HRBF_OK;
+}
+int hrbf_odometry_set_tracker(hrbf_odometry* o, int use_kernel_graph)
+{
+    HRBF_CHECK_ARG(o);
+    o->use_graph = use_kernel_graph != 0;
+    return HRBF_OK;
+}
 int hrbf_odometry_set_params(hrbf_odometry* o, float curvThr, int useSearch, int searchRadius, int rgbGradWeight)
 {
     HRBF_CHECK_ARG(o && searchRadius >= 0 && searchRadius <= 2);
@@ -601,11 +649,19 @@ int hrbf_odometry_get_incremental_transformation(hrbf_odometry* o, float* trans,
     cudaStream_t s = (cudaStream_t)stream;
     memcpy(o->h_pose, rot, 36);
     memcpy(o->h_pose + 9, trans, 12);
-    cudaGraphExec_t exec = nullptr;
-    int nk = 0;
-    if (int rc = get_graph(o, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0, true, &exec, &nk)) return rc;
-    HRBF_CUDA(cudaGraphLaunch(exec, s));
-    count_launch(nk);
+    int nk = 1;
+    if (o->use_graph) {
+        cudaGraphExec_t exec = nullptr;
+        if (int rc = get_graph(o, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0, true, &exec, &nk)) return rc;
+        HRBF_CUDA(cudaGraphLaunch(exec, s));
+        count_launch(nk);
+    } else {
+        HRBF_CUDA(cudaMemcpyAsync(o->pose_scratch + 12, o->h_pose, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (int rc = launch_track_persistent(o, s, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0,
+                                             o->pose_scratch + 12, o->pose_scratch + 24)) return rc;
+        HRBF_CUDA(cudaMemcpyAsync(o->h_pose + 12, o->pose_scratch + 24, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        HRBF_CUDA(cudaMemcpyAsync(o->h_state, &o->work->st, sizeof(TrackState), cudaMemcpyDeviceToHost, s));
+    }
     HRBF_CUDA(cudaStreamSynchronize(s));
     if (so3) swap_so3_images(o);
     memcpy(rot, o->h_pose + 12, 36);
@@ -628,12 +684,17 @@ int hrbf_odometry_track_async(hrbf_odometry* o, const float* prev_pose_dev, floa
     HRBF_CHECK_ARG(o && prev_pose_dev && pose_out_dev);
     cudaStream_t s = (cudaStream_t)stream;
     HRBF_CUDA(cudaMemcpyAsync(o->pose_scratch + 12, prev_pose_dev, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    int nk = 0;
-    cudaGraphExec_t exec = nullptr;
-    if (int rc = get_graph(o, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0, false, &exec, &nk)) return rc;
-    HRBF_CUDA(cudaGraphLaunch(exec, s));
+    if (o->use_graph) {
+        int nk = 0;
+        cudaGraphExec_t exec = nullptr;
+        if (int rc = get_graph(o, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0, false, &exec, &nk)) return rc;
+        HRBF_CUDA(cudaGraphLaunch(exec, s));
+        count_launch(nk);
+    } else {
+        if (int rc = launch_track_persistent(o, s, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0, so3 != 0, if_curvature_info != 0,
+                                             o->pose_scratch + 12, o->pose_scratch + 24)) return rc;
+    }
     if (so3) swap_so3_images(o);
-    count_launch(nk);
     HRBF_CUDA(cudaMemcpyAsync(pose_out_dev, o->pose_scratch + 24, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return HRBF_OK;
 }

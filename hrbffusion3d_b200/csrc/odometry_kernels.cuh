@@ -341,10 +341,8 @@ __global__ void rgba_to_intensity_kernel(int n, const uchar4* __restrict__ rgba,
     const int value = (int)((float)s.x * 0.114f + (float)s.y * 0.299f + (float)s.z * 0.587f);
     dst[i] = (unsigned char)value;
 }
-__global__ void sobel_kernel(int rows, int cols, const unsigned char* __restrict__ src, short* dx, short* dy)
+__device__ __forceinline__ void sobel_pixel(int rows, int cols, const unsigned char* __restrict__ src, short* dx, short* dy, int x, int y)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= cols || y >= rows) return;
     const float gx[9] = { 1, 0, -1, 2, 0, -2, 1, 0, -1 }, gy[9] = { 1, 2, 1, 0, 0, 0, -1, -2, -1 };
     float dxv = 0, dyv = 0;
     int k = 8;
@@ -357,16 +355,26 @@ __global__ void sobel_kernel(int rows, int cols, const unsigned char* __restrict
     dx[(size_t)y * cols + x] = (short)dxv;
     dy[(size_t)y * cols + x] = (short)dyv;
 }
-__global__ void project_cloud_kernel(int rows, int cols, const float* __restrict__ depth, float* cloud3,
-                                     float invFx, float invFy, float cx, float cy)
+__global__ void sobel_kernel(int rows, int cols, const unsigned char* __restrict__ src, short* dx, short* dy)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
+    sobel_pixel(rows, cols, src, dx, dy, x, y);
+}
+__device__ __forceinline__ void project_pixel(int rows, int cols, const float* __restrict__ depth, float* cloud3, float invFx, float invFy, float cx, float cy, int x, int y)
+{
     const size_t i = (size_t)y * cols + x;
     const float z = depth[i];
     cloud3[3 * i + 0] = (x - cx) * z * invFx;
     cloud3[3 * i + 1] = (y - cy) * z * invFy;
     cloud3[3 * i + 2] = z;
+}
+__global__ void project_cloud_kernel(int rows, int cols, const float* __restrict__ depth, float* cloud3,
+                                     float invFx, float invFy, float cx, float cy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    project_pixel(rows, cols, depth, cloud3, invFx, invFy, cx, cy, x, y);
 }
 
 // -------------------------------------------------------------- rows 1-3 ---
@@ -514,6 +522,56 @@ struct RgbResArgs {
     int rows, cols;
 };
 
+// one pixel of computeRgbResidual (reduce.cu:986-1060); s_k = krkinv[9], kt[3]
+__device__ __forceinline__ void rgb_residual_pixel(const RgbResArgs& a, const float* s_k, int k, int& cnt, int& sig)
+{
+    const int cols = a.cols, rows = a.rows;
+    const int i = k / cols, j0 = k - i * cols;
+    hrbf_dataterm c;
+    c.zero_x = c.zero_y = c.one_x = c.one_y = 0; c.diff = 0.f; c.valid = 0; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    if (j0 < cols - 5 && i < rows - 1) {
+        // 4x4 "not an isolated pixel" test (reduce.cu:1005-1011); all loads issued up front
+        // (clamped addresses, out-of-window taps ignored) instead of a short-circuit chain
+        unsigned int zero_seen = 0;
+#pragma unroll
+        for (int du = -2; du < 2; ++du)
+#pragma unroll
+            for (int dv = -2; dv < 2; ++dv) {
+                const int u = i + du, v = j0 + dv;
+                const bool in = u >= 0 && u < rows && v >= 0 && v < cols;
+                const unsigned char px = __ldg(a.nextImage + (size_t)min(max(u, 0), rows - 1) * cols + min(max(v, 0), cols - 1));
+                zero_seen |= (in && px == 0) ? 1u : 0u;
+            }
+        const bool valid = zero_seen == 0;
+        if (valid) {
+            const short valx = __ldg(a.dIdx + k), valy = __ldg(a.dIdy + k);
+            const float mTwo = (float)((valx * valx) + (valy * valy));
+            if (mTwo >= a.minScale) {
+                const int y = i, x = j0;
+                const float d1 = __ldg(a.nextDepth + k);
+                if (!isnan(d1)) {
+                    const float td1 = d1 * (s_k[6] * x + s_k[7] * y + s_k[8]) + s_k[11];
+                    const int u0 = __float2int_rn((d1 * (s_k[0] * x + s_k[1] * y + s_k[2]) + s_k[9]) / td1);
+                    const int v0 = __float2int_rn((d1 * (s_k[3] * x + s_k[4] * y + s_k[5]) + s_k[10]) / td1);
+                    if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+                        const float d0 = __ldg(a.lastDepth + (size_t)v0 * cols + u0);
+                        const unsigned char li = __ldg(a.lastImage + (size_t)v0 * cols + u0);
+                        if (d0 > 0 && fabsf(td1 - d0) <= a.maxDepthDelta && li != 0) {
+                            c.zero_x = (short)u0; c.zero_y = (short)v0; c.one_x = (short)x; c.one_y = (short)y;
+                            c.diff = (float)__ldg(a.nextImage + k) - (float)li;
+                            c.valid = 1;
+                            cnt += 1;
+                            sig += (int)(c.diff * c.diff);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    a.corres[k] = c;
+
+}
+
 // reduce.cu:986-1060; the int2 {count, sum diff^2} goes through redux + one atomic per warp.
 // When the caller is the tracking loop, the last block also evaluates sigma / the rgbOnly break
 // (RGBDOdometry.cpp:1017-1032).
@@ -525,55 +583,11 @@ __global__ void __launch_bounds__(256) rgb_residual_kernel(RgbResArgs a, ReduceW
     if (threadIdx.x < 9) s_k[threadIdx.x] = st->krkinv[threadIdx.x];
     if (threadIdx.x < 3) s_k[9 + threadIdx.x] = st->kt[threadIdx.x];
     __syncthreads();
-    const int N = a.rows * a.cols, cols = a.cols, rows = a.rows;
+    const int N = a.rows * a.cols;
     int cnt = 0, sig = 0;
     const bool level_done = (st->done_level == cur_level);
     if (!level_done)
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += blockDim.x * gridDim.x) {
-            const int i = k / cols, j0 = k - i * cols;
-            hrbf_dataterm c;
-            c.zero_x = c.zero_y = c.one_x = c.one_y = 0; c.diff = 0.f; c.valid = 0; c.pad[0] = c.pad[1] = c.pad[2] = 0;
-            if (j0 < cols - 5 && i < rows - 1) {
-                // 4x4 "not an isolated pixel" test (reduce.cu:1005-1011); all loads issued up front
-                // (clamped addresses, out-of-window taps ignored) instead of a short-circuit chain
-                unsigned int zero_seen = 0;
-#pragma unroll
-                for (int du = -2; du < 2; ++du)
-#pragma unroll
-                    for (int dv = -2; dv < 2; ++dv) {
-                        const int u = i + du, v = j0 + dv;
-                        const bool in = u >= 0 && u < rows && v >= 0 && v < cols;
-                        const unsigned char px = __ldg(a.nextImage + (size_t)min(max(u, 0), rows - 1) * cols + min(max(v, 0), cols - 1));
-                        zero_seen |= (in && px == 0) ? 1u : 0u;
-                    }
-                const bool valid = zero_seen == 0;
-                if (valid) {
-                    const short valx = __ldg(a.dIdx + k), valy = __ldg(a.dIdy + k);
-                    const float mTwo = (float)((valx * valx) + (valy * valy));
-                    if (mTwo >= a.minScale) {
-                        const int y = i, x = j0;
-                        const float d1 = __ldg(a.nextDepth + k);
-                        if (!isnan(d1)) {
-                            const float td1 = d1 * (s_k[6] * x + s_k[7] * y + s_k[8]) + s_k[11];
-                            const int u0 = __float2int_rn((d1 * (s_k[0] * x + s_k[1] * y + s_k[2]) + s_k[9]) / td1);
-                            const int v0 = __float2int_rn((d1 * (s_k[3] * x + s_k[4] * y + s_k[5]) + s_k[10]) / td1);
-                            if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
-                                const float d0 = __ldg(a.lastDepth + (size_t)v0 * cols + u0);
-                                const unsigned char li = __ldg(a.lastImage + (size_t)v0 * cols + u0);
-                                if (d0 > 0 && fabsf(td1 - d0) <= a.maxDepthDelta && li != 0) {
-                                    c.zero_x = (short)u0; c.zero_y = (short)v0; c.one_x = (short)x; c.one_y = (short)y;
-                                    c.diff = (float)__ldg(a.nextImage + k) - (float)li;
-                                    c.valid = 1;
-                                    cnt += 1;
-                                    sig += (int)(c.diff * c.diff);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            a.corres[k] = c;
-        }
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += blockDim.x * gridDim.x) rgb_residual_pixel(a, s_k, k, cnt, sig);
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     sig = __reduce_add_sync(0xffffffffu, sig);
     if ((threadIdx.x & 31) == 0 && (cnt | sig)) { atomicAdd(&st->rgb_count, cnt); atomicAdd(&st->rgb_sigma, sig); }
@@ -614,6 +628,40 @@ struct RgbStepArgs {
     int rows, cols;
 };
 
+// one pixel of rgbStep (reduce.cu:718-811)
+__device__ __forceinline__ void rgb_step_pixel(const RgbStepArgs& a, float sigma, int i, float (&acc)[32])
+{
+    const int cols = a.cols;
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(a.corres) + i);
+    hrbf_dataterm c;
+    memcpy(&c, &raw, sizeof c);
+    float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    float rgb_weight = 1.f;
+    if (c.valid) {
+        float w = sigma + fabsf(c.diff);
+        w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+        if (sigma == -1.f) w = 1.f;
+        row[6] = -w * c.diff;
+        const float* cp = a.cloud3 + 3 * ((size_t)c.zero_y * cols + c.zero_x);
+        const float px = __ldg(cp), py = __ldg(cp + 1), pz = __ldg(cp + 2);
+        const float invz = 1.0f / pz;
+        const size_t o1 = (size_t)c.one_y * cols + c.one_x;
+        const float gx = w * a.sobelScale * (float)__ldg(a.dIdx + o1), gy = w * a.sobelScale * (float)__ldg(a.dIdy + o1);
+        const float v0 = gx * a.fx * invz, v1 = gy * a.fy * invz;
+        const float v2 = -(v0 * px + v1 * py) * invz;
+        row[0] = v0; row[1] = v1; row[2] = v2;
+        row[3] = -pz * v1 + py * v2;
+        row[4] = pz * v0 - px * v2;
+        row[5] = -py * v0 + px * v1;
+        if (a.use_grad_weight) {
+            const float gm = sqrtf(gx * gx + gy * gy);
+            rgb_weight = expf(-0.5f * (10.f / gm) * (10.f / gm));
+        }
+    }
+    accumulate_row7(acc, row, rgb_weight, c.valid != 0);
+
+}
+
 // reduce.cu:718-811.  sigma < -1.5 => take st->sigmaVal (tracking loop).
 __global__ void __launch_bounds__(kReduceThreads, 2) rgb_step_kernel(RgbStepArgs a, float sigma_arg, ReduceWork* wk, int mode, int cur_level, int next_level)
 {
@@ -623,43 +671,56 @@ __global__ void __launch_bounds__(kReduceThreads, 2) rgb_step_kernel(RgbStepArgs
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-    const int N = a.rows * a.cols, cols = a.cols;
+    const int N = a.rows * a.cols;
     const bool level_done = (st->done_level == cur_level);
     if (!level_done)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) {
-            const int4 raw = __ldg(reinterpret_cast<const int4*>(a.corres) + i);
-            hrbf_dataterm c;
-            memcpy(&c, &raw, sizeof c);
-            float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
-            float rgb_weight = 1.f;
-            if (c.valid) {
-                float w = sigma + fabsf(c.diff);
-                w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
-                if (sigma == -1.f) w = 1.f;
-                row[6] = -w * c.diff;
-                const float* cp = a.cloud3 + 3 * ((size_t)c.zero_y * cols + c.zero_x);
-                const float px = __ldg(cp), py = __ldg(cp + 1), pz = __ldg(cp + 2);
-                const float invz = 1.0f / pz;
-                const size_t o1 = (size_t)c.one_y * cols + c.one_x;
-                const float gx = w * a.sobelScale * (float)__ldg(a.dIdx + o1), gy = w * a.sobelScale * (float)__ldg(a.dIdy + o1);
-                const float v0 = gx * a.fx * invz, v1 = gy * a.fy * invz;
-                const float v2 = -(v0 * px + v1 * py) * invz;
-                row[0] = v0; row[1] = v1; row[2] = v2;
-                row[3] = -pz * v1 + py * v2;
-                row[4] = pz * v0 - px * v2;
-                row[5] = -py * v0 + px * v1;
-                if (a.use_grad_weight) {
-                    const float gm = sqrtf(gx * gx + gy * gy);
-                    rgb_weight = expf(-0.5f * (10.f / gm) * (10.f / gm));
-                }
-            }
-            accumulate_row7(acc, row, rgb_weight, c.valid != 0);
-        }
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) rgb_step_pixel(a, sigma, i, acc);
     if (grid_reduce32(acc, wk->partials, &st->ticket, s_total)) {
         if (threadIdx.x < 32) st->rgb_sums[threadIdx.x] = s_total[threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0 && mode == 1 && !level_done) gn_update(st, cur_level, next_level);
     }
+}
+
+// one pixel of so3Step (reduce.cu:1172-1273); s_m = imageBasis[9], kinv[9], krlr[9]
+__device__ __forceinline__ void so3_pixel(const unsigned char* __restrict__ lastImage, const unsigned char* __restrict__ nextImage,
+                                          int rows, int cols, const float* s_m, int k, float (&acc)[32])
+{
+    const int y = k / cols, x = k - y * cols;
+    const float3 up = make_float3((float)x, (float)y, 1.0f);
+    const float3 wp = mul(s_m, up);
+    const int wx = __float2int_rn(wp.x / wp.z), wy = __float2int_rn(wp.y / wp.z);
+    const bool found = wx >= 1 && wx < cols - 1 && wy >= 1 && wy < rows - 1 && x >= 1 && x < cols - 1 && y >= 1 && y < rows - 1;
+    float row[4] = { 0, 0, 0, 0 };
+    if (found) {
+        auto grad = [&](const unsigned char* img, int px, int py, float& gx, float& gy) {
+            const float actu = (float)__ldg(img + (size_t)py * cols + px);
+            float back = (float)__ldg(img + (size_t)py * cols + px - 1), fore = (float)__ldg(img + (size_t)py * cols + px + 1);
+            gx = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+            back = (float)__ldg(img + (size_t)(py - 1) * cols + px); fore = (float)__ldg(img + (size_t)(py + 1) * cols + px);
+            gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+        };
+        float gnx, gny, glx, gly;
+        grad(nextImage, wx, wy, gnx, gny);
+        grad(lastImage, x, y, glx, gly);
+        const float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
+        const float3 pt = mul(s_m + 9, up);
+        const float z2 = pt.z * pt.z;
+        const float* kr = s_m + 18;
+        const float3 lp = make_float3(((pt.z * (kr[3] * gy + kr[0] * gx)) - (gy * kr[6] * y) - (gx * kr[6] * x)) / z2,
+                                      ((pt.z * (kr[4] * gy + kr[1] * gx)) - (gy * kr[7] * y) - (gx * kr[7] * x)) / z2,
+                                      ((pt.z * (kr[5] * gy + kr[2] * gx)) - (gy * kr[8] * y) - (gx * kr[8] * x)) / z2);
+        const float3 jr = cross(lp, pt);
+        row[0] = jr.x; row[1] = jr.y; row[2] = jr.z;
+        row[3] = -((float)__ldg(nextImage + (size_t)wy * cols + wx) - (float)__ldg(lastImage + (size_t)y * cols + x));
+    }
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) acc[q++] += row[i] * row[j];
+    acc[10] += found ? 1.f : 0.f;
+
 }
 
 // reduce.cu:1172-1273.  mode 1: run the SO3 control flow in the last block.
@@ -677,42 +738,7 @@ __global__ void __launch_bounds__(kReduceThreads, 2) so3_reduce_kernel(const uns
     const int N = rows * cols;
     const bool skip = (mode == 1) && st->so3_done;
     if (!skip)
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += blockDim.x * gridDim.x) {
-            const int y = k / cols, x = k - y * cols;
-            const float3 up = make_float3((float)x, (float)y, 1.0f);
-            const float3 wp = mul(s_m, up);
-            const int wx = __float2int_rn(wp.x / wp.z), wy = __float2int_rn(wp.y / wp.z);
-            const bool found = wx >= 1 && wx < cols - 1 && wy >= 1 && wy < rows - 1 && x >= 1 && x < cols - 1 && y >= 1 && y < rows - 1;
-            float row[4] = { 0, 0, 0, 0 };
-            if (found) {
-                auto grad = [&](const unsigned char* img, int px, int py, float& gx, float& gy) {
-                    const float actu = (float)__ldg(img + (size_t)py * cols + px);
-                    float back = (float)__ldg(img + (size_t)py * cols + px - 1), fore = (float)__ldg(img + (size_t)py * cols + px + 1);
-                    gx = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
-                    back = (float)__ldg(img + (size_t)(py - 1) * cols + px); fore = (float)__ldg(img + (size_t)(py + 1) * cols + px);
-                    gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
-                };
-                float gnx, gny, glx, gly;
-                grad(nextImage, wx, wy, gnx, gny);
-                grad(lastImage, x, y, glx, gly);
-                const float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
-                const float3 pt = mul(s_m + 9, up);
-                const float z2 = pt.z * pt.z;
-                const float* kr = s_m + 18;
-                const float3 lp = make_float3(((pt.z * (kr[3] * gy + kr[0] * gx)) - (gy * kr[6] * y) - (gx * kr[6] * x)) / z2,
-                                              ((pt.z * (kr[4] * gy + kr[1] * gx)) - (gy * kr[7] * y) - (gx * kr[7] * x)) / z2,
-                                              ((pt.z * (kr[5] * gy + kr[2] * gx)) - (gy * kr[8] * y) - (gx * kr[8] * x)) / z2);
-                const float3 jr = cross(lp, pt);
-                row[0] = jr.x; row[1] = jr.y; row[2] = jr.z;
-                row[3] = -((float)__ldg(nextImage + (size_t)wy * cols + wx) - (float)__ldg(lastImage + (size_t)y * cols + x));
-            }
-            int q = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = i; j < 4; ++j) acc[q++] += row[i] * row[j];
-            acc[10] += found ? 1.f : 0.f;
-        }
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += blockDim.x * gridDim.x) so3_pixel(lastImage, nextImage, rows, cols, s_m, k, acc);
     if (grid_reduce32(acc, wk->partials, &st->ticket, s_total)) {
         if (!skip) {
             if (threadIdx.x < 16) st->so3_sums[threadIdx.x] = s_total[threadIdx.x];

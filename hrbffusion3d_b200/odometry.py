@@ -37,6 +37,10 @@ class RGBDOdometry:
 
     __del__ = close
 
+    def setTracker(self, use_kernel_graph=False):
+        """False (default): one persistent cooperative kernel; True: one kernel per reduction in a CUDA graph"""
+        check(lib().hrbf_odometry_set_tracker(self._h, int(use_kernel_graph)))
+
     def setParams(self, curvValidThreshold=300.0, useCorrespondenceSearch=False, searchRadius=2, rgbUseGradientWeight=False):
         check(lib().hrbf_odometry_set_params(self._h, C.c_float(curvValidThreshold), int(useCorrespondenceSearch), int(searchRadius), int(rgbUseGradientWeight)))
 

@@ -154,6 +154,9 @@ int hrbf_odometry_destroy(hrbf_odometry*);
 /* knobs read from GlobalStateParam inside the reference path */
 int hrbf_odometry_set_params(hrbf_odometry*, float curvValidThreshold, int useCorrespondenceSearch,
                              int searchRadius, int rgbUseGradientWeight);
+/* Tracker implementation: 0 (default) = the whole coarse-to-fine loop as ONE persistent cooperative kernel;
+ * 1 = one kernel per reduction, replayed as a CUDA graph (kept for comparison and for the per-kernel timing hook) */
+int hrbf_odometry_set_tracker(hrbf_odometry*, int use_kernel_graph);
 /* initICP(depth) [GPUTest path], RGBDOdometry.cpp:161-181 : depth_dev = float[h][w] raw units */
 int hrbf_odometry_init_icp_depth(hrbf_odometry*, const float* depth_dev, float depthCutoff, float depthMapFactor, void* stream);
 /* initICP(vertices, normals), RGBDOdometry.cpp:183-206 */

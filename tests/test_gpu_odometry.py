@@ -210,6 +210,23 @@ def test_tracking_pose_matches_oracle(orc, cuda, W, H, kw):
         assert dt1 < dt0 and ang1 < ang0
 
 
+def test_persistent_and_graph_trackers_agree(orc, cuda):
+    """The persistent cooperative kernel (default) and the first-generation kernel-per-reduction graph run the same
+    arithmetic with a different cross-CTA summation grouping (fp64): poses agree to round-off."""
+    for kw in (dict(icpWeight=100.0, so3=False), dict(icpWeight=10.0, so3=True), dict(icpWeight=100.0, so3=False, pyramid=False, fastOdom=True)):
+        res = []
+        for graph in (False, True):
+            oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, 320, 240)
+            go.setTracker(graph)
+            t, R, st = go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **kw)
+            res.append((t, R, st))
+        ang, dt = pose_err(res[0][1], res[0][0], res[1][1], res[1][0])
+        tol = 1e-6 if kw["icpWeight"] >= 100 else 2e-4
+        assert ang <= tol and dt <= tol, (kw, ang, dt)
+        assert res[0][2].icp_iterations_run == res[1][2].icp_iterations_run
+        assert res[0][2].kernel_launches == 1 and res[1][2].kernel_launches > 1
+
+
 def test_tracking_two_frames_so3_swap(orc, cuda):
     """Second call exercises the lastNextImage/nextImage swap (RGBDOdometry.cpp:1239-1245)."""
     oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, 320, 240)
