@@ -39,12 +39,13 @@ ICP_BYTES_PER_PIXEL_ITER = 68.0
 FUSION_KW = {}               # reference defaults: RGB+ICP (weight 10), SO3 pre-alignment, iterations 10/5/4, HRBF win 3 / K 10
 
 
-def make_sequence(seed, n=RING):
+def make_sequence(seed, n=RING, only=None):
     """plane z = 1.5 m tilted 15 deg, camera on a 5 cm circle with 2 deg yaw wobble, Kinect-style
-    noise.  One closed loop of n frames (3.3 mm / 0.13 deg per frame), replayed for as many steps as asked."""
+    noise.  One closed loop of n frames (3.3 mm / 0.13 deg per frame), replayed for as many steps as asked.
+    only = k: render just the first k frames of that loop."""
     sc = synth.Scene("plane")
     cam = synth.default_camera(W, H)
-    poses = synth.circle_trajectory(n, frames_per_rev=n)
+    poses = synth.circle_trajectory(n, frames_per_rev=n)[:only]
     frames = [synth.render_depth(sc, p, W, H, cam, noise=True, seed=seed * 100000 + i) for i, p in enumerate(poses)]
     depth = np.stack([f[0] for f in frames])
     rgb = np.stack([f[1] for f in frames])
@@ -94,15 +95,15 @@ def measured_peak_hbm():
 class OracleRunner:
     """The CPU oracle's processFrame (oracle/orc_pipeline.py, a restatement of HRBFFusion::processFrame) on the same frames."""
 
-    def __init__(self, depth, rgb, cam, threads):
+    def __init__(self, depth, rgb, cam, threads, ring=RING):
         os.environ["OMP_NUM_THREADS"] = str(threads)
         from oracle import orc_pipeline as op
         self.f = op.HRBFFusion(W, H, cam, **FUSION_KW)
-        self.depth, self.rgb, self.i = depth, rgb, 0
+        self.depth, self.rgb, self.i, self.ring = depth, rgb, 0, ring
 
     def step(self):
         t0 = time.perf_counter()
-        self.f.processFrame(self.rgb[self.i % RING], self.depth[self.i % RING])
+        self.f.processFrame(self.rgb[self.i % self.ring], self.depth[self.i % self.ring])
         self.i += 1
         return time.perf_counter() - t0
 
@@ -120,12 +121,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    global RING
     cores = os.cpu_count() or 1
-    n_gen = min(RING, args.steps + args.warmup)
-    RING = n_gen
-    depth, rgb, poses, cam = make_sequence(0, n_gen)
-    r = OracleRunner(depth, rgb, cam, cores)
+    n_gen = min(RING, args.steps + args.warmup)       # the first frames of the same closed loop (rendering all 96 is not needed)
+    depth, rgb, poses, cam = make_sequence(0, RING, only=n_gen)
+    r = OracleRunner(depth, rgb, cam, cores, ring=n_gen)
     for _ in range(args.warmup):
         r.step()
     t = sum(r.step() for _ in range(args.steps))
@@ -152,12 +151,12 @@ def ours_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # rank 0 scatters the per-sequence seeds (stand-in for the .klg byte ranges); trajectories are gathered at the end
-    seed_t = torch.zeros(1, dtype=torch.int64, device="cuda")
-    if world > 1:
-        seeds = [torch.tensor([r], dtype=torch.int64, device="cuda") for r in range(world)] if rank == 0 else None
-        dist.scatter(seed_t, seeds, src=0)
-    depth, rgb, poses, cam = make_sequence(int(seed_t.item()))
+    # rank 0 scatters one sequence descriptor per rank (stand-in for the .klg byte blobs, same code path: multigpu.scatter_blobs);
+    # trajectories are gathered at the end.  No collective inside the frame loop.
+    from hrbffusion3d_b200 import multigpu
+    blobs = [json.dumps({"sequence": r, "seed": r, "frames": RING}).encode() for r in range(world)] if rank == 0 else None
+    desc = json.loads(multigpu.scatter_blobs(blobs, device="cuda"))
+    depth, rgb, poses, cam = make_sequence(int(desc["seed"]))
     depth_pin = torch.from_numpy(depth.view(np.int16)).pin_memory()
     rgb_pin = torch.from_numpy(rgb).pin_memory()
     depth_dev, rgb_dev = depth_pin.cuda(), rgb_pin.cuda()
@@ -208,14 +207,19 @@ def ours_arm(args):
     ms_e2e, _, F2 = run(True)
     del F2
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        n = traj.shape[0]
-        gathered = [torch.zeros_like(traj) for _ in range(world)] if rank == 0 else None
-        dist.gather(traj, gathered, dst=0)       # per-sequence trajectories back to rank 0
+    gathered = multigpu.gather_trajectories(traj)       # per-sequence trajectories back to rank 0
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    # sanity of the measured work: absolute trajectory error of every gathered sequence against the synthetic ground truth
+    ate = []
+    for r, g in enumerate(gathered):
+        gt = poses if r == 0 else synth.circle_trajectory(RING, frames_per_rev=RING)      # same camera loop for every seed
+        P0inv = np.linalg.inv(np.asarray(gt[0], np.float64))
+        est_t = g.numpy()[:, 9:12].astype(np.float64)
+        gt_t = np.stack([(P0inv @ np.asarray(gt[i % RING], np.float64))[:3, 3] for i in range(est_t.shape[0])])
+        ate.append(float(np.sqrt(np.mean(np.sum((est_t - gt_t) ** 2, axis=1)))))
 
     peak, peak_src = measured_peak_hbm()
     alg_bytes = ICP_BYTES_PER_PIXEL_ITER * W * H
@@ -231,6 +235,7 @@ def ours_arm(args):
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
            "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 48},
            "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count,
+           "trajectory_ate_rmse_m": ate,
            "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false> level 0 (640x480), incl. in-kernel Gauss-Newton solve",
                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                         "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": 20927232.0,
