@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhrbf_b200.so")
+LIB_PATH = os.environ.get("HRBF_B200_LIB") or os.path.join(_HERE, "libhrbf_b200.so")      # override: development builds with other tuning macros
 _lib = None
 
 

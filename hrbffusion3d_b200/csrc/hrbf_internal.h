@@ -28,9 +28,12 @@ struct hrbf_odometry {
     unsigned char* lastImage[HRBF_NUM_PYRS] = {}; unsigned char* nextImage[HRBF_NUM_PYRS] = {}; unsigned char* lastNextImage[HRBF_NUM_PYRS] = {};
     short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
     float* cloud[HRBF_NUM_PYRS] = {};
+    unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
+    size_t tp_dyn_set = 0;                       // dynamic shared memory the persistent kernel is currently allowed
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
     hrbf::ReduceWork* work = nullptr;
-    float* tp_partials = nullptr; int* tp_ipartials = nullptr; unsigned int* tp_barrier = nullptr;   // persistent tracker scratch
+    unsigned long long *tp_ll_f = nullptr, *tp_ll_i = nullptr;   // persistent tracker: tagged-word exchange buffers
+    unsigned int tp_epoch = 0;                                   // launch counter feeding the tags
     int num_sms = 0;
     long long* tp_dbg = nullptr;
     bool use_graph = false;          // true: one kernel per reduction replayed as a CUDA graph (first-generation path)

@@ -147,8 +147,18 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
         p.lvl[l].icp = icp_args(o, l, use_weight);
         p.lvl[l].res = rgbres_args(o, l);
         p.lvl[l].step = rgbstep_args(o, l);
-        p.lvl[l].cloud = o->cloud[l];
+        p.lvl[l].cand = o->cand[l];
         p.lvl[l].iters = iters[l];
+    }
+    // RGB slots: one per pixel of a CTA's range and thread
+    int max_slots = 1;
+    for (int l = 0; l < 3; ++l)
+        if (iters[l] > 0) { const int s_l = div_up(div_up(o->rows(l) * o->cols(l), o->num_sms), kTrackThreads); if (s_l > max_slots) max_slots = s_l; }
+    p.max_slots = max_slots;
+    const size_t dyn = track_slots_bytes(max_slots);
+    if (dyn > o->tp_dyn_set) {
+        HRBF_CUDA(cudaFuncSetAttribute((const void*)track_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        o->tp_dyn_set = dyn;
     }
     p.so3_last = o->lastNextImage[2]; p.so3_next = o->nextImage[2];
     p.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
@@ -156,11 +166,13 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     p.rgbOnly = rgbOnly; p.so3 = so3; p.icpWeight = icpWeight;
     p.prev_pose = prev_pose_dev; p.pose_out = pose_out_dev;
     p.st_global = &o->work->st;
-    p.partials = o->tp_partials; p.ipartials = o->tp_ipartials; p.barrier = o->tp_barrier;
+    p.ll_f = o->tp_ll_f; p.ll_i = o->tp_ll_i;
+    o->tp_epoch = (o->tp_epoch + 1) & 0xfffffu;
+    if (o->tp_epoch == 0) o->tp_epoch = 1;
+    p.epoch = o->tp_epoch;
     p.dbg = o->tp_dbg;
-    HRBF_CUDA(cudaMemsetAsync(o->tp_barrier, 0, sizeof(unsigned int), s));
     void* args[] = { (void*)&p };
-    HRBF_CUDA(cudaLaunchCooperativeKernel((const void*)track_persistent_kernel, dim3(o->num_sms), dim3(kTrackThreads), args, 0, s));
+    HRBF_CUDA(cudaLaunchCooperativeKernel((const void*)track_persistent_kernel, dim3(o->num_sms), dim3(kTrackThreads), args, dyn, s));
     count_launch();
     return HRBF_OK;
 }
@@ -413,20 +425,20 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
     // one slab, 256-B aligned sub-buffers
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
-    size_t o_maps[M_COUNT][3], o_dt[3], o_ld[3], o_nd[3], o_li[3], o_ni[3], o_lni[3], o_dx[3], o_dy[3], o_cl[3], o_ci[3];
+    size_t o_maps[M_COUNT][3], o_dt[3], o_ld[3], o_nd[3], o_li[3], o_ni[3], o_lni[3], o_dx[3], o_dy[3], o_cl[3], o_ci[3], o_cd[3];
     for (int l = 0; l < 3; ++l) {
         const size_t P = (size_t)o->rows(l) * o->cols(l);
         for (int m = 0; m < M_W; ++m) o_maps[m][l] = take(4 * P * sizeof(float));
         o_maps[M_W][l] = take(P * sizeof(float));
         o_dt[l] = take(P * 4); o_ld[l] = take(P * 4); o_nd[l] = take(P * 4);
         o_li[l] = take(P); o_ni[l] = take(P); o_lni[l] = take(P);
-        o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cl[l] = take(P * 12); o_ci[l] = take(P * sizeof(hrbf_dataterm));
+        o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cl[l] = take(P * 12); o_ci[l] = take(P * sizeof(hrbf_dataterm)); o_cd[l] = take(P);
     }
     const size_t o_vd = take((size_t)width * height * 4), o_work = take(sizeof(ReduceWork)), o_pose = take(64 * sizeof(float));
     cudaDeviceGetAttribute(&o->num_sms, cudaDevAttrMultiProcessorCount, 0);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&o->num_sms, cudaDevAttrMultiProcessorCount, dev); }
     if (o->num_sms <= 0) o->num_sms = kNumSMs;
-    const size_t o_tpp = take((size_t)2 * o->num_sms * 64 * sizeof(float)), o_tpi = take((size_t)2 * o->num_sms * 2 * sizeof(int)), o_tpb = take(256);
+    const size_t o_tpp = take((size_t)2 * o->num_sms * 64 * sizeof(unsigned long long)), o_tpi = take((size_t)2 * o->num_sms * kIntStride * sizeof(unsigned long long));
     if (cudaMalloc(&o->slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); delete o; return HRBF_ERR_CUDA; }
     cudaMemset(o->slab, 0, off);
     for (int l = 0; l < 3; ++l) {
@@ -434,12 +446,12 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
         o->depth_tmp[l] = (float*)(o->slab + o_dt[l]); o->lastDepth[l] = (float*)(o->slab + o_ld[l]); o->nextDepth[l] = (float*)(o->slab + o_nd[l]);
         o->lastImage[l] = (unsigned char*)(o->slab + o_li[l]); o->nextImage[l] = (unsigned char*)(o->slab + o_ni[l]); o->lastNextImage[l] = (unsigned char*)(o->slab + o_lni[l]);
         o->dIdx[l] = (short*)(o->slab + o_dx[l]); o->dIdy[l] = (short*)(o->slab + o_dy[l]);
-        o->cloud[l] = (float*)(o->slab + o_cl[l]); o->corresImg[l] = (hrbf_dataterm*)(o->slab + o_ci[l]);
+        o->cloud[l] = (float*)(o->slab + o_cl[l]); o->corresImg[l] = (hrbf_dataterm*)(o->slab + o_ci[l]); o->cand[l] = (unsigned char*)(o->slab + o_cd[l]);
     }
     o->vdepth_tmp = (float*)(o->slab + o_vd);
     o->work = (ReduceWork*)(o->slab + o_work);
     o->pose_scratch = (float*)(o->slab + o_pose);
-    o->tp_partials = (float*)(o->slab + o_tpp); o->tp_ipartials = (int*)(o->slab + o_tpi); o->tp_barrier = (unsigned int*)(o->slab + o_tpb);
+    o->tp_ll_f = (unsigned long long*)(o->slab + o_tpp); o->tp_ll_i = (unsigned long long*)(o->slab + o_tpi);      // zeroed with the slab: tag 0 never matches
     cudaMallocHost(&o->h_pose, 24 * sizeof(float));
     cudaMallocHost(&o->h_state, sizeof(TrackState));
     cudaMallocHost(&o->h_model_pose, 8 * 12 * sizeof(float));

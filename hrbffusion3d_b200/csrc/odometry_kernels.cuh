@@ -522,6 +522,30 @@ struct RgbResArgs {
     int rows, cols;
 };
 
+// The pose-independent tests of computeRgbResidual (reduce.cu:1000-1023) for pixel k: inside the processed region, no
+// zero pixel of the next image in the 4x4 window (:1005-1011), gradient magnitude^2 >= minScale, next depth not NaN.
+// All loads are issued up front (clamped addresses, out-of-window taps ignored) instead of a short-circuit chain.
+__device__ __forceinline__ bool rgb_static_candidate(const RgbResArgs& a, int k, short valx, short valy)
+{
+    const int cols = a.cols, rows = a.rows;
+    const int i = k / cols, j0 = k - i * cols;
+    if (!(j0 < cols - 5 && i < rows - 1)) return false;
+    unsigned int zero_seen = 0;
+#pragma unroll
+    for (int du = -2; du < 2; ++du)
+#pragma unroll
+        for (int dv = -2; dv < 2; ++dv) {
+            const int u = i + du, v = j0 + dv;
+            const bool in = u >= 0 && u < rows && v >= 0 && v < cols;
+            const unsigned char px = __ldg(a.nextImage + (size_t)min(max(u, 0), rows - 1) * cols + min(max(v, 0), cols - 1));
+            zero_seen |= (in && px == 0) ? 1u : 0u;
+        }
+    if (zero_seen != 0) return false;
+    const float mTwo = (float)((valx * valx) + (valy * valy));
+    if (!(mTwo >= a.minScale)) return false;
+    return !isnan(__ldg(a.nextDepth + k));
+}
+
 // one pixel of computeRgbResidual (reduce.cu:986-1060); s_k = krkinv[9], kt[3]
 __device__ __forceinline__ void rgb_residual_pixel(const RgbResArgs& a, const float* s_k, int k, int& cnt, int& sig)
 {
@@ -529,47 +553,25 @@ __device__ __forceinline__ void rgb_residual_pixel(const RgbResArgs& a, const fl
     const int i = k / cols, j0 = k - i * cols;
     hrbf_dataterm c;
     c.zero_x = c.zero_y = c.one_x = c.one_y = 0; c.diff = 0.f; c.valid = 0; c.pad[0] = c.pad[1] = c.pad[2] = 0;
-    if (j0 < cols - 5 && i < rows - 1) {
-        // 4x4 "not an isolated pixel" test (reduce.cu:1005-1011); all loads issued up front
-        // (clamped addresses, out-of-window taps ignored) instead of a short-circuit chain
-        unsigned int zero_seen = 0;
-#pragma unroll
-        for (int du = -2; du < 2; ++du)
-#pragma unroll
-            for (int dv = -2; dv < 2; ++dv) {
-                const int u = i + du, v = j0 + dv;
-                const bool in = u >= 0 && u < rows && v >= 0 && v < cols;
-                const unsigned char px = __ldg(a.nextImage + (size_t)min(max(u, 0), rows - 1) * cols + min(max(v, 0), cols - 1));
-                zero_seen |= (in && px == 0) ? 1u : 0u;
-            }
-        const bool valid = zero_seen == 0;
-        if (valid) {
-            const short valx = __ldg(a.dIdx + k), valy = __ldg(a.dIdy + k);
-            const float mTwo = (float)((valx * valx) + (valy * valy));
-            if (mTwo >= a.minScale) {
-                const int y = i, x = j0;
-                const float d1 = __ldg(a.nextDepth + k);
-                if (!isnan(d1)) {
-                    const float td1 = d1 * (s_k[6] * x + s_k[7] * y + s_k[8]) + s_k[11];
-                    const int u0 = __float2int_rn((d1 * (s_k[0] * x + s_k[1] * y + s_k[2]) + s_k[9]) / td1);
-                    const int v0 = __float2int_rn((d1 * (s_k[3] * x + s_k[4] * y + s_k[5]) + s_k[10]) / td1);
-                    if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
-                        const float d0 = __ldg(a.lastDepth + (size_t)v0 * cols + u0);
-                        const unsigned char li = __ldg(a.lastImage + (size_t)v0 * cols + u0);
-                        if (d0 > 0 && fabsf(td1 - d0) <= a.maxDepthDelta && li != 0) {
-                            c.zero_x = (short)u0; c.zero_y = (short)v0; c.one_x = (short)x; c.one_y = (short)y;
-                            c.diff = (float)__ldg(a.nextImage + k) - (float)li;
-                            c.valid = 1;
-                            cnt += 1;
-                            sig += (int)(c.diff * c.diff);
-                        }
-                    }
-                }
+    if (rgb_static_candidate(a, k, __ldg(a.dIdx + k), __ldg(a.dIdy + k))) {
+        const int y = i, x = j0;
+        const float d1 = __ldg(a.nextDepth + k);
+        const float td1 = d1 * (s_k[6] * x + s_k[7] * y + s_k[8]) + s_k[11];
+        const int u0 = __float2int_rn((d1 * (s_k[0] * x + s_k[1] * y + s_k[2]) + s_k[9]) / td1);
+        const int v0 = __float2int_rn((d1 * (s_k[3] * x + s_k[4] * y + s_k[5]) + s_k[10]) / td1);
+        if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+            const float d0 = __ldg(a.lastDepth + (size_t)v0 * cols + u0);
+            const unsigned char li = __ldg(a.lastImage + (size_t)v0 * cols + u0);
+            if (d0 > 0 && fabsf(td1 - d0) <= a.maxDepthDelta && li != 0) {
+                c.zero_x = (short)u0; c.zero_y = (short)v0; c.one_x = (short)x; c.one_y = (short)y;
+                c.diff = (float)__ldg(a.nextImage + k) - (float)li;
+                c.valid = 1;
+                cnt += 1;
+                sig += (int)(c.diff * c.diff);
             }
         }
     }
     a.corres[k] = c;
-
 }
 
 // reduce.cu:986-1060; the int2 {count, sum diff^2} goes through redux + one atomic per warp.

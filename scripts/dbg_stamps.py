@@ -13,6 +13,7 @@ go.initFirstRGB(d0["rgba"])
 go.initICPModel(d0["vertex"], d0["normal"], 20.0, pose0); go.initRGBModel(d0["rgba"]); go.initCurvatureModel(d0["k1"], d0["k2"], pose0)
 go.initICP(d1["vertex"], d1["normal"], 20.0); go.initRGB(d1["rgba"]); go.initCurvature(d1["k1"], d1["k2"]); go.initICPweight(d0["icpw"])
 buf = (C.c_longlong * 512)()
+
 check(lib().hrbf_odometry_debug_stamps(go._h, buf, 512))
 for kw in (dict(icpWeight=100.0, so3=False), dict(icpWeight=10.0, so3=True)):
     for _ in range(3): go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **kw)
@@ -20,7 +21,7 @@ for kw in (dict(icpWeight=100.0, so3=False), dict(icpWeight=10.0, so3=True)):
     a = np.array(buf[:], dtype=np.int64); a = a[a != 0]
     slot = (a >> 56).astype(int); t = (a & ((1 << 56) - 1)).astype(np.int64)
     print(kw, "stamps", len(a), "total us", (t[-1] - t[0]) / 1e3)
-    names = {2: "icp pass", 3: "block reduce", 4: "rest(rgb step)+grid barrier", 5: "all-reduce", 6: "solve", 1: "residual phase / loop overhead"}
+    names = {2: "icp pass", 3: "block reduce", 4: "block reduce (rgb) / none", 5: "all-reduce", 6: "solve", 1: "loop overhead", 7: "residual pass", 8: "cta int reduce + publish", 9: "int all-reduce (wait for all CTAs)", 10: "sigma", 11: "step pass"}
     agg = {}
     for i in range(1, len(a)):
         agg.setdefault((slot[i - 1], slot[i]), []).append((t[i] - t[i - 1]) / 1e3)
