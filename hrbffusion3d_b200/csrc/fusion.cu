@@ -505,15 +505,20 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
         HRBF_CUDA(cudaMemcpyAsync(lastPose, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         should_fill_kernel<<<1, 256, 0, s>>>((const float4*)IT(HRBF_TEX_VERTEX_HRBF), p.frame.height, p.frame.width, p.denseEnoughThresh, shouldFill);
         HRBF_KERNEL_CHECK();
-        if (int rc = odom_init_icp_model_dev(F->odom, (const float*)IT(HRBF_TEX_VERTEX_HRBF), (const float*)IT(HRBF_TEX_NORMAL_HRBF),
-                                             (const float*)LT(HRBF_FILL_VERTEX), (const float*)LT(HRBF_FILL_NORMAL), shouldFill, currPose, s)) return rc;
-        if (int rc = odom_init_rgb_model_dev(F->odom, (const unsigned char*)IT(HRBF_TEX_IMAGE_HRBF), (const unsigned char*)LT(HRBF_FILL_IMAGE), shouldFill, s)) return rc;
-        if (int rc = odom_init_curvature_model_dev(F->odom, (const float*)IT(HRBF_TEX_CURVK1_HRBF), (const float*)IT(HRBF_TEX_CURVK2_HRBF),
-                                                   (const float*)LT(HRBF_FILL_CURVK1), (const float*)LT(HRBF_FILL_CURVK2), shouldFill, currPose, s)) return rc;
-        if (int rc = hrbf_odometry_init_icp(F->odom, (const float*)FT(HRBF_FT_VERTEX_FILTERED), (const float*)FT(HRBF_FT_NORMAL), p.maxDepthProcessed, s)) return rc;
-        if (int rc = hrbf_odometry_init_rgb(F->odom, (const unsigned char*)FT(HRBF_FT_RGBA), s)) return rc;
-        if (int rc = hrbf_odometry_init_curvature(F->odom, (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2), s)) return rc;
-        if (int rc = odom_init_icp_weight_dev(F->odom, (const float*)IT(HRBF_TEX_ICPW_HRBF), (const float*)LT(HRBF_FILL_ICPWEIGHT), shouldFill, s)) return rc;
+        {   // the reference's 7 init* calls (HRBFFusion.cpp:1073-1099) as one launch
+            OdomPrepInputs in;
+            in.vm = (const float*)IT(HRBF_TEX_VERTEX_HRBF); in.nm = (const float*)IT(HRBF_TEX_NORMAL_HRBF);
+            in.vm_alt = (const float*)LT(HRBF_FILL_VERTEX); in.nm_alt = (const float*)LT(HRBF_FILL_NORMAL);
+            in.k1m = (const float*)IT(HRBF_TEX_CURVK1_HRBF); in.k2m = (const float*)IT(HRBF_TEX_CURVK2_HRBF);
+            in.k1m_alt = (const float*)LT(HRBF_FILL_CURVK1); in.k2m_alt = (const float*)LT(HRBF_FILL_CURVK2);
+            in.w = (const float*)IT(HRBF_TEX_ICPW_HRBF); in.w_alt = (const float*)LT(HRBF_FILL_ICPWEIGHT);
+            in.rgba_m = (const unsigned char*)IT(HRBF_TEX_IMAGE_HRBF); in.rgba_m_alt = (const unsigned char*)LT(HRBF_FILL_IMAGE);
+            in.vc = (const float*)FT(HRBF_FT_VERTEX_FILTERED); in.nc = (const float*)FT(HRBF_FT_NORMAL);
+            in.k1c = (const float*)FT(HRBF_FT_PRINCIPAL_CURV1); in.k2c = (const float*)FT(HRBF_FT_PRINCIPAL_CURV2);
+            in.rgba_c = (const unsigned char*)FT(HRBF_FT_RGBA);
+            in.sel = shouldFill; in.pose_dev = currPose;
+            if (int rc = odom_prep_all_dev(F->odom, in, s)) return rc;
+        }
         if (int rc = hrbf_odometry_track_async(F->odom, lastPose, currPose, p.rgbOnly, p.icpWeight, p.pyramid, p.fastOdom, p.so3, p.weightedICP, s)) return rc;
         velocity_weighting_kernel<<<1, 32, 0, s>>>(currPose, lastPose, weightMultiplier, weighting);
         HRBF_KERNEL_CHECK();

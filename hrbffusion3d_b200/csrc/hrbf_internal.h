@@ -79,4 +79,17 @@ int odom_init_curvature_model_dev(hrbf_odometry* o, const float* k1, const float
                                   const float* pose_dev, cudaStream_t s);
 int odom_init_icp_weight_dev(hrbf_odometry* o, const float* w, const float* w_alt, const int* sel, cudaStream_t s);
 int odom_init_rgb_model_dev(hrbf_odometry* o, const unsigned char* rgba, const unsigned char* rgba_alt, const int* sel, cudaStream_t s);
+// all seven init* calls of one frame (initICPModel, initRGBModel, initCurvatureModel, initICP, initRGB, initCurvature,
+// initICPweight; HRBFFusion.cpp:1073-1099) as ONE launch.  Textures as in the single calls; `_alt` = fill-in alternates.
+struct OdomPrepInputs {
+    const float *vm, *nm, *vm_alt, *nm_alt;          // model vertex / normal (RGBA32F)
+    const float *k1m, *k2m, *k1m_alt, *k2m_alt;      // model curvature
+    const float *w, *w_alt;                          // model icp weight (R32F)
+    const unsigned char *rgba_m, *rgba_m_alt;        // model image (RGBA8)
+    const float *vc, *nc, *k1c, *k2c;                // current frame
+    const unsigned char* rgba_c;
+    const int* sel;                                  // device fill-in decision
+    const float* pose_dev;                           // device model pose R[9], t[3]
+};
+int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s);
 }

@@ -149,40 +149,57 @@ inline PredTable make_pred_table()
     return t;
 }
 
-struct Nb { float cx, cy, cz, sx, sy, sz, T2, invT; };   // s = (200 / rho^2) n (the gradient recovers 10 n = s rho^2 / 20)
+// One neighbour as the ray march sees it.  Every sample point lies on the pixel's viewing ray, p(t) = c0 + t r, so with
+// w0 = c0 - c_i:   |p - c_i|^2 / rho_i^2 = a + t (b + t c)      (a = |w0|^2/rho^2, b = 2 w0.r/rho^2, c = |r|^2/rho^2)
+//                  (p - c_i) . s_i        = cs + t ds            (s_i = (200/rho_i^2) n_i, cs = w0.s, ds = r.s)
+// f(p(t)) = -sum_i grad phi_i . (10 n_i) = sum_i (1 - sqrt(u_i))_+^3 (cs_i + t ds_i)   (hrbfbase.glsl:20-34,126-145):
+// 9 instructions per neighbour and evaluation, 5 registers per neighbour (40 for the 8 slots: no spills at 80 registers).
+// An empty slot has a = 4 (outside every support) and contributes exactly 0.
+struct NbRay { float a, b, c, cs, ds; };
 
-__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// f(p) = -sum_i grad phi_i(p - c_i) . (10 n_i) with grad phi = -20 (1-r)^3 (p - c)/rho^2, r = |p - c|/rho  (hrbfbase.glsl:20-34,126-145)
-//      =  sum_i (1-r)^3 (p - c_i) . s_i,  s_i = (200/rho_i^2) n_i  precomputed per neighbour: ~15 instructions per
-// neighbour and evaluation (FMA, sqrt.approx); differs from the shader's operation order by float round-off only.
-
-// hrbfbase.glsl:147-166 (+ getWeightH :37-69)
-__device__ __forceinline__ float3 hrbf_gradient_group(const Nb (&nb)[kPredSlots], int nslots, float px, float py, float pz, unsigned gmask)
+__device__ __forceinline__ float hrbf_ray_value(const NbRay (&nb)[kPredSlots], bool upper_half, float t)
 {
-    float gx = 0.f, gy = 0.f, gz = 0.f;
+    float value = 0.f;
 #pragma unroll
     for (int s = 0; s < kPredSlots; ++s) {
-        if (s < nslots) {
-            const float vx = px - nb[s].cx, vy = py - nb[s].cy, vz = pz - nb[s].cz;
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
-            const float T2 = nb[s].T2;
-            if (d2 > T2) continue;
-            if (d2 == 0.0f) {
-                const float h = -20.0f / T2;
-                gx -= (nb[s].sx * (0.05f * T2)) * h; gy -= (nb[s].sy * (0.05f * T2)) * h; gz -= (nb[s].sz * (0.05f * T2)) * h;
-                continue;
-            }
-            const float r = sqrtf(d2 / T2);
-            const float q = 1.0f - r;
-            const float t1 = 20.0f * (q * q) / (T2 * T2 * r);
-            const float t2 = -r * q * T2;
-            const float h0 = t1 * (3.0f * vx * vx + t2), h1 = t1 * 3.0f * vx * vy, h2 = t1 * 3.0f * vx * vz;
-            const float h4 = t1 * (3.0f * vy * vy + t2), h5 = t1 * 3.0f * vy * vz, h8 = t1 * (3.0f * vz * vz + t2);
-            gx -= (nb[s].sx * (0.05f * T2)) * h0 + (nb[s].sy * (0.05f * T2)) * h1 + (nb[s].sz * (0.05f * T2)) * h2;
-            gy -= (nb[s].sx * (0.05f * T2)) * h1 + (nb[s].sy * (0.05f * T2)) * h4 + (nb[s].sz * (0.05f * T2)) * h5;
-            gz -= (nb[s].sx * (0.05f * T2)) * h2 + (nb[s].sy * (0.05f * T2)) * h5 + (nb[s].sz * (0.05f * T2)) * h8;
+        if (s >= kPredSlots / 2 && !upper_half) break;              // warp-uniform
+        const float u = fmaf(t, fmaf(t, nb[s].c, nb[s].b), nb[s].a);
+        const float q = fmaxf(1.0f - sqrt_approx(u), 0.0f);
+        value = fmaf(q * q * q, fmaf(t, nb[s].ds, nb[s].cs), value);
+    }
+    return value;
+}
+
+// hrbfbase.glsl:147-166 (+ getWeightH :37-69) at point p, over this lane's neighbours (slot s -> s_sel[s * 4 + sub]), summed
+// over the 4 lanes of the pixel.  Runs once per found pixel: the neighbours are re-read from the shared-memory tile.
+template <typename CenterAt>
+__device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots, float px, float py, float pz, unsigned gmask)
+{
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int s = 0; s < nslots; ++s) {
+        float4 v, n;
+        nb_at(s, v, n);
+        const float vx = px - v.x, vy = py - v.y, vz = pz - v.z;
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        const float T2 = __fmul_rn(n.w, n.w);
+        if (d2 > T2) continue;
+        const float nx = 10.0f * n.x, ny = 10.0f * n.y, nz = 10.0f * n.z;
+        if (d2 == 0.0f) {
+            const float h = -20.0f / T2;
+            gx -= nx * h; gy -= ny * h; gz -= nz * h;
+            continue;
         }
+        const float r = sqrtf(d2 / T2);
+        const float q = 1.0f - r;
+        const float t1 = 20.0f * (q * q) / (T2 * T2 * r);
+        const float t2 = -r * q * T2;
+        const float h0 = t1 * (3.0f * vx * vx + t2), h1 = t1 * 3.0f * vx * vy, h2 = t1 * 3.0f * vx * vz;
+        const float h4 = t1 * (3.0f * vy * vy + t2), h5 = t1 * 3.0f * vy * vz, h8 = t1 * (3.0f * vz * vz + t2);
+        gx -= nx * h0 + ny * h1 + nz * h2;
+        gy -= nx * h1 + ny * h4 + nz * h5;
+        gz -= nx * h2 + ny * h5 + nz * h8;
     }
     gx += __shfl_xor_sync(gmask, gx, 1); gy += __shfl_xor_sync(gmask, gy, 1); gz += __shfl_xor_sync(gmask, gz, 1);
     gx += __shfl_xor_sync(gmask, gx, 2); gy += __shfl_xor_sync(gmask, gy, 2); gz += __shfl_xor_sync(gmask, gz, 2);
@@ -250,120 +267,119 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     if (N > 32) N = 32;                                 // cannot happen for maxN <= 16, win <= 3 (host-checked)
     __syncwarp(gmask);
 
-    Nb nb[kPredSlots];
     const int nslots = (N - sub + kPredLanes - 1) / kPredLanes;       // slots s with s*4+sub < N
-#pragma unroll
-    for (int s = 0; s < kPredSlots; ++s) {
-        nb[s].cx = nb[s].cy = nb[s].cz = nb[s].sx = nb[s].sy = nb[s].sz = 0.f; nb[s].T2 = -1.f; nb[s].invT = 0.f;
-        if (s < nslots) {
-            const int c = s_sel[grp][s * kPredLanes + sub];
-            const float4 v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
-            const float4 n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
-            nb[s].cx = v.x; nb[s].cy = v.y; nb[s].cz = v.z;
-            nb[s].T2 = __fmul_rn(n.w, n.w);
-            nb[s].invT = 1.0f / n.w;
-            const float k = 200.0f / nb[s].T2;
-            nb[s].sx = k * n.x; nb[s].sy = k * n.y; nb[s].sz = k * n.z;
-        }
-    }
+    auto nb_at = [&](int sl, float4& v, float4& n) {
+        const int c = s_sel[grp][sl * kPredLanes + sub];
+        v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
+        n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
+    };
 
     // ---- viewing ray through the pixel centre (:42-50) ----
     const float xl = ((float)px + 0.5f - a.cx) * a.icx, yl = ((float)py + 0.5f - a.cy) * a.icy;
     const float rl = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xl, xl), __fmul_rn(yl, yl)), 1.0f));
     const float rx = xl / rl, ry = yl / rl, rz = 1.0f / rl;
+    const float rr = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 
     // closest projection onto the ray (:134-142)
     float projmin = 1000000.0f;
-#pragma unroll
-    for (int s = 0; s < kPredSlots; ++s)
-        if (s < nslots) {
-            const float pj = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(nb[s].cx, rx), __fmul_rn(nb[s].cy, ry)), __fmul_rn(nb[s].cz, rz)));
-            projmin = fminf(projmin, pj);
-        }
+    for (int sl = 0; sl < nslots; ++sl) {
+        float4 v, n;
+        nb_at(sl, v, n);
+        const float pj = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(v.x, rx), __fmul_rn(v.y, ry)), __fmul_rn(v.z, rz)));
+        projmin = fminf(projmin, pj);
+    }
     projmin = fminf(projmin, __shfl_xor_sync(gmask, projmin, 1));
     projmin = fminf(projmin, __shfl_xor_sync(gmask, projmin, 2));
     const float c0x = projmin * rx, c0y = projmin * ry, c0z = projmin * rz;
 
-    // ---- interval search + bisection (:152-270) as ONE warp-convergent state machine ----
+    // per-neighbour ray coefficients (registers)
+    NbRay nb[kPredSlots];
+    int cnt0 = 0;                                        // neighbours whose support contains the start point c0 (:152-157)
+#pragma unroll
+    for (int sl = 0; sl < kPredSlots; ++sl) {
+        nb[sl].a = 4.0f; nb[sl].b = nb[sl].c = nb[sl].cs = nb[sl].ds = 0.f;
+        if (sl < nslots) {
+            float4 v, n;
+            nb_at(sl, v, n);
+            const float T2 = __fmul_rn(n.w, n.w), iT2 = 1.0f / T2;
+            const float wx = c0x - v.x, wy = c0y - v.y, wz = c0z - v.z;
+            const float d2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+            const float k = 200.0f * iT2;
+            nb[sl].a = d2 * iT2;
+            nb[sl].b = 2.0f * fmaf(wz, rz, fmaf(wy, ry, wx * rx)) * iT2;
+            nb[sl].c = rr * iT2;
+            nb[sl].cs = k * fmaf(wz, n.z, fmaf(wy, n.y, wx * n.x));
+            nb[sl].ds = k * fmaf(rz, n.z, fmaf(ry, n.y, rx * n.x));
+            cnt0 += !(T2 < d2) ? 1 : 0;
+        }
+    }
+
+    // ---- interval search + bisection (:152-270) as ONE warp-convergent state machine over the ray parameter t ----
     // The shader runs three data-dependent loops in sequence (coarse march of 4 mm steps, fine march of 0.4 mm steps
     // back, bisection); run as written, a warp pays the SUM of its pixels' worst trip counts with ~60 % of the lanes
-    // idle.  Here every lane evaluates f once per iteration at the point its pixel's state asks for, so a warp pays
-    // the MAXIMUM of its pixels' total evaluation counts and the evaluation itself is executed convergently.
-    enum { ST_FIRST = 0, ST_COARSE, ST_FINE, ST_BISECT, ST_DONE };
+    // idle.  Here every lane evaluates f once per iteration at the t its pixel's state asks for, so a warp pays the
+    // MAXIMUM of its pixels' total evaluation counts and the evaluation itself is executed convergently.
+    enum { ST_COARSE = 0, ST_FINE, ST_BISECT, ST_DONE };
     int nmax = nslots;                                   // warp-uniform slot bound
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, m));
-    int state = (inside && N > a.minN) ? ST_FIRST : ST_DONE;
+    const bool upper_half = nmax > kPredSlots / 2;
+    // the first evaluation, at the start point itself (every pixel with enough neighbours does exactly this one)
+    float v0 = hrbf_ray_value(nb, upper_half, 0.0f);
+    v0 += __shfl_xor_sync(0xffffffffu, v0, 1); cnt0 += __shfl_xor_sync(0xffffffffu, cnt0, 1);
+    v0 += __shfl_xor_sync(0xffffffffu, v0, 2); cnt0 += __shfl_xor_sync(0xffffffffu, cnt0, 2);
+    const float dir = v0 > 0.f ? -1.0f : 1.0f;           // v0 > 0: search backward for f < 0; else forward for f > 0
+    // i = 0 of the shader's coarse march re-evaluates the start point: never a sign change, skipped
+    int state = (inside && N > a.minN && cnt0 > a.minN) ? ST_COARSE : ST_DONE;
     int step = 1, bis = 0;
-    float v0 = 0.f, dir = 1.f;
-    float bx = 0.f, by = 0.f, bz = 0.f;                  // anchor of the fine march
-    float sx_ = 0.f, sy_ = 0.f, sz_ = 0.f, ex_ = 0.f, ey_ = 0.f, ez_ = 0.f;   // starting / ending point of the bisection
-    float tx = 0.f, ty = 0.f, tz = 0.f;                  // p_temp
+    float tb = 0.f;                                      // anchor of the fine march
+    float ts = 0.f, te = 0.f, tm = 0.f;                  // starting / ending point of the bisection, last midpoint (p_temp)
     bool found = false;
     while (__any_sync(0xffffffffu, state != ST_DONE)) {
-        // 1. the sample point this pixel's state asks for
-        float qx = c0x, qy = c0y, qz = c0z;
-        if (state == ST_COARSE) { const float tt = 0.004f * (float)step * dir; qx = c0x + tt * rx; qy = c0y + tt * ry; qz = c0z + tt * rz; }
-        else if (state == ST_FINE) { const float tt = -0.0004f * (float)step * dir; qx = bx + tt * rx; qy = by + tt * ry; qz = bz + tt * rz; }
+        // 1. the ray parameter this pixel's state asks for
+        float t = 0.f;
+        if (state == ST_COARSE) t = 0.004f * (float)step * dir;
+        else if (state == ST_FINE) t = tb - 0.0004f * (float)step * dir;
         else if (state == ST_BISECT) {
-            const float dx = ex_ - sx_, dy = ey_ - sy_, dz = ez_ - sz_;
-            if (sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))) < 0.00001f) { found = true; state = ST_DONE; }
-            else { tx = sx_ + 0.5f * dx; ty = sy_ + 0.5f * dy; tz = sz_ + 0.5f * dz; qx = tx; qy = ty; qz = tz; }
+            if (fabsf(te - ts) < 0.00001f) { found = true; state = ST_DONE; }
+            else { tm = ts + 0.5f * (te - ts); t = tm; }
         }
-        // 2. f(q) = sum over this lane's neighbours, reduced over the 4 lanes of the pixel (hrbfbase.glsl:126-145)
-        float value = 0.f;
-        int cnt = 0;
-#pragma unroll
-        for (int s = 0; s < kPredSlots; ++s) {
-            if (s < nmax) {                              // warp-uniform; empty slots have T2 = -1 and contribute 0
-                const float vx = qx - nb[s].cx, vy = qy - nb[s].cy, vz = qz - nb[s].cz;
-                const float d2 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
-                const bool in = !(nb[s].T2 < d2);
-                const float q = 1.0f - sqrt_approx(d2) * nb[s].invT;
-                const float w = in ? q * q * q : 0.f;
-                value = fmaf(w, fmaf(vz, nb[s].sz, fmaf(vy, nb[s].sy, vx * nb[s].sx)), value);
-                cnt += in ? 1 : 0;
-            }
-        }
-        value += __shfl_xor_sync(0xffffffffu, value, 1); cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-        value += __shfl_xor_sync(0xffffffffu, value, 2); cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        // 2. f(c0 + t r): this lane's neighbours, reduced over the 4 lanes of the pixel
+        float value = hrbf_ray_value(nb, upper_half, t);
+        value += __shfl_xor_sync(0xffffffffu, value, 1);
+        value += __shfl_xor_sync(0xffffffffu, value, 2);
         // 3. state transition
-        if (state == ST_FIRST) {
-            v0 = value;
-            dir = v0 > 0.f ? -1.0f : 1.0f;               // v0 > 0: search backward for f < 0; else forward for f > 0
-            state = (cnt > a.minN) ? ST_COARSE : ST_DONE; // i = 0 of the coarse march re-evaluates this point: never a sign change
-            step = 1;
-        } else if (state == ST_COARSE) {
-            if (v0 > 0.f ? (value < 0.f) : (value > 0.f)) { bx = qx; by = qy; bz = qz; state = ST_FINE; step = 1; }
+        if (state == ST_COARSE) {
+            if (v0 > 0.f ? (value < 0.f) : (value > 0.f)) { tb = t; state = ST_FINE; step = 1; }
             else if (++step >= 25) state = ST_DONE;
         } else if (state == ST_FINE) {
             if (v0 > 0.f ? (value > 0.f) : (value < 0.f)) {
-                if (v0 > 0.f) { sx_ = bx; sy_ = by; sz_ = bz; ex_ = qx; ey_ = qy; ez_ = qz; }
-                else { ex_ = bx; ey_ = by; ez_ = bz; sx_ = qx; sy_ = qy; sz_ = qz; }
+                if (v0 > 0.f) { ts = tb; te = t; } else { te = tb; ts = t; }
                 state = ST_BISECT; bis = 0;
             } else if (++step >= 11) state = ST_DONE;
         } else if (state == ST_BISECT) {
             if (fabsf(value) < 0.00001f) { found = true; state = ST_DONE; }
             else {
-                if (value < 0.f) { sx_ = tx; sy_ = ty; sz_ = tz; } else { ex_ = tx; ey_ = ty; ez_ = tz; }
+                if (value < 0.f) ts = tm; else te = tm;
                 if (++bis >= 10) state = ST_DONE;
             }
         }
     }
+    const float tx = fmaf(tm, rx, c0x), ty = fmaf(tm, ry, c0y), tz = fmaf(tm, rz, c0z);
     float3 g = make_float3(0.f, 0.f, 0.f);
-    if (found) g = hrbf_gradient_group(nb, nslots, tx, ty, tz, gmask);
+    if (found) g = hrbf_gradient_group(nb_at, nslots, tx, ty, tz, gmask);
 
     // ---- attributes of the nearest neighbour (:273-303) ----
     float best = 1000000.f;
     int besti = 0x7fffffff;
     if (found) {
-#pragma unroll
-        for (int s = 0; s < kPredSlots; ++s)
-            if (s < nslots) {
-                const float dx = tx - nb[s].cx, dy = ty - nb[s].cy, dz = tz - nb[s].cz;
-                const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-                if (d < best) { best = d; besti = s * kPredLanes + sub; }
-            }
+        for (int s = 0; s < nslots; ++s) {
+            float4 v, n;
+            nb_at(s, v, n);
+            const float dx = tx - v.x, dy = ty - v.y, dz = tz - v.z;
+            const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            if (d < best) { best = d; besti = s * kPredLanes + sub; }
+        }
 #pragma unroll
         for (int m = 1; m <= 2; m <<= 1) {
             const float ob = __shfl_xor_sync(gmask, best, m);

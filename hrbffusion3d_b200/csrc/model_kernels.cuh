@@ -231,14 +231,23 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
     int counter = 0;
     float bestDist = 1000;
     unsigned int best = 0;
+    size_t qs[16];
+    unsigned int cur[16];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const float ox = -1.0f + 0.5f * (float)a, oy = -1.0f + 0.5f * (float)b;
             const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
-            const size_t q = (size_t)sy * W + sx;
-            const unsigned int current = __ldg(f.index + q);
+            qs[a * 4 + b] = (size_t)sy * W + sx;
+            cur[a * 4 + b] = __ldg(f.index + qs[a * 4 + b]);
+        }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const size_t q = qs[a * 4 + b];
+            const unsigned int current = cur[a * 4 + b];
             if (current > 0u) {
                 const float4 vc = __ldg(f.vertConf + q);
                 if (fabsf((vc.z * lambda) - (vloc.z * lambda)) < 0.05f) {
@@ -314,19 +323,40 @@ __device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& 
     const int kf = (sub >= 0.0f && sub < (float)c.kf_dim) ? (int)sub : -1;
     const float active = kf >= 0 ? __ldg(c.active_kf + kf) : 0.0f;
     if (lp.z < m.maxDepth && lp.z > 0 && x > 0 && y > 0 && x < (float)W && y < (float)H) {
-        const int ns = 2 * m.cleanWindow;
-        for (int a = 0; a < ns; ++a)
-            for (int b = 0; b < ns; ++b) {
-                const float ox = 0.5f * (float)(a - m.cleanWindow), oy = 0.5f * (float)(b - m.cleanWindow);
-                const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
-                const size_t q = (size_t)sy * W + sx;
-                if (__ldg(c.index + q) > 0u) {
-                    const float4 vc = __ldg(c.vertConf + q), ct = __ldg(c.colorTime + q);
-                    const float dx = vc.x - lp.x, dy = vc.y - lp.y;
-                    if (ct.z < rec[1].z && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z < 0.01f && sqrtf(dx * dx + dy * dy) < rec[2].w * 1.4f) count++;
-                    if (ct.w == (float)c.time && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z > 0.01f && fabsf(lnz) > 0.85f && active > 0.0f) zCount++;
-                }
+        auto sample = [&](unsigned int idx, size_t q) {
+            if (idx > 0u) {
+                const float4 vc = __ldg(c.vertConf + q), ct = __ldg(c.colorTime + q);
+                const float dx = vc.x - lp.x, dy = vc.y - lp.y;
+                if (ct.z < rec[1].z && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z < 0.01f && sqrtf(dx * dx + dy * dy) < rec[2].w * 1.4f) count++;
+                if (ct.w == (float)c.time && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z > 0.01f && fabsf(lnz) > 0.85f && active > 0.0f) zCount++;
             }
+        };
+        if (m.cleanWindow == 2) {
+            // the reference default: 4 x 4 half-pixel offsets.  All 16 index loads are issued before the first dependent
+            // texture read (the rolled loop below serialises 32 L2 round trips per surfel).
+            size_t q[16];
+            unsigned int idx[16];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float ox = 0.5f * (float)(a - 2), oy = 0.5f * (float)(b - 2);
+                    const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
+                    q[a * 4 + b] = (size_t)sy * W + sx;
+                    idx[a * 4 + b] = __ldg(c.index + q[a * 4 + b]);
+                }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sample(idx[k], q[k]);
+        } else {
+            const int ns = 2 * m.cleanWindow;
+            for (int a = 0; a < ns; ++a)
+                for (int b = 0; b < ns; ++b) {
+                    const float ox = 0.5f * (float)(a - m.cleanWindow), oy = 0.5f * (float)(b - m.cleanWindow);
+                    const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
+                    const size_t q = (size_t)sy * W + sx;
+                    sample(__ldg(c.index + q), q);
+                }
+        }
     }
     if (rec[3].w < -m.curvThr || rec[3].w > m.curvThr || rec[4].w < -m.curvThr || rec[4].w > m.curvThr) test = false;
     if (count > 8 || zCount > 4) test = false;

@@ -553,6 +553,33 @@ int odom_init_curvature_model_dev(hrbf_odometry* o, const float* k1, const float
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }
+int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s)
+{
+    PrepAllArgs A;
+    A.rows = o->height; A.cols = o->width; A.sel = in.sel; A.pose = in.pose_dev; A.curv_thr = o->curvThr; A.depth_cutoff = o->maxDepthRGB;
+    A.vm = (const float4*)in.vm; A.nm = (const float4*)in.nm; A.vm_alt = (const float4*)in.vm_alt; A.nm_alt = (const float4*)in.nm_alt;
+    A.vc = (const float4*)in.vc; A.nc = (const float4*)in.nc;
+    A.k1m = (const float4*)in.k1m; A.k2m = (const float4*)in.k2m; A.k1m_alt = (const float4*)in.k1m_alt; A.k2m_alt = (const float4*)in.k2m_alt;
+    A.k1c = (const float4*)in.k1c; A.k2c = (const float4*)in.k2c;
+    A.w = in.w; A.w_alt = in.w_alt;
+    A.o_vg = pyr_out(o, M_VG); A.o_ng = pyr_out(o, M_NG); A.o_vc = pyr_out(o, M_VC); A.o_nc = pyr_out(o, M_NC);
+    A.o_k1g = pyr_out(o, M_K1G); A.o_k2g = pyr_out(o, M_K2G); A.o_k1c = pyr_out(o, M_K1C); A.o_k2c = pyr_out(o, M_K2C);
+    for (int l = 0; l < 3; ++l) { A.o_w[l] = o->maps[M_W][l]; A.w_pitch[l] = o->cols(l); }
+    A.rgbd[0].rgba = (const uchar4*)in.rgba_m; A.rgbd[0].rgba_alt = (const uchar4*)in.rgba_m_alt;
+    A.rgbd[0].vertex = (const float4*)in.vm; A.rgbd[0].vertex_alt = (const float4*)in.vm_alt;
+    A.rgbd[1].rgba = (const uchar4*)in.rgba_c; A.rgbd[1].rgba_alt = nullptr;
+    A.rgbd[1].vertex = (const float4*)in.vc; A.rgbd[1].vertex_alt = nullptr;
+    for (int l = 0; l < 3; ++l) {
+        A.rgbd[0].img[l] = o->lastImage[l]; A.rgbd[0].depth[l] = o->lastDepth[l];
+        A.rgbd[1].img[l] = o->nextImage[l]; A.rgbd[1].depth[l] = o->nextDepth[l];
+    }
+    A.pyr_bx = div_up(o->width, 32); A.pyr_by = div_up(o->height, 8);
+    A.rgbd_bx = div_up(o->cols(2), 8); A.rgbd_by = div_up(o->rows(2), 8);
+    const int blocks = 5 * A.pyr_bx * A.pyr_by + 2 * A.rgbd_bx * A.rgbd_by;
+    prep_all_kernel<<<blocks, 256, 0, s>>>(A);
+    HRBF_KERNEL_CHECK();
+    return HRBF_OK;
+}
 int odom_init_icp_weight_dev(hrbf_odometry* o, const float* w, const float* w_alt, const int* sel, cudaStream_t s)
 {
     pyr_weight_kernel<<<pyr_grid(o), 256, 0, s>>>(w, o->height, o->width, o->maps[M_W][0], o->cols(0), o->maps[M_W][1], o->cols(1), o->maps[M_W][2], o->cols(2), w_alt, sel);

@@ -37,16 +37,17 @@ __device__ __forceinline__ void store4(float* base, int pitch, int rows, int y, 
 // sel != nullptr && *sel != 0 : read the alternate textures (a_alt, b_alt) instead -- the device-side form of
 //                  `shouldFillIn ? &fillIn.xTexture : indexMap.xTexHRBF()` (HRBFFusion.cpp:1073-1086), no host round trip.
 template <int KIND>
-__global__ void __launch_bounds__(256) pyr_pair_kernel(const float4* __restrict__ a_aos, const float4* __restrict__ b_aos,
-                                                       int rows, int cols, float thr, const float* __restrict__ pose,
-                                                       PyrOut oa, PyrOut ob, float* __restrict__ depth_out, float depth_cutoff,
-                                                       const float4* __restrict__ a_alt, const float4* __restrict__ b_alt, const int* __restrict__ sel)
+__device__ __forceinline__ void pyr_pair_tile(const float4* __restrict__ a_aos, const float4* __restrict__ b_aos,
+                                              int rows, int cols, float thr, const float* __restrict__ pose,
+                                              const PyrOut& oa, const PyrOut& ob, float* __restrict__ depth_out, float depth_cutoff,
+                                              const float4* __restrict__ a_alt, const float4* __restrict__ b_alt, const int* __restrict__ sel,
+                                              int bx, int by)
 {
     if (sel != nullptr && *sel != 0) { a_aos = a_alt; b_aos = b_alt; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
-    const int x = (blockIdx.x * 4 + (warp & 3)) * 8 + lx;
-    const int y = (blockIdx.y * 2 + (warp >> 2)) * 4 + ly;
+    const int x = (bx * 4 + (warp & 3)) * 8 + lx;
+    const int y = (by * 2 + (warp >> 2)) * 4 + ly;
     const bool inb = x < cols && y < rows;
     const float qn = qnan();
 
@@ -123,16 +124,25 @@ __global__ void __launch_bounds__(256) pyr_pair_kernel(const float4* __restrict_
     }
 }
 
+template <int KIND>
+__global__ void __launch_bounds__(256) pyr_pair_kernel(const float4* __restrict__ a_aos, const float4* __restrict__ b_aos,
+                                                       int rows, int cols, float thr, const float* __restrict__ pose,
+                                                       PyrOut oa, PyrOut ob, float* __restrict__ depth_out, float depth_cutoff,
+                                                       const float4* __restrict__ a_alt, const float4* __restrict__ b_alt, const int* __restrict__ sel)
+{
+    pyr_pair_tile<KIND>(a_aos, b_aos, rows, cols, thr, pose, oa, ob, depth_out, depth_cutoff, a_alt, b_alt, sel, blockIdx.x, blockIdx.y);
+}
+
 // icp weight: copy (w>0 else NaN, cudafuncs.cu:464) + 2 resize levels (:718-725)
-__global__ void __launch_bounds__(256) pyr_weight_kernel(const float* __restrict__ w_src, int rows, int cols,
-                                                         float* o0, int p0, float* o1, int p1, float* o2, int p2,
-                                                         const float* __restrict__ w_alt, const int* __restrict__ sel)
+__device__ __forceinline__ void pyr_weight_tile(const float* __restrict__ w_src, int rows, int cols,
+                                                float* o0, int p0, float* o1, int p1, float* o2, int p2,
+                                                const float* __restrict__ w_alt, const int* __restrict__ sel, int bx, int by)
 {
     if (sel != nullptr && *sel != 0) w_src = w_alt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
-    const int x = (blockIdx.x * 4 + (warp & 3)) * 8 + lx;
-    const int y = (blockIdx.y * 2 + (warp >> 2)) * 4 + ly;
+    const int x = (bx * 4 + (warp & 3)) * 8 + lx;
+    const int y = (by * 2 + (warp >> 2)) * 4 + ly;
     const bool inb = x < cols && y < rows;
     const float qn = qnan();
     float w = qn;
@@ -153,6 +163,13 @@ __global__ void __launch_bounds__(256) pyr_weight_kernel(const float* __restrict
         w = bad ? qn : (w + a + b + c) / 4;
         if (inb && !(lx & 3) && !(ly & 3) && (x >> 2) < (cols >> 2) && (y >> 2) < (rows >> 2)) o2[(size_t)(y >> 2) * p2 + (x >> 2)] = w;
     }
+}
+
+__global__ void __launch_bounds__(256) pyr_weight_kernel(const float* __restrict__ w_src, int rows, int cols,
+                                                         float* o0, int p0, float* o1, int p1, float* o2, int p2,
+                                                         const float* __restrict__ w_alt, const int* __restrict__ sel)
+{
+    pyr_weight_tile(w_src, rows, cols, o0, p0, o1, p1, o2, p2, w_alt, sel, blockIdx.x, blockIdx.y);
 }
 
 // ---- single-function mirrors of the reference's per-map kernels (C-ABI row 5 entry points) ----
@@ -292,36 +309,34 @@ __global__ void create_nmap_kernel(int rows, int cols, const float* __restrict__
 // ---- RGB branch prep: cudafuncs.cu:493-524, 818-848, 898-911, 930-954, 995-1013 ----
 __constant__ float c_gauss25[25] = { 1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1 };
 
-__global__ void pyrdown_gauss_f32_kernel(int srows, int scols, const float* __restrict__ src, float* dst)
+// pyrDownGaussF (cudafuncs.cu:493-524) for destination pixel (x, y); src_at(cx, cy) reads the source level
+template <typename At>
+__device__ __forceinline__ float gauss_down_f32(int srows, int scols, int x, int y, At src_at)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int drows = srows / 2, dcols = scols / 2;
-    if (x >= dcols || y >= drows) return;
     const int D = 5;
     const int tx = min(2 * x - D / 2 + D, scols - 1), ty = min(2 * y - D / 2 + D, srows - 1);
     float sum = 0; int count = 0;
     for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
         for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
-            const float s = src[(size_t)cy * scols + cx];
+            const float s = src_at(cx, cy);
             if (!isnan(s)) {
                 const float g = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
                 sum += s * g;
                 count = (int)((float)count + g);
             }
         }
-    dst[(size_t)y * dcols + x] = sum / (float)count;
+    return sum / (float)count;
 }
-__global__ void pyrdown_gauss_u8_kernel(int srows, int scols, const unsigned char* __restrict__ src, unsigned char* dst)
+// pyrDownUcharGauss (cudafuncs.cu:818-848)
+template <typename At>
+__device__ __forceinline__ unsigned char gauss_down_u8(int srows, int scols, int x, int y, At src_at)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int drows = srows / 2, dcols = scols / 2;
-    if (x >= dcols || y >= drows) return;
     const int D = 5;
     const int tx = min(2 * x - D / 2 + D, scols - 1), ty = min(2 * y - D / 2 + D, srows - 1);
     float sum = 0; int count = 0;
     for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
         for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
-            const unsigned char s = src[(size_t)cy * scols + cx];
+            const unsigned char s = src_at(cx, cy);
             if (s > 0) {
                 const float g = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
                 sum += (float)s * g;
@@ -329,7 +344,26 @@ __global__ void pyrdown_gauss_u8_kernel(int srows, int scols, const unsigned cha
             }
         }
     const float r = sum / (float)count;
-    dst[(size_t)y * dcols + x] = isnan(r) ? (unsigned char)0 : (unsigned char)(int)r;
+    return isnan(r) ? (unsigned char)0 : (unsigned char)(int)r;
+}
+__global__ void pyrdown_gauss_f32_kernel(int srows, int scols, const float* __restrict__ src, float* dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int drows = srows / 2, dcols = scols / 2;
+    if (x >= dcols || y >= drows) return;
+    dst[(size_t)y * dcols + x] = gauss_down_f32(srows, scols, x, y, [&](int cx, int cy) { return src[(size_t)cy * scols + cx]; });
+}
+__global__ void pyrdown_gauss_u8_kernel(int srows, int scols, const unsigned char* __restrict__ src, unsigned char* dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int drows = srows / 2, dcols = scols / 2;
+    if (x >= dcols || y >= drows) return;
+    dst[(size_t)y * dcols + x] = gauss_down_u8(srows, scols, x, y, [&](int cx, int cy) { return src[(size_t)cy * scols + cx]; });
+}
+// imageBGRToIntensity (cudafuncs.cu:898-911)
+__device__ __forceinline__ unsigned char bgr_intensity(uchar4 s)
+{
+    return (unsigned char)(int)((float)s.x * 0.114f + (float)s.y * 0.299f + (float)s.z * 0.587f);
 }
 __global__ void rgba_to_intensity_kernel(int n, const uchar4* __restrict__ rgba, unsigned char* dst,
                                          const uchar4* __restrict__ rgba_alt, const int* __restrict__ sel)
@@ -337,9 +371,102 @@ __global__ void rgba_to_intensity_kernel(int n, const uchar4* __restrict__ rgba,
     if (sel != nullptr && *sel != 0) rgba = rgba_alt;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uchar4 s = __ldg(rgba + i);
-    const int value = (int)((float)s.x * 0.114f + (float)s.y * 0.299f + (float)s.z * 0.587f);
-    dst[i] = (unsigned char)value;
+    dst[i] = bgr_intensity(__ldg(rgba + i));
+}
+
+// ---- the whole per-frame map preparation of RGBDOdometry in ONE launch (the fused frame pipeline's replacement of the
+// 7 init* calls = 17 launches: RGBDOdometry.cpp:183-247, 689-794).  blockIdx.x selects a job and a tile:
+//   jobs 0-3 : pyr_pair_tile  (model vertex/normal, current vertex/normal, model curvature, current curvature)
+//   job  4   : pyr_weight_tile
+//   jobs 5-6 : rgbd_pyramid_tile (model = "last", current = "next"): intensity + verticesToDepth + both Gauss pyramids, all
+//              three levels from one 41x41 shared-memory tile (the level-1 / level-2 taps are recomputed per tile
+//              instead of going through HBM with a dependent launch per level)
+struct RgbdJob {
+    const uchar4 *rgba, *rgba_alt;               // image texture (+ fill-in alternate)
+    const float4 *vertex, *vertex_alt;           // vertex texture verticesToDepth reads (cudafuncs.cu:874-885)
+    unsigned char* img[3];
+    float* depth[3];
+};
+struct PrepAllArgs {
+    int rows, cols;
+    const int* sel;                              // device fill-in decision (model jobs only)
+    const float* pose;                           // device model pose R[9], t[3]
+    float curv_thr, depth_cutoff;
+    const float4 *vm, *nm, *vm_alt, *nm_alt, *vc, *nc;              // vertex / normal textures: model (+alt), current
+    const float4 *k1m, *k2m, *k1m_alt, *k2m_alt, *k1c, *k2c;        // curvature textures
+    const float *w, *w_alt;
+    PyrOut o_vg, o_ng, o_vc, o_nc, o_k1g, o_k2g, o_k1c, o_k2c;
+    float* o_w[3]; int w_pitch[3];
+    RgbdJob rgbd[2];                             // [0] model ("last"), [1] current ("next")
+    int pyr_bx, pyr_by, rgbd_bx, rgbd_by;        // tiles per job
+};
+
+constexpr int kRgbdL0 = 41, kRgbdL1 = 19;        // tile edge at level 0 / 1 for an 8x8 level-2 tile
+
+__device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, int cols, float depth_cutoff, bool use_alt, int bx, int by)
+{
+    __shared__ unsigned char s_g0[kRgbdL0][kRgbdL0 + 3];
+    __shared__ float s_d0[kRgbdL0][kRgbdL0];
+    __shared__ unsigned char s_g1[kRgbdL1][kRgbdL1 + 1];
+    __shared__ float s_d1[kRgbdL1][kRgbdL1];
+    const uchar4* rgba = use_alt ? j.rgba_alt : j.rgba;
+    const float4* vert = use_alt ? j.vertex_alt : j.vertex;
+    const int rows1 = rows / 2, cols1 = cols / 2, rows2 = rows1 / 2, cols2 = cols1 / 2;
+    const int X0 = 32 * bx - 6, Y0 = 32 * by - 6;            // level-0 origin of the tile
+    const int X1 = 16 * bx - 2, Y1 = 16 * by - 2;            // level-1 origin
+    const float qn = qnan();
+    for (int t = threadIdx.x; t < kRgbdL0 * kRgbdL0; t += blockDim.x) {
+        const int sy = t / kRgbdL0, sx = t - sy * kRgbdL0;
+        const int gx = X0 + sx, gy = Y0 + sy;
+        if (gx < 0 || gy < 0 || gx >= cols || gy >= rows) continue;
+        const size_t o = (size_t)gy * cols + gx;
+        const unsigned char g = bgr_intensity(__ldg(rgba + o));
+        const float z = __ldg(reinterpret_cast<const float*>(vert + o) + 2);
+        const float d = (z > depth_cutoff || z <= 0.f) ? qn : z;
+        s_g0[sy][sx] = g; s_d0[sy][sx] = d;
+        if (sx >= 6 && sx < 38 && sy >= 6 && sy < 38) { j.img[0][o] = g; j.depth[0][o] = d; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kRgbdL1 * kRgbdL1; t += blockDim.x) {
+        const int sy = t / kRgbdL1, sx = t - sy * kRgbdL1;
+        const int x1 = X1 + sx, y1 = Y1 + sy;
+        if (x1 < 0 || y1 < 0 || x1 >= cols1 || y1 >= rows1) continue;
+        const unsigned char g = gauss_down_u8(rows, cols, x1, y1, [&](int cx, int cy) { return s_g0[cy - Y0][cx - X0]; });
+        const float d = gauss_down_f32(rows, cols, x1, y1, [&](int cx, int cy) { return s_d0[cy - Y0][cx - X0]; });
+        s_g1[sy][sx] = g; s_d1[sy][sx] = d;
+        if (sx >= 2 && sx < 18 && sy >= 2 && sy < 18) { j.img[1][(size_t)y1 * cols1 + x1] = g; j.depth[1][(size_t)y1 * cols1 + x1] = d; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int x2 = 8 * bx + (threadIdx.x & 7), y2 = 8 * by + (threadIdx.x >> 3);
+        if (x2 < cols2 && y2 < rows2) {
+            j.img[2][(size_t)y2 * cols2 + x2] = gauss_down_u8(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_g1[cy - Y1][cx - X1]; });
+            j.depth[2][(size_t)y2 * cols2 + x2] = gauss_down_f32(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_d1[cy - Y1][cx - X1]; });
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
+{
+    const int per_pyr = A.pyr_bx * A.pyr_by, per_rgbd = A.rgbd_bx * A.rgbd_by;
+    int b = blockIdx.x;
+    if (b < 5 * per_pyr) {
+        const int job = b / per_pyr, t = b - job * per_pyr;
+        const int by = t / A.pyr_bx, bx = t - by * A.pyr_bx;
+        switch (job) {
+        case 0: pyr_pair_tile<PYR_VN>(A.vm, A.nm, A.rows, A.cols, 0.f, A.pose, A.o_vg, A.o_ng, nullptr, 0.f, A.vm_alt, A.nm_alt, A.sel, bx, by); break;
+        case 1: pyr_pair_tile<PYR_VN>(A.vc, A.nc, A.rows, A.cols, 0.f, nullptr, A.o_vc, A.o_nc, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
+        case 2: pyr_pair_tile<PYR_K>(A.k1m, A.k2m, A.rows, A.cols, A.curv_thr, A.pose, A.o_k1g, A.o_k2g, nullptr, 0.f, A.k1m_alt, A.k2m_alt, A.sel, bx, by); break;
+        case 3: pyr_pair_tile<PYR_K>(A.k1c, A.k2c, A.rows, A.cols, A.curv_thr, nullptr, A.o_k1c, A.o_k2c, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
+        default: pyr_weight_tile(A.w, A.rows, A.cols, A.o_w[0], A.w_pitch[0], A.o_w[1], A.w_pitch[1], A.o_w[2], A.w_pitch[2], A.w_alt, A.sel, bx, by); break;
+        }
+        return;
+    }
+    b -= 5 * per_pyr;
+    const int job = b / per_rgbd, t = b - job * per_rgbd;
+    const int by = t / A.rgbd_bx, bx = t - by * A.rgbd_bx;
+    const bool use_alt = job == 0 && A.sel != nullptr && *A.sel != 0;
+    rgbd_pyramid_tile(A.rgbd[job], A.rows, A.cols, A.depth_cutoff, use_alt, bx, by);
 }
 __device__ __forceinline__ void sobel_pixel(int rows, int cols, const unsigned char* __restrict__ src, short* dx, short* dy, int x, int y)
 {
