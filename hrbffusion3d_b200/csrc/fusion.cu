@@ -64,6 +64,11 @@ int hrbf_frame_create(hrbf_frame** out, const hrbf_frame_params* p)
     for (int t = 0; t < HRBF_FT_COUNT; ++t) f->tex[t] = f->slab + o[t];
     f->weighting = (float*)(f->slab + o_w);
     cudaMallocHost(&f->h_w, 8 * sizeof(float));
+    {
+        float tab[(2 * kBilR + 1) * (2 * kBilR + 1)];
+        make_bilateral_table(tab);
+        if (cudaMemcpyToSymbol(c_bil_space, tab, sizeof tab) != cudaSuccess) { set_error("frame_create: constant upload failed"); hrbf_frame_destroy(f); return HRBF_ERR_CUDA; }
+    }
     *out = f;
     return HRBF_OK;
 }

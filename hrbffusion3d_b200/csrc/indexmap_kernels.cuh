@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
 {
     __shared__ float4 s_v[kPredSH][kPredSW];
     __shared__ float4 s_n[kPredSH][kPredSW];
-    __shared__ unsigned char s_sel[64][32];
+    __shared__ unsigned char s_sel[64][32];              // per pixel: tile cell (row * kPredSW + col) of each selected neighbour
+    __shared__ PredTable s_tab;                          // the candidate tables: per-lane indices would serialise in the constant cache
+    if (threadIdx.x < sizeof(PredTable)) reinterpret_cast<unsigned char*>(&s_tab)[threadIdx.x] = reinterpret_cast<const unsigned char*>(&c_pred)[threadIdx.x];
 
     const int tx0 = blockIdx.x * kPredTileW, ty0 = blockIdx.y * kPredTileH;
     for (int t = threadIdx.x; t < kPredSH * kPredSW; t += blockDim.x) {
@@ -237,13 +239,14 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     const bool inside = px < a.cols && py < a.rows;     // uniform within the 4-lane group
 
     // ---- neighbour gather (predict_hrbf.frag:74-113) ----
-    const int ncand = c_pred.ring_end[a.win];
+    const int ncand = s_tab.ring_end[a.win];
     unsigned long long valid = 0ull;
     for (int c = sub; c < ncand; c += kPredLanes) {
-        const int qx = px + c_pred.dx[c], qy = py + c_pred.dy[c];
+        const int dx = s_tab.dx[c], dy = s_tab.dy[c];
+        const int qx = px + dx, qy = py + dy;
         if (qx < 0 || qx >= a.cols || qy < 0 || qy >= a.rows) continue;
-        const float4 v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
-        const float4 n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
+        const float4 v = s_v[ly + kPredHalo + dy][lx + kPredHalo + dx];
+        const float4 n = s_n[ly + kPredHalo + dy][lx + kPredHalo + dx];
         const float nl2 = __fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z));     // length < 0.1 <=> length^2 < 0.01
         if (v.z < 0.1f || nl2 < 0.01f || v.w < a.confThr || n.z < 0.0f) continue;
         valid |= 1ull << c;
@@ -256,9 +259,9 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
         int c = 0;
         while (c < ncand) {
             if ((valid >> c) & 1ull) {
-                if (N < 32) s_sel[grp][N] = (unsigned char)c;
+                if (N < 32) s_sel[grp][N] = (unsigned char)((ly + kPredHalo + s_tab.dy[c]) * kPredSW + lx + kPredHalo + s_tab.dx[c]);
                 ++N;
-                if (N > a.maxN) { c = c_pred.next_col[c]; continue; }
+                if (N > a.maxN) { c = s_tab.next_col[c]; continue; }
             }
             ++c;
         }
@@ -269,9 +272,9 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
 
     const int nslots = (N - sub + kPredLanes - 1) / kPredLanes;       // slots s with s*4+sub < N
     auto nb_at = [&](int sl, float4& v, float4& n) {
-        const int c = s_sel[grp][sl * kPredLanes + sub];
-        v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
-        n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
+        const int cell = s_sel[grp][sl * kPredLanes + sub];
+        v = (&s_v[0][0])[cell];
+        n = (&s_n[0][0])[cell];
     };
 
     // ---- viewing ray through the pixel centre (:42-50) ----
@@ -396,11 +399,11 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     unsigned short tstamp = 0;
     float icpw = 0.f;
     if (found && besti < 32) {
-        const int c = s_sel[grp][besti];
-        const int qx = px + c_pred.dx[c], qy = py + c_pred.dy[c];
+        const int cell = s_sel[grp][besti];
+        const int qy = ty0 + cell / kPredSW - kPredHalo, qx = tx0 + cell % kPredSW - kPredHalo;
         const size_t q = (size_t)qy * a.cols + qx;
-        const float4 v = s_v[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
-        const float4 n = s_n[ly + kPredHalo + c_pred.dy[c]][lx + kPredHalo + c_pred.dx[c]];
+        const float4 v = (&s_v[0][0])[cell];
+        const float4 n = (&s_n[0][0])[cell];
         const float4 ct = __ldg(a.colorTime + q);
         kmax = __ldg(a.curvMax + q); kmin = __ldg(a.curvMin + q);
         const int col = (int)ct.x;                                   // color.glsl:27-34

@@ -39,8 +39,40 @@ __device__ __forceinline__ float exp_bilateral(float x)
     return ldexpf(p, (int)n);
 }
 
+// exp_bilateral for the filter loop: same operation sequence, with ldexpf(p, n) done as an exponent add.  n <= 0 here and
+// p is in [0.70, 1.42], so p * 2^n is a normal number for n >= -125; for n = -126 (weights < 1.7e-38, which the oracle
+// produces as denormals) 0 is returned: such a weight cannot change sums that contain the centre tap's weight 1.
+__device__ __forceinline__ float exp_bilateral_fast(float x)
+{
+    const float t = __fmul_rn(x, 1.44269504088896341f);
+    const float n = rintf(t);
+    const float f = __fsub_rn(t, n);
+    float p = 1.54035304e-4f;
+    p = __fadd_rn(__fmul_rn(p, f), 1.33335581e-3f);
+    p = __fadd_rn(__fmul_rn(p, f), 9.61812911e-3f);
+    p = __fadd_rn(__fmul_rn(p, f), 5.55041087e-2f);
+    p = __fadd_rn(__fmul_rn(p, f), 2.40226507e-1f);
+    p = __fadd_rn(__fmul_rn(p, f), 6.93147181e-1f);
+    p = __fadd_rn(__fmul_rn(p, f), 1.0f);
+    const int e = (int)n;
+    return (x > -87.0f && e >= -125) ? __int_as_float(__float_as_int(p) + (e << 23)) : 0.0f;
+}
+
 // ---- depth_bilateral.frag + depth_metric_raw.frag + depth_metric_filtered.frag -------------------------
 constexpr int kBilR = 6, kBilTW = 32, kBilTH = 8;
+// the pose-independent spatial term (dx^2 + dy^2) * 0.024691358f of each of the 13 x 13 taps, rounded like the shader does
+__constant__ float c_bil_space[(2 * kBilR + 1) * (2 * kBilR + 1)];
+inline void make_bilateral_table(float* t)
+{
+    for (int dy = -kBilR; dy <= kBilR; ++dy)
+        for (int dx = -kBilR; dx <= kBilR; ++dx) {
+            const float fx = (float)dx, fy = (float)dy;
+            volatile float a = fx * fx, b = fy * fy;       // volatile: keep the two products and the sum separately rounded
+            volatile float s2 = a + b;
+            volatile float r = s2 * 0.024691358f;
+            t[(dy + kBilR) * (2 * kBilR + 1) + dx + kBilR] = r;
+        }
+}
 __global__ void __launch_bounds__(256) depth_filter_metric_kernel(PrepArgs a, const unsigned short* __restrict__ raw,
                                                                   float* __restrict__ filtered, float* __restrict__ metric, float* __restrict__ metric_filtered)
 {
@@ -63,20 +95,25 @@ __global__ void __launch_bounds__(256) depth_filter_metric_kernel(PrepArgs a, co
     float out = 0.f;
     if (!(value > a.maxD * 1000.0f || value < 300.0f)) {
         if (a.bilateral) {
-            const float ss = 0.024691358f, sc = 0.000555556f;
-            const int cx0 = max(x - kBilR, 0), cx1 = min(x + kBilR + 1, W), cy0 = max(y - kBilR, 0), cy1 = min(y + kBilR + 1, H);
+            // the shader's loops run over the window clamped to the image (row-major); here every lane walks the full
+            // 13 x 13 window in the same order and a tap outside the image gets weight 0 (adds exactly 0 to both sums)
+            const float sc = 0.000555556f;
             float sum1 = 0.f, sum2 = 0.f;
-            for (int cy = cy0; cy < cy1; ++cy)
-                for (int cx = cx0; cx < cx1; ++cx) {
-                    const float tmp = s_t[cy - y0][cx - x0];
-                    const float dx = (float)x - (float)cx, dy = (float)y - (float)cy;
-                    const float space2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            for (int dy = -kBilR; dy <= kBilR; ++dy) {
+                const bool iny = (unsigned)(y + dy) < (unsigned)H;
+                const float* row = &s_t[ly + kBilR + dy][lx];
+                const float* sp = c_bil_space + (dy + kBilR) * (2 * kBilR + 1);
+#pragma unroll
+                for (int dx = -kBilR; dx <= kBilR; ++dx) {
+                    const float tmp = row[kBilR + dx];
                     const float dc = __fsub_rn(value, tmp);
                     const float color2 = __fmul_rn(dc, dc);
-                    const float weight = exp_bilateral(-__fadd_rn(__fmul_rn(space2, ss), __fmul_rn(color2, sc)));
+                    float weight = exp_bilateral_fast(-__fadd_rn(sp[dx + kBilR], __fmul_rn(color2, sc)));
+                    if (!(iny && (unsigned)(x + dx) < (unsigned)W)) weight = 0.f;
                     sum1 = __fadd_rn(sum1, __fmul_rn(tmp, weight));
                     sum2 = __fadd_rn(sum2, weight);
                 }
+            }
             out = __fmul_rn(__fdiv_rn(sum1, sum2), adj);
         } else out = (float)rv;
     }
@@ -231,22 +268,30 @@ __global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, con
                                                                  float4* __restrict__ normal_opt)
 {
     constexpr int TW = 16, TH = 8, R = 3;
-    __shared__ float4 s_v[TH + 2 * R][TW + 2 * R];
-    __shared__ float4 s_n[TH + 2 * R][TW + 2 * R];
+    __shared__ float4 s_v[TH + 2 * R][TW + 2 * R];      // filtered vertex; z = -1000 when the pixel can never be a neighbour
+    __shared__ float4 s_n[TH + 2 * R][TW + 2 * R];      // 10 n (the HRBF coefficient), w = 1 / rho^2
     const int W = a.cols, H = a.rows, win = a.curvWin;
     const int x0 = blockIdx.x * TW - R, y0 = blockIdx.y * TH - R;
+    const int px = blockIdx.x * TW + (threadIdx.x & 15), py = blockIdx.y * TH + (threadIdx.x >> 4);
+    float4 vf = make_float4(0.f, 0.f, 0.f, 0.f), vn = vf;
     for (int t = threadIdx.x; t < (TH + 2 * R) * (TW + 2 * R); t += 128) {
         const int sy = t / (TW + 2 * R), sx = t - sy * (TW + 2 * R);
         const int gx = x0 + sx, gy = y0 + sy;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) { v = __ldg(vertex_filtered + (size_t)gy * W + gx); n = __ldg(normal + (size_t)gy * W + gx); }
+        float4 v = make_float4(0.f, 0.f, -1000.f, 0.f), n = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const float4 v_ = __ldg(vertex_filtered + (size_t)gy * W + gx), n_ = __ldg(normal + (size_t)gy * W + gx);
+            // the pose-independent half of the neighbour test (depth_curvature_gradient.frag:60-64)
+            if (v_.z > 0.3f && sqrtf(n_.x * n_.x + n_.y * n_.y + n_.z * n_.z) > 0.8f) {
+                v = v_;
+                n = make_float4(10.0f * n_.x, 10.0f * n_.y, 10.0f * n_.z, 1.0f / (n_.w * n_.w));
+            }
+        }
         s_v[sy][sx] = v; s_n[sy][sx] = n;
     }
+    if (px < W && py < H) { vf = __ldg(vertex_filtered + (size_t)py * W + px); vn = __ldg(normal + (size_t)py * W + px); }
     __syncthreads();
-    const int px = blockIdx.x * TW + (threadIdx.x & 15), py = blockIdx.y * TH + (threadIdx.x >> 4);
     if (px >= W || py >= H) return;
     const size_t o = (size_t)py * W + px;
-    const float4 vf = s_v[py - y0][px - x0], vn = s_n[py - y0][px - x0];
     float4 kmax = make_float4(0.f, 0.f, 0.f, 1000.0f), kmin = kmax, nopt = make_float4(0.f, 0.f, 0.f, 0.f);
     float gm = 0.f;
     if (vf.z > 0.3f && sqrtf(vn.x * vn.x + vn.y * vn.y + vn.z * vn.z) > 0.5f) {
@@ -258,56 +303,48 @@ __global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, con
         float h0 = 0.f, h1 = 0.f, h2 = 0.f, h4 = 0.f, h5 = 0.f, h8 = 0.f;   // "Hessian" entries g[0], g[1], g[2], g[4], g[5], g[8]
         for (int qx = qx0; qx <= qx1; ++qx)
             for (int qy = qy0; qy <= qy1; ++qy) {
-                const float4 v = s_v[qy - y0][qx - x0], n = s_n[qy - y0][qx - x0];
-                if (!(fabsf(v.z - vf.z) < 0.10f && v.z > 0.3f && sqrtf(n.x * n.x + n.y * n.y + n.z * n.z) > 0.8f)) continue;
+                const float4 v = s_v[qy - y0][qx - x0];
+                if (!(fabsf(v.z - vf.z) < 0.10f)) continue;
                 ++N;
-                const float sx = 10.0f * n.x, sy = 10.0f * n.y, sz = 10.0f * n.z;
+                const float4 n = s_n[qy - y0][qx - x0];                    // (sx, sy, sz) = 10 n, iT2 = 1 / rho^2
+                const float iT2 = n.w;
                 const float vx = vf.x - v.x, vy = vf.y - v.y, vz = vf.z - v.z;
                 const float d2 = vx * vx + vy * vy + vz * vz;
-                const float T2 = n.w * n.w;
-                if (d2 > T2) continue;
+                const float u = d2 * iT2;                                  // (|v| / rho)^2
+                if (u > 1.0f) continue;
                 if (d2 == 0.0f) {            // getWeightH: -20/T2 I ; getWeightT: 0
-                    const float h = -20.0f / T2;
-                    gx -= sx * h; gy -= sy * h; gz -= sz * h;
+                    const float h = -20.0f * iT2;
+                    gx -= n.x * h; gy -= n.y * h; gz -= n.z * h;
                     continue;
                 }
-                const float r = sqrtf(d2 / T2);
-                const float s = 1.0f - r;
-                {   // hrbfbase.glsl:51-68
-                    const float t1 = 20.0f * (s * s) / (T2 * T2 * r), t2 = -r * s * T2;
-                    const float w0 = t1 * (3.0f * (vx * vx) + t2), w1 = t1 * 3.0f * vx * vy, w2 = t1 * 3.0f * vx * vz;
-                    const float w4 = t1 * (3.0f * (vy * vy) + t2), w5 = t1 * 3.0f * vy * vz, w8 = t1 * (3.0f * (vz * vz) + t2);
-                    gx -= sx * w0 + sy * w1 + sz * w2;
-                    gy -= sx * w1 + sy * w4 + sz * w5;
-                    gz -= sx * w2 + sy * w5 + sz * w8;
+                // With s = 10 n, dvs = v.s, r = |v|/rho, q = 1 - r (hrbfbase.glsl:37-69, 72-123, 147-195):
+                //   gradient  -= H s,  H = t1 (3 v v^T + t2 I)          ->  t1 (3 dvs v + t2 s)
+                //   g[ij]     -= sum_k T_ijk s_k  with the shader's T (its 27 entries are restated in the oracle); collecting
+                //   terms:  diagonal ii : A v_i^2 + B + C s_i v_i      off-diagonal ij (i<j) : A v_i v_j + D s_i v_j + E s_j v_i
+                const float ir = rsqrtf(u), r = u * ir, q = 1.0f - r;
+                const float dvs = vx * n.x + vy * n.y + vz * n.z;
+                {
+                    const float t1 = 20.0f * (q * q) * (iT2 * iT2) * ir;
+                    const float t2 = -r * q * d2 * (ir * ir);              // -r q T2  (T2 = d2 / u)
+                    const float c3 = 3.0f * t1 * dvs, ct = t1 * t2;
+                    gx -= c3 * vx + ct * n.x;
+                    gy -= c3 * vy + ct * n.y;
+                    gz -= c3 * vz + ct * n.z;
                 }
-                {   // hrbfbase.glsl:81-123, only the entries hrbfHessianMatrix consumes
-                    const float s2 = r - 2 + 1 / r;
-                    const float s3 = 60 / (T2 * T2);
-                    const float s4 = 1 / (r * r);
-                    const float prx = vx / (T2 * r), pry = vy / (T2 * r), prz = vz / (T2 * r);
-                    const float qx_ = prx - s4 * prx, qy_ = pry - s4 * pry, qz_ = prz - s4 * prz;
-                    const float Tss = T2 * s * s;
-                    const float t0 = s3 * (Tss * prx + 2 * vx * s2 + vx * vx * qx_);
-                    const float t1 = s3 * vy * (qx_ * vx + s2);
-                    const float t2 = s3 * vz * (qx_ * vx + s2);
-                    const float t3 = s3 * (Tss * pry + vx * vx * qy_);
-                    const float t4 = s3 * vx * (qy_ * vy + s2);
-                    const float t5 = s3 * vx * vz * qy_;
-                    const float t6 = s3 * (Tss * prz + vx * vx * qz_);
-                    const float t7 = s3 * vx * vy * qz_;
-                    const float t8 = s3 * vx * (qz_ * vz + s2);
-                    const float t13 = s3 * (Tss * pry + 2 * vy * s2 + vy * vy * qy_);
-                    const float t14 = s3 * vz * (qy_ * vy + s2);
-                    const float t16 = s3 * (Tss * prz + vy * vy * qz_);
-                    const float t17 = s3 * vy * (qz_ * vz + s2);
-                    const float t26 = s3 * (Tss * prz + 2 * vz * s2 + vz * vz * qz_);
-                    h0 -= sx * t0 + sy * t1 + sz * t2;
-                    h1 -= sx * t3 + sy * t4 + sz * t5;
-                    h2 -= sx * t6 + sy * t7 + sz * t8;
-                    h4 -= sx * t4 + sy * t13 + sz * t14;       // t[12] = t[4]
-                    h5 -= sx * t7 + sy * t16 + sz * t17;       // t[15] = t[7]
-                    h8 -= sx * t8 + sy * t17 + sz * t26;       // t[24] = t[8], t[25] = t[17]
+                {
+                    const float s2 = r - 2.0f + ir;
+                    const float s3 = 60.0f * (iT2 * iT2);
+                    const float pi_ = iT2 * ir;                            // 1 / (T2 r)
+                    const float kap = (1.0f - ir * ir) * pi_;
+                    const float tss_pi = q * q * ir;                       // T2 q^2 / (T2 r)
+                    const float A = s3 * kap * dvs, B = s3 * s2 * dvs, Cc = s3 * (tss_pi + s2), D = s3 * tss_pi, E = s3 * s2;
+                    (void)pi_;
+                    h0 -= A * (vx * vx) + B + Cc * (n.x * vx);
+                    h4 -= A * (vy * vy) + B + Cc * (n.y * vy);
+                    h8 -= A * (vz * vz) + B + Cc * (n.z * vz);
+                    h1 -= A * (vx * vy) + D * (n.x * vy) + E * (n.y * vx);
+                    h2 -= A * (vx * vz) + D * (n.x * vz) + E * (n.z * vx);
+                    h5 -= A * (vy * vz) + D * (n.y * vz) + E * (n.z * vy);
                 }
             }
         if (N > 15) {
