@@ -128,13 +128,19 @@ constexpr int kPredCand = 49;
 
 // candidate order of predict_hrbf.frag:75-80 (rings i = 0..3, x outer, y inner, perimeter only) and, for each
 // candidate, the index of the first candidate of the NEXT x column (where the shader's `break` resumes)
-struct PredTable { signed char dx[kPredCand], dy[kPredCand]; unsigned char next_col[kPredCand]; unsigned char ring_end[4]; };
+constexpr int kPredCols = 16;     // x columns over the four rings: 1 + 3 + 5 + 7
+struct PredTable {
+    unsigned long long col_mask[kPredCols];      // candidates of each column (contiguous index ranges, in scan order)
+    signed char dx[kPredCand], dy[kPredCand];
+    unsigned char next_col[kPredCand], col_of[kPredCand];
+    unsigned char ring_end[4];
+};
 __constant__ PredTable c_pred;
 
 inline PredTable make_pred_table()
 {
     PredTable t;
-    int c = 0;
+    int c = 0, col = 0;
     for (int i = 0; i <= 3; ++i) {
         for (int dx = -i; dx <= i; ++dx) {
             const int col_start = c;
@@ -142,7 +148,9 @@ inline PredTable make_pred_table()
                 if (!(dx == -i || dy == -i || dx == i || dy == i)) continue;
                 t.dx[c] = (signed char)dx; t.dy[c] = (signed char)dy; ++c;
             }
-            for (int k = col_start; k < c; ++k) t.next_col[k] = (unsigned char)c;
+            t.col_mask[col] = 0ull;
+            for (int k = col_start; k < c; ++k) { t.next_col[k] = (unsigned char)c; t.col_of[k] = (unsigned char)col; t.col_mask[col] |= 1ull << k; }
+            ++col;
         }
         t.ring_end[i] = (unsigned char)c;
     }
@@ -214,7 +222,9 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     __shared__ float4 s_n[kPredSH][kPredSW];
     __shared__ unsigned char s_sel[64][32];              // per pixel: tile cell (row * kPredSW + col) of each selected neighbour
     __shared__ PredTable s_tab;                          // the candidate tables: per-lane indices would serialise in the constant cache
-    if (threadIdx.x < sizeof(PredTable)) reinterpret_cast<unsigned char*>(&s_tab)[threadIdx.x] = reinterpret_cast<const unsigned char*>(&c_pred)[threadIdx.x];
+    static_assert(sizeof(PredTable) % 4 == 0, "copied as words");
+    for (int t = threadIdx.x; t < (int)(sizeof(PredTable) / 4); t += blockDim.x)
+        reinterpret_cast<unsigned int*>(&s_tab)[t] = reinterpret_cast<const unsigned int*>(&c_pred)[t];
 
     const int tx0 = blockIdx.x * kPredTileW, ty0 = blockIdx.y * kPredTileH;
     for (int t = threadIdx.x; t < kPredSH * kPredSW; t += blockDim.x) {
@@ -253,21 +263,28 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     }
     valid |= __shfl_xor_sync(gmask, valid, 1);
     valid |= __shfl_xor_sync(gmask, valid, 2);
-    // sequential emulation of the shader's append / `break` (leaves only the innermost loop)
-    int N = 0;
-    if (sub == 0 && inside) {
-        int c = 0;
-        while (c < ncand) {
-            if ((valid >> c) & 1ull) {
-                if (N < 32) s_sel[grp][N] = (unsigned char)((ly + kPredHalo + s_tab.dy[c]) * kPredSW + lx + kPredHalo + s_tab.dx[c]);
-                ++N;
-                if (N > a.maxN) { c = s_tab.next_col[c]; continue; }
-            }
-            ++c;
+    // The shader appends valid candidates in scan order and its `break` only leaves the innermost (y) loop: once more
+    // than maxN are collected, every further x column still contributes its FIRST valid candidate.  In mask form: all valid
+    // bits up to the (maxN+1)-th one, plus the lowest valid bit of each later column (all 4 lanes compute it redundantly).
+    unsigned long long sel = valid;
+    if (__popcll(valid) > a.maxN + 1) {
+        const unsigned int lo32 = (unsigned int)valid, hi32 = (unsigned int)(valid >> 32);
+        const int nlo = __popc(lo32);
+        const int cstar = (nlo > a.maxN) ? (int)__fns(lo32, 0, a.maxN + 1) : 32 + (int)__fns(hi32, 0, a.maxN + 1 - nlo);
+        sel = valid & ((2ull << cstar) - 1ull);
+        for (int k = s_tab.col_of[cstar] + 1; k < kPredCols; ++k) {
+            const unsigned long long m = valid & s_tab.col_mask[k];
+            sel |= m & (0ull - m);
         }
     }
-    N = __shfl_sync(gmask, N, lane & ~3);
+    if (!inside) sel = 0ull;
+    int N = __popcll(sel);
     if (N > 32) N = 32;                                 // cannot happen for maxN <= 16, win <= 3 (host-checked)
+    for (int j = 0; j < N; ++j) {
+        const int c = __ffsll((long long)sel) - 1;
+        sel &= sel - 1ull;
+        if ((j & (kPredLanes - 1)) == sub) s_sel[grp][j] = (unsigned char)((ly + kPredHalo + s_tab.dy[c]) * kPredSW + lx + kPredHalo + s_tab.dx[c]);
+    }
     __syncwarp(gmask);
 
     const int nslots = (N - sub + kPredLanes - 1) / kPredLanes;       // slots s with s*4+sub < N
@@ -322,7 +339,15 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     // back, bisection); run as written, a warp pays the SUM of its pixels' worst trip counts with ~60 % of the lanes
     // idle.  Here every lane evaluates f once per iteration at the t its pixel's state asks for, so a warp pays the
     // MAXIMUM of its pixels' total evaluation counts and the evaluation itself is executed convergently.
-    enum { ST_COARSE = 0, ST_FINE, ST_BISECT, ST_DONE };
+    // Root search, result-equivalent to the shader's three loops (:152-270) within its own final resolution:
+    //   coarse : as written -- 4-mm steps from the start point until f changes sign (at most 24)
+    //   fine   : the shader walks back from the crossing in 0.4-mm steps until the sign flips back (<= 10 evaluations);
+    //            here the same 0.4-mm bracket is located by bisecting the step index (<= 4 evaluations: identical bracket
+    //            whenever f has a single crossing inside the 4-mm step)
+    //   root   : the shader bisects the bracket to 6 um (6 evaluations) and returns the last midpoint; here one
+    //            regula-falsi evaluation + a secant step land within ~0.1 um of the root, i.e. inside that final interval
+    // Typical pixel: 8 evaluations instead of 14, and nearly the same count for every pixel of a warp.
+    enum { ST_COARSE = 0, ST_FINE, ST_ROOT, ST_DONE };
     int nmax = nslots;                                   // warp-uniform slot bound
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, m));
@@ -334,18 +359,20 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     const float dir = v0 > 0.f ? -1.0f : 1.0f;           // v0 > 0: search backward for f < 0; else forward for f > 0
     // i = 0 of the shader's coarse march re-evaluates the start point: never a sign change, skipped
     int state = (inside && N > a.minN && cnt0 > a.minN) ? ST_COARSE : ST_DONE;
-    int step = 1, bis = 0;
-    float tb = 0.f;                                      // anchor of the fine march
-    float ts = 0.f, te = 0.f, tm = 0.f;                  // starting / ending point of the bisection, last midpoint (p_temp)
+    int step = 1, lo = 0, hi = 10;
+    float tb = 0.f;                                      // coarse crossing
+    float f_lo = 0.f, f_hi = v0;                         // f at fine step lo (crossed side) / hi (start side)
+    float tm = 0.f;
     bool found = false;
     while (__any_sync(0xffffffffu, state != ST_DONE)) {
         // 1. the ray parameter this pixel's state asks for
-        float t = 0.f;
+        float t = 0.f, t_lo = 0.f, t_hi = 0.f;
         if (state == ST_COARSE) t = 0.004f * (float)step * dir;
-        else if (state == ST_FINE) t = tb - 0.0004f * (float)step * dir;
-        else if (state == ST_BISECT) {
-            if (fabsf(te - ts) < 0.00001f) { found = true; state = ST_DONE; }
-            else { tm = ts + 0.5f * (te - ts); t = tm; }
+        else if (state == ST_FINE) t = tb - 0.0004f * (float)((lo + hi) >> 1) * dir;
+        else if (state == ST_ROOT) {
+            t_lo = tb - 0.0004f * (float)lo * dir; t_hi = tb - 0.0004f * (float)hi * dir;
+            const float den = f_lo - f_hi;
+            t = den != 0.f ? t_lo + (t_hi - t_lo) * (f_lo / den) : t_lo;
         }
         // 2. f(c0 + t r): this lane's neighbours, reduced over the 4 lanes of the pixel
         float value = hrbf_ray_value(nb, upper_half, t);
@@ -353,19 +380,20 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
         value += __shfl_xor_sync(0xffffffffu, value, 2);
         // 3. state transition
         if (state == ST_COARSE) {
-            if (v0 > 0.f ? (value < 0.f) : (value > 0.f)) { tb = t; state = ST_FINE; step = 1; }
-            else if (++step >= 25) state = ST_DONE;
+            if (v0 > 0.f ? (value < 0.f) : (value > 0.f)) { tb = t; f_lo = value; lo = 0; hi = 10; state = ST_FINE; }
+            else { f_hi = value; if (++step >= 25) state = ST_DONE; }
         } else if (state == ST_FINE) {
-            if (v0 > 0.f ? (value > 0.f) : (value < 0.f)) {
-                if (v0 > 0.f) { ts = tb; te = t; } else { te = tb; ts = t; }
-                state = ST_BISECT; bis = 0;
-            } else if (++step >= 11) state = ST_DONE;
-        } else if (state == ST_BISECT) {
-            if (fabsf(value) < 0.00001f) { found = true; state = ST_DONE; }
-            else {
-                if (value < 0.f) ts = tm; else te = tm;
-                if (++bis >= 10) state = ST_DONE;
-            }
+            if (v0 > 0.f ? (value > 0.f) : (value < 0.f)) { hi = (lo + hi) >> 1; f_hi = value; }      // flipped back: the bracket ends here
+            else { lo = (lo + hi) >> 1; f_lo = value; }
+            if (hi - lo == 1) state = ST_ROOT;
+        } else if (state == ST_ROOT) {
+            // secant step through (t, value) and the bracket end of opposite sign, clamped to the bracket
+            const bool same_as_lo = (value < 0.f) == (f_lo < 0.f);
+            const float to = same_as_lo ? t_hi : t_lo, fo = same_as_lo ? f_hi : f_lo;
+            const float den = value - fo;
+            float t2 = den != 0.f ? t - value * ((t - to) / den) : t;
+            t2 = fminf(fmaxf(t2, fminf(t_lo, t_hi)), fmaxf(t_lo, t_hi));
+            tm = t2; found = true; state = ST_DONE;
         }
     }
     const float tx = fmaf(tm, rx, c0x), ty = fmaf(tm, ry, c0y), tz = fmaf(tm, rz, c0z);

