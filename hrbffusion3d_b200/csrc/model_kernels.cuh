@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
     int counter = 0;
     float bestDist = 1000;
     unsigned int best = 0;
+    // 4 x 4 half-pixel offsets around the pixel centre (data.vert:123-138) hit texels {px-1, px, px, px+1} x {py-1, py, py, py+1}.
+    // A texel seen again can never replace the best (strict <) and `counter` is only tested for > 0, so a repeated texel is
+    // skipped; the scan order of the distinct ones is kept.
     size_t qs[16];
     unsigned int cur[16];
 #pragma unroll
@@ -240,8 +243,14 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
             const float ox = -1.0f + 0.5f * (float)a, oy = -1.0f + 0.5f * (float)b;
             const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
             qs[a * 4 + b] = (size_t)sy * W + sx;
-            cur[a * 4 + b] = __ldg(f.index + qs[a * 4 + b]);
         }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j < k) first = first && qs[j] != qs[k];
+        cur[k] = first ? __ldg(f.index + qs[k]) : 0u;
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -332,21 +341,42 @@ __device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& 
             }
         };
         if (m.cleanWindow == 2) {
-            // the reference default: 4 x 4 half-pixel offsets.  All 16 index loads are issued before the first dependent
-            // texture read (the rolled loop below serialises 32 L2 round trips per surfel).
-            size_t q[16];
+            // the reference default: 4 x 4 half-pixel offsets {-1, -1/2, 0, +1/2}, GL_NEAREST.  Per axis they hit only the texels
+            // floor(x - 1), floor(x - 1/2), floor(x), floor(x + 1/2): each DISTINCT texel is fetched once and counted with its
+            // multiplicity (the tests only count), and all index loads are issued before the first dependent texture read.
+            int tx[4], ty[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                tx[a] = min(max((int)floorf(x + 0.5f * (float)(a - 2)), 0), W - 1);
+                ty[a] = min(max((int)floorf(y + 0.5f * (float)(a - 2)), 0), H - 1);
+            }
+            int mx[4], my[4];        // multiplicity of sample a if it is the first of a run of equal texels, else 0
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                int cx_ = 0, cy_ = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) { cx_ += (tx[b] == tx[a]) ? 1 : 0; cy_ += (ty[b] == ty[a]) ? 1 : 0; }
+                bool fx = true, fy = true;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) if (b < a) { fx = fx && tx[b] != tx[a]; fy = fy && ty[b] != ty[a]; }
+                mx[a] = fx ? cx_ : 0; my[a] = fy ? cy_ : 0;
+            }
             unsigned int idx[16];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const float ox = 0.5f * (float)(a - 2), oy = 0.5f * (float)(b - 2);
-                    const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
-                    q[a * 4 + b] = (size_t)sy * W + sx;
-                    idx[a * 4 + b] = __ldg(c.index + q[a * 4 + b]);
-                }
+                for (int b = 0; b < 4; ++b) idx[a * 4 + b] = (mx[a] * my[b] > 0) ? __ldg(c.index + (size_t)ty[b] * W + tx[a]) : 0u;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) sample(idx[k], q[k]);
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int mult = mx[a] * my[b];
+                    if (mult > 0 && idx[a * 4 + b] > 0u) {
+                        const int c0 = count, z0 = zCount;
+                        sample(idx[a * 4 + b], (size_t)ty[b] * W + tx[a]);
+                        count = c0 + (count - c0) * mult; zCount = z0 + (zCount - z0) * mult;
+                    }
+                }
         } else {
             const int ns = 2 * m.cleanWindow;
             for (int a = 0; a < ns; ++a)

@@ -450,7 +450,9 @@ __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
 {
     const int per_pyr = A.pyr_bx * A.pyr_by, per_rgbd = A.rgbd_bx * A.rgbd_by;
     int b = blockIdx.x;
-    if (b < 5 * per_pyr) {
+    // the (heavier) RGB-D pyramid tiles take the lowest block indices: they are scheduled first and the light map tiles fill in
+    if (b >= 2 * per_rgbd) {
+        b -= 2 * per_rgbd;
         const int job = b / per_pyr, t = b - job * per_pyr;
         const int by = t / A.pyr_bx, bx = t - by * A.pyr_bx;
         switch (job) {
@@ -462,7 +464,6 @@ __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
         }
         return;
     }
-    b -= 5 * per_pyr;
     const int job = b / per_rgbd, t = b - job * per_rgbd;
     const int by = t / A.rgbd_bx, bx = t - by * A.rgbd_bx;
     const bool use_alt = job == 0 && A.sel != nullptr && *A.sel != 0;

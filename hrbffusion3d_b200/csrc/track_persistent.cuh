@@ -12,7 +12,10 @@
 
 namespace hrbf {
 
-constexpr int kTrackThreads = 512;       // x 148 CTAs; 128 registers per thread
+#ifndef HRBF_TRACK_THREADS
+#define HRBF_TRACK_THREADS 512
+#endif
+constexpr int kTrackThreads = HRBF_TRACK_THREADS;       // x 148 CTAs (one per SM)
 constexpr int kTrackWarps = kTrackThreads / 32;
 
 struct TrackLevel {
@@ -343,7 +346,7 @@ __device__ __forceinline__ void rgb_step_pass(const RgbStepArgs& a, float sigma,
 // dynamic shared memory of the persistent tracker: the RGB slots, max_slots x kTrackThreads
 inline size_t track_slots_bytes(int max_slots) { return (size_t)max_slots * kTrackThreads * sizeof(RgbSlot); }
 
-__global__ void __launch_bounds__(kTrackThreads, 1) track_persistent_kernel(const TrackParams p)
+__global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     RgbSlot* s_slots = reinterpret_cast<RgbSlot*>(s_dyn);
