@@ -28,6 +28,8 @@ struct hrbf_odometry {
     unsigned char* lastImage[HRBF_NUM_PYRS] = {}; unsigned char* nextImage[HRBF_NUM_PYRS] = {}; unsigned char* lastNextImage[HRBF_NUM_PYRS] = {};
     short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
     float* cloud[HRBF_NUM_PYRS] = {};
+    float4* pk[4][HRBF_NUM_PYRS] = {};           // packed ICP operands: [0] curr pk0, [1] curr pk1, [2] model pk0, [3] model pk1
+    bool pack_dirty_curr = false, pack_dirty_model = false;   // SoA written by a builder that does not pack (GPUTest path)
     unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
     size_t tp_dyn_set = 0;                       // dynamic shared memory the persistent kernel is currently allowed
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};

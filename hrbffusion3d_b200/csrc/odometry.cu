@@ -39,7 +39,12 @@ namespace hrbf {
 static PyrOut pyr_out(hrbf_odometry* o, int which)
 {
     PyrOut r;
-    for (int l = 0; l < 3; ++l) { r.p[l] = o->maps[which][l]; r.pitch[l] = o->cols(l); }
+    for (int l = 0; l < 3; ++l) {
+        r.p[l] = o->maps[which][l]; r.pitch[l] = o->cols(l);
+        const bool curr = which == M_VC || which == M_K1C, model = which == M_VG || which == M_K1G;
+        r.pk0[l] = curr ? o->pk[0][l] : model ? o->pk[2][l] : nullptr;
+        r.pk1[l] = curr ? o->pk[1][l] : model ? o->pk[3][l] : nullptr;
+    }
     return r;
 }
 
@@ -64,6 +69,7 @@ static IcpArgs icp_args(const hrbf_odometry* o, int l, bool use_weight)
     ia.fx = o->intr.fx / div; ia.fy = o->intr.fy / div; ia.cx = o->intr.cx / div; ia.cy = o->intr.cy / div;
     ia.dist_thres = o->distThres; ia.angle_thres = o->angleThres;
     ia.use_search = o->useSearch; ia.radius = o->searchRadius; ia.use_weight = use_weight; ia.corres = nullptr;
+    ia.pc0 = o->pk[0][l]; ia.pc1 = o->pk[1][l]; ia.pg0 = o->pk[2][l]; ia.pg1 = o->pk[3][l];
     return ia;
 }
 static RgbResArgs rgbres_args(const hrbf_odometry* o, int l)
@@ -174,6 +180,23 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     void* args[] = { (void*)&p };
     HRBF_CUDA(cudaLaunchCooperativeKernel((const void*)track_persistent_kernel, dim3(o->num_sms), dim3(kTrackThreads), args, dyn, s));
     count_launch();
+    return HRBF_OK;
+}
+
+// bring the packed records up to date after a builder that only wrote the SoA maps
+static int repack_if_dirty(hrbf_odometry* o, cudaStream_t s)
+{
+    for (int side = 0; side < 2; ++side) {
+        bool& dirty = side == 0 ? o->pack_dirty_curr : o->pack_dirty_model;
+        if (!dirty) continue;
+        for (int l = 0; l < 3; ++l) {
+            const int n = o->rows(l) * o->cols(l);
+            if (side == 0) pack_maps_kernel<<<div_up(n, 256), 256, 0, s>>>(n, o->maps[M_VC][l], o->maps[M_NC][l], o->maps[M_K1C][l], o->maps[M_K2C][l], o->pk[0][l], o->pk[1][l]);
+            else pack_maps_kernel<<<div_up(n, 256), 256, 0, s>>>(n, o->maps[M_VG][l], o->maps[M_NG][l], o->maps[M_K1G][l], o->maps[M_K2G][l], o->pk[2][l], o->pk[3][l]);
+            HRBF_KERNEL_CHECK();
+        }
+        dirty = false;
+    }
     return HRBF_OK;
 }
 
@@ -322,6 +345,7 @@ int hrbf_icp_step(const float* Rcurr, const float* tcurr, const float* vc, const
     ia.rows = rows; ia.cols = cols; ia.fx = intr.fx; ia.fy = intr.fy; ia.cx = intr.cx; ia.cy = intr.cy;
     ia.dist_thres = opts->dist_thres; ia.angle_thres = opts->angle_thres;
     ia.use_search = opts->use_search; ia.radius = opts->search_radius; ia.use_weight = opts->use_weight; ia.corres = (int2*)corres;
+    ia.pc0 = ia.pc1 = ia.pg0 = ia.pg1 = nullptr;          // caller-owned SoA maps
     const int nb = reduce_blocks(rows * cols);
     if (opts->use_search) icp_reduce_kernel<true><<<nb, kReduceThreads, 0, s>>>(ia, wk, 0, 0, -1);
     else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, wk, 0, 0, -1);
@@ -425,7 +449,7 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
     // one slab, 256-B aligned sub-buffers
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
-    size_t o_maps[M_COUNT][3], o_dt[3], o_ld[3], o_nd[3], o_li[3], o_ni[3], o_lni[3], o_dx[3], o_dy[3], o_cl[3], o_ci[3], o_cd[3];
+    size_t o_maps[M_COUNT][3], o_dt[3], o_ld[3], o_nd[3], o_li[3], o_ni[3], o_lni[3], o_dx[3], o_dy[3], o_cl[3], o_ci[3], o_cd[3], o_pk[4][3];
     for (int l = 0; l < 3; ++l) {
         const size_t P = (size_t)o->rows(l) * o->cols(l);
         for (int m = 0; m < M_W; ++m) o_maps[m][l] = take(4 * P * sizeof(float));
@@ -433,6 +457,7 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
         o_dt[l] = take(P * 4); o_ld[l] = take(P * 4); o_nd[l] = take(P * 4);
         o_li[l] = take(P); o_ni[l] = take(P); o_lni[l] = take(P);
         o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cl[l] = take(P * 12); o_ci[l] = take(P * sizeof(hrbf_dataterm)); o_cd[l] = take(P);
+        for (int k = 0; k < 4; ++k) o_pk[k][l] = take(P * sizeof(float4));
     }
     const size_t o_vd = take((size_t)width * height * 4), o_work = take(sizeof(ReduceWork)), o_pose = take(64 * sizeof(float));
     cudaDeviceGetAttribute(&o->num_sms, cudaDevAttrMultiProcessorCount, 0);
@@ -447,6 +472,7 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
         o->lastImage[l] = (unsigned char*)(o->slab + o_li[l]); o->nextImage[l] = (unsigned char*)(o->slab + o_ni[l]); o->lastNextImage[l] = (unsigned char*)(o->slab + o_lni[l]);
         o->dIdx[l] = (short*)(o->slab + o_dx[l]); o->dIdy[l] = (short*)(o->slab + o_dy[l]);
         o->cloud[l] = (float*)(o->slab + o_cl[l]); o->corresImg[l] = (hrbf_dataterm*)(o->slab + o_ci[l]); o->cand[l] = (unsigned char*)(o->slab + o_cd[l]);
+        for (int k = 0; k < 4; ++k) o->pk[k][l] = (float4*)(o->slab + o_pk[k][l]);
     }
     o->vdepth_tmp = (float*)(o->slab + o_vd);
     o->work = (ReduceWork*)(o->slab + o_work);
@@ -519,6 +545,7 @@ int hrbf_odometry_init_icp_depth(hrbf_odometry* o, const float* depth, float cut
         create_nmap_kernel<<<grid2d(o->cols(i), o->rows(i), b), b, 0, s>>>(o->rows(i), o->cols(i), o->maps[M_VC][i], o->cols(i), o->maps[M_NC][i], o->cols(i));
         HRBF_KERNEL_CHECK();
     }
+    o->pack_dirty_curr = true;
     return HRBF_OK;
 }
 
@@ -627,6 +654,7 @@ int hrbf_odometry_fill_neutral_curvature(hrbf_odometry* o, void* stream)
         HRBF_CUDA(cudaMemcpyAsync(o->maps[M_W][l], ones.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
         HRBF_CUDA(cudaStreamSynchronize(s));
     }
+    o->pack_dirty_curr = o->pack_dirty_model = true;
     return HRBF_OK;
 }
 
@@ -686,6 +714,7 @@ int hrbf_odometry_get_incremental_transformation(hrbf_odometry* o, float* trans,
     (void)index_frame;
     HRBF_CHECK_ARG(o && trans && rot);
     cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = repack_if_dirty(o, s)) return rc;
     memcpy(o->h_pose, rot, 36);
     memcpy(o->h_pose + 9, trans, 12);
     int nk = 1;
@@ -722,6 +751,7 @@ int hrbf_odometry_track_async(hrbf_odometry* o, const float* prev_pose_dev, floa
 {
     HRBF_CHECK_ARG(o && prev_pose_dev && pose_out_dev);
     cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = repack_if_dirty(o, s)) return rc;
     HRBF_CUDA(cudaMemcpyAsync(o->pose_scratch + 12, prev_pose_dev, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (o->use_graph) {
         int nk = 0;
@@ -742,6 +772,7 @@ int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_u
 {
     HRBF_CHECK_ARG(o && avg_us && which >= 0 && which <= 3 && level >= 0 && level <= 2 && reps > 0);
     cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = repack_if_dirty(o, s)) return rc;
     cudaEvent_t e0, e1;
     HRBF_CUDA(cudaEventCreate(&e0));
     HRBF_CUDA(cudaEventCreate(&e1));

@@ -13,6 +13,11 @@ namespace hrbf {
 struct PyrOut {            // three pyramid levels of one SoA map
     float* p[3];
     int pitch[3];          // elements
+    // the tracker's packed copy of the 17 floats ICP consumes (dense, one record per pixel, 16-byte loads):
+    //   pk0 = {v.x, v.y, v.z, n.x}   pk1 = {n.y, n.z, k1.w, k2.w}
+    // set on the FIRST map of a pair only (vertex map of a vertex/normal pair, k1 map of a curvature pair)
+    float4* pk0[3];
+    float4* pk1[3];
 };
 
 enum { PYR_VN = 0, PYR_K = 1 };
@@ -120,6 +125,13 @@ __device__ __forceinline__ void pyr_pair_tile(const float4* __restrict__ a_aos, 
             }
             store4(oa.p[L], oa.pitch[L], lrows, lyy, lxx, ax, ay, az, qa[3]);
             store4(ob.p[L], ob.pitch[L], lrows, lyy, lxx, bx, by, bz, qb[3]);
+            if (oa.pk1[L]) {
+                const size_t o = (size_t)lyy * lcols + lxx;
+                if (KIND == PYR_VN) {
+                    oa.pk0[L][o] = make_float4(ax, ay, az, bx);
+                    reinterpret_cast<float2*>(oa.pk1[L] + o)[0] = make_float2(by, bz);
+                } else reinterpret_cast<float2*>(oa.pk1[L] + o)[1] = make_float2(qa[3], qb[3]);
+            }
         }
     }
 }
@@ -515,6 +527,7 @@ struct IcpArgs {
     float dist_thres, angle_thres;
     int use_search, radius, use_weight;
     int2* corres;                                      // optional output
+    const float4 *pc0, *pc1, *pg0, *pg1;               // packed maps (PyrOut::pk0/pk1) of the current frame / the model, or null
 };
 
 // acc[0..27] += w*row_i*row_j (i<=j<7), acc[28] += inlier  (reduce.cu:511-545)
@@ -609,6 +622,126 @@ __device__ __forceinline__ void icp_pixel(const IcpArgs& a, const float* Rc, con
     accumulate_row7(acc, row, weight, found);
 }
 
+// ---- the no-search ICP pixel split into load / gather / finish stages so that two pixels per thread are in flight
+// (the pass is bound by two dependent L2 round trips per pixel, not by bandwidth or issue slots) ----
+struct IcpCurr { float vx, vy, vz, nx, ny, nz, k1, k2; };
+struct IcpModel { float vx, vy, vz, nx, ny, nz, k1, k2, w; int ok, ux, uy; float3 vg, ng; };
+
+template <bool PACKED>
+__device__ __forceinline__ IcpCurr icp_load_curr(const IcpArgs& a, int i)
+{
+    if (PACKED) {
+        const float4 p0 = __ldg(a.pc0 + i), p1 = __ldg(a.pc1 + i);
+        IcpCurr c;
+        c.vx = p0.x; c.vy = p0.y; c.vz = p0.z; c.nx = p0.w; c.ny = p1.x; c.nz = p1.y; c.k1 = p1.z; c.k2 = p1.w;
+        return c;
+    }
+    const int y = i / a.cols, x = i - y * a.cols, rows = a.rows;
+    auto ld = [&](const float* p, int plane) { return __ldg(p + (size_t)(plane * rows + y) * a.cpitch + x); };
+    IcpCurr c;
+    c.vx = ld(a.vc, 0); c.vy = ld(a.vc, 1); c.vz = ld(a.vc, 2);
+    c.nx = ld(a.nc, 0); c.ny = ld(a.nc, 1); c.nz = ld(a.nc, 2);
+    c.k1 = ld(a.k1c, 3); c.k2 = ld(a.k2c, 3);
+    return c;
+}
+template <bool PACKED>
+__device__ __forceinline__ IcpModel icp_gather_model(const IcpArgs& a, const IcpCurr& c, const float* Rc, const float* tc, const float* Rpi, const float* tp)
+{
+    IcpModel m;
+    const int rows = a.rows;
+    m.vg = mul(Rc, make_float3(c.vx, c.vy, c.vz)) + make_float3(tc[0], tc[1], tc[2]);
+    const float3 vcp = mul(Rpi, m.vg - make_float3(tp[0], tp[1], tp[2]));
+    // approximate division, as the reference's own build does (--prec-div=false, Core/src/CMakeLists.txt:74-75)
+    m.ux = __float2int_rn(__fdividef(vcp.x * a.fx, vcp.z) + a.cx);
+    m.uy = __float2int_rn(__fdividef(vcp.y * a.fy, vcp.z) + a.cy);
+    m.ok = !(m.ux < 0 || m.uy < 0 || m.ux >= a.cols || m.uy >= rows || vcp.z < 0) && !(isnan(c.vx) || isnan(c.nx) || isnan(c.k1) || isnan(c.k2));
+    m.ng = mul(Rc, make_float3(c.nx, c.ny, c.nz));
+    m.vx = m.vy = m.vz = m.nx = m.ny = m.nz = m.k1 = m.k2 = m.w = 0.f;
+    if (m.ok && PACKED) {
+        const int q = m.uy * a.cols + m.ux;
+        const float4 p0 = __ldg(a.pg0 + q), p1 = __ldg(a.pg1 + q);
+        m.vx = p0.x; m.vy = p0.y; m.vz = p0.z; m.nx = p0.w; m.ny = p1.x; m.nz = p1.y; m.k1 = p1.z; m.k2 = p1.w;
+        m.w = a.use_weight ? __ldg(a.w + q) : 1.f;
+    } else if (m.ok) {
+        auto ld = [&](const float* p, int plane) { return __ldg(p + (size_t)(plane * rows + m.uy) * a.gpitch + m.ux); };
+        m.vx = ld(a.vg, 0); m.vy = ld(a.vg, 1); m.vz = ld(a.vg, 2);
+        m.nx = ld(a.ng, 0); m.ny = ld(a.ng, 1); m.nz = ld(a.ng, 2);
+        m.k1 = ld(a.k1g, 3); m.k2 = ld(a.k2g, 3);
+        m.w = a.use_weight ? __ldg(a.w + (size_t)m.uy * a.wpitch + m.ux) : 1.f;
+    }
+    return m;
+}
+__device__ __forceinline__ void icp_finish(const IcpArgs& a, const IcpModel& m, const float* Rpi, const float* tp, int i, float (&acc)[32])
+{
+    float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    float weight = 1.f;
+    bool found = false;
+    if (m.ok) {
+        const float3 vp = make_float3(m.vx, m.vy, m.vz), np = make_float3(m.nx, m.ny, m.nz);
+        // ||.|| > thres  <=>  ||.||^2 > thres^2 (both sides non-negative): no square roots
+        const float3 dv = vp - m.vg, cr = cross(m.ng, np);
+        const float dist2 = dot(dv, dv), sine2 = dot(cr, cr);
+        found = !(isnan(vp.x) || isnan(np.x) || isnan(m.k1) || isnan(m.k2)) && !(sine2 > a.angle_thres * a.angle_thres || dist2 > a.dist_thres * a.dist_thres);
+        if (found) {
+            const float3 tpv = make_float3(tp[0], tp[1], tp[2]);
+            const float3 s_cp = mul(Rpi, m.vg - tpv), d_cp = mul(Rpi, vp - tpv), n_cp = mul(Rpi, np);
+            if (a.use_weight) weight = isnan(m.w) ? 0.f : m.w;
+            const float3 c = cross(s_cp, n_cp);
+            row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z; row[3] = c.x; row[4] = c.y; row[5] = c.z;
+            row[6] = dot(n_cp, s_cp - d_cp);
+        }
+    }
+    if (a.corres) a.corres[i] = found ? make_int2(m.ux, m.uy) : make_int2(-1, -1);
+    accumulate_row7(acc, row, weight, found);
+}
+// this CTA's contiguous pixel range [begin, end), kIcpInFlight pixels in flight per thread: all their current-frame loads
+// are issued together, then all their model gathers, then the rows are accumulated (2 dependent memory round trips per
+// trip of the loop; 640x480 level 0 = 2076 pixels per CTA = one full trip + a 28-pixel tail).
+#ifndef HRBF_ICP_INFLIGHT
+#define HRBF_ICP_INFLIGHT 2
+#endif
+constexpr int kIcpInFlight = HRBF_ICP_INFLIGHT;
+template <int kThreads, bool PACKED>
+__device__ __forceinline__ void icp_pass_nosearch_t(const IcpArgs& a, const float* Rc, const float* tc, const float* Rpi, const float* tp,
+                                                    int begin, int end, float (&acc)[32])
+{
+    constexpr int kTrackThreads = kThreads;
+    for (int i0 = begin + (int)threadIdx.x; i0 < end; i0 += kIcpInFlight * kTrackThreads) {
+        IcpCurr c[kIcpInFlight];
+#pragma unroll
+        for (int u = 0; u < kIcpInFlight; ++u) {
+            const int i = i0 + u * kTrackThreads;
+            c[u] = icp_load_curr<PACKED>(a, i < end ? i : i0);
+        }
+        IcpModel m[kIcpInFlight];
+#pragma unroll
+        for (int u = 0; u < kIcpInFlight; ++u) m[u] = icp_gather_model<PACKED>(a, c[u], Rc, tc, Rpi, tp);
+#pragma unroll
+        for (int u = 0; u < kIcpInFlight; ++u) {
+            const int i = i0 + u * kTrackThreads;
+            if (i < end) icp_finish(a, m[u], Rpi, tp, i, acc);
+        }
+    }
+}
+
+template <int kThreads>
+__device__ __forceinline__ void icp_pass_nosearch(const IcpArgs& a, const float* Rc, const float* tc, const float* Rpi, const float* tp,
+                                                  int begin, int end, float (&acc)[32])
+{
+    if (a.pc0 != nullptr) icp_pass_nosearch_t<kThreads, true>(a, Rc, tc, Rpi, tp, begin, end, acc);      // uniform branch
+    else icp_pass_nosearch_t<kThreads, false>(a, Rc, tc, Rpi, tp, begin, end, acc);
+}
+
+// SoA planes -> packed records, for the map builders that only write SoA (GPUTest path: createVMap / createNMap, neutral curvature)
+__global__ void pack_maps_kernel(int n, const float* __restrict__ v, const float* __restrict__ nm, const float* __restrict__ k1, const float* __restrict__ k2,
+                                 float4* __restrict__ pk0, float4* __restrict__ pk1)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pk0[i] = make_float4(v[i], v[n + i], v[2 * n + i], nm[i]);
+    pk1[i] = make_float4(nm[n + i], nm[2 * n + i], k1[3 * n + i], k2[3 * n + i]);
+}
+
 // mode 0: store the 29 sums in st->icp_sums only (hrbf_icp_step, or RGB still to come)
 // mode 1: store and run the Gauss-Newton update in the last block
 template <bool SEARCH>
@@ -631,8 +764,14 @@ __global__ void __launch_bounds__(kReduceThreads, 2) icp_reduce_kernel(IcpArgs a
     for (int k = 0; k < 32; ++k) acc[k] = 0.f;
     const int N = a.rows * a.cols;
     const bool level_done = (st->done_level == cur_level);
-    if (!level_done)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) icp_pixel<SEARCH>(a, Rc, tc, Rpi, tp, i, acc);
+    if (!level_done) {
+        if (SEARCH) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) icp_pixel<true>(a, Rc, tc, Rpi, tp, i, acc);
+        else {
+            // contiguous pixel range per CTA, several pixels per thread in flight (same pass as the persistent tracker)
+            const int begin = (int)(((long long)N * blockIdx.x) / gridDim.x), end = (int)(((long long)N * (blockIdx.x + 1)) / gridDim.x);
+            icp_pass_nosearch<kReduceThreads>(a, Rc, tc, Rpi, tp, begin, end, acc);
+        }
+    }
 
     if (grid_reduce32(acc, wk->partials, &st->ticket, s_total)) {
         if (threadIdx.x < 32) st->icp_sums[threadIdx.x] = s_total[threadIdx.x];

@@ -93,19 +93,17 @@ __device__ __forceinline__ bool grid_reduce32(float (&v)[32], float (*partials)[
     __threadfence();
     // final: 8 slices x 32 values, fp64, fixed order
     {
-        // each warp sums every 8th partial; loads are batched 8 deep for memory-level parallelism,
-        // the additions stay in a fixed order
+        // each warp sums every 8th partial; ALL of a warp's loads are issued together (one L2 round trip for up to
+        // 8 x 40 = 320 blocks), the additions stay in a fixed order
         double acc = 0.0;
-        constexpr int W = kReduceThreads / 32, U = 8;
-        unsigned int b = warp;
-        for (; b + (U - 1) * W < gridDim.x; b += U * W) {
+        constexpr int W = kReduceThreads / 32, U = 40;
+        for (unsigned int b0 = warp; b0 < gridDim.x; b0 += U * W) {
             float t[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) t[u] = __ldcg(&partials[b + u * W][lane]);
+            for (int u = 0; u < U; ++u) { const unsigned int b = b0 + u * W; t[u] = b < gridDim.x ? __ldcg(&partials[b][lane]) : 0.f; }
 #pragma unroll
             for (int u = 0; u < U; ++u) acc += (double)t[u];
         }
-        for (; b < gridDim.x; b += W) acc += (double)__ldcg(&partials[b][lane]);
         s_d[warp][lane] = acc;
     }
     __syncthreads();

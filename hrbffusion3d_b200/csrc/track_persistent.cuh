@@ -142,90 +142,6 @@ __device__ __forceinline__ void all_reduce_int2(const unsigned long long* ip /* 
     __syncthreads();
 }
 
-// ---- the no-search ICP pixel split into load / gather / finish stages so that two pixels per thread are in flight
-// (the pass is bound by two dependent L2 round trips per pixel, not by bandwidth or issue slots) ----
-struct IcpCurr { float vx, vy, vz, nx, ny, nz, k1, k2; };
-struct IcpModel { float vx, vy, vz, nx, ny, nz, k1, k2, w; int ok, ux, uy; float3 vg, ng; };
-
-__device__ __forceinline__ IcpCurr icp_load_curr(const IcpArgs& a, int i)
-{
-    const int y = i / a.cols, x = i - y * a.cols, rows = a.rows;
-    auto ld = [&](const float* p, int plane) { return __ldg(p + (size_t)(plane * rows + y) * a.cpitch + x); };
-    IcpCurr c;
-    c.vx = ld(a.vc, 0); c.vy = ld(a.vc, 1); c.vz = ld(a.vc, 2);
-    c.nx = ld(a.nc, 0); c.ny = ld(a.nc, 1); c.nz = ld(a.nc, 2);
-    c.k1 = ld(a.k1c, 3); c.k2 = ld(a.k2c, 3);
-    return c;
-}
-__device__ __forceinline__ IcpModel icp_gather_model(const IcpArgs& a, const IcpCurr& c, const float* Rc, const float* tc, const float* Rpi, const float* tp)
-{
-    IcpModel m;
-    const int rows = a.rows;
-    m.vg = mul(Rc, make_float3(c.vx, c.vy, c.vz)) + make_float3(tc[0], tc[1], tc[2]);
-    const float3 vcp = mul(Rpi, m.vg - make_float3(tp[0], tp[1], tp[2]));
-    m.ux = __float2int_rn(vcp.x * a.fx / vcp.z + a.cx);
-    m.uy = __float2int_rn(vcp.y * a.fy / vcp.z + a.cy);
-    m.ok = !(m.ux < 0 || m.uy < 0 || m.ux >= a.cols || m.uy >= rows || vcp.z < 0) && !(isnan(c.vx) || isnan(c.nx) || isnan(c.k1) || isnan(c.k2));
-    m.ng = mul(Rc, make_float3(c.nx, c.ny, c.nz));
-    m.vx = m.vy = m.vz = m.nx = m.ny = m.nz = m.k1 = m.k2 = m.w = 0.f;
-    if (m.ok) {
-        auto ld = [&](const float* p, int plane) { return __ldg(p + (size_t)(plane * rows + m.uy) * a.gpitch + m.ux); };
-        m.vx = ld(a.vg, 0); m.vy = ld(a.vg, 1); m.vz = ld(a.vg, 2);
-        m.nx = ld(a.ng, 0); m.ny = ld(a.ng, 1); m.nz = ld(a.ng, 2);
-        m.k1 = ld(a.k1g, 3); m.k2 = ld(a.k2g, 3);
-        m.w = a.use_weight ? __ldg(a.w + (size_t)m.uy * a.wpitch + m.ux) : 1.f;
-    }
-    return m;
-}
-__device__ __forceinline__ void icp_finish(const IcpArgs& a, const IcpModel& m, const float* Rpi, const float* tp, int i, float (&acc)[32])
-{
-    float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
-    float weight = 1.f;
-    bool found = false;
-    if (m.ok) {
-        const float3 vp = make_float3(m.vx, m.vy, m.vz), np = make_float3(m.nx, m.ny, m.nz);
-        const float dist = norm(vp - m.vg), sine = norm(cross(m.ng, np));
-        found = !(isnan(vp.x) || isnan(np.x) || isnan(m.k1) || isnan(m.k2)) && !(sine > a.angle_thres || dist > a.dist_thres);
-        if (found) {
-            const float3 tpv = make_float3(tp[0], tp[1], tp[2]);
-            const float3 s_cp = mul(Rpi, m.vg - tpv), d_cp = mul(Rpi, vp - tpv), n_cp = mul(Rpi, np);
-            if (a.use_weight) weight = isnan(m.w) ? 0.f : m.w;
-            const float3 c = cross(s_cp, n_cp);
-            row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z; row[3] = c.x; row[4] = c.y; row[5] = c.z;
-            row[6] = dot(n_cp, s_cp - d_cp);
-        }
-    }
-    if (a.corres) a.corres[i] = found ? make_int2(m.ux, m.uy) : make_int2(-1, -1);
-    accumulate_row7(acc, row, weight, found);
-}
-// this CTA's contiguous pixel range [begin, end), kIcpInFlight pixels in flight per thread: all their current-frame loads
-// are issued together, then all their model gathers, then the rows are accumulated (2 dependent memory round trips per
-// trip of the loop; 640x480 level 0 = 2076 pixels per CTA = one full trip + a 28-pixel tail).
-#ifndef HRBF_ICP_INFLIGHT
-#define HRBF_ICP_INFLIGHT 2
-#endif
-constexpr int kIcpInFlight = HRBF_ICP_INFLIGHT;
-__device__ __forceinline__ void icp_pass_nosearch(const IcpArgs& a, const float* Rc, const float* tc, const float* Rpi, const float* tp,
-                                                  int begin, int end, float (&acc)[32])
-{
-    for (int i0 = begin + (int)threadIdx.x; i0 < end; i0 += kIcpInFlight * kTrackThreads) {
-        IcpCurr c[kIcpInFlight];
-#pragma unroll
-        for (int u = 0; u < kIcpInFlight; ++u) {
-            const int i = i0 + u * kTrackThreads;
-            c[u] = icp_load_curr(a, i < end ? i : i0);
-        }
-        IcpModel m[kIcpInFlight];
-#pragma unroll
-        for (int u = 0; u < kIcpInFlight; ++u) m[u] = icp_gather_model(a, c[u], Rc, tc, Rpi, tp);
-#pragma unroll
-        for (int u = 0; u < kIcpInFlight; ++u) {
-            const int i = i0 + u * kTrackThreads;
-            if (i < end) icp_finish(a, m[u], Rpi, tp, i, acc);
-        }
-    }
-}
-
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TP_STAMP(slot) do { if (p.dbg && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) p.dbg[dbg_n < 500 ? dbg_n++ : 499] = ((long long)(slot) << 56) | (gtimer() & 0x00ffffffffffffffll); } while (0)
 
@@ -460,7 +376,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { tc[k] = S.tcurr[k]; tp[k] = S.tprev[k]; }
                 if (L.icp.use_search) for (int i = gtid; i < N; i += gstride) icp_pixel<true>(L.icp, Rc, tc, Rpi, tp, i, acc);
-                else icp_pass_nosearch(L.icp, Rc, tc, Rpi, tp, begin, end, acc);
+                else icp_pass_nosearch<kTrackThreads>(L.icp, Rc, tc, Rpi, tp, begin, end, acc);
                 TP_STAMP(2);
                 block_partial32(acc, s_w, part + (size_t)blockIdx.x * 64, tag);
                 TP_STAMP(3);
