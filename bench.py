@@ -36,6 +36,8 @@ from hrbffusion3d_b200 import synth  # noqa: E402
 W, H = 640, 480
 RING = 96                    # frames of one closed camera loop, cycled (96 x 1.54 MB of inputs = 147 MB > 126 MB L2)
 ICP_BYTES_PER_PIXEL_ITER = 68.0
+ICP_NCU_TRAFFIC = 20927232.0      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, cold cache
+ICP_NCU_TRAFFIC_SRC = "ncu --set full, profiles/r1_icp_l0_ncu_full_summary.txt"
 FUSION_KW = {}               # reference defaults: RGB+ICP (weight 10), SO3 pre-alignment, iterations 10/5/4, HRBF win 3 / K 10
 
 
@@ -97,6 +99,10 @@ class OracleRunner:
 
     def __init__(self, depth, rgb, cam, threads, ring=RING):
         os.environ["OMP_NUM_THREADS"] = str(threads)
+        try:        # torchrun exports OMP_NUM_THREADS=1 and libgomp has read it long ago: set the team size explicitly
+            C.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+        except OSError:
+            pass
         from oracle import orc_pipeline as op
         self.f = op.HRBFFusion(W, H, cam, **FUSION_KW)
         self.depth, self.rgb, self.i, self.ring = depth, rgb, 0, ring
@@ -199,9 +205,13 @@ def ours_arm(args):
     ms_dev, launches, F = run(False)
     count = F.globalModel.lastCount()
     traj = F.trajectory().clone()
-    # roofline of the dominant kernel: level-0 ICP reduction, timed live with CUDA events on this pipeline's maps
-    us = C.c_float()
-    check(lib().hrbf_odometry_time_kernel(C.c_void_p(lib().hrbf_fusion_odometry(F._h)), 0, 0, 1, 200, C.byref(us), stream_ptr()))
+    # roofline: the level-0 ICP JTJ/JTr reduction (what hrbf_icp_step = the reference's icpStep launches), timed live with CUDA
+    # events over 200 back-to-back launches on this pipeline's maps; and the same reduction in its production form, as one
+    # iteration of the persistent tracker (reduction + cross-CTA exchange + fp64 solve inside ONE launch)
+    us, us_iter = C.c_float(), C.c_float()
+    odom = C.c_void_p(lib().hrbf_fusion_odometry(F._h))
+    check(lib().hrbf_odometry_time_kernel(odom, 0, 0, 0, 200, C.byref(us), stream_ptr()))
+    check(lib().hrbf_odometry_time_kernel(odom, 4, 0, 0, 200, C.byref(us_iter), stream_ptr()))
     torch.cuda.synchronize()
     del F
     ms_e2e, _, F2 = run(True)
@@ -226,9 +236,13 @@ def ours_arm(args):
     achieved = alg_bytes / (us.value * 1e-6) / 1e9
     cores = os.cpu_count() or 1
     n_cpu = 6
-    r = OracleRunner(depth, rgb, cam, cores)
-    r.step()
-    cpu_s = sum(r.step() for _ in range(n_cpu))
+    cpu_baseline = None
+    if world == 1:        # reported baseline, N = 1 only
+        r = OracleRunner(depth, rgb, cam, cores)
+        r.step()
+        cpu_s = sum(r.step() for _ in range(n_cpu))
+        cpu_baseline = {"value": n_cpu / cpu_s, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": "frames 2-%d of the same sequence (oracle pipeline, OpenMP over %d threads)" % (n_cpu + 1, cores)}
     total_frames = args.steps * world
     out = {"metric": "frames/sec HRBF+ICP 640x480", "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -236,12 +250,14 @@ def ours_arm(args):
            "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 48},
            "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count,
            "trajectory_ate_rmse_m": ate,
-           "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false> level 0 (640x480), incl. in-kernel Gauss-Newton solve",
+           "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false>, level 0 (640x480): the ICP JTJ/JTr reduction as hrbf_icp_step launches it",
                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                        "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": 20927232.0,
-                        "traffic_source": "ncu --set full, profiles/r1_icp_l0_ncu_full_summary.txt (dram__bytes_read.sum, cold cache)"},
-           "cpu_baseline": {"value": n_cpu / cpu_s, "unit": "frames/s", "cores": cores, "kind": "port",
-                            "sample": "frames 2-%d of the same sequence (oracle pipeline, OpenMP over %d threads)" % (n_cpu + 1, cores)}}
+                        "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": ICP_NCU_TRAFFIC,
+                        "traffic_source": ICP_NCU_TRAFFIC_SRC,
+                        "in_tracker": {"what": "the same reduction as one Gauss-Newton iteration of track_persistent_kernel (reduction + cross-CTA exchange "
+                                               "+ fp64 solve; 200 iterations in one launch, CUDA events)",
+                                       "us_per_iteration": us_iter.value, "achieved": alg_bytes / (us_iter.value * 1e-6) / 1e9, "unit": "GB/s"}},
+           "cpu_baseline": cpu_baseline}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

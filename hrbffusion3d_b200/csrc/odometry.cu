@@ -145,10 +145,11 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
 
 // The whole tracking loop as one cooperative persistent kernel (track_persistent.cuh).
 static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
-                                   bool so3, bool use_weight, const float* prev_pose_dev, float* pose_out_dev)
+                                   bool so3, bool use_weight, const float* prev_pose_dev, float* pose_out_dev, const int* iters_override = nullptr)
 {
     TrackParams p;
-    const int iters[3] = { fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0 };
+    int iters[3] = { fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0 };
+    if (iters_override) for (int l = 0; l < 3; ++l) iters[l] = iters_override[l];
     for (int l = 0; l < 3; ++l) {
         p.lvl[l].icp = icp_args(o, l, use_weight);
         p.lvl[l].res = rgbres_args(o, l);
@@ -770,7 +771,7 @@ int hrbf_odometry_track_async(hrbf_odometry* o, const float* prev_pose_dev, floa
 
 int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_update, int reps, float* avg_us, void* stream)
 {
-    HRBF_CHECK_ARG(o && avg_us && which >= 0 && which <= 3 && level >= 0 && level <= 2 && reps > 0);
+    HRBF_CHECK_ARG(o && avg_us && which >= 0 && which <= 4 && level >= 0 && level <= 2 && reps > 0 && reps <= 2000);
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = repack_if_dirty(o, s)) return rc;
     cudaEvent_t e0, e1;
@@ -780,21 +781,50 @@ int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_u
     const RgbResArgs ra = rgbres_args(o, level);
     const RgbStepArgs sa = rgbstep_args(o, level);
     const int nb = reduce_blocks(o->rows(level) * o->cols(level));
-    // one warm-up launch outside the timed region, then `reps` back-to-back launches between two events
-    for (int r = -1; r < reps; ++r) {
-        if (r == 0) HRBF_CUDA(cudaEventRecord(e0, s));
-        switch (which) {
-        case 0: icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, o->work, with_update ? 1 : 0, level, -1); break;
-        case 1: rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, o->work, 1, level, 0); break;
-        case 2: rgb_step_kernel<<<nb, kReduceThreads, 0, s>>>(sa, -2.0f, o->work, with_update ? 1 : 0, level, -1); break;
-        default: so3_reduce_kernel<<<reduce_blocks(o->rows(2) * o->cols(2)), kReduceThreads, 0, s>>>(o->lastNextImage[2], o->nextImage[2], o->rows(2), o->cols(2), o->work, 0); break;
+    if (which == 4) {
+        // ONE launch of the persistent tracker doing `reps` ICP-only Gauss-Newton iterations at `level` (reduction + cross-CTA
+        // exchange + fp64 solve each): the production form of the reduction.  Returns the time per iteration.
+        int it[3] = { 0, 0, 0 };
+        it[level] = reps;
+        for (int r = 0; r < 2; ++r) {
+            if (r == 1) HRBF_CUDA(cudaEventRecord(e0, s));
+            if (int rc = launch_track_persistent(o, s, false, 100.0f, true, false, false, true, o->pose_scratch + 12, o->pose_scratch + 24, it)) return rc;
         }
+        HRBF_CUDA(cudaEventRecord(e1, s));
+        HRBF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        HRBF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        *avg_us = ms * 1000.f / (float)reps;
+        return HRBF_OK;
     }
+    // `reps` back-to-back launches captured into ONE graph (so the host's launch rate is not what is measured), replayed once
+    // untimed and once between two events on `s`
+    auto launch_once = [&](cudaStream_t q) {
+        switch (which) {
+        case 0: icp_reduce_kernel<false><<<nb, kReduceThreads, 0, q>>>(ia, o->work, with_update ? 1 : 0, level, -1); break;
+        case 1: rgb_residual_kernel<<<nb, 256, 0, q>>>(ra, o->work, 1, level, 0); break;
+        case 2: rgb_step_kernel<<<nb, kReduceThreads, 0, q>>>(sa, -2.0f, o->work, with_update ? 1 : 0, level, -1); break;
+        default: so3_reduce_kernel<<<reduce_blocks(o->rows(2) * o->cols(2)), kReduceThreads, 0, q>>>(o->lastNextImage[2], o->nextImage[2], o->rows(2), o->cols(2), o->work, 0); break;
+        }
+    };
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    HRBF_CUDA(cudaStreamBeginCapture(o->cap_stream, cudaStreamCaptureModeThreadLocal));
+    for (int r = 0; r < reps; ++r) launch_once(o->cap_stream);
+    HRBF_CUDA(cudaStreamEndCapture(o->cap_stream, &g));
+    HRBF_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    HRBF_CUDA(cudaGraphLaunch(ge, s));
+    HRBF_CUDA(cudaEventRecord(e0, s));
+    HRBF_CUDA(cudaGraphLaunch(ge, s));
     HRBF_CUDA(cudaEventRecord(e1, s));
-    count_launch(reps + 1);
+    count_launch(2 * reps);
     HRBF_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
     HRBF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaGraphExecDestroy(ge);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     HRBF_CUDA(cudaGetLastError());
     *avg_us = ms * 1000.f / (float)reps;

@@ -199,7 +199,9 @@ int hrbf_odometry_track_async(hrbf_odometry*, const float* prev_pose_dev, float*
 /* Measurement hook (bench.py roofline): average duration in microseconds of `reps` back-to-back launches of
  * one reduction kernel of the tracking loop at pyramid `level`, timed with CUDA events on `stream`.
  * which: 0 ICP JTJ/JTr reduction, 1 RGB residual, 2 RGB step, 3 SO3 step.  with_update != 0 keeps the
- * in-kernel Gauss-Newton solve.  Needs initialised pyramids and one prior tracking call. */
+ * in-kernel Gauss-Newton solve.  which = 4: ONE launch of the persistent tracker running `reps` ICP-only Gauss-Newton
+ * iterations at `level` (reduction + cross-CTA exchange + fp64 solve); avg_us is the time per iteration.
+ * Needs initialised pyramids and one prior tracking call. */
 int hrbf_odometry_time_kernel(hrbf_odometry*, int which, int level, int with_update, int reps, float* avg_us, void* stream);
 /* device views of the internal pyramid maps (tests, chaining):
  * which = 0..8 -> vmap_g_prev,nmap_g_prev,ck1_g_prev,ck2_g_prev,vmap_curr,nmap_curr,ck1_curr,ck2_curr,icpWeight */
