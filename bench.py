@@ -120,7 +120,7 @@ def config_dict(n_gpus):
                         "SO3 pre-align, iterations 10/5/4) + splat/fuse/splat/clean + splat/HRBF predict (win 3, K 10) + fill-in",
             "width": W, "height": H, "frames_in_loop": RING,
             "l2": "inputs cycle through a closed loop of %d frames x 1.54 MB = %d MB > 126 MB L2; a frame also streams ~30 full-resolution textures" % (RING, int(RING * 1.536)),
-            "sequences": n_gpus, "parallelism": "one independent sequence per GPU, no collective inside the frame loop"}
+            "sequences": n_gpus, "parallelism": "one independent sequence per GPU (rank 0 scatters the .klg streams, trajectories are gathered back), no collective inside the frame loop"}
 
 
 def reference_arm(args):
@@ -157,12 +157,30 @@ def ours_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # rank 0 scatters one sequence descriptor per rank (stand-in for the .klg byte blobs, same code path: multigpu.scatter_blobs);
-    # trajectories are gathered at the end.  No collective inside the frame loop.
-    from hrbffusion3d_b200 import multigpu
-    blobs = [json.dumps({"sequence": r, "seed": r, "frames": RING}).encode() for r in range(world)] if rank == 0 else None
-    desc = json.loads(multigpu.scatter_blobs(blobs, device="cuda"))
-    depth, rgb, poses, cam = make_sequence(int(desc["seed"]))
+    # Offline batch: rank 0 owns the logs and scatters one .klg byte stream per rank (NCCL over NVLink for N > 1);
+    # every rank decodes its own log; trajectories are gathered at the end.  No collective inside the frame loop.
+    # Sequence r is the same closed camera loop entered r * RING / N frames later (a rotation of a closed loop is a valid sequence).
+    from hrbffusion3d_b200 import klg, multigpu
+    blobs = None
+    cam = synth.default_camera(W, H)
+    poses_all = synth.circle_trajectory(RING, frames_per_rev=RING)
+    if rank == 0:
+        depth0, rgb0, _, _ = make_sequence(0)
+        blobs = []
+        for r in range(world):
+            o = (r * RING) // world
+            blobs.append(klg.write_klg(((33333 * i, depth0[(i + o) % RING], rgb0[(i + o) % RING]) for i in range(RING)), W, H))
+        del depth0, rgb0
+    blob = multigpu.scatter_blobs(blobs, device="cuda")
+    del blobs
+    frames = list(klg.KlgReader(blob, W, H))
+    assert len(frames) == RING
+    depth = np.stack([f[1] for f in frames])
+    rgb = np.stack([f[2] for f in frames])
+    klg_bytes = len(blob)
+    del blob, frames
+    offset = (rank * RING) // world
+    poses = [poses_all[(i + offset) % RING] for i in range(RING)]
     depth_pin = torch.from_numpy(depth.view(np.int16)).pin_memory()
     rgb_pin = torch.from_numpy(rgb).pin_memory()
     depth_dev, rgb_dev = depth_pin.cuda(), rgb_pin.cuda()
@@ -225,7 +243,8 @@ def ours_arm(args):
     # sanity of the measured work: absolute trajectory error of every gathered sequence against the synthetic ground truth
     ate = []
     for r, g in enumerate(gathered):
-        gt = poses if r == 0 else synth.circle_trajectory(RING, frames_per_rev=RING)      # same camera loop for every seed
+        o_r = (r * RING) // world
+        gt = [poses_all[(i + o_r) % RING] for i in range(RING)]
         P0inv = np.linalg.inv(np.asarray(gt[0], np.float64))
         est_t = g.numpy()[:, 9:12].astype(np.float64)
         gt_t = np.stack([(P0inv @ np.asarray(gt[i % RING], np.float64))[:3, 3] for i in range(est_t.shape[0])])
@@ -248,7 +267,7 @@ def ours_arm(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
            "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 48},
-           "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count,
+           "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count, "klg_bytes_per_sequence": klg_bytes,
            "trajectory_ate_rmse_m": ate,
            "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false>, level 0 (640x480): the ICP JTJ/JTr reduction as hrbf_icp_step launches it",
                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,

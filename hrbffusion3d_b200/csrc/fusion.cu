@@ -233,6 +233,8 @@ struct hrbf_model {
     unsigned int bound = 0;      // host-side upper bound of the device count (grid sizing only)
     int n_slots = 0;
     int staged_time = -1;        // time of the fuse whose staging buffer clean() must append
+    float* delta = nullptr;      // updateModel: device copy of the per-sub-map corrections
+    size_t delta_bytes = 0;
 };
 
 static int model_upload_pose(hrbf_model* m, const float* pose16, cudaStream_t s, const float** pose_dev, const float** inv_dev)
@@ -369,6 +371,7 @@ int hrbf_model_destroy(hrbf_model* m)
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_kf) cudaFreeHost(m->h_kf);
     if (m->h_count) cudaFreeHost(m->h_count);
+    if (m->delta) cudaFree(m->delta);
     if (m->slab) cudaFree(m->slab);
     delete m;
     return HRBF_OK;
@@ -429,6 +432,26 @@ int hrbf_model_set_model(hrbf_model* m, const float* surfels, unsigned int count
     HRBF_CUDA(cudaStreamSynchronize(s));
     m->bound = count;
     m->staged_time = -1;
+    return HRBF_OK;
+}
+int hrbf_model_update_model(hrbf_model* m, const float* delta16_host, int n_delta, void* stream)
+{
+    HRBF_CHECK_ARG(m && delta16_host && n_delta > 0 && n_delta <= 4096);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)n_delta * 16 * sizeof(float);
+    if (bytes > m->delta_bytes) {
+        if (m->delta) { HRBF_CUDA(cudaStreamSynchronize(s)); cudaFree(m->delta); m->delta = nullptr; m->delta_bytes = 0; }
+        HRBF_CUDA(cudaMalloc(&m->delta, bytes));
+        m->delta_bytes = bytes;
+    }
+    HRBF_CUDA(cudaMemcpyAsync(m->delta, delta16_host, bytes, cudaMemcpyHostToDevice, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));          // pageable source: the caller may reuse its buffer on return
+    if (m->bound > 0) {
+        int blocks = (int)((m->bound + 255u) / 256u);
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        update_model_kernel<<<blocks, 256, 0, s>>>(m->vbo[m->cur], m->count[m->cur], m->delta, n_delta);
+        HRBF_KERNEL_CHECK();
+    }
     return HRBF_OK;
 }
 const float* hrbf_model_model(hrbf_model* m) { return m ? (const float*)m->vbo[m->cur] : nullptr; }

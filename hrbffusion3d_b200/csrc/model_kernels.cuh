@@ -448,6 +448,25 @@ __global__ void __launch_bounds__(kScanBlock) clean_scatter_kernel(CleanArgs c, 
     }
 }
 
+// ------------------------------------------------------------------ updateModel ---
+// GlobalModel::updateModel (GlobalModel.cpp:690-767, update_delta_trans.vert:41-91): rigid correction per sub-map, in place.
+// Streams 32 of the 80 bytes of every surfel (position and normal records); delta = n_delta row-major 4x4 matrices.
+__global__ void __launch_bounds__(256) update_model_kernel(float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
+                                                           const float* __restrict__ delta, int n_delta)
+{
+    const unsigned int count = *count_dev;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += blockDim.x * gridDim.x) {
+        float4* s = surfels + 5 * (size_t)i;
+        const unsigned int sub = (unsigned int)reinterpret_cast<const float*>(s + 1)[1];
+        if (sub >= (unsigned int)n_delta) continue;
+        const float* T = delta + 16 * (size_t)sub;
+        const float4 p = s[0], n = s[2];
+        s[0] = make_float4(((T[0] * p.x + T[1] * p.y) + T[2] * p.z) + T[3], ((T[4] * p.x + T[5] * p.y) + T[6] * p.z) + T[7],
+                           ((T[8] * p.x + T[9] * p.y) + T[10] * p.z) + T[11], p.w);
+        s[2] = make_float4((T[0] * n.x + T[1] * n.y) + T[2] * n.z, (T[4] * n.x + T[5] * n.y) + T[6] * n.z, (T[8] * n.x + T[9] * n.y) + T[10] * n.z, n.w);
+    }
+}
+
 __global__ void fill_u32_kernel(unsigned int* p, size_t n, unsigned int v)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;

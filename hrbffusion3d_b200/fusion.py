@@ -166,6 +166,11 @@ class GlobalModel:
         else:
             check(lib().hrbf_model_set_model(self._h, ptr(surfels.contiguous()), C.c_uint(surfels.shape[0]), 0, stream_ptr()))
 
+    def updateModel(self, deltaTransformKF):
+        """GlobalModel::updateModel: deltaTransformKF [n, 4, 4] rigid corrections indexed by sub-map id"""
+        d = np.ascontiguousarray(deltaTransformKF, np.float32).reshape(-1, 16)
+        check(lib().hrbf_model_update_model(self._h, d.ctypes.data_as(C.POINTER(C.c_float)), int(d.shape[0]), stream_ptr()))
+
     def lastCount(self):
         c = C.c_uint(0)
         check(lib().hrbf_model_last_count(self._h, C.byref(c), stream_ptr()))

@@ -341,6 +341,9 @@ int hrbf_model_fuse(hrbf_model*, const float* pose16_host, int time, const unsig
 int hrbf_model_clean(hrbf_model*, const float* pose16_host, int time, const unsigned int* indexMap, const float* vertConfMap,
                      const float* colorTimeMap, const float* normRadMap, const float* depthMap, float confThreshold,
                      float maxDepth, void* stream);
+/* GlobalModel::updateModel, GlobalModel.cpp:690-767 (+ Shaders/update_delta_trans.vert): rigid correction of every surfel by
+ * the matrix of its sub-map, DeltaTransformKF[(int)colour.y]; delta16_host = n_delta row-major 4x4 matrices.  In place. */
+int hrbf_model_update_model(hrbf_model*, const float* delta16_host, int n_delta, void* stream);
 /* load a surfel array (e.g. a saved map) as the current model; host != 0: `surfels` is host memory.  Synchronous. */
 int hrbf_model_set_model(hrbf_model*, const float* surfels, unsigned int count, int host, void* stream);
 /* GlobalModel::model() / lastCount(): device pointer of the current surfel array; lastCount synchronises */

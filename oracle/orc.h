@@ -248,6 +248,9 @@ void orc_fillIn(const orc_prep_params* p, int passthrough, float lambda, float c
 /* HRBFFusion.cpp:974-988 + Shaders/Resize.cpp (1/20 nearest sample at texel centres) */
 int orc_denseEnough(int rows, int cols, const float* vertex, float thresh);
 
+/* GlobalModel::updateModel, GlobalModel.cpp:690-767 + Shaders/update_delta_trans.vert:41-91 (in place) */
+void orc_model_update(float* surfels, int count, const float* delta, int n_delta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -272,3 +272,24 @@ int orc_model_clean(const orc_model_params* p, const float pose[16], int time,
     }
     return n;
 }
+
+/* GlobalModel::updateModel (GlobalModel.cpp:690-767) + Shaders/update_delta_trans.vert:41-91: every surfel is moved by the
+ * rigid correction of its sub-map, T = DeltaTransformKF[(int)colour.y]: position <- T * (p, 1) (confidence kept), normal <- R n
+ * (radius kept); colour/time and both curvature vectors pass through unchanged (the directions are NOT rotated there).
+ * delta: n_delta row-major 4x4 matrices.  In place; order and count unchanged. */
+void orc_model_update(float* surfels, int count, const float* delta, int n_delta)
+{
+    for (int i = 0; i < count; ++i) {
+        float* s = surfels + 20 * (size_t)i;
+        const unsigned int sub = (unsigned int)s[5];
+        if (sub >= (unsigned int)n_delta) continue;      /* texel outside the uploaded range: the texture holds its initial zeros there; restated as "no-op" */
+        const float* T = delta + 16 * (size_t)sub;
+        const float x = s[0], y = s[1], z = s[2], nx = s[8], ny = s[9], nz = s[10];
+        s[0] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+        s[1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+        s[2] = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
+        s[8] = (T[0] * nx + T[1] * ny) + T[2] * nz;
+        s[9] = (T[4] * nx + T[5] * ny) + T[6] * nz;
+        s[10] = (T[8] * nx + T[9] * ny) + T[10] * nz;
+    }
+}

@@ -403,3 +403,11 @@ def modelClean(mp, pose, time, idx, surfels, unstable, active_kf=None):
                               _p(_f(idx["colorTime"])), _p(_f(idx["normRad"])), _p(_f(active_kf)), int(len(active_kf)),
                               _p(_f(surfels)), int(surfels.shape[0]), _p(_f(unstable)), int(unstable.shape[0]), _p(out))
     return out[:n].copy()
+
+
+def modelUpdate(surfels, delta):
+    """GlobalModel::updateModel: delta [n, 4, 4] row-major rigid corrections indexed by sub-map id"""
+    out = np.ascontiguousarray(surfels, np.float32).copy()
+    d = np.ascontiguousarray(delta, np.float32).reshape(-1, 16)
+    lib().orc_model_update(_p(out), int(out.shape[0]), _p(d), int(d.shape[0]))
+    return out

@@ -175,3 +175,32 @@ def test_process_frame_sequence_matches_oracle(orc, cuda, W, H, kw):
     tr = gpu.trajectory().cpu().numpy()
     assert tr.shape == (n, 12)
     np.testing.assert_allclose(tr[-1, 9:], Tg[:3, 3], atol=1e-7)
+
+
+def test_update_model_matches_oracle(orc, cuda):
+    """GlobalModel::updateModel (SURVEY 8f row 3): per-sub-map rigid correction, bit-exact positions / normals, order kept."""
+    from hrbffusion3d_b200.fusion import GlobalModel
+    W, H = 160, 120
+    cam = synth.default_camera(W, H)
+    rng = np.random.default_rng(7)
+    n = 5000
+    s = rng.standard_normal((n, 20)).astype(np.float32)
+    s[:, 5] = rng.integers(0, 6, n).astype(np.float32)          # sub-map ids 0..5; only 0..3 get a correction
+    delta = np.stack([synth.make_pose(0.01 * k, -0.02 * k, 0.005 * k, (0.01 * k, 0.02, -0.01 * k)) for k in range(4)]).astype(np.float32)
+    ref = orc.modelUpdate(s, delta)
+    gm = GlobalModel(W, H, cam, capacity=1 << 14)
+    gm.setModel(s)
+    gm.updateModel(delta)
+    out, cnt = gm.model()
+    assert cnt == n
+    out = out.cpu().numpy()
+    # FMA contraction differs from the oracle's separately rounded products: 1-ulp level
+    np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-6)
+    untouched = s[:, 5] >= 4
+    assert np.array_equal(out[untouched], s[untouched])
+    cols = [3, 4, 5, 6, 7, 11] + list(range(12, 20))
+    assert np.array_equal(out[:, cols], s[:, cols])              # confidence, colour/time, radius, curvature pass through
+    # empty model and argument checks
+    gm.setModel(s[:0])
+    gm.updateModel(delta)
+    assert gm.lastCount() == 0
