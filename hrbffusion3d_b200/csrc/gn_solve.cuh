@@ -48,17 +48,27 @@ __device__ __noinline__ void ldlt_solve_pivoted(const double* Ain, const double*
     for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
 }
 
+// 1/d for a pivot of the normal matrix (|d| within float range): float seed + two Newton steps in fp64 (~1e-15 relative),
+// a fraction of the instruction count of the IEEE fp64 division on the single thread that runs the solve
+__device__ __forceinline__ double rcp_pivot(double d)
+{
+    double r = (double)(1.0f / (float)d);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return r;
+}
+
 // Fast path: unpivoted LDL^T in registers (the normal matrix is SPD whenever tracking has
 // support).  Returns false if a pivot is not safely positive -> caller takes the pivoted path.
 template <int N>
 __device__ __forceinline__ bool ldlt_solve_spd(const double (&A)[N * N], const double (&b)[N], double (&x)[N])
 {
-    double L[N][N], D[N], y[N];
+    double L[N][N], D[N], Dinv[N], y[N];
     double amax = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) amax = fmax(amax, fabs(A[i * N + i]));
     const double tiny = amax * 1e-13;
-    bool ok = amax > 0.0;
+    bool ok = amax > 1e-30 && amax < 1e30;               // rcp_pivot seeds in float
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         double d = A[j * N + j];
@@ -66,7 +76,8 @@ __device__ __forceinline__ bool ldlt_solve_spd(const double (&A)[N * N], const d
         for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
         D[j] = d;
         ok = ok && (d > tiny);
-        const double inv = 1.0 / d;
+        const double inv = rcp_pivot(d);
+        Dinv[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             double s = A[i * N + j];
@@ -84,7 +95,7 @@ __device__ __forceinline__ bool ldlt_solve_spd(const double (&A)[N * N], const d
         y[i] = s;
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) y[i] /= D[i];
+    for (int i = 0; i < N; ++i) y[i] *= Dinv[i];
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
         double s = y[i];
@@ -115,7 +126,19 @@ __device__ __forceinline__ void ldlt_solve(const double (&A)[N * N], const doubl
 __device__ __forceinline__ void rodrigues(const double (&w)[3], double (&R)[9])
 {
     double rx = w[0], ry = w[1], rz = w[2];
-    const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    const double t2 = rx * rx + ry * ry + rz * rz;
+    if (t2 < 0.0625) {
+        // Gauss-Newton increments are tiny: R = cos(t) I + A [w]x + B w w^T with A = sin(t)/t and B = (1 - cos t)/t^2 as
+        // series in t^2 (truncation < 1e-19 for t < 0.25): no square root, division or library sincos on the critical thread
+        const double A = 1.0 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880 + t2 * (-1.0 / 39916800 + t2 * (1.0 / 6227020800.0))))));
+        const double B = 0.5 + t2 * (-1.0 / 24 + t2 * (1.0 / 720 + t2 * (-1.0 / 40320 + t2 * (1.0 / 3628800 + t2 * (-1.0 / 479001600 + t2 * (1.0 / 87178291200.0))))));
+        const double c = 1.0 - B * t2;
+        R[0] = c + B * rx * rx; R[1] = B * rx * ry - A * rz; R[2] = B * rx * rz + A * ry;
+        R[3] = B * rx * ry + A * rz; R[4] = c + B * ry * ry; R[5] = B * ry * rz - A * rx;
+        R[6] = B * rx * rz - A * ry; R[7] = B * ry * rz + A * rx; R[8] = c + B * rz * rz;
+        return;
+    }
+    const double theta = sqrt(t2);
     R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
     if (theta >= DBL_EPSILON) {
         double s, c;
@@ -277,6 +300,94 @@ __device__ __forceinline__ void gn_update(TrackState* st, int cur_level, int nex
         st->tcurr[a] = Rp[a * 3] * ti[0] + Rp[a * 3 + 1] * ti[1] + Rp[a * 3 + 2] * ti[2] + tp[a];
     }
     if (next_level >= 0 && rgb) update_krk(st, nrt, next_level);
+}
+
+// gn_update for a state in SHARED memory, run by warps 0 and 1 of the CTA (call with all of their 64 threads):
+// the normal equations, the pose composition and the new camera pose are spread over lanes; the fp64 solve itself stays on
+// one lane; the photometric warp matrices (update_krk) run on warp 1 while warp 0 composes the pose.
+#ifndef GN_STAMP
+#define GN_STAMP(k)
+#endif
+__device__ __forceinline__ void gn_update_warps(TrackState* st, int next_level, long long* dbg = nullptr, int* dbg_n_ptr = nullptr)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool icp = st->icp != 0, rgb = st->rgb != 0;
+    if (warp == 0) {
+        for (int e = lane; e < 42; e += 32) {
+            int i, j;
+            if (e < 36) { i = e / 6; j = e - 6 * i; if (i > j) { const int t = i; i = j; j = t; } } else { i = e - 36; j = 6; }
+            const int idx = i * 7 - (i * (i - 1)) / 2 + (j - i);
+            const double vr = (double)(float)st->rgb_sums[idx], vi = (double)(float)st->icp_sums[idx];
+            const double w = st->icpWeight;
+            double val;
+            if (icp && rgb) val = (e < 36) ? vr + w * w * vi : vr + w * vi;
+            else val = icp ? vi : vr;
+            if (e < 36) st->lastA[e] = val; else st->lastb[e - 36] = val;
+        }
+        if (lane == 0 && icp) {
+            const float r0 = (float)st->icp_sums[27], r1 = (float)st->icp_sums[28];
+            st->lastICPError = sqrtf(r0) / r1;
+            st->lastICPCount = r1;
+            st->icp_iterations_run++;
+        }
+        __syncwarp();
+        GN_STAMP(12);
+        if (lane == 0) {
+            double A[36], b[6], x[6], Rupd[9];
+#pragma unroll
+            for (int k = 0; k < 36; ++k) A[k] = st->lastA[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) b[k] = st->lastb[k];
+            ldlt_solve<6>(A, b, x);
+            GN_STAMP(13);
+            const double wv[3] = { x[3], x[4], x[5] };
+            rodrigues(wv, Rupd);
+            GN_STAMP(14);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st->gn_t[k] = x[k];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st->gn_R[k] = Rupd[k];
+        }
+        __syncwarp();
+        // resultRt = [exp(w) | t] * resultRt (OdometryProvider.h:71-93): one entry of the top 3 rows per lane
+        double nv = 0.0;
+        if (lane < 12) {
+            const int a = lane >> 2, b = lane & 3;
+            nv = st->gn_R[a * 3 + 0] * st->resultRt[0 * 4 + b] + st->gn_R[a * 3 + 1] * st->resultRt[1 * 4 + b] + st->gn_R[a * 3 + 2] * st->resultRt[2 * 4 + b] +
+                 st->gn_t[a] * st->resultRt[3 * 4 + b];
+        }
+        __syncwarp();
+        if (lane < 12) st->resultRt[lane] = nv;
+        GN_STAMP(15);
+    }
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (warp == 0) {
+        // currentT = [Rprev|tprev] * rgbOdom^-1 in float (RGBDOdometry.cpp:1196-1204): one entry per lane
+        if (lane < 12) {
+            float Rf[9], tf[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int b = 0; b < 3; ++b) Rf[a * 3 + b] = (float)st->resultRt[a * 4 + b];
+                tf[a] = (float)st->resultRt[a * 4 + 3];
+            }
+            if (lane < 9) {
+                const int a = lane / 3, b = lane - 3 * a;
+                st->Rcurr[lane] = st->Rprev[a * 3] * Rf[b * 3] + st->Rprev[a * 3 + 1] * Rf[b * 3 + 1] + st->Rprev[a * 3 + 2] * Rf[b * 3 + 2];
+            } else {
+                const int a = lane - 9;
+                float ti[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ti[k] = -(Rf[0 * 3 + k] * tf[0] + Rf[1 * 3 + k] * tf[1] + Rf[2 * 3 + k] * tf[2]);
+                st->tcurr[a] = st->Rprev[a * 3] * ti[0] + st->Rprev[a * 3 + 1] * ti[1] + st->Rprev[a * 3 + 2] * ti[2] + st->tprev[a];
+            }
+        }
+    } else if (lane == 0 && next_level >= 0 && rgb) {
+        double nrt[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) nrt[k] = st->resultRt[k];
+        update_krk(st, nrt, next_level);
+    }
 }
 
 // SO3 control flow of one iteration (RGBDOdometry.cpp:879-912) from st->so3_sums

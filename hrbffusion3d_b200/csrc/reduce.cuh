@@ -34,6 +34,7 @@ struct TrackState {
     // statistics mirrored to the host (RGBDOdometry.h:124-134)
     float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
     double lastA[36], lastb[6];
+    double gn_t[3], gn_R[9];             // scratch of the warp-parallel update (translation and rotation increment)
     int icp_iterations_run;
     unsigned int ticket;                 // last-block-done counter
     int pad_;

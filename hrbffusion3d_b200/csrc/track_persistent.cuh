@@ -8,6 +8,7 @@
 // step-function ABI) this removes ~70 dependent kernel boundaries per frame, the ticket atomics and the
 // __threadfence of the last-block-done scheme.
 #pragma once
+#define GN_STAMP(k) do { if (dbg && dbg_n_ptr && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); dbg[*dbg_n_ptr < 500 ? (*dbg_n_ptr)++ : 499] = ((long long)(k) << 56) | (t_ & 0x00ffffffffffffffll); } } while (0)
 #include "odometry_kernels.cuh"
 
 namespace hrbf {
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
             TP_STAMP(5);
             if (tid < 32) { if (p.icp) S.icp_sums[tid] = s_tot[tid]; if (p.rgb) S.rgb_sums[tid] = s_tot[32 + tid]; }
             __syncthreads();
-            if (tid == 0) gn_update(&S, l, next_level);
+            if (tid < 64) gn_update_warps(&S, next_level, p.dbg, &dbg_n);
             __syncthreads();
             TP_STAMP(6);
             ++phase;

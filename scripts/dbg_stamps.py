@@ -21,7 +21,7 @@ for kw in (dict(icpWeight=100.0, so3=False), dict(icpWeight=10.0, so3=True)):
     a = np.array(buf[:], dtype=np.int64); a = a[a != 0]
     slot = (a >> 56).astype(int); t = (a & ((1 << 56) - 1)).astype(np.int64)
     print(kw, "stamps", len(a), "total us", (t[-1] - t[0]) / 1e3)
-    names = {2: "icp pass", 3: "block reduce", 4: "block reduce (rgb) / none", 5: "all-reduce", 6: "solve", 1: "loop overhead", 7: "residual pass", 8: "cta int reduce + publish", 9: "int all-reduce (wait for all CTAs)", 10: "sigma", 11: "step pass"}
+    names = {2: "icp pass", 3: "block reduce", 4: "block reduce (rgb) / none", 5: "all-reduce", 6: "solve", 1: "loop overhead", 7: "residual pass", 8: "cta int reduce + publish", 9: "int all-reduce (wait for all CTAs)", 10: "sigma", 11: "step pass", 12: "gn: normal equations (lanes)", 13: "gn: LDLT", 14: "gn: rodrigues", 15: "gn: compose"}
     agg = {}
     for i in range(1, len(a)):
         agg.setdefault((slot[i - 1], slot[i]), []).append((t[i] - t[i - 1]) / 1e3)
