@@ -183,7 +183,8 @@ __device__ __forceinline__ float hrbf_ray_value(const NbRay (&nb)[kPredSlots], b
 // hrbfbase.glsl:147-166 (+ getWeightH :37-69) at point p, over this lane's neighbours (slot s -> s_sel[s * 4 + sub]), summed
 // over the 4 lanes of the pixel.  Runs once per found pixel: the neighbours are re-read from the shared-memory tile.
 template <typename CenterAt>
-__device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots, float px, float py, float pz, unsigned gmask)
+__device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots, float px, float py, float pz, unsigned gmask, int sub,
+                                                      float& best, int& besti)
 {
     float gx = 0.f, gy = 0.f, gz = 0.f;
     for (int s = 0; s < nslots; ++s) {
@@ -191,6 +192,10 @@ __device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots
         nb_at(s, v, n);
         const float vx = px - v.x, vy = py - v.y, vz = pz - v.z;
         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        {   // nearest neighbour of the root: smallest distance, ties -> lowest rank
+            const float d = sqrtf(d2);
+            if (d < best) { best = d; besti = s * kPredLanes + sub; }
+        }
         const float T2 = __fmul_rn(n.w, n.w);
         if (d2 > T2) continue;
         const float nx = 10.0f * n.x, ny = 10.0f * n.y, nz = 10.0f * n.z;
@@ -280,10 +285,11 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
     if (!inside) sel = 0ull;
     int N = __popcll(sel);
     if (N > 32) N = 32;                                 // cannot happen for maxN <= 16, win <= 3 (host-checked)
-    for (int j = 0; j < N; ++j) {
-        const int c = __ffsll((long long)sel) - 1;
-        sel &= sel - 1ull;
-        if ((j & (kPredLanes - 1)) == sub) s_sel[grp][j] = (unsigned char)((ly + kPredHalo + s_tab.dy[c]) * kPredSW + lx + kPredHalo + s_tab.dx[c]);
+    // neighbour of rank j (in scan order) -> lane j & 3, slot j >> 2.  Every lane ranks the candidates it tested itself.
+    for (int c = sub; c < ncand; c += kPredLanes) {
+        if (!((sel >> c) & 1ull)) continue;
+        const int j = __popcll(sel & ((1ull << c) - 1ull));
+        if (j < 32) s_sel[grp][j] = (unsigned char)((ly + kPredHalo + s_tab.dy[c]) * kPredSW + lx + kPredHalo + s_tab.dx[c]);
     }
     __syncwarp(gmask);
 
@@ -397,20 +403,12 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
         }
     }
     const float tx = fmaf(tm, rx, c0x), ty = fmaf(tm, ry, c0y), tz = fmaf(tm, rz, c0z);
+    // ---- gradient at the root (hrbfbase.glsl:147-166) and attributes of the nearest neighbour (:273-303), one pass ----
     float3 g = make_float3(0.f, 0.f, 0.f);
-    if (found) g = hrbf_gradient_group(nb_at, nslots, tx, ty, tz, gmask);
-
-    // ---- attributes of the nearest neighbour (:273-303) ----
     float best = 1000000.f;
     int besti = 0x7fffffff;
+    if (found) g = hrbf_gradient_group(nb_at, nslots, tx, ty, tz, gmask, sub, best, besti);
     if (found) {
-        for (int s = 0; s < nslots; ++s) {
-            float4 v, n;
-            nb_at(s, v, n);
-            const float dx = tx - v.x, dy = ty - v.y, dz = tz - v.z;
-            const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-            if (d < best) { best = d; besti = s * kPredLanes + sub; }
-        }
 #pragma unroll
         for (int m = 1; m <= 2; m <<= 1) {
             const float ob = __shfl_xor_sync(gmask, best, m);
