@@ -61,6 +61,37 @@ __device__ __forceinline__ float3 cross(float3 a, float3 b)
 }
 __device__ __forceinline__ float norm(float3 a) { return sqrtf(dot(a, a)); }
 
+// pose (R[9], t[3]) -> its rigid inverse (R^T, -R^T t), the arithmetic of the host path (IndexMap.cpp:207, pose.inverse())
+__device__ __forceinline__ void pose_inverse_dev(const float* pose, float* inv)
+{
+    float Ri[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = pose[j * 3 + i];
+    for (int k = 0; k < 9; ++k) inv[k] = Ri[k];
+    for (int i = 0; i < 3; ++i) inv[9 + i] = -(__fadd_rn(__fadd_rn(__fmul_rn(Ri[i * 3], pose[9]), __fmul_rn(Ri[i * 3 + 1], pose[10])), __fmul_rn(Ri[i * 3 + 2], pose[11])));
+}
+// HRBFFusion.cpp:1112-1123 : fusion weight from the inter-frame motion (|t| vs rotation angle)
+__device__ __forceinline__ float velocity_weighting_dev(const float* curr, const float* last, float weightMultiplier)
+{
+    // diff = curr^-1 * last
+    float R[9], t[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = (curr[0 * 3 + i] * last[0 * 3 + j] + curr[1 * 3 + i] * last[1 * 3 + j]) + curr[2 * 3 + i] * last[2 * 3 + j];
+        const float d0 = last[9] - curr[9], d1 = last[10] - curr[10], d2 = last[11] - curr[11];
+        t[i] = (curr[0 * 3 + i] * d0 + curr[1 * 3 + i] * d1) + curr[2 * 3 + i] * d2;
+    }
+    const double rx = (double)R[7] - (double)R[5], ry = (double)R[2] - (double)R[6], rz = (double)R[3] - (double)R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = ((double)((R[0] + R[4]) + R[8]) - 1.0) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    double theta = acos(c);
+    if (s < 1e-5 && c > 0) theta = 0.0;
+    const float tn = sqrtf((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]);
+    float w = fmaxf(tn, (float)theta);
+    const float largest = 0.01f, minWeight = 0.5f;
+    if (w > largest) w = largest;
+    return fmaxf(1.0f - (w / largest), minWeight) * weightMultiplier;
+}
+
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // SoA map view: plane k, row y, col x -> p[(k*rows + y)*pitch + x]   (pitch in elements)

@@ -80,17 +80,25 @@ int hrbf_frame_destroy(hrbf_frame* f)
     delete f;
     return HRBF_OK;
 }
-int hrbf_frame_upload(hrbf_frame* f, const unsigned char* rgb8, const unsigned short* depth16, int host, void* stream)
+}  // extern "C"
+// make_rgba = false: the RGBA texture is not refreshed (the frame pipeline reads the RGB8 upload directly after the first frame)
+static int frame_upload(hrbf_frame* f, const unsigned char* rgb8, const unsigned short* depth16, int host, bool make_rgba, cudaStream_t s)
 {
-    HRBF_CHECK_ARG(f && rgb8 && depth16);
-    cudaStream_t s = (cudaStream_t)stream;
     const size_t P = (size_t)f->p.width * f->p.height;
     const cudaMemcpyKind k = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     HRBF_CUDA(cudaMemcpyAsync(f->tex[HRBF_FT_RGB], rgb8, P * 3, k, s));
     HRBF_CUDA(cudaMemcpyAsync(f->tex[HRBF_FT_DEPTH_RAW], depth16, P * 2, k, s));
-    rgb_to_rgba_kernel<<<div_up((int)P, 256), 256, 0, s>>>((int)P, (const unsigned char*)f->tex[HRBF_FT_RGB], (uchar4*)f->tex[HRBF_FT_RGBA]);
-    HRBF_KERNEL_CHECK();
+    if (make_rgba) {
+        rgb_to_rgba_kernel<<<div_up((int)P, 256), 256, 0, s>>>((int)P, (const unsigned char*)f->tex[HRBF_FT_RGB], (uchar4*)f->tex[HRBF_FT_RGBA]);
+        HRBF_KERNEL_CHECK();
+    }
     return HRBF_OK;
+}
+extern "C" {
+int hrbf_frame_upload(hrbf_frame* f, const unsigned char* rgb8, const unsigned short* depth16, int host, void* stream)
+{
+    HRBF_CHECK_ARG(f && rgb8 && depth16);
+    return frame_upload(f, rgb8, depth16, host, true, (cudaStream_t)stream);
 }
 int hrbf_frame_preprocess(hrbf_frame* f, void* stream)
 {
@@ -140,6 +148,7 @@ void* hrbf_frame_texture(hrbf_frame* f, int which)
 // ======================================================================== hrbf_fillin
 }  // extern "C"
 struct hrbf_fillin {
+    const float* inline_weighting = nullptr;   // frame pipeline: device fusion weight (confidence evaluated in place)
     int width = 0, height = 0;
     char* slab = nullptr;
     void* tex[HRBF_FILL_COUNT] = {};
@@ -181,6 +190,8 @@ int hrbf_fillin_run(hrbf_fillin* f, hrbf_indexmap* im, hrbf_frame* fr, int passt
     a.oVertex = (float4*)f->tex[HRBF_FILL_VERTEX]; a.oNormal = (float4*)f->tex[HRBF_FILL_NORMAL]; a.oK1 = (float4*)f->tex[HRBF_FILL_CURVK1];
     a.oK2 = (float4*)f->tex[HRBF_FILL_CURVK2]; a.oIcpW = (float*)f->tex[HRBF_FILL_ICPWEIGHT]; a.oImage = (uchar4*)f->tex[HRBF_FILL_IMAGE];
     a.n = f->width * f->height; a.passthrough = passthrough; a.lambda = lambda; a.curvThr = curvThr;
+    a.weighting = (f->inline_weighting && !fr->p.useConfEval) ? f->inline_weighting : nullptr;
+    a.cols = fr->p.width; a.rows = fr->p.height; a.cx = fr->p.cx; a.cy = fr->p.cy;
     fill_in_kernel<<<div_up(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a);
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
@@ -272,14 +283,14 @@ int model_initialise_dev(hrbf_model* m, const float* vertexMap, const float* nor
 
 int model_fuse_dev(hrbf_model* m, const float* pose_dev, int time, const unsigned char* rgb8, const float* depthRaw, const float* depthFiltered,
                    const float* curv1, const float* curv2, const float* confidence, const unsigned int* indexMap, const float* vertConf,
-                   const float* normRad, float depthCutoff, int indexSubmap, cudaStream_t s)
+                   const float* normRad, float depthCutoff, int indexSubmap, cudaStream_t s, const float* inline_weighting = nullptr)
 {
     ModelArgs a = m->a;
     a.maxDepth = depthCutoff;
     FuseArgs f;
     f.rgb = rgb8; f.depthRaw = depthRaw; f.depthFiltered = depthFiltered; f.curv1 = (const float4*)curv1; f.curv2 = (const float4*)curv2;
     f.confidence = confidence; f.index = indexMap; f.vertConf = (const float4*)vertConf; f.normRad = (const float4*)normRad;
-    f.pose = pose_dev; f.time = time; f.indexSubmap = (float)indexSubmap;
+    f.pose = pose_dev; f.time = time; f.indexSubmap = (float)indexSubmap; f.weighting = inline_weighting;
     f.staging = m->staging; f.update_id = m->update_id; f.best = m->best; f.winner = m->winner;
     const int nb = div_up(m->n_slots, 128);
     fuse_associate_kernel<<<nb, 128, 0, s>>>(a, m->pa, f, m->count[m->cur]);
@@ -509,7 +520,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
     hrbf_indexmap* im = F->im;
     hrbf_model* M = F->model;
     float* currPose = F->dev, *lastPose = F->dev + 12, *invPose = F->dev + 24, *weighting = F->dev + 36;
-    int* shouldFill = (int*)(F->dev + 40);
+    unsigned int* denseCount = (unsigned int*)(F->dev + 44);      // two counters, by frame parity
     auto FT = [&](int t) { return fr->tex[t]; };
     auto IT = [&](int t) { return im->tex[t]; };
     auto LT = [&](int t) { return F->fill->tex[t]; };
@@ -530,9 +541,6 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
         mark(2); mark(3);
     } else {
         // ---- Registration (HRBFFusion.cpp:1063-1109) ----
-        HRBF_CUDA(cudaMemcpyAsync(lastPose, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        should_fill_kernel<<<1, 256, 0, s>>>((const float4*)IT(HRBF_TEX_VERTEX_HRBF), p.frame.height, p.frame.width, p.denseEnoughThresh, shouldFill);
-        HRBF_KERNEL_CHECK();
         {   // the reference's 7 init* calls (HRBFFusion.cpp:1073-1099) as one launch
             OdomPrepInputs in;
             in.vm = (const float*)IT(HRBF_TEX_VERTEX_HRBF); in.nm = (const float*)IT(HRBF_TEX_NORMAL_HRBF);
@@ -544,15 +552,31 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
             in.vc = (const float*)FT(HRBF_FT_VERTEX_FILTERED); in.nc = (const float*)FT(HRBF_FT_NORMAL);
             in.k1c = (const float*)FT(HRBF_FT_PRINCIPAL_CURV1); in.k2c = (const float*)FT(HRBF_FT_PRINCIPAL_CURV2);
             in.rgba_c = (const unsigned char*)FT(HRBF_FT_RGBA);
-            in.sel = shouldFill; in.pose_dev = currPose;
+            // denseEnough (HRBFFusion.cpp:1069-1070): the previous prediction counted its samples, no separate reduction kernel
+            in.sel = nullptr; in.dense_count = denseCount + ((F->tick - 1) & 1); in.dense_count_reset = denseCount + (F->tick & 1);
+            in.dense_thresh = p.denseEnoughThresh; in.pose_dev = currPose;
+            in.rgb8_c = (const unsigned char*)FT(HRBF_FT_RGB);
             if (int rc = odom_prep_all_dev(F->odom, in, s)) return rc;
         }
-        if (int rc = hrbf_odometry_track_async(F->odom, lastPose, currPose, p.rgbOnly, p.icpWeight, p.pyramid, p.fastOdom, p.so3, p.weightedICP, s)) return rc;
-        velocity_weighting_kernel<<<1, 32, 0, s>>>(currPose, lastPose, weightMultiplier, weighting);
-        HRBF_KERNEL_CHECK();
-        if (int rc = frame_confidence_dev(fr, weighting, s)) return rc;
-        pose_inverse_kernel<<<1, 32, 0, s>>>(currPose, invPose);
-        HRBF_KERNEL_CHECK();
+        {
+            // the persistent tracker also writes lastPose, the inverse pose, the fusion weight and the trajectory row
+            const OdomFrameEpilogue ep = { lastPose, invPose, weighting, weightMultiplier, F->traj_n < F->traj_cap ? F->traj + 12 * (size_t)F->traj_n : nullptr };
+            const int rc = odom_track_frame_dev(F->odom, currPose, ep, p.rgbOnly != 0, p.icpWeight, p.pyramid != 0, p.fastOdom != 0, p.so3 != 0, p.weightedICP != 0, s);
+            if (rc < 0) return rc;
+            if (rc == 1) {      // kernel-graph tracker: the separate calls
+                HRBF_CUDA(cudaMemcpyAsync(lastPose, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                if (int rc2 = hrbf_odometry_track_async(F->odom, lastPose, currPose, p.rgbOnly, p.icpWeight, p.pyramid, p.fastOdom, p.so3, p.weightedICP, s)) return rc2;
+                velocity_weighting_kernel<<<1, 32, 0, s>>>(currPose, lastPose, weightMultiplier, weighting);
+                HRBF_KERNEL_CHECK();
+                pose_inverse_kernel<<<1, 32, 0, s>>>(currPose, invPose);
+                HRBF_KERNEL_CHECK();
+                if (ep.traj_out) HRBF_CUDA(cudaMemcpyAsync(ep.traj_out, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            }
+        }
+        // VertexConfidence (HRBFFusion.cpp:1124): evaluated in place by fuse and fill-in; the texture only with preprocessingUseConfEval
+        const float* inline_w = p.frame.useConfEval ? nullptr : weighting;
+        F->fill->inline_weighting = inline_w;
+        if (!inline_w) { if (int rc = frame_confidence_dev(fr, weighting, s)) return rc; }
         mark(2);
         // ---- Integration (HRBFFusion.cpp:1192-1227) ----
         if (!p.rgbOnly) {
@@ -560,7 +584,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
             if (int rc = model_fuse_dev(M, currPose, F->tick, (const unsigned char*)FT(HRBF_FT_RGB), (const float*)FT(HRBF_FT_DEPTH_METRIC),
                                         (const float*)FT(HRBF_FT_DEPTH_METRIC_FILTERED), (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2),
                                         (const float*)FT(HRBF_FT_CONFIDENCE), (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
-                                        (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s)) return rc;
+                                        (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s, inline_w)) return rc;
             if (int rc = splat()) return rc;
             if (int rc = model_clean_dev(M, invPose, F->tick, (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                          (const float*)IT(HRBF_TEX_COLORTIME), p.confidenceThreshold, p.maxDepthProcessed, s)) return rc;
@@ -570,10 +594,11 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
     if (F->tick == 1) { pose_inverse_kernel<<<1, 32, 0, s>>>(currPose, invPose); HRBF_KERNEL_CHECK(); }
     // ---- Prediction (HRBFFusion.cpp:1244-1260) ----
     if (int rc = splat()) return rc;
+    im->dense_count_next = denseCount + (F->tick & 1);
     if (int rc = hrbf_indexmap_predict_hrbf(im, 0, p.predWindow, p.predMinNeighbors, p.predMaxNeighbors, p.predConfThreshold, p.icpWeightLambda, s)) return rc;
     if (int rc = hrbf_fillin_run(F->fill, im, fr, 0, p.icpWeightLambda, p.curvValidThreshold, s)) return rc;
     mark(4);
-    if (F->traj_n < F->traj_cap) HRBF_CUDA(cudaMemcpyAsync(F->traj + 12 * (size_t)F->traj_n, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (F->tick == 1 && F->traj_n < F->traj_cap) HRBF_CUDA(cudaMemcpyAsync(F->traj + 12 * (size_t)F->traj_n, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ++F->traj_n;
     ++F->tick;
     return HRBF_OK;
@@ -644,7 +669,7 @@ int hrbf_fusion_process_frame_dev(hrbf_fusion* F, const unsigned char* rgb8, con
 {
     (void)timestamp;
     HRBF_CHECK_ARG(F && rgb8 && depth16);
-    if (int rc = hrbf_frame_upload(F->frame, rgb8, depth16, 0, stream)) return rc;
+    if (int rc = frame_upload(F->frame, rgb8, depth16, 0, F->tick == 1, (cudaStream_t)stream)) return rc;
     return fusion_frame(F, weightMultiplier, (cudaStream_t)stream);
 }
 int hrbf_fusion_process_frame(hrbf_fusion* F, const unsigned char* rgb8, const unsigned short* depth16, long long timestamp, float weightMultiplier,
@@ -652,7 +677,7 @@ int hrbf_fusion_process_frame(hrbf_fusion* F, const unsigned char* rgb8, const u
 {
     (void)timestamp;
     HRBF_CHECK_ARG(F && rgb8 && depth16);
-    if (int rc = hrbf_frame_upload(F->frame, rgb8, depth16, 1, stream)) return rc;
+    if (int rc = frame_upload(F->frame, rgb8, depth16, 1, F->tick == 1, (cudaStream_t)stream)) return rc;
     if (int rc = fusion_frame(F, weightMultiplier, (cudaStream_t)stream)) return rc;
     float tmp[16];
     if (int rc = hrbf_fusion_get_pose(F, pose16_out ? pose16_out : tmp, stream)) return rc;

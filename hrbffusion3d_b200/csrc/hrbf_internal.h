@@ -67,6 +67,7 @@ struct hrbf_indexmap {
     float* h_stage = nullptr;            // pinned ring: 8 x 16 floats
     float* h_kf = nullptr;               // pinned keyframe mask
     int slot = 0;
+    unsigned int* dense_count_next = nullptr;   // frame pipeline: where the next ACTIVE prediction counts its dense-enough samples (or null)
 };
 
 
@@ -90,8 +91,15 @@ struct OdomPrepInputs {
     const unsigned char *rgba_m, *rgba_m_alt;        // model image (RGBA8)
     const float *vc, *nc, *k1c, *k2c;                // current frame
     const unsigned char* rgba_c;
-    const int* sel;                                  // device fill-in decision
+    const int* sel;                                  // device fill-in decision (or null, then dense_count decides)
+    const unsigned int* dense_count;                 // samples with a predicted surface on the 1/20 grid, counted by the prediction kernel
+    unsigned int* dense_count_reset;                 // the counter the NEXT prediction will use: zeroed here
+    float dense_thresh;                              // globalDenseEnoughThresh
     const float* pose_dev;                           // device model pose R[9], t[3]
+    const unsigned char* rgb8_c;                     // current image as RGB8 (used instead of rgba_c when non-null)
 };
 int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s);
+struct OdomFrameEpilogue { float* last_pose_out; float* inv_pose_out; float* weighting_out; float weight_multiplier; float* traj_out; };
+int odom_track_frame_dev(hrbf_odometry* o, float* pose_inout, const OdomFrameEpilogue& ep, bool rgbOnly, float icpWeight, bool pyramid,
+                         bool fastOdom, bool so3, bool use_weight, cudaStream_t s);
 }

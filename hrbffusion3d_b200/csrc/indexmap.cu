@@ -119,6 +119,7 @@ int hrbf_indexmap_predict_hrbf(hrbf_indexmap* m, int predictionType, int win, in
     a.cols = m->width; a.rows = m->height; a.cx = m->cx; a.cy = m->cy;
     a.icx = (float)(1.0 / (double)m->fx); a.icy = (float)(1.0 / (double)m->fy);      // IndexMap.cpp:449-452
     a.win = win; a.minN = minNeighbors; a.maxN = maxNeighbors; a.confThr = confThreshold; a.lambda = icpWeightLambda;
+    a.dense_count = predictionType == 0 ? m->dense_count_next : nullptr;
     const dim3 grid(div_up(m->width, kPredTileW), div_up(m->height, kPredTileH));
     predict_hrbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     HRBF_KERNEL_CHECK();

@@ -119,6 +119,8 @@ struct PredictArgs {
     float cx, cy, icx, icy;      // uniform cam = (cx, cy, 1/fx, 1/fy)
     int win, minN, maxN;
     float confThr, lambda;
+    unsigned int* dense_count;   // optional: += 1 for every texel centre (20 i + 10, 20 j + 10) of the 1/20 grid with a predicted surface
+                                 // (the sample set of HRBFFusion::denseEnough, HRBFFusion.cpp:974-987, Shaders/Resize.cpp:106-139)
 };
 
 constexpr int kPredTileW = 16, kPredTileH = 4, kPredHalo = 3;
@@ -441,6 +443,7 @@ __global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
         const float cm = fmaxf(fabsf(kmax.w), fabsf(kmin.w));
         icpw = (1.0f / (tz * tz)) * (v.w / 256.0f + expf(-0.5f * (a.lambda * a.lambda) / (cm * cm)));
     }
+    if (a.dense_count != nullptr && vout.z > 0.f && px % 20 == 10 && py % 20 == 10 && px / 20 < a.cols / 20 && py / 20 < a.rows / 20) atomicAdd(a.dense_count, 1u);
     a.image[o] = img; a.vertex[o] = vout; a.normal[o] = nout; a.ocurvMax[o] = kmax; a.ocurvMin[o] = kmin;
     a.time[o] = tstamp; a.icpw[o] = icpw;
 }

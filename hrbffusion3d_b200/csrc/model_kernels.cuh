@@ -45,38 +45,15 @@ __device__ __forceinline__ float3 decode_color(float c)
     return make_float3((float)(i >> 16 & 0xFF) / 255.0f, (float)(i >> 8 & 0xFF) / 255.0f, (float)(i & 0xFF) / 255.0f);
 }
 
-// pose (R[9], t[3]) -> its rigid inverse, same arithmetic as the host path (R^T, -R^T t)
 __global__ void pose_inverse_kernel(const float* __restrict__ pose, float* __restrict__ inv)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float Ri[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = pose[j * 3 + i];
-    for (int k = 0; k < 9; ++k) inv[k] = Ri[k];
-    for (int i = 0; i < 3; ++i) inv[9 + i] = -(__fadd_rn(__fadd_rn(__fmul_rn(Ri[i * 3], pose[9]), __fmul_rn(Ri[i * 3 + 1], pose[10])), __fmul_rn(Ri[i * 3 + 2], pose[11])));
+    pose_inverse_dev(pose, inv);
 }
-
-// HRBFFusion.cpp:1112-1123 : fusion weight from the inter-frame motion (|t| vs rotation angle), on the device
 __global__ void velocity_weighting_kernel(const float* __restrict__ curr, const float* __restrict__ last, float weightMultiplier, float* __restrict__ weighting)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    // diff = curr^-1 * last
-    float R[9], t[3];
-    for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) R[i * 3 + j] = (curr[0 * 3 + i] * last[0 * 3 + j] + curr[1 * 3 + i] * last[1 * 3 + j]) + curr[2 * 3 + i] * last[2 * 3 + j];
-        const float d0 = last[9] - curr[9], d1 = last[10] - curr[10], d2 = last[11] - curr[11];
-        t[i] = (curr[0 * 3 + i] * d0 + curr[1 * 3 + i] * d1) + curr[2 * 3 + i] * d2;
-    }
-    const double rx = (double)R[7] - (double)R[5], ry = (double)R[2] - (double)R[6], rz = (double)R[3] - (double)R[1];
-    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
-    double c = ((double)((R[0] + R[4]) + R[8]) - 1.0) * 0.5;
-    c = c > 1. ? 1. : c < -1. ? -1. : c;
-    double theta = acos(c);
-    if (s < 1e-5 && c > 0) theta = 0.0;
-    const float tn = sqrtf((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]);
-    float w = fmaxf(tn, (float)theta);
-    const float largest = 0.01f, minWeight = 0.5f;
-    if (w > largest) w = largest;
-    weighting[0] = fmaxf(1.0f - (w / largest), minWeight) * weightMultiplier;
+    weighting[0] = velocity_weighting_dev(curr, last, weightMultiplier);
 }
 
 // ------------------------------------------------------------------ generic order-preserving compaction ---
@@ -188,6 +165,7 @@ struct FuseArgs {
     const unsigned int* index; const float4 *vertConf, *normRad;
     const float* pose;               // device R[9], t[3]
     int time; float indexSubmap;
+    const float* weighting;          // frame pipeline: non-null -> confidence evaluated in place (see FillArgs::weighting)
     float4* staging;                 // [(cols/2+1)*(rows/2+1)][5] : this frame's candidate records
     unsigned char* update_id;        // per slot: 0 none, 1 merge, 2 new
     unsigned int* best;              // per slot: surfel to merge with
@@ -270,7 +248,12 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
         }
     const bool merge = counter > 0 && best < count;
     float4* rec = f.staging + 5 * (size_t)slot;
-    rec[0] = make_float4(g.x, g.y, g.z, __ldg(f.confidence + o));
+    float conf;
+    if (f.weighting != nullptr) {
+        const float max_dist = sqrtf(((float)H * 0.5f) * ((float)H * 0.5f) + ((float)W * 0.5f) * ((float)W * 0.5f));
+        conf = confidence_fn(m.cx, m.cy, x, y, max_dist, __ldg(f.weighting));
+    } else conf = __ldg(f.confidence + o);
+    rec[0] = make_float4(g.x, g.y, g.z, conf);
     rec[1] = make_float4(encode_rgb8(f.rgb + 3 * o), f.indexSubmap, (float)f.time, counter > 0 ? -1.0f : -2.0f);
     rec[2] = make_float4(ng.x, ng.y, ng.z, m.radiusMultiplier * get_radius(m.icx, m.icy, zf, n.z));
     rec[3] = k1; rec[4] = k2;

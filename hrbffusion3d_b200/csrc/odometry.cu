@@ -145,7 +145,8 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
 
 // The whole tracking loop as one cooperative persistent kernel (track_persistent.cuh).
 static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
-                                   bool so3, bool use_weight, const float* prev_pose_dev, float* pose_out_dev, const int* iters_override = nullptr)
+                                   bool so3, bool use_weight, const float* prev_pose_dev, float* pose_out_dev, const int* iters_override = nullptr,
+                                   const OdomFrameEpilogue* ep = nullptr)
 {
     TrackParams p;
     int iters[3] = { fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0 };
@@ -172,6 +173,9 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     p.rgb = (rgbOnly || icpWeight < 100) ? 1 : 0;
     p.rgbOnly = rgbOnly; p.so3 = so3; p.icpWeight = icpWeight;
     p.prev_pose = prev_pose_dev; p.pose_out = pose_out_dev;
+    p.last_pose_out = ep ? ep->last_pose_out : nullptr; p.inv_pose_out = ep ? ep->inv_pose_out : nullptr;
+    p.weighting_out = ep ? ep->weighting_out : nullptr; p.weight_multiplier = ep ? ep->weight_multiplier : 1.f;
+    p.traj_out = ep ? ep->traj_out : nullptr;
     p.st_global = &o->work->st;
     p.ll_f = o->tp_ll_f; p.ll_i = o->tp_ll_i;
     o->tp_epoch = (o->tp_epoch + 1) & 0xfffffu;
@@ -581,10 +585,27 @@ int odom_init_curvature_model_dev(hrbf_odometry* o, const float* k1, const float
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }
+// Tracking call of the frame pipeline: pose_inout holds the previous pose on entry and the new one on exit; the epilogue
+// outputs (HRBFFusion.cpp:1109-1123) are written by the tracking kernel itself.  Returns 1 if the configured tracker cannot do
+// that (kernel-graph tracker): the caller then issues the separate calls.
+int odom_track_frame_dev(hrbf_odometry* o, float* pose_inout, const OdomFrameEpilogue& ep, bool rgbOnly, float icpWeight, bool pyramid,
+                         bool fastOdom, bool so3, bool use_weight, cudaStream_t s)
+{
+    if (o->use_graph) return 1;
+    if (int rc = repack_if_dirty(o, s)) return rc;
+    if (int rc = launch_track_persistent(o, s, rgbOnly, icpWeight, pyramid, fastOdom, so3, use_weight, pose_inout, pose_inout, nullptr, &ep)) return rc;
+    if (so3) {      // RGBDOdometry.cpp:1239-1245 (swap_so3_images)
+        for (int i = 0; i < 3; ++i) std::swap(o->lastNextImage[i], o->nextImage[i]);
+        o->so3_parity ^= 1;
+    }
+    return HRBF_OK;
+}
+
 int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s)
 {
     PrepAllArgs A;
-    A.rows = o->height; A.cols = o->width; A.sel = in.sel; A.pose = in.pose_dev; A.curv_thr = o->curvThr; A.depth_cutoff = o->maxDepthRGB;
+    A.rows = o->height; A.cols = o->width; A.sel = in.sel; A.pose = in.pose_dev;
+    A.dense_count = in.dense_count; A.dense_count_reset = in.dense_count_reset; A.dense_thresh = in.dense_thresh; A.curv_thr = o->curvThr; A.depth_cutoff = o->maxDepthRGB;
     A.vm = (const float4*)in.vm; A.nm = (const float4*)in.nm; A.vm_alt = (const float4*)in.vm_alt; A.nm_alt = (const float4*)in.nm_alt;
     A.vc = (const float4*)in.vc; A.nc = (const float4*)in.nc;
     A.k1m = (const float4*)in.k1m; A.k2m = (const float4*)in.k2m; A.k1m_alt = (const float4*)in.k1m_alt; A.k2m_alt = (const float4*)in.k2m_alt;
@@ -595,6 +616,7 @@ int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s
     for (int l = 0; l < 3; ++l) { A.o_w[l] = o->maps[M_W][l]; A.w_pitch[l] = o->cols(l); }
     A.rgbd[0].rgba = (const uchar4*)in.rgba_m; A.rgbd[0].rgba_alt = (const uchar4*)in.rgba_m_alt;
     A.rgbd[0].vertex = (const float4*)in.vm; A.rgbd[0].vertex_alt = (const float4*)in.vm_alt;
+    A.rgbd[0].rgb8 = nullptr; A.rgbd[1].rgb8 = in.rgb8_c;
     A.rgbd[1].rgba = (const uchar4*)in.rgba_c; A.rgbd[1].rgba_alt = nullptr;
     A.rgbd[1].vertex = (const float4*)in.vc; A.rgbd[1].vertex_alt = nullptr;
     for (int l = 0; l < 3; ++l) {

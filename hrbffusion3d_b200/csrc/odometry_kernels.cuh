@@ -395,13 +395,15 @@ __global__ void rgba_to_intensity_kernel(int n, const uchar4* __restrict__ rgba,
 //              instead of going through HBM with a dependent launch per level)
 struct RgbdJob {
     const uchar4 *rgba, *rgba_alt;               // image texture (+ fill-in alternate)
+    const unsigned char* rgb8;                   // RGB8 source used instead of rgba when non-null (the frame's upload buffer)
     const float4 *vertex, *vertex_alt;           // vertex texture verticesToDepth reads (cudafuncs.cu:874-885)
     unsigned char* img[3];
     float* depth[3];
 };
 struct PrepAllArgs {
     int rows, cols;
-    const int* sel;                              // device fill-in decision (model jobs only)
+    const int* sel;                              // device fill-in decision (model jobs only), or null: decided from dense_count
+    const unsigned int* dense_count; unsigned int* dense_count_reset; float dense_thresh;
     const float* pose;                           // device model pose R[9], t[3]
     float curv_thr, depth_cutoff;
     const float4 *vm, *nm, *vm_alt, *nm_alt, *vc, *nc;              // vertex / normal textures: model (+alt), current
@@ -432,7 +434,8 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
         const int gx = X0 + sx, gy = Y0 + sy;
         if (gx < 0 || gy < 0 || gx >= cols || gy >= rows) continue;
         const size_t o = (size_t)gy * cols + gx;
-        const unsigned char g = bgr_intensity(__ldg(rgba + o));
+        const unsigned char g = j.rgb8 != nullptr ? bgr_intensity(make_uchar4(__ldg(j.rgb8 + 3 * o), __ldg(j.rgb8 + 3 * o + 1), __ldg(j.rgb8 + 3 * o + 2), 255))
+                                                  : bgr_intensity(__ldg(rgba + o));
         const float z = __ldg(reinterpret_cast<const float*>(vert + o) + 2);
         const float d = (z > depth_cutoff || z <= 0.f) ? qn : z;
         s_g0[sy][sx] = g; s_d0[sy][sx] = d;
@@ -462,23 +465,31 @@ __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
 {
     const int per_pyr = A.pyr_bx * A.pyr_by, per_rgbd = A.rgbd_bx * A.rgbd_by;
     int b = blockIdx.x;
+    // HRBFFusion::denseEnough (HRBFFusion.cpp:974-987): fill-in textures replace the prediction when <= thresh of the 1/20 samples are set
+    bool alt;
+    if (A.sel != nullptr) alt = *A.sel != 0;
+    else if (A.dense_count != nullptr) {
+        const int total = (A.cols / 20) * (A.rows / 20);
+        alt = !((float)*A.dense_count / (float)total > A.dense_thresh);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && A.dense_count_reset != nullptr) *A.dense_count_reset = 0u;
+    } else alt = false;
     // the (heavier) RGB-D pyramid tiles take the lowest block indices: they are scheduled first and the light map tiles fill in
     if (b >= 2 * per_rgbd) {
         b -= 2 * per_rgbd;
         const int job = b / per_pyr, t = b - job * per_pyr;
         const int by = t / A.pyr_bx, bx = t - by * A.pyr_bx;
         switch (job) {
-        case 0: pyr_pair_tile<PYR_VN>(A.vm, A.nm, A.rows, A.cols, 0.f, A.pose, A.o_vg, A.o_ng, nullptr, 0.f, A.vm_alt, A.nm_alt, A.sel, bx, by); break;
+        case 0: pyr_pair_tile<PYR_VN>(alt ? A.vm_alt : A.vm, alt ? A.nm_alt : A.nm, A.rows, A.cols, 0.f, A.pose, A.o_vg, A.o_ng, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
         case 1: pyr_pair_tile<PYR_VN>(A.vc, A.nc, A.rows, A.cols, 0.f, nullptr, A.o_vc, A.o_nc, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
-        case 2: pyr_pair_tile<PYR_K>(A.k1m, A.k2m, A.rows, A.cols, A.curv_thr, A.pose, A.o_k1g, A.o_k2g, nullptr, 0.f, A.k1m_alt, A.k2m_alt, A.sel, bx, by); break;
+        case 2: pyr_pair_tile<PYR_K>(alt ? A.k1m_alt : A.k1m, alt ? A.k2m_alt : A.k2m, A.rows, A.cols, A.curv_thr, A.pose, A.o_k1g, A.o_k2g, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
         case 3: pyr_pair_tile<PYR_K>(A.k1c, A.k2c, A.rows, A.cols, A.curv_thr, nullptr, A.o_k1c, A.o_k2c, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
-        default: pyr_weight_tile(A.w, A.rows, A.cols, A.o_w[0], A.w_pitch[0], A.o_w[1], A.w_pitch[1], A.o_w[2], A.w_pitch[2], A.w_alt, A.sel, bx, by); break;
+        default: pyr_weight_tile(alt ? A.w_alt : A.w, A.rows, A.cols, A.o_w[0], A.w_pitch[0], A.o_w[1], A.w_pitch[1], A.o_w[2], A.w_pitch[2], nullptr, nullptr, bx, by); break;
         }
         return;
     }
     const int job = b / per_rgbd, t = b - job * per_rgbd;
     const int by = t / A.rgbd_bx, bx = t - by * A.rgbd_bx;
-    const bool use_alt = job == 0 && A.sel != nullptr && *A.sel != 0;
+    const bool use_alt = job == 0 && alt;
     rgbd_pyramid_tile(A.rgbd[job], A.rows, A.cols, A.depth_cutoff, use_alt, bx, by);
 }
 __device__ __forceinline__ void sobel_pixel(int rows, int cols, const unsigned char* __restrict__ src, short* dx, short* dy, int x, int y)

@@ -398,6 +398,9 @@ struct FillArgs {
     float4 *oVertex, *oNormal, *oK1, *oK2; float* oIcpW; uchar4* oImage;
     int n, passthrough;
     float lambda, curvThr;
+    // frame pipeline: when non-null the confidence of depth_confidence_evaluation.frag is evaluated in place from this device scalar
+    // instead of being read from the CONFIDENCE texture (same expression, confidence_kernel below)
+    const float* weighting; int cols, rows; float cx, cy;
 };
 __global__ void fill_in_kernel(FillArgs f)
 {
@@ -411,7 +414,12 @@ __global__ void fill_in_kernel(FillArgs f)
     if (s.z == 0 || pass) {
         if (rk1.w > -f.curvThr && rk1.w < f.curvThr && rk2.w > -f.curvThr && rk2.w < f.curvThr) {
             const float4 fv = __ldg(f.vertexFiltered + o);
-            const float vConf = __ldg(f.confidence + o);
+            float vConf;
+            if (f.weighting != nullptr) {
+                const int py = o / f.cols, px = o - py * f.cols;
+                const float max_dist = sqrtf(((float)f.rows * 0.5f) * ((float)f.rows * 0.5f) + ((float)f.cols * 0.5f) * ((float)f.cols * 0.5f));
+                vConf = confidence_fn(f.cx, f.cy, (float)px + 0.5f, (float)py + 0.5f, max_dist, __ldg(f.weighting));
+            } else vConf = __ldg(f.confidence + o);
             const float cmax = fmaxf(fabsf(rk1.w), fabsf(rk2.w));
             w = (1.0f / (fv.z * fv.z)) * (vConf / 256.0f + expf(-0.5f * (f.lambda * f.lambda) / (cmax * cmax)));
             v = make_float4(fv.x, fv.y, fv.z, vConf);

@@ -32,7 +32,12 @@ struct TrackParams {
     int icp, rgb, rgbOnly, so3;
     float icpWeight;
     const float* prev_pose;                        // device R[9], t[3]
-    float* pose_out;                               // device R[9], t[3]
+    float* pose_out;                               // device R[9], t[3] (may alias prev_pose: written by CTA 0 after the last exchange)
+    // optional frame-pipeline epilogue (HRBFFusion.cpp:1109-1123, 1195): null = not written
+    float* last_pose_out;                          // copy of the pose tracking started from
+    float* inv_pose_out;                           // rigid inverse of the new pose (the splats' t_inv)
+    float* weighting_out; float weight_multiplier; // fusion weight from the inter-frame motion
+    float* traj_out;                               // this frame's row of the trajectory
     TrackState* st_global;                         // camera in, statistics out
     int max_slots;                                 // dynamic shared memory holds max_slots x kTrackThreads RgbSlots
     unsigned long long* ll_f;                      // [2][gridDim.x][64] (float, tag) words: the per-CTA partial sums
@@ -448,8 +453,14 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 for (int k = 0; k < 3; ++k) S.tcurr[k] = S.tprev[k];
             }
         }
-        for (int k = 0; k < 9; ++k) p.pose_out[k] = S.Rcurr[k];
-        for (int k = 0; k < 3; ++k) p.pose_out[9 + k] = S.tcurr[k];
+        float cur[12], prev[12];
+        for (int k = 0; k < 9; ++k) { cur[k] = S.Rcurr[k]; prev[k] = S.Rprev[k]; }
+        for (int k = 0; k < 3; ++k) { cur[9 + k] = S.tcurr[k]; prev[9 + k] = S.tprev[k]; }
+        for (int k = 0; k < 12; ++k) p.pose_out[k] = cur[k];
+        if (p.last_pose_out) for (int k = 0; k < 12; ++k) p.last_pose_out[k] = prev[k];
+        if (p.traj_out) for (int k = 0; k < 12; ++k) p.traj_out[k] = cur[k];
+        if (p.inv_pose_out) pose_inverse_dev(cur, p.inv_pose_out);
+        if (p.weighting_out) p.weighting_out[0] = velocity_weighting_dev(cur, prev, p.weight_multiplier);
         TrackState* g = p.st_global;
         g->lastICPError = S.lastICPError; g->lastICPCount = S.lastICPCount; g->lastRGBError = S.lastRGBError; g->lastRGBCount = S.lastRGBCount;
         g->lastSO3Error = S.lastSO3Error; g->lastSO3Count = S.lastSO3Count; g->icp_iterations_run = S.icp_iterations_run;
