@@ -495,7 +495,13 @@ struct hrbf_fusion {
     hrbf_odometry* odom = nullptr;
     hrbf_indexmap* im = nullptr;
     hrbf_model* model = nullptr;
-    hrbf_frame* frame = nullptr;
+    hrbf_frame* frame = nullptr;     // the buffer of the frame being / last processed (= frames[cur] while processing)
+    hrbf_frame* frames[2] = { nullptr, nullptr };   // ping-pong: frame t+1 is uploaded + preprocessed while frame t is tracked and fused
+    int cur = 0;                     // buffer the next processed frame uses
+    bool staged[2] = { false, false };
+    cudaStream_t pre_stream = nullptr;              // staging stream (lowest priority)
+    cudaEvent_t ev_staged[2] = {}, ev_free[2] = {};
+    bool ev_free_valid[2] = { false, false };
     hrbf_fillin* fill = nullptr;
     int tick = 1;
     int indexSubmap = 0;
@@ -513,10 +519,12 @@ __global__ void set_identity_pose_kernel(float* p)
     if (threadIdx.x < 12) p[threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.f : 0.f;
 }
 
-static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
+// preprocessed = true: frames[cur] was uploaded and preprocessed by hrbf_fusion_stage_frame (on the staging stream)
+static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, bool preprocessed = false)
 {
     const hrbf_fusion_params& p = F->p;
-    hrbf_frame* fr = F->frame;
+    hrbf_frame* fr = F->frames[F->cur];
+    F->frame = fr;
     hrbf_indexmap* im = F->im;
     hrbf_model* M = F->model;
     float* currPose = F->dev, *lastPose = F->dev + 12, *invPose = F->dev + 24, *weighting = F->dev + 36;
@@ -528,7 +536,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
     auto splat = [&]() { return indexmap_splat(im, invPose, (const float*)M->vbo[M->cur], M->count[M->cur], M->bound, p.maxDepthProcessed, s); };
 
     mark(0);
-    if (int rc = hrbf_frame_preprocess(fr, s)) return rc;
+    if (!preprocessed) { if (int rc = hrbf_frame_preprocess(fr, s)) return rc; }
     mark(1);
     if (F->tick == 1) {
         set_identity_pose_kernel<<<1, 32, 0, s>>>(currPose);
@@ -601,6 +609,9 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s)
     if (F->tick == 1 && F->traj_n < F->traj_cap) HRBF_CUDA(cudaMemcpyAsync(F->traj + 12 * (size_t)F->traj_n, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ++F->traj_n;
     ++F->tick;
+    // the buffer is free for the frame after next once everything above has run
+    HRBF_CUDA(cudaEventRecord(F->ev_free[F->cur], s));
+    F->ev_free_valid[F->cur] = true;
     return HRBF_OK;
 }
 
@@ -627,7 +638,9 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
     HRBF_CHECK_ARG(F != nullptr);
     F->p = *p;
     const hrbf_frame_params& fp = p->frame;
-    int rc = hrbf_frame_create(&F->frame, &fp);
+    int rc = hrbf_frame_create(&F->frames[0], &fp);
+    if (!rc) rc = hrbf_frame_create(&F->frames[1], &fp);
+    F->frame = F->frames[0];
     if (!rc) rc = hrbf_fillin_create(&F->fill, fp.width, fp.height);
     if (!rc) rc = hrbf_indexmap_create(&F->im, fp.width, fp.height, fp.cx, fp.cy, fp.fx, fp.fy);
     if (!rc) rc = hrbf_model_create(&F->model, fp.width, fp.height, fp.cx, fp.cy, fp.fx, fp.fy, p->capacity);
@@ -638,7 +651,14 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
         F->traj_cap = 1 << 16;
         if (cudaMalloc(&F->dev, 64 * sizeof(float)) != cudaSuccess || cudaMalloc(&F->traj, (size_t)F->traj_cap * 12 * sizeof(float)) != cudaSuccess ||
             cudaMallocHost(&F->h_pose, 16 * sizeof(float)) != cudaSuccess) { set_error("fusion_create: allocation failed"); rc = HRBF_ERR_CUDA; }
-        else { cudaMemset(F->dev, 0, 64 * sizeof(float)); for (auto& e : F->ev) cudaEventCreate(&e); }
+        else {
+            cudaMemset(F->dev, 0, 64 * sizeof(float));
+            for (auto& e : F->ev) cudaEventCreate(&e);
+            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); }
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&F->pre_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { set_error("fusion_create: stream creation failed"); rc = HRBF_ERR_CUDA; }
+        }
     }
     if (rc) { hrbf_fusion_destroy(F); return rc; }
     *out = F;
@@ -647,7 +667,9 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
 int hrbf_fusion_destroy(hrbf_fusion* F)
 {
     if (!F) return HRBF_OK;
-    hrbf_odometry_destroy(F->odom); hrbf_model_destroy(F->model); hrbf_indexmap_destroy(F->im); hrbf_fillin_destroy(F->fill); hrbf_frame_destroy(F->frame);
+    hrbf_odometry_destroy(F->odom); hrbf_model_destroy(F->model); hrbf_indexmap_destroy(F->im); hrbf_fillin_destroy(F->fill); hrbf_frame_destroy(F->frames[0]); hrbf_frame_destroy(F->frames[1]);
+    if (F->pre_stream) cudaStreamDestroy(F->pre_stream);
+    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); }
     if (F->dev) cudaFree(F->dev);
     if (F->traj) cudaFree(F->traj);
     if (F->h_pose) cudaFreeHost(F->h_pose);
@@ -669,7 +691,8 @@ int hrbf_fusion_process_frame_dev(hrbf_fusion* F, const unsigned char* rgb8, con
 {
     (void)timestamp;
     HRBF_CHECK_ARG(F && rgb8 && depth16);
-    if (int rc = frame_upload(F->frame, rgb8, depth16, 0, F->tick == 1, (cudaStream_t)stream)) return rc;
+    if (F->staged[F->cur]) { set_error("process_frame_dev: a staged frame is pending, call hrbf_fusion_process_staged"); return HRBF_ERR_INVALID_ARG; }
+    if (int rc = frame_upload(F->frames[F->cur], rgb8, depth16, 0, F->tick == 1, (cudaStream_t)stream)) return rc;
     return fusion_frame(F, weightMultiplier, (cudaStream_t)stream);
 }
 int hrbf_fusion_process_frame(hrbf_fusion* F, const unsigned char* rgb8, const unsigned short* depth16, long long timestamp, float weightMultiplier,
@@ -677,11 +700,47 @@ int hrbf_fusion_process_frame(hrbf_fusion* F, const unsigned char* rgb8, const u
 {
     (void)timestamp;
     HRBF_CHECK_ARG(F && rgb8 && depth16);
-    if (int rc = frame_upload(F->frame, rgb8, depth16, 1, F->tick == 1, (cudaStream_t)stream)) return rc;
+    if (F->staged[F->cur]) { set_error("process_frame: a staged frame is pending, call hrbf_fusion_process_staged"); return HRBF_ERR_INVALID_ARG; }
+    if (int rc = frame_upload(F->frames[F->cur], rgb8, depth16, 1, F->tick == 1, (cudaStream_t)stream)) return rc;
     if (int rc = fusion_frame(F, weightMultiplier, (cudaStream_t)stream)) return rc;
     float tmp[16];
     if (int rc = hrbf_fusion_get_pose(F, pose16_out ? pose16_out : tmp, stream)) return rc;
     if (F->timings) for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&F->last_ms[k], F->ev[k], F->ev[k + 1]);
+    return HRBF_OK;
+}
+// Pipelined form of processFrame for log replay: stage_frame uploads and preprocesses the NEXT frame(s) on an internal
+// low-priority stream while the main stream still tracks / fuses the current one; process_staged consumes the oldest staged frame.
+int hrbf_fusion_stage_frame(hrbf_fusion* F, const unsigned char* rgb8, const unsigned short* depth16, int host, void* stream)
+{
+    (void)stream;
+    HRBF_CHECK_ARG(F && rgb8 && depth16);
+    int b;
+    if (!F->staged[F->cur]) b = F->cur;
+    else if (!F->staged[F->cur ^ 1]) b = F->cur ^ 1;
+    else { set_error("stage_frame: two frames are already staged"); return HRBF_ERR_CAPACITY; }
+    // the first frame ever builds the RGBA texture (initFirstRGB); staged frame index = tick (+1 if it is the one after next)
+    const bool first = F->tick + (b != F->cur ? 1 : 0) == 1;
+    if (F->ev_free_valid[b]) HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_free[b], 0));
+    if (int rc = frame_upload(F->frames[b], rgb8, depth16, host, first, F->pre_stream)) return rc;
+    if (int rc = hrbf_frame_preprocess(F->frames[b], F->pre_stream)) return rc;
+    HRBF_CUDA(cudaEventRecord(F->ev_staged[b], F->pre_stream));
+    F->staged[b] = true;
+    return HRBF_OK;
+}
+int hrbf_fusion_process_staged(hrbf_fusion* F, long long timestamp, float weightMultiplier, float* pose16_out, void* stream)
+{
+    (void)timestamp;
+    HRBF_CHECK_ARG(F);
+    if (!F->staged[F->cur]) { set_error("process_staged: no staged frame"); return HRBF_ERR_INVALID_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_staged[F->cur], 0));
+    if (int rc = fusion_frame(F, weightMultiplier, s, true)) return rc;
+    F->staged[F->cur] = false;
+    F->cur ^= 1;
+    if (pose16_out) {
+        if (int rc = hrbf_fusion_get_pose(F, pose16_out, stream)) return rc;
+        if (F->timings) for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&F->last_ms[k], F->ev[k], F->ev[k + 1]);
+    }
     return HRBF_OK;
 }
 int hrbf_fusion_tick(const hrbf_fusion* F) { return F ? F->tick : 0; }

@@ -268,7 +268,11 @@ __device__ __forceinline__ void rgb_step_pass(const RgbStepArgs& a, float sigma,
 // dynamic shared memory of the persistent tracker: the RGB slots, max_slots x kTrackThreads
 inline size_t track_slots_bytes(int max_slots) { return (size_t)max_slots * kTrackThreads * sizeof(RgbSlot); }
 
+#ifdef HRBF_TRACK_MAXNREG      // development builds: cap the registers so that other kernels can co-reside with the tracker
+__global__ void __launch_bounds__(kTrackThreads) __maxnreg__(HRBF_TRACK_MAXNREG) track_persistent_kernel(const TrackParams p)
+#else
 __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
+#endif
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     RgbSlot* s_slots = reinterpret_cast<RgbSlot*>(s_dyn);

@@ -243,6 +243,16 @@ class HRBFFusion:
         """CUDA tensors in; enqueue only"""
         check(lib().hrbf_fusion_process_frame_dev(self._h, ptr(rgb_dev), ptr(depth_dev), C.c_longlong(timestamp), C.c_float(weightMultiplier), stream_ptr()))
 
+    def stageFrame(self, rgb, depth):
+        """upload + preprocess of the next frame on the internal staging stream; CUDA tensors or pinned host tensors"""
+        host = 0 if rgb.is_cuda else 1
+        check(lib().hrbf_fusion_stage_frame(self._h, C.c_void_p(rgb.data_ptr()), C.c_void_p(depth.data_ptr()), host, stream_ptr()))
+
+    def processStaged(self, pose_out=None, timestamp=0, weightMultiplier=1.0):
+        """processFrame of the oldest staged frame; pose_out: numpy float32[16] (synchronises) or None (enqueue only)"""
+        p = pose_out.ctypes.data_as(C.POINTER(C.c_float)) if pose_out is not None else None
+        check(lib().hrbf_fusion_process_staged(self._h, C.c_longlong(timestamp), C.c_float(weightMultiplier), p, stream_ptr()))
+
     def getPose(self):
         pose = np.zeros(16, np.float32)
         check(lib().hrbf_fusion_get_pose(self._h, pose.ctypes.data_as(C.POINTER(C.c_float)), stream_ptr()))

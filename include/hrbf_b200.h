@@ -385,6 +385,13 @@ int hrbf_fusion_process_frame(hrbf_fusion*, const unsigned char* rgb8_host, cons
 int hrbf_fusion_process_frame_dev(hrbf_fusion*, const unsigned char* rgb8_dev, const unsigned short* depth16_dev,
                                   long long timestamp, float weightMultiplier, void* stream);
 int hrbf_fusion_get_pose(hrbf_fusion*, float* pose16_out_host, void* stream);
+/* Pipelined processFrame for log replay (the reference reads frame t+1 from the .klg while the GPU works on t: MainController.cpp).
+ * stage_frame: upload (host != 0: pinned host memory) + preprocess of the next unprocessed frame, on an internal low-priority
+ * stream, concurrently with whatever `stream` is still doing for the previous frame; at most two frames may be staged.
+ * process_staged: processFrame of the oldest staged frame on `stream`; pose16_out_host == NULL -> enqueue only.
+ * Results are identical to hrbf_fusion_process_frame on the same frames. */
+int hrbf_fusion_stage_frame(hrbf_fusion*, const unsigned char* rgb8, const unsigned short* depth16, int host, void* stream);
+int hrbf_fusion_process_staged(hrbf_fusion*, long long timestamp, float weightMultiplier, float* pose16_out_host, void* stream);
 int hrbf_fusion_tick(const hrbf_fusion*);
 /* per-frame poses since creation, device array float[frames][12] (R row-major, t): gathered by the multi-GPU bench */
 const float* hrbf_fusion_trajectory_dev(hrbf_fusion*, int* n_frames);

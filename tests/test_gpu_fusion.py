@@ -204,3 +204,41 @@ def test_update_model_matches_oracle(orc, cuda):
     gm.setModel(s[:0])
     gm.updateModel(delta)
     assert gm.lastCount() == 0
+
+
+def test_staged_pipeline_is_identical_to_process_frame(orc, cuda):
+    """hrbf_fusion_stage_frame / process_staged (upload + preprocess of frame t+1 on the staging stream while frame t is tracked)
+    must give bit-identical poses and the same map as processFrame on the same frames; API misuse fails loudly."""
+    torch = cuda
+    from hrbffusion3d_b200.fusion import HRBFFusion
+    from hrbffusion3d_b200._lib import HrbfError
+    W, H, n = 320, 240, 7
+    cam, poses, fr = _frames(W, H, n)
+    ref = HRBFFusion(W, H, cam, capacity=1 << 20)
+    ref_poses = [ref.processFrame(rgb, depth).copy() for depth, rgb in fr]
+    d_dev = [torch.from_numpy(d.view(np.int16)).cuda() for d, _ in fr]
+    c_dev = [torch.from_numpy(c).cuda() for _, c in fr]
+    d_pin = [torch.from_numpy(d.view(np.int16)).pin_memory() for d, _ in fr]
+    c_pin = [torch.from_numpy(c).pin_memory() for _, c in fr]
+    for dsrc, csrc in ((d_dev, c_dev), (d_pin, c_pin)):
+        g = HRBFFusion(W, H, cam, capacity=1 << 20)
+        with pytest.raises(HrbfError):
+            g.processStaged()                                   # nothing staged
+        g.stageFrame(csrc[0], dsrc[0])
+        with pytest.raises(HrbfError):
+            g.processFrame(fr[0][1], fr[0][0])                  # a staged frame is pending
+        out = []
+        for i in range(n):
+            if i + 1 < n:
+                g.stageFrame(csrc[i + 1], dsrc[i + 1])          # two frames staged: i and i + 1
+                if i == 0:
+                    with pytest.raises(HrbfError):
+                        g.stageFrame(csrc[2], dsrc[2])          # a third one does not fit
+            pose = np.zeros(16, np.float32)
+            g.processStaged(pose)
+            out.append(pose.reshape(4, 4).copy())
+        for a, b in zip(out, ref_poses):
+            assert np.array_equal(a, b)
+        assert g.globalModel.lastCount() == ref.globalModel.lastCount()
+        assert torch.equal(g.trajectory(), ref.trajectory())
+        assert g.tick == n + 1
