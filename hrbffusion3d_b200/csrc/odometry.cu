@@ -810,7 +810,8 @@ int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_u
         it[level] = reps;
         for (int r = 0; r < 2; ++r) {
             if (r == 1) HRBF_CUDA(cudaEventRecord(e0, s));
-            if (int rc = launch_track_persistent(o, s, false, 100.0f, true, false, false, true, o->pose_scratch + 12, o->pose_scratch + 24, it)) return rc;
+            // start pose = the one the last tracking call started from (TrackState begins with Rprev[9], tprev[3]): consistent with the loaded maps
+            if (int rc = launch_track_persistent(o, s, false, 100.0f, true, false, false, true, (const float*)&o->work->st, o->pose_scratch + 24, it)) return rc;
         }
         HRBF_CUDA(cudaEventRecord(e1, s));
         HRBF_CUDA(cudaEventSynchronize(e1));

@@ -385,7 +385,8 @@ int hrbf_fusion_process_frame(hrbf_fusion*, const unsigned char* rgb8_host, cons
 int hrbf_fusion_process_frame_dev(hrbf_fusion*, const unsigned char* rgb8_dev, const unsigned short* depth16_dev,
                                   long long timestamp, float weightMultiplier, void* stream);
 int hrbf_fusion_get_pose(hrbf_fusion*, float* pose16_out_host, void* stream);
-/* Pipelined processFrame for log replay (the reference reads frame t+1 from the .klg while the GPU works on t: MainController.cpp).
+/* Pipelined processFrame for log replay, where frame t+1 is available while frame t is still being processed (the reference's
+ * MainController loop reads and processes strictly in turn; this is an addition, not a mirrored call).
  * stage_frame: upload (host != 0: pinned host memory) + preprocess of the next unprocessed frame, on an internal low-priority
  * stream, concurrently with whatever `stream` is still doing for the previous frame; at most two frames may be staged.
  * process_staged: processFrame of the oldest staged frame on `stream`; pose16_out_host == NULL -> enqueue only.
