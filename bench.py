@@ -36,8 +36,8 @@ from hrbffusion3d_b200 import synth  # noqa: E402
 W, H = 640, 480
 RING = 96                    # frames of one closed camera loop, cycled (96 x 1.54 MB of inputs = 147 MB > 126 MB L2)
 ICP_BYTES_PER_PIXEL_ITER = 68.0
-ICP_NCU_TRAFFIC = 20927232.0      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, cold cache
-ICP_NCU_TRAFFIC_SRC = "ncu --set full, profiles/r1_icp_l0_ncu_full_summary.txt"
+ICP_NCU_TRAFFIC = 20.9e6          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, cold cache
+ICP_NCU_TRAFFIC_SRC = "ncu --set full, profiles/r1_final_icp_reduce_ncu_full.txt"
 FUSION_KW = {}               # reference defaults: RGB+ICP (weight 10), SO3 pre-alignment, iterations 10/5/4, HRBF win 3 / K 10
 
 

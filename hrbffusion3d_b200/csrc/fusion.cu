@@ -533,7 +533,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
     auto IT = [&](int t) { return im->tex[t]; };
     auto LT = [&](int t) { return F->fill->tex[t]; };
     auto mark = [&](int k) { if (F->timings) cudaEventRecord(F->ev[k], s); };
-    auto splat = [&]() { return indexmap_splat(im, invPose, (const float*)M->vbo[M->cur], M->count[M->cur], M->bound, p.maxDepthProcessed, s); };
+    auto splat = [&](int out_mask) { return indexmap_splat(im, invPose, (const float*)M->vbo[M->cur], M->count[M->cur], M->bound, p.maxDepthProcessed, s, out_mask); };
 
     mark(0);
     if (!preprocessed) { if (int rc = hrbf_frame_preprocess(fr, s)) return rc; }
@@ -588,12 +588,12 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
         mark(2);
         // ---- Integration (HRBFFusion.cpp:1192-1227) ----
         if (!p.rgbOnly) {
-            if (int rc = splat()) return rc;
+            if (int rc = splat(2)) return rc;                  // fuse reads index, vertConf, normRad (data.vert)
             if (int rc = model_fuse_dev(M, currPose, F->tick, (const unsigned char*)FT(HRBF_FT_RGB), (const float*)FT(HRBF_FT_DEPTH_METRIC),
                                         (const float*)FT(HRBF_FT_DEPTH_METRIC_FILTERED), (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2),
                                         (const float*)FT(HRBF_FT_CONFIDENCE), (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                         (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s, inline_w)) return rc;
-            if (int rc = splat()) return rc;
+            if (int rc = splat(1)) return rc;                  // clean reads index, vertConf, colorTime (copy_unstable.vert)
             if (int rc = model_clean_dev(M, invPose, F->tick, (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                          (const float*)IT(HRBF_TEX_COLORTIME), p.confidenceThreshold, p.maxDepthProcessed, s)) return rc;
         }
@@ -601,7 +601,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
     }
     if (F->tick == 1) { pose_inverse_kernel<<<1, 32, 0, s>>>(currPose, invPose); HRBF_KERNEL_CHECK(); }
     // ---- Prediction (HRBFFusion.cpp:1244-1260) ----
-    if (int rc = splat()) return rc;
+    if (int rc = splat(7)) return rc;
     im->dense_count_next = denseCount + (F->tick & 1);
     if (int rc = hrbf_indexmap_predict_hrbf(im, 0, p.predWindow, p.predMinNeighbors, p.predMaxNeighbors, p.predConfThreshold, p.icpWeightLambda, s)) return rc;
     if (int rc = hrbf_fillin_run(F->fill, im, fr, 0, p.icpWeightLambda, p.curvValidThreshold, s)) return rc;

@@ -72,8 +72,9 @@ struct hrbf_indexmap {
 
 
 namespace hrbf {
+// out_mask: 1 colorTime | 2 normRad | 4 curvature maps (index and vertConf are always written); 7 = everything (IndexMap::predictIndices)
 int indexmap_splat(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels, const unsigned int* count_dev, unsigned int bound,
-                   float depthCutoff, cudaStream_t s);
+                   float depthCutoff, cudaStream_t s, int out_mask = 7);
 // device-pose / device-select forms of the RGBDOdometry init* calls (odometry.cu), used by fusion.cu:
 // when `sel` is non-null and *sel != 0 the `_alt` textures are read instead (shouldFillIn, HRBFFusion.cpp:1069-1086)
 int odom_init_icp_model_dev(hrbf_odometry* o, const float* v, const float* n, const float* v_alt, const float* n_alt, const int* sel,

@@ -135,7 +135,7 @@ void* hrbf_indexmap_texture(hrbf_indexmap* m, int which)
 }  // extern "C"
 
 int hrbf::indexmap_splat(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels, const unsigned int* count_dev, unsigned int bound,
-                         float depthCutoff, cudaStream_t s)
+                         float depthCutoff, cudaStream_t s, int out_mask)
 {
     SplatArgs a;
     a.inv_pose = inv_pose_dev;
@@ -150,7 +150,7 @@ int hrbf::indexmap_splat(hrbf_indexmap* m, const float* inv_pose_dev, const floa
     }
     splat_gather_kernel<<<div_up(P, 256), 256, 0, s>>>((const float4*)surfels, a, m->keys, (unsigned int*)m->tex[HRBF_TEX_INDEX],
                                                       (float4*)m->tex[HRBF_TEX_VERTCONF], (float4*)m->tex[HRBF_TEX_COLORTIME], (float4*)m->tex[HRBF_TEX_NORMRAD],
-                                                      (float4*)m->tex[HRBF_TEX_CURVMAX], (float4*)m->tex[HRBF_TEX_CURVMIN]);
+                                                      (float4*)m->tex[HRBF_TEX_CURVMAX], (float4*)m->tex[HRBF_TEX_CURVMIN], out_mask);
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }

@@ -73,16 +73,22 @@ __global__ void __launch_bounds__(256) splat_keys_kernel(const float4* __restric
 }
 
 // pass 2: one thread per pixel; re-arms the key buffer for the next call
+// out_mask: which of the optional maps are produced (kSplatColorTime | kSplatNormRad | kSplatCurv); index and vertConf always are.
+// The frame pipeline's splats before fuse / clean skip the maps those passes never read (data.vert, copy_unstable.vert).
+enum { kSplatColorTime = 1, kSplatNormRad = 2, kSplatCurv = 4, kSplatAll = 7 };
 __global__ void __launch_bounds__(256) splat_gather_kernel(const float4* __restrict__ surfels, SplatArgs a, unsigned long long* __restrict__ keys,
                                                            unsigned int* __restrict__ index, float4* __restrict__ vertConf, float4* __restrict__ colorTime,
-                                                           float4* __restrict__ normRad, float4* __restrict__ curvMax, float4* __restrict__ curvMin)
+                                                           float4* __restrict__ normRad, float4* __restrict__ curvMax, float4* __restrict__ curvMin, int out_mask)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.cols * a.rows) return;
     const unsigned long long key = keys[k];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (key == kEmptyKey) {
-        index[k] = 0u; vertConf[k] = z4; colorTime[k] = z4; normRad[k] = z4; curvMax[k] = z4; curvMin[k] = z4;
+        index[k] = 0u; vertConf[k] = z4;
+        if (out_mask & kSplatColorTime) colorTime[k] = z4;
+        if (out_mask & kSplatNormRad) normRad[k] = z4;
+        if (out_mask & kSplatCurv) { curvMax[k] = z4; curvMin[k] = z4; }
         return;
     }
     keys[k] = kEmptyKey;
@@ -93,16 +99,18 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float4* __restr
     for (int q = 0; q < 3; ++q) ti[q] = __ldg(a.inv_pose + 9 + q);
     const unsigned int id = (unsigned int)(key & 0xffffffffull);
     const float4* s = surfels + 5 * (size_t)id;
-    const float4 pos = __ldg(s), ct = __ldg(s + 1), nr = __ldg(s + 2);
+    const float4 pos = __ldg(s);
     const float3 P = rigid_apply(Ri, ti, pos.x, pos.y, pos.z);
-    const float3 n = rot_apply(Ri, nr.x, nr.y, nr.z);
-    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z))));
     index[k] = id;
     vertConf[k] = make_float4(P.x, P.y, P.z, pos.w);
-    colorTime[k] = ct;
-    normRad[k] = make_float4(__fmul_rn(n.x, inv), __fmul_rn(n.y, inv), __fmul_rn(n.z, inv), nr.w);
-    curvMax[k] = __ldg(s + 3);
-    curvMin[k] = __ldg(s + 4);
+    if (out_mask & kSplatColorTime) colorTime[k] = __ldg(s + 1);
+    if (out_mask & kSplatNormRad) {
+        const float4 nr = __ldg(s + 2);
+        const float3 n = rot_apply(Ri, nr.x, nr.y, nr.z);
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z))));
+        normRad[k] = make_float4(__fmul_rn(n.x, inv), __fmul_rn(n.y, inv), __fmul_rn(n.z, inv), nr.w);
+    }
+    if (out_mask & kSplatCurv) { curvMax[k] = __ldg(s + 3); curvMin[k] = __ldg(s + 4); }
 }
 
 __global__ void fill_keys_kernel(unsigned long long* keys, int n)
@@ -223,7 +231,10 @@ __device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots
 
 // 256 threads = 64 pixels (16 x 4 tile) x 4 lanes.  The (16+6) x (4+6) halo tile of the two maps the
 // ray march needs (position+confidence, normal+radius) is staged in shared memory once per CTA.
-__global__ void __launch_bounds__(256, 3) predict_hrbf_kernel(PredictArgs a)
+#ifndef HRBF_PRED_MINBLOCKS
+#define HRBF_PRED_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(PredictArgs a)
 {
     __shared__ float4 s_v[kPredSH][kPredSW];
     __shared__ float4 s_n[kPredSH][kPredSW];
