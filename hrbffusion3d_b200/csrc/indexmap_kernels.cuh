@@ -232,7 +232,7 @@ __device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots
 // 256 threads = 64 pixels (16 x 4 tile) x 4 lanes.  The (16+6) x (4+6) halo tile of the two maps the
 // ray march needs (position+confidence, normal+radius) is staged in shared memory once per CTA.
 #ifndef HRBF_PRED_MINBLOCKS
-#define HRBF_PRED_MINBLOCKS 3
+#define HRBF_PRED_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(PredictArgs a)
 {
