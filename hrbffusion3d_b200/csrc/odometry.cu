@@ -625,8 +625,8 @@ int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s
     }
     A.pyr_bx = div_up(o->width, 32); A.pyr_by = div_up(o->height, 8);
     A.rgbd_bx = div_up(o->cols(2), 8); A.rgbd_by = div_up(o->rows(2), 8);
-    const int blocks = 5 * A.pyr_bx * A.pyr_by + 2 * A.rgbd_bx * A.rgbd_by;
-    prep_all_kernel<<<blocks, 256, 0, s>>>(A);
+    const dim3 grid(A.pyr_bx > A.rgbd_bx ? A.pyr_bx : A.rgbd_bx, A.pyr_by > A.rgbd_by ? A.pyr_by : A.rgbd_by, 7);
+    prep_all_kernel<<<grid, 256, 0, s>>>(A);
     HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }

@@ -463,22 +463,20 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
 
 __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
 {
-    const int per_pyr = A.pyr_bx * A.pyr_by, per_rgbd = A.rgbd_bx * A.rgbd_by;
-    int b = blockIdx.x;
+    // grid = (tiles x, tiles y, 7 jobs): z = 0, 1 are the (heavier) RGB-D pyramid jobs -- lowest block indices, scheduled first --
+    // z = 2..6 the map jobs; no index arithmetic beyond blockIdx
+    const int job_z = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;
+    if (job_z < 2 ? (bx >= A.rgbd_bx || by >= A.rgbd_by) : (bx >= A.pyr_bx || by >= A.pyr_by)) return;
     // HRBFFusion::denseEnough (HRBFFusion.cpp:974-987): fill-in textures replace the prediction when <= thresh of the 1/20 samples are set
     bool alt;
     if (A.sel != nullptr) alt = *A.sel != 0;
     else if (A.dense_count != nullptr) {
         const int total = (A.cols / 20) * (A.rows / 20);
         alt = !((float)*A.dense_count / (float)total > A.dense_thresh);
-        if (blockIdx.x == 0 && threadIdx.x == 0 && A.dense_count_reset != nullptr) *A.dense_count_reset = 0u;
+        if (bx == 0 && by == 0 && job_z == 6 && threadIdx.x == 0 && A.dense_count_reset != nullptr) *A.dense_count_reset = 0u;
     } else alt = false;
-    // the (heavier) RGB-D pyramid tiles take the lowest block indices: they are scheduled first and the light map tiles fill in
-    if (b >= 2 * per_rgbd) {
-        b -= 2 * per_rgbd;
-        const int job = b / per_pyr, t = b - job * per_pyr;
-        const int by = t / A.pyr_bx, bx = t - by * A.pyr_bx;
-        switch (job) {
+    if (job_z >= 2) {
+        switch (job_z - 2) {
         case 0: pyr_pair_tile<PYR_VN>(alt ? A.vm_alt : A.vm, alt ? A.nm_alt : A.nm, A.rows, A.cols, 0.f, A.pose, A.o_vg, A.o_ng, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
         case 1: pyr_pair_tile<PYR_VN>(A.vc, A.nc, A.rows, A.cols, 0.f, nullptr, A.o_vc, A.o_nc, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
         case 2: pyr_pair_tile<PYR_K>(alt ? A.k1m_alt : A.k1m, alt ? A.k2m_alt : A.k2m, A.rows, A.cols, A.curv_thr, A.pose, A.o_k1g, A.o_k2g, nullptr, 0.f, nullptr, nullptr, nullptr, bx, by); break;
@@ -487,8 +485,7 @@ __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
         }
         return;
     }
-    const int job = b / per_rgbd, t = b - job * per_rgbd;
-    const int by = t / A.rgbd_bx, bx = t - by * A.rgbd_bx;
+    const int job = job_z;
     const bool use_alt = job == 0 && alt;
     rgbd_pyramid_tile(A.rgbd[job], A.rows, A.cols, A.depth_cutoff, use_alt, bx, by);
 }

@@ -9,6 +9,7 @@
 //   fill_{vertex,normal,curvature,rgb}.frag                       -> fill_in_kernel (4 passes fused)
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace hrbf {
 
@@ -20,7 +21,7 @@ struct PrepArgs {
     int pca, curvWin, bilateral;
 };
 
-// exp() of the bilateral weights as a fixed sequence of IEEE fp32 operations (no FMA), identical to the oracle's
+// exp() of the bilateral weights as a fixed sequence of IEEE fp32 operations (explicit FMAs in the Horner scheme), identical to the oracle's
 // orc_exp_bilateral: the filtered depth must be bit-reproducible because the PCA normal estimation downstream
 // amplifies 1-ulp depth differences to ~1e-3 in the normal.
 __device__ __forceinline__ float exp_bilateral(float x)
@@ -30,12 +31,12 @@ __device__ __forceinline__ float exp_bilateral(float x)
     const float n = rintf(t);
     const float f = __fsub_rn(t, n);
     float p = 1.54035304e-4f;
-    p = __fadd_rn(__fmul_rn(p, f), 1.33335581e-3f);
-    p = __fadd_rn(__fmul_rn(p, f), 9.61812911e-3f);
-    p = __fadd_rn(__fmul_rn(p, f), 5.55041087e-2f);
-    p = __fadd_rn(__fmul_rn(p, f), 2.40226507e-1f);
-    p = __fadd_rn(__fmul_rn(p, f), 6.93147181e-1f);
-    p = __fadd_rn(__fmul_rn(p, f), 1.0f);
+    p = fmaf(p, f, 1.33335581e-3f);
+    p = fmaf(p, f, 9.61812911e-3f);
+    p = fmaf(p, f, 5.55041087e-2f);
+    p = fmaf(p, f, 2.40226507e-1f);
+    p = fmaf(p, f, 6.93147181e-1f);
+    p = fmaf(p, f, 1.0f);
     return ldexpf(p, (int)n);
 }
 
@@ -48,12 +49,12 @@ __device__ __forceinline__ float exp_bilateral_fast(float x)
     const float n = rintf(t);
     const float f = __fsub_rn(t, n);
     float p = 1.54035304e-4f;
-    p = __fadd_rn(__fmul_rn(p, f), 1.33335581e-3f);
-    p = __fadd_rn(__fmul_rn(p, f), 9.61812911e-3f);
-    p = __fadd_rn(__fmul_rn(p, f), 5.55041087e-2f);
-    p = __fadd_rn(__fmul_rn(p, f), 2.40226507e-1f);
-    p = __fadd_rn(__fmul_rn(p, f), 6.93147181e-1f);
-    p = __fadd_rn(__fmul_rn(p, f), 1.0f);
+    p = fmaf(p, f, 1.33335581e-3f);
+    p = fmaf(p, f, 9.61812911e-3f);
+    p = fmaf(p, f, 5.55041087e-2f);
+    p = fmaf(p, f, 2.40226507e-1f);
+    p = fmaf(p, f, 6.93147181e-1f);
+    p = fmaf(p, f, 1.0f);
     const int e = (int)n;
     return (x > -87.0f && e >= -125) ? __int_as_float(__float_as_int(p) + (e << 23)) : 0.0f;
 }
@@ -99,21 +100,26 @@ __global__ void __launch_bounds__(256) depth_filter_metric_kernel(PrepArgs a, co
             // 13 x 13 window in the same order and a tap outside the image gets weight 0 (adds exactly 0 to both sums)
             const float sc = 0.000555556f;
             float sum1 = 0.f, sum2 = 0.f;
-            for (int dy = -kBilR; dy <= kBilR; ++dy) {
-                const bool iny = (unsigned)(y + dy) < (unsigned)H;
-                const float* row = &s_t[ly + kBilR + dy][lx];
-                const float* sp = c_bil_space + (dy + kBilR) * (2 * kBilR + 1);
+            // tiles whose 13 x 13 windows lie inside the image (all but the border tiles) skip the per-tap bounds test
+            const bool interior = x0 >= 0 && y0 >= 0 && x0 + kBilTW + 2 * kBilR <= W && y0 + kBilTH + 2 * kBilR <= H;
+            auto window = [&](auto checked) {
+                for (int dy = -kBilR; dy <= kBilR; ++dy) {
+                    const bool iny = (unsigned)(y + dy) < (unsigned)H;
+                    const float* row = &s_t[ly + kBilR + dy][lx];
+                    const float* sp = c_bil_space + (dy + kBilR) * (2 * kBilR + 1);
 #pragma unroll
-                for (int dx = -kBilR; dx <= kBilR; ++dx) {
-                    const float tmp = row[kBilR + dx];
-                    const float dc = __fsub_rn(value, tmp);
-                    const float color2 = __fmul_rn(dc, dc);
-                    float weight = exp_bilateral_fast(-__fadd_rn(sp[dx + kBilR], __fmul_rn(color2, sc)));
-                    if (!(iny && (unsigned)(x + dx) < (unsigned)W)) weight = 0.f;
-                    sum1 = __fadd_rn(sum1, __fmul_rn(tmp, weight));
-                    sum2 = __fadd_rn(sum2, weight);
+                    for (int dx = -kBilR; dx <= kBilR; ++dx) {
+                        const float tmp = row[kBilR + dx];
+                        const float dc = __fsub_rn(value, tmp);
+                        const float color2 = __fmul_rn(dc, dc);
+                        float weight = exp_bilateral_fast(-fmaf(color2, sc, sp[dx + kBilR]));
+                        if (decltype(checked)::value && !(iny && (unsigned)(x + dx) < (unsigned)W)) weight = 0.f;
+                        sum1 = fmaf(tmp, weight, sum1);
+                        sum2 = __fadd_rn(sum2, weight);
+                    }
                 }
-            }
+            };
+            if (interior) window(std::false_type{}); else window(std::true_type{});
             out = __fmul_rn(__fdiv_rn(sum1, sum2), adj);
         } else out = (float)rv;
     }

@@ -26,7 +26,8 @@
 /* GLSL exp() is only specified to a few ULP and differs between drivers; the bilateral weights feed the PCA
  * normal estimation, which amplifies 1-ulp depth differences to ~1e-3 in the normal (E[x^2]-E[x]^2 cancellation,
  * geometry.glsl:163-187).  The oracle therefore DEFINES exp for this pass by a fixed sequence of IEEE fp32
- * operations (no FMA): 2^(x*log2 e) with round-to-nearest range reduction and a degree-6 polynomial, relative
+ * operations (explicit fused multiply-adds in the Horner scheme and the two accumulations -- what a GPU compiler makes of the
+ * shader's `a * b + c` -- and nothing else contracted): 2^(x*log2 e) with round-to-nearest range reduction and a degree-6 polynomial, relative
  * error < 4e-6 (range reduction at large |x|, where the weight is negligible) -- any implementation that repeats the sequence reproduces the filtered depth bit for bit. */
 float orc_exp_bilateral(float x)
 {
@@ -35,12 +36,12 @@ float orc_exp_bilateral(float x)
     const float n = rintf(t);
     const float f = t - n;                      /* [-0.5, 0.5] */
     float p = 1.54035304e-4f;                   /* 2^f, minimax-ish Taylor coefficients ln2^k / k! */
-    p = p * f + 1.33335581e-3f;
-    p = p * f + 9.61812911e-3f;
-    p = p * f + 5.55041087e-2f;
-    p = p * f + 2.40226507e-1f;
-    p = p * f + 6.93147181e-1f;
-    p = p * f + 1.0f;
+    p = fmaf(p, f, 1.33335581e-3f);
+    p = fmaf(p, f, 9.61812911e-3f);
+    p = fmaf(p, f, 5.55041087e-2f);
+    p = fmaf(p, f, 2.40226507e-1f);
+    p = fmaf(p, f, 6.93147181e-1f);
+    p = fmaf(p, f, 1.0f);
     return ldexpf(p, (int)n);
 }
 
@@ -65,8 +66,8 @@ void orc_filterDepth(const orc_prep_params* p, const unsigned short* raw, float*
                             const float tmp = (float)raw[(size_t)cy * W + cx] / adj;
                             const float space2 = ((float)x - (float)cx) * ((float)x - (float)cx) + ((float)y - (float)cy) * ((float)y - (float)cy);
                             const float color2 = (value - tmp) * (value - tmp);
-                            const float weight = orc_exp_bilateral(-(space2 * ss + color2 * sc));
-                            sum1 += tmp * weight;
+                            const float weight = orc_exp_bilateral(-fmaf(color2, sc, space2 * ss));
+                            sum1 = fmaf(tmp, weight, sum1);
                             sum2 += weight;
                         }
                     out = (sum1 / sum2) * adj;
