@@ -269,7 +269,7 @@ __device__ __forceinline__ void rgb_step_pass(const RgbStepArgs& a, float sigma,
 inline size_t track_slots_bytes(int max_slots) { return (size_t)max_slots * kTrackThreads * sizeof(RgbSlot); }
 
 #ifdef HRBF_TRACK_MAXNREG      // development builds: cap the registers so that other kernels can co-reside with the tracker
-__global__ void __launch_bounds__(kTrackThreads) __maxnreg__(HRBF_TRACK_MAXNREG) track_persistent_kernel(const TrackParams p)
+__global__ void __maxnreg__(HRBF_TRACK_MAXNREG) track_persistent_kernel(const TrackParams p)
 #else
 __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
 #endif
