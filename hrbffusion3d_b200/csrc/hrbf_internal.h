@@ -67,6 +67,7 @@ struct hrbf_indexmap {
     float* h_stage = nullptr;            // pinned ring: 8 x 16 floats
     float* h_kf = nullptr;               // pinned keyframe mask
     int slot = 0;
+    unsigned long long* row_lut = nullptr;      // device: make_pred_row_lut()
     unsigned int* dense_count_next = nullptr;   // frame pipeline: where the next ACTIVE prediction counts its dense-enough samples (or null)
 };
 

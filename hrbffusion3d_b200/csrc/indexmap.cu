@@ -33,7 +33,7 @@ int hrbf_indexmap_create(hrbf_indexmap** out, int width, int height, float cx, f
     size_t off = 0, o_tex[HRBF_TEX_COUNT];
     auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
     for (int t = 0; t < HRBF_TEX_COUNT; ++t) o_tex[t] = take(tex_bytes(t, P));
-    const size_t o_keys = take(P * 8), o_kf = take(HRBF_ACTIVE_KEYFRAME_DIMENSION * 4), o_pose = take(8 * 12 * 4), o_cnt = take(8 * 4);
+    const size_t o_keys = take(P * 8), o_kf = take(HRBF_ACTIVE_KEYFRAME_DIMENSION * 4), o_pose = take(8 * 12 * 4), o_cnt = take(8 * 4), o_lut = take(7 * 128 * 8);
     if (cudaMalloc(&m->slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); delete m; return HRBF_ERR_CUDA; }
     cudaMemset(m->slab, 0, off);
     for (int t = 0; t < HRBF_TEX_COUNT; ++t) m->tex[t] = m->slab + o_tex[t];
@@ -41,6 +41,12 @@ int hrbf_indexmap_create(hrbf_indexmap** out, int width, int height, float cx, f
     m->active_kf = (float*)(m->slab + o_kf);
     m->inv_pose = (float*)(m->slab + o_pose);
     m->count_slot = (unsigned int*)(m->slab + o_cnt);
+    m->row_lut = (unsigned long long*)(m->slab + o_lut);
+    {
+        unsigned long long lut[7 * 128];
+        make_pred_row_lut(lut);
+        cudaMemcpy(m->row_lut, lut, sizeof lut, cudaMemcpyHostToDevice);
+    }
     cudaMallocHost(&m->h_stage, 8 * 16 * sizeof(float));
     cudaMallocHost(&m->h_kf, HRBF_ACTIVE_KEYFRAME_DIMENSION * sizeof(float));
     fill_keys_kernel<<<div_up((int)P, 256), 256>>>(m->keys, (int)P);
@@ -120,6 +126,7 @@ int hrbf_indexmap_predict_hrbf(hrbf_indexmap* m, int predictionType, int win, in
     a.icx = (float)(1.0 / (double)m->fx); a.icy = (float)(1.0 / (double)m->fy);      // IndexMap.cpp:449-452
     a.win = win; a.minN = minNeighbors; a.maxN = maxNeighbors; a.confThr = confThreshold; a.lambda = icpWeightLambda;
     a.dense_count = predictionType == 0 ? m->dense_count_next : nullptr;
+    a.row_lut = m->row_lut;
     const dim3 grid(div_up(m->width, kPredTileW), div_up(m->height, kPredTileH));
     predict_hrbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     HRBF_KERNEL_CHECK();

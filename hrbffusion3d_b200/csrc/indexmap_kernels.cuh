@@ -127,6 +127,7 @@ struct PredictArgs {
     float cx, cy, icx, icy;      // uniform cam = (cx, cy, 1/fx, 1/fy)
     int win, minN, maxN;
     float confThr, lambda;
+    const unsigned long long* row_lut;   // device copy of make_pred_row_lut(): [7][128] candidate masks of a window row
     unsigned int* dense_count;   // optional: += 1 for every texel centre (20 i + 10, 20 j + 10) of the 1/20 grid with a predicted surface
                                  // (the sample set of HRBFFusion::denseEnough, HRBFFusion.cpp:974-987, Shaders/Resize.cpp:106-139)
 };
@@ -174,6 +175,20 @@ inline PredTable make_pred_table()
 // 9 instructions per neighbour and evaluation, 5 registers per neighbour (40 for the 8 slots: no spills at 80 registers).
 // An empty slot has a = 4 (outside every support) and contributes exactly 0.
 struct NbRay { float a, b, c, cs, ds; };
+
+// Window row r (dy = r - 3) with validity bits m (bit k: dx = k - 3) -> the mask of valid candidates in the shader's scan order.
+// A pixel's 49-candidate mask is the OR of 7 table entries instead of 49 tests.
+inline void make_pred_row_lut(unsigned long long* lut /* [7][128] */)
+{
+    const PredTable t = make_pred_table();
+    for (int r = 0; r < 7; ++r)
+        for (int m = 0; m < 128; ++m) {
+            unsigned long long v = 0ull;
+            for (int c = 0; c < kPredCand; ++c)
+                if (t.dy[c] == r - 3 && ((m >> (t.dx[c] + 3)) & 1)) v |= 1ull << c;
+            lut[r * 128 + m] = v;
+        }
+}
 
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -239,6 +254,11 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
     __shared__ float4 s_v[kPredSH][kPredSW];
     __shared__ float4 s_n[kPredSH][kPredSW];
     __shared__ unsigned char s_sel[64][32];              // per pixel: tile cell (row * kPredSW + col) of each selected neighbour
+    __shared__ unsigned long long s_lut[7 * 128];        // make_pred_row_lut
+    __shared__ unsigned int s_rowmask[kPredSH];          // per tile row: bit sx = the cell passes the (pixel-independent) neighbour tests
+    for (int t = threadIdx.x; t < 7 * 128; t += blockDim.x) s_lut[t] = __ldg(a.row_lut + t);
+    if (threadIdx.x < kPredSH) s_rowmask[threadIdx.x] = 0u;
+    __syncthreads();
     __shared__ PredTable s_tab;                          // the candidate tables: per-lane indices would serialise in the constant cache
     static_assert(sizeof(PredTable) % 4 == 0, "copied as words");
     for (int t = threadIdx.x; t < (int)(sizeof(PredTable) / 4); t += blockDim.x)
@@ -254,6 +274,9 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
             n = __ldg(a.normRad + (size_t)gy * a.cols + gx);
         }
         s_v[sy][sx] = v; s_n[sy][sx] = n;
+        // predict_hrbf.frag:94-97, evaluated once per cell instead of once per (pixel, candidate)
+        const float nl2 = __fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z));     // length < 0.1 <=> length^2 < 0.01
+        if (!(v.z < 0.1f || nl2 < 0.01f || v.w < a.confThr || n.z < 0.0f)) atomicOr(&s_rowmask[sy], 1u << sx);
     }
     __syncthreads();
 
@@ -269,16 +292,8 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
     // ---- neighbour gather (predict_hrbf.frag:74-113) ----
     const int ncand = s_tab.ring_end[a.win];
     unsigned long long valid = 0ull;
-    for (int c = sub; c < ncand; c += kPredLanes) {
-        const int dx = s_tab.dx[c], dy = s_tab.dy[c];
-        const int qx = px + dx, qy = py + dy;
-        if (qx < 0 || qx >= a.cols || qy < 0 || qy >= a.rows) continue;
-        const float4 v = s_v[ly + kPredHalo + dy][lx + kPredHalo + dx];
-        const float4 n = s_n[ly + kPredHalo + dy][lx + kPredHalo + dx];
-        const float nl2 = __fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z));     // length < 0.1 <=> length^2 < 0.01
-        if (v.z < 0.1f || nl2 < 0.01f || v.w < a.confThr || n.z < 0.0f) continue;
-        valid |= 1ull << c;
-    }
+    for (int r = sub; r < 7; r += kPredLanes) valid |= s_lut[r * 128 + ((s_rowmask[ly + r] >> lx) & 127u)];      // cells outside the image are invalid (z = 0)
+    valid &= (1ull << ncand) - 1ull;                     // rings beyond `win` are not scanned
     valid |= __shfl_xor_sync(gmask, valid, 1);
     valid |= __shfl_xor_sync(gmask, valid, 2);
     // The shader appends valid candidates in scan order and its `break` only leaves the innermost (y) loop: once more
