@@ -283,7 +283,8 @@ int model_initialise_dev(hrbf_model* m, const float* vertexMap, const float* nor
 
 int model_fuse_dev(hrbf_model* m, const float* pose_dev, int time, const unsigned char* rgb8, const float* depthRaw, const float* depthFiltered,
                    const float* curv1, const float* curv2, const float* confidence, const unsigned int* indexMap, const float* vertConf,
-                   const float* normRad, float depthCutoff, int indexSubmap, cudaStream_t s, const float* inline_weighting = nullptr)
+                   const float* normRad, float depthCutoff, int indexSubmap, cudaStream_t s, const float* inline_weighting = nullptr,
+                   const float* normal_pca_tex = nullptr)
 {
     ModelArgs a = m->a;
     a.maxDepth = depthCutoff;
@@ -291,6 +292,7 @@ int model_fuse_dev(hrbf_model* m, const float* pose_dev, int time, const unsigne
     f.rgb = rgb8; f.depthRaw = depthRaw; f.depthFiltered = depthFiltered; f.curv1 = (const float4*)curv1; f.curv2 = (const float4*)curv2;
     f.confidence = confidence; f.index = indexMap; f.vertConf = (const float4*)vertConf; f.normRad = (const float4*)normRad;
     f.pose = pose_dev; f.time = time; f.indexSubmap = (float)indexSubmap; f.weighting = inline_weighting;
+    f.normal_pca = (const float4*)normal_pca_tex;
     f.staging = m->staging; f.update_id = m->update_id; f.best = m->best; f.winner = m->winner;
     const int nb = div_up(m->n_slots, 128);
     fuse_associate_kernel<<<nb, 128, 0, s>>>(a, m->pa, f, m->count[m->cur]);
@@ -592,7 +594,8 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
             if (int rc = model_fuse_dev(M, currPose, F->tick, (const unsigned char*)FT(HRBF_FT_RGB), (const float*)FT(HRBF_FT_DEPTH_METRIC),
                                         (const float*)FT(HRBF_FT_DEPTH_METRIC_FILTERED), (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2),
                                         (const float*)FT(HRBF_FT_CONFIDENCE), (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
-                                        (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s, inline_w)) return rc;
+                                        (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s, inline_w,
+                                        p.frame.normalPCA ? (const float*)FT(HRBF_FT_NORMAL_PCA) : nullptr)) return rc;
             if (int rc = splat(1)) return rc;                  // clean reads index, vertConf, colorTime (copy_unstable.vert)
             if (int rc = model_clean_dev(M, invPose, F->tick, (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                          (const float*)IT(HRBF_TEX_COLORTIME), p.confidenceThreshold, p.maxDepthProcessed, s)) return rc;

@@ -166,6 +166,9 @@ struct FuseArgs {
     const float* pose;               // device R[9], t[3]
     int time; float indexSubmap;
     const float* weighting;          // frame pipeline: non-null -> confidence evaluated in place (see FillArgs::weighting)
+    const float4* normal_pca;        // frame pipeline: the frame's NORMAL_PCA texture.  data.vert recomputes the PCA normal of the filtered depth
+                                     // at each candidate pixel; depth_vertex_normal_radius.frag already did exactly that (same function, same
+                                     // window, same input) for every pixel, and zeroes it only where fuse rejects the pixel anyway
     float4* staging;                 // [(cols/2+1)*(rows/2+1)][5] : this frame's candidate records
     unsigned char* update_id;        // per slot: 0 none, 1 merge, 2 new
     unsigned int* best;              // per slot: surfel to merge with
@@ -191,7 +194,10 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
     const float4 k1 = __ldg(f.curv1 + o), k2 = __ldg(f.curv2 + o);
     if (!(z > 0.3f && z <= m.maxDepth && k1.w > -300.0f && k1.w < 300.0f && k2.w > -300.0f && k2.w < 300.0f)) return;
     float3 n = make_float3(0.f, 0.f, 0.f);
-    if (m.pca) n = normal_pca(pa, [&](int qx, int qy) { return __ldg(f.depthFiltered + (size_t)qy * W + qx); }, px, py, zf);
+    if (m.pca) {
+        if (f.normal_pca != nullptr) { const float4 t = __ldg(f.normal_pca + o); n = make_float3(t.x, t.y, t.z); }
+        else n = normal_pca(pa, [&](int qx, int qy) { return __ldg(f.depthFiltered + (size_t)qy * W + qx); }, px, py, zf);
+    }
     const float nlen = norm(n);
     if (!(nlen > 0.8f)) return;
 
