@@ -323,10 +323,15 @@ __device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& 
     if (lp.z < m.maxDepth && lp.z > 0 && x > 0 && y > 0 && x < (float)W && y < (float)H) {
         auto sample = [&](unsigned int idx, size_t q) {
             if (idx > 0u) {
-                const float4 vc = __ldg(c.vertConf + q), ct = __ldg(c.colorTime + q);
-                const float dx = vc.x - lp.x, dy = vc.y - lp.y;
-                if (ct.z < rec[1].z && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z < 0.01f && sqrtf(dx * dx + dy * dy) < rec[2].w * 1.4f) count++;
-                if (ct.w == (float)c.time && vc.w > m.confThreshold && vc.z > lp.z && vc.z - lp.z > 0.01f && fabsf(lnz) > 0.85f && active > 0.0f) zCount++;
+                const float4 vc = __ldg(c.vertConf + q);
+                // both tests need a confident texel strictly behind the surfel: the colour/time texel is only fetched then (the common
+                // case -- the texel shows this very surfel, vc.z == lp.z -- costs one gather instead of two)
+                if (vc.w > m.confThreshold && vc.z > lp.z) {
+                    const float4 ct = __ldg(c.colorTime + q);
+                    const float dx = vc.x - lp.x, dy = vc.y - lp.y;
+                    if (ct.z < rec[1].z && vc.z - lp.z < 0.01f && sqrtf(dx * dx + dy * dy) < rec[2].w * 1.4f) count++;
+                    if (ct.w == (float)c.time && vc.z - lp.z > 0.01f && fabsf(lnz) > 0.85f && active > 0.0f) zCount++;
+                }
             }
         };
         if (m.cleanWindow == 2) {
