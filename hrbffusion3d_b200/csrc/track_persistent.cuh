@@ -374,8 +374,26 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
             const int next_level = (j + 1 < L.iters) ? l : next_lower;
             unsigned long long* part = p.ll_f + (size_t)(phase & 1) * gridDim.x * 64;
             const unsigned int tag = tag_base | (phase + 1);
-            // ---- phase A: everything that only needs the current pose ----
+            // ---- phase A: everything that only needs the current pose.  The photometric residuals go first: their integer
+            // pair is published before the (longer) ICP pass, so the exchange is complete by the time anybody asks for it ----
             TP_STAMP(1);
+            unsigned long long* ip = p.ll_i + (size_t)(iphase & 1) * gridDim.x * kIntStride;
+            const unsigned int itag = tag_base | (iphase + 1);
+            if (p.rgb) {
+                // computeRgbResidual (reduce.cu:986-1060): the correspondence of each of this thread's pixels stays in its
+                // shared-memory slot for the step pass below (the reference's corresImg round trip through HBM is gone)
+                int cnt = 0, sig = 0;
+                rgb_residual_pass(L.res, L.cand, S.krkinv, begin, end, s_slots, cnt, sig);      // krkinv[9], kt[3] contiguous
+                TP_STAMP(7);
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                sig = __reduce_add_sync(0xffffffffu, sig);
+                if (tid < 2) s_i[tid] = 0;
+                __syncthreads();
+                if ((tid & 31) == 0 && (cnt | sig)) { atomicAdd(&s_i[0], cnt); atomicAdd(&s_i[1], sig); }
+                __syncthreads();
+                if (tid < 2) ll_store(ip + (size_t)blockIdx.x * kIntStride + tid, (unsigned int)s_i[tid], itag);
+                TP_STAMP(8);
+            }
             if (p.icp) {
                 float acc[32];
 #pragma unroll
@@ -392,23 +410,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 TP_STAMP(3);
             }
             if (p.rgb) {
-                // computeRgbResidual (reduce.cu:986-1060): the correspondence of each of this thread's pixels stays in its
-                // shared-memory slot for the step pass below (the reference's corresImg round trip through HBM is gone)
-                int cnt = 0, sig = 0;
-                rgb_residual_pass(L.res, L.cand, S.krkinv, begin, end, s_slots, cnt, sig);      // krkinv[9], kt[3] contiguous
-                TP_STAMP(7);
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                sig = __reduce_add_sync(0xffffffffu, sig);
-                if (tid < 2) s_i[tid] = 0;
-                __syncthreads();
-                if ((tid & 31) == 0 && (cnt | sig)) { atomicAdd(&s_i[0], cnt); atomicAdd(&s_i[1], sig); }
-                __syncthreads();
-                unsigned long long* ip = p.ll_i + (size_t)(iphase & 1) * gridDim.x * kIntStride;
-                const unsigned int itag = tag_base | (iphase + 1);
-                if (tid < 2) ll_store(ip + (size_t)blockIdx.x * kIntStride + tid, (unsigned int)s_i[tid], itag);
-                __syncthreads();
                 // ---- phase B: sigma of ALL residuals, then rgbStep (reduce.cu:718-811) from the slots ----
-                TP_STAMP(8);
                 all_reduce_int2(ip, itag, s_i);
                 TP_STAMP(9);
                 ++iphase;
