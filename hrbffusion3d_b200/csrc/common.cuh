@@ -40,6 +40,29 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
         HRBF_CUDA(cudaGetLastError());                                                   \
     } while (0)
 
+// Programmatic dependent launch: a kernel launched with HRBF_LAUNCH_PDL may be scheduled while the previous kernel of the
+// stream is still draining (its launch latency disappears from the dependent chain of ~18 kernels per frame); pdl_wait() --
+// the first statement of every such kernel -- blocks until that previous kernel has completed and its writes are visible,
+// so the stream-order semantics are unchanged.  A no-op in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define HRBF_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                          \
+    do {                                                                                 \
+        cudaError_t e__ = hrbf::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__); \
+        hrbf::count_launch();                                                            \
+        if (e__ != cudaSuccess) { hrbf::set_error("%s:%d launch of %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(e__)); return HRBF_ERR_CUDA; } \
+    } while (0)
+
 __device__ __forceinline__ float qnan() { return __int_as_float(0x7fffffff); }
 
 struct Mat33 { float m[9]; };   // row-major

@@ -105,19 +105,16 @@ int hrbf_frame_preprocess(hrbf_frame* f, void* stream)
     HRBF_CHECK_ARG(f);
     cudaStream_t s = (cudaStream_t)stream;
     const int W = f->p.width, H = f->p.height;
-    depth_filter_metric_kernel<<<dim3(div_up(W, kBilTW), div_up(H, kBilTH)), 256, 0, s>>>(f->a, (const unsigned short*)f->tex[HRBF_FT_DEPTH_RAW],
+    HRBF_LAUNCH_PDL(depth_filter_metric_kernel, dim3(div_up(W, kBilTW), div_up(H, kBilTH)), dim3(256), 0, s, f->a, (const unsigned short*)f->tex[HRBF_FT_DEPTH_RAW],
                                                                                        (float*)f->tex[HRBF_FT_DEPTH_FILTERED], (float*)f->tex[HRBF_FT_DEPTH_METRIC],
                                                                                        (float*)f->tex[HRBF_FT_DEPTH_METRIC_FILTERED]);
-    HRBF_KERNEL_CHECK();
-    vertex_normal_radius_kernel<<<dim3(div_up(W, 32), div_up(H, 8)), 256, 0, s>>>(f->a, (const float*)f->tex[HRBF_FT_DEPTH_METRIC], (const float*)f->tex[HRBF_FT_DEPTH_METRIC_FILTERED],
+    HRBF_LAUNCH_PDL(vertex_normal_radius_kernel, dim3(div_up(W, 32), div_up(H, 8)), dim3(256), 0, s, f->a, (const float*)f->tex[HRBF_FT_DEPTH_METRIC], (const float*)f->tex[HRBF_FT_DEPTH_METRIC_FILTERED],
                                                                                (float4*)f->tex[HRBF_FT_VERTEX_RAW], (float4*)f->tex[HRBF_FT_VERTEX_FILTERED],
                                                                                (float4*)f->tex[HRBF_FT_NORMAL_PCA], (float*)f->tex[HRBF_FT_RADIUS]);
-    HRBF_KERNEL_CHECK();
     // computeCurvatureGradient writes NORMAL_OPT, which updateNormalRad copies into NORMAL: written to NORMAL directly
-    curvature_gradient_kernel<<<dim3(div_up(W, 16), div_up(H, 8)), 128, 0, s>>>(f->a, (const float4*)f->tex[HRBF_FT_VERTEX_FILTERED], (const float4*)f->tex[HRBF_FT_NORMAL_PCA],
+    HRBF_LAUNCH_PDL(curvature_gradient_kernel, dim3(div_up(W, 16), div_up(H, 8)), dim3(128), 0, s, f->a, (const float4*)f->tex[HRBF_FT_VERTEX_FILTERED], (const float4*)f->tex[HRBF_FT_NORMAL_PCA],
                                                                              (float4*)f->tex[HRBF_FT_PRINCIPAL_CURV1], (float4*)f->tex[HRBF_FT_PRINCIPAL_CURV2],
                                                                              (float*)f->tex[HRBF_FT_GRADIENT_MAG], (float4*)f->tex[HRBF_FT_NORMAL]);
-    HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }
 }  // extern "C"
@@ -192,8 +189,7 @@ int hrbf_fillin_run(hrbf_fillin* f, hrbf_indexmap* im, hrbf_frame* fr, int passt
     a.n = f->width * f->height; a.passthrough = passthrough; a.lambda = lambda; a.curvThr = curvThr;
     a.weighting = (f->inline_weighting && !fr->p.useConfEval) ? f->inline_weighting : nullptr;
     a.cols = fr->p.width; a.rows = fr->p.height; a.cx = fr->p.cx; a.cy = fr->p.cy;
-    fill_in_kernel<<<div_up(a.n, 256), 256, 0, (cudaStream_t)stream>>>(a);
-    HRBF_KERNEL_CHECK();
+    HRBF_LAUNCH_PDL(fill_in_kernel, dim3(div_up(a.n, 256)), dim3(256), 0, (cudaStream_t)stream, a);
     return HRBF_OK;
 }
 void* hrbf_fillin_texture(hrbf_fillin* f, int which)
@@ -295,10 +291,8 @@ int model_fuse_dev(hrbf_model* m, const float* pose_dev, int time, const unsigne
     f.normal_pca = (const float4*)normal_pca_tex;
     f.staging = m->staging; f.update_id = m->update_id; f.best = m->best; f.winner = m->winner;
     const int nb = div_up(m->n_slots, 128);
-    fuse_associate_kernel<<<nb, 128, 0, s>>>(a, m->pa, f, m->count[m->cur]);
-    HRBF_KERNEL_CHECK();
-    fuse_merge_kernel<<<nb, 128, 0, s>>>(a, f, m->vbo[m->cur], m->count[m->cur]);
-    HRBF_KERNEL_CHECK();
+    HRBF_LAUNCH_PDL(fuse_associate_kernel, dim3(nb), dim3(128), 0, s, a, m->pa, f, m->count[m->cur]);
+    HRBF_LAUNCH_PDL(fuse_merge_kernel, dim3(nb), dim3(128), 0, s, a, f, m->vbo[m->cur], m->count[m->cur]);
     m->staged_time = time;
     return HRBF_OK;
 }
@@ -318,12 +312,9 @@ int model_clean_dev(hrbf_model* m, const float* inv_pose_dev, int time, const un
     if (nb < 1) nb = 1;
     const int grid = nb < kNumSMs * 8 ? nb : kNumSMs * 8;
     const int nxt = m->cur ^ 1;
-    clean_flags_kernel<<<grid, kScanBlock, 0, s>>>(a, c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_counts);
-    HRBF_KERNEL_CHECK();
-    scan_blocks_kernel<<<1, 1024, 0, s>>>(m->block_counts, m->block_offsets, m->count[m->cur], (unsigned int)c.n_slots, m->capacity, m->count[nxt], m->overflow);
-    HRBF_KERNEL_CHECK();
-    clean_scatter_kernel<<<grid, kScanBlock, 0, s>>>(c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_offsets, m->capacity, m->vbo[nxt]);
-    HRBF_KERNEL_CHECK();
+    HRBF_LAUNCH_PDL(clean_flags_kernel, dim3(grid), dim3(kScanBlock), 0, s, a, c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_counts);
+    HRBF_LAUNCH_PDL(scan_blocks_kernel, dim3(1), dim3(1024), 0, s, m->block_counts, m->block_offsets, m->count[m->cur], (unsigned int)c.n_slots, m->capacity, m->count[nxt], m->overflow);
+    HRBF_LAUNCH_PDL(clean_scatter_kernel, dim3(grid), dim3(kScanBlock), 0, s, c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_offsets, m->capacity, m->vbo[nxt]);
     m->cur = nxt;
     m->bound = n_bound < m->capacity ? n_bound : m->capacity;
     m->staged_time = -1;

@@ -128,8 +128,7 @@ int hrbf_indexmap_predict_hrbf(hrbf_indexmap* m, int predictionType, int win, in
     a.dense_count = predictionType == 0 ? m->dense_count_next : nullptr;
     a.row_lut = m->row_lut;
     const dim3 grid(div_up(m->width, kPredTileW), div_up(m->height, kPredTileH));
-    predict_hrbf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    HRBF_KERNEL_CHECK();
+    HRBF_LAUNCH_PDL(predict_hrbf_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a);
     return HRBF_OK;
 }
 
@@ -152,12 +151,10 @@ int hrbf::indexmap_splat(hrbf_indexmap* m, const float* inv_pose_dev, const floa
     if (bound > 0) {
         int blocks = (int)((bound + 255u) / 256u);
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-        splat_keys_kernel<<<blocks, 256, 0, s>>>((const float4*)surfels, count_dev, a, m->keys);
-        HRBF_KERNEL_CHECK();
+        HRBF_LAUNCH_PDL(splat_keys_kernel, dim3(blocks), dim3(256), 0, s, (const float4*)surfels, count_dev, a, m->keys);
     }
-    splat_gather_kernel<<<div_up(P, 256), 256, 0, s>>>((const float4*)surfels, a, m->keys, (unsigned int*)m->tex[HRBF_TEX_INDEX],
+    HRBF_LAUNCH_PDL(splat_gather_kernel, dim3(div_up(P, 256)), dim3(256), 0, s, (const float4*)surfels, a, m->keys, (unsigned int*)m->tex[HRBF_TEX_INDEX],
                                                       (float4*)m->tex[HRBF_TEX_VERTCONF], (float4*)m->tex[HRBF_TEX_COLORTIME], (float4*)m->tex[HRBF_TEX_NORMRAD],
                                                       (float4*)m->tex[HRBF_TEX_CURVMAX], (float4*)m->tex[HRBF_TEX_CURVMIN], out_mask);
-    HRBF_KERNEL_CHECK();
     return HRBF_OK;
 }

@@ -55,6 +55,7 @@ __device__ __forceinline__ int splat_project(const SplatArgs& a, const float* Ri
 __global__ void __launch_bounds__(256) splat_keys_kernel(const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
                                                          SplatArgs a, unsigned long long* __restrict__ keys)
 {
+    pdl_wait();
     const unsigned int count = *count_dev;
     float Ri[9], ti[3];
 #pragma unroll
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float4* __restr
                                                            unsigned int* __restrict__ index, float4* __restrict__ vertConf, float4* __restrict__ colorTime,
                                                            float4* __restrict__ normRad, float4* __restrict__ curvMax, float4* __restrict__ curvMin, int out_mask)
 {
+    pdl_wait();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.cols * a.rows) return;
     const unsigned long long key = keys[k];
@@ -251,6 +253,7 @@ __device__ __forceinline__ float3 hrbf_gradient_group(CenterAt nb_at, int nslots
 #endif
 __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(PredictArgs a)
 {
+    pdl_wait();
     __shared__ float4 s_v[kPredSH][kPredSW];
     __shared__ float4 s_n[kPredSH][kPredSW];
     __shared__ unsigned char s_sel[64][32];              // per pixel: tile cell (row * kPredSW + col) of each selected neighbour

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const unsigned int* _
                                                            const unsigned int* __restrict__ n_items_dev, unsigned int n_items_add,
                                                            unsigned int capacity, unsigned int* __restrict__ total_out, unsigned int* __restrict__ overflow)
 {
+    pdl_wait();
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned int s_carry;
     const unsigned int n_items = (n_items_dev ? *n_items_dev : 0u) + n_items_add;
@@ -180,6 +181,7 @@ __host__ __device__ inline int fuse_slots_y(int rows) { return (rows + 1) / 2; }
 // One thread per candidate pixel (x%2 == t%2 && y%2 == t%2, data.vert:113).  Slot order = uv order (x outer, y inner).
 __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepArgs pa, FuseArgs f, const unsigned int* __restrict__ count_dev)
 {
+    pdl_wait();
     const int sxn = fuse_slots_x(m.cols), syn = fuse_slots_y(m.rows);
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= sxn * syn) return;
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
 // update.vert:51-115, applied in place to the winners only
 __global__ void __launch_bounds__(128) fuse_merge_kernel(ModelArgs m, FuseArgs f, float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev)
 {
+    pdl_wait();
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= fuse_slots_x(m.cols) * fuse_slots_y(m.rows)) return;
     if (f.update_id[slot] != 1) return;
@@ -405,6 +408,7 @@ __device__ __forceinline__ bool clean_load(const CleanArgs& c, const float4* __r
 __global__ void __launch_bounds__(kScanBlock) clean_flags_kernel(ModelArgs m, CleanArgs c, const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
                                                                  unsigned char* __restrict__ flags, unsigned int* __restrict__ block_counts)
 {
+    pdl_wait();
     const unsigned int count = *count_dev, n = count + (unsigned int)c.n_slots;
     float Pi[12];
 #pragma unroll
@@ -425,6 +429,7 @@ __global__ void __launch_bounds__(kScanBlock) clean_scatter_kernel(CleanArgs c, 
                                                                    const unsigned char* __restrict__ flags, const unsigned int* __restrict__ block_offsets,
                                                                    unsigned int capacity, float4* __restrict__ out)
 {
+    pdl_wait();
     __shared__ unsigned int s_warp[kScanBlock / 32];
     const unsigned int count = *count_dev, n = count + (unsigned int)c.n_slots;
     for (unsigned int blk = blockIdx.x; blk * kScanBlock < n; blk += gridDim.x) {

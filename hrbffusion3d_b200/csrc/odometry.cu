@@ -626,8 +626,7 @@ int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s
     A.pyr_bx = div_up(o->width, 32); A.pyr_by = div_up(o->height, 8);
     A.rgbd_bx = div_up(o->cols(2), 8); A.rgbd_by = div_up(o->rows(2), 8);
     const dim3 grid(A.pyr_bx > A.rgbd_bx ? A.pyr_bx : A.rgbd_bx, A.pyr_by > A.rgbd_by ? A.pyr_by : A.rgbd_by, 7);
-    prep_all_kernel<<<grid, 256, 0, s>>>(A);
-    HRBF_KERNEL_CHECK();
+    HRBF_LAUNCH_PDL(prep_all_kernel, dim3(grid), dim3(256), 0, s, A);
     return HRBF_OK;
 }
 int odom_init_icp_weight_dev(hrbf_odometry* o, const float* w, const float* w_alt, const int* sel, cudaStream_t s)

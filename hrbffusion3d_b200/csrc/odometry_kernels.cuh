@@ -463,6 +463,7 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
 
 __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
 {
+    pdl_wait();
     // grid = (tiles x, tiles y, 7 jobs): z = 0, 1 are the (heavier) RGB-D pyramid jobs -- lowest block indices, scheduled first --
     // z = 2..6 the map jobs; no index arithmetic beyond blockIdx
     const int job_z = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;

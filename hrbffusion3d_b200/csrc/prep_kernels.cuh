@@ -77,6 +77,7 @@ inline void make_bilateral_table(float* t)
 __global__ void __launch_bounds__(256) depth_filter_metric_kernel(PrepArgs a, const unsigned short* __restrict__ raw,
                                                                   float* __restrict__ filtered, float* __restrict__ metric, float* __restrict__ metric_filtered)
 {
+    pdl_wait();
     __shared__ float s_t[kBilTH + 2 * kBilR][kBilTW + 2 * kBilR];
     const int W = a.cols, H = a.rows;
     const float adj = 1.0f / (a.depthFactor * 1000.0f);
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(256) vertex_normal_radius_kernel(PrepArgs a, c
                                                                    float4* __restrict__ vertex_raw, float4* __restrict__ vertex_filtered,
                                                                    float4* __restrict__ normal, float* __restrict__ radius)
 {
+    pdl_wait();
     constexpr int TW = 32, TH = 8, R = 3;
     __shared__ float s_d[TH + 2 * R][TW + 2 * R];
     const int W = a.cols, H = a.rows;
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, con
                                                                  float4* __restrict__ curv1, float4* __restrict__ curv2, float* __restrict__ gradient_mag,
                                                                  float4* __restrict__ normal_opt)
 {
+    pdl_wait();
     constexpr int TW = 16, TH = 8, R = 3;
     __shared__ float4 s_v[TH + 2 * R][TW + 2 * R];      // filtered vertex; z = -1000 when the pixel can never be a neighbour
     __shared__ float4 s_n[TH + 2 * R][TW + 2 * R];      // 10 n (the HRBF coefficient), w = 1 / rho^2
@@ -410,6 +413,7 @@ struct FillArgs {
 };
 __global__ void fill_in_kernel(FillArgs f)
 {
+    pdl_wait();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= f.n) return;
     const bool pass = f.passthrough == 1;
