@@ -35,6 +35,7 @@ struct hrbf_odometry {
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
     hrbf::ReduceWork* work = nullptr;
     unsigned long long *tp_ll_f = nullptr, *tp_ll_i = nullptr;   // persistent tracker: tagged-word exchange buffers
+    bool tp_no_pdl = false;                                      // the driver refused cooperative + programmatic serialization
     unsigned int tp_epoch = 0;                                   // launch counter feeding the tags
     int num_sms = 0;
     long long* tp_dbg = nullptr;

@@ -182,8 +182,22 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     if (o->tp_epoch == 0) o->tp_epoch = 1;
     p.epoch = o->tp_epoch;
     p.dbg = o->tp_dbg;
-    void* args[] = { (void*)&p };
-    HRBF_CUDA(cudaLaunchCooperativeKernel((const void*)track_persistent_kernel, dim3(o->num_sms), dim3(kTrackThreads), args, dyn, s));
+    {   // cooperative (all CTAs co-resident: they spin on each other's words) + programmatic stream serialization (see pdl_wait)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(o->num_sms); cfg.blockDim = dim3(kTrackThreads); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = o->tp_no_pdl ? 1 : 2;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, track_persistent_kernel, p);
+        if (e != cudaSuccess && !o->tp_no_pdl) {      // a driver that refuses the combination: cooperative only, from now on
+            (void)cudaGetLastError();
+            o->tp_no_pdl = true;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, track_persistent_kernel, p);
+        }
+        HRBF_CUDA(e);
+    }
     count_launch();
     return HRBF_OK;
 }

@@ -274,6 +274,7 @@ __global__ void __maxnreg__(HRBF_TRACK_MAXNREG) track_persistent_kernel(const Tr
 __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
 #endif
 {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char s_dyn[];
     RgbSlot* s_slots = reinterpret_cast<RgbSlot*>(s_dyn);
     int dbg_n = 0;
