@@ -146,6 +146,7 @@ void* hrbf_frame_texture(hrbf_frame* f, int which)
 }  // extern "C"
 struct hrbf_fillin {
     const float* inline_weighting = nullptr;   // frame pipeline: device fusion weight (confidence evaluated in place)
+    const unsigned int* skip_if_dense = nullptr; float dense_thresh = 0.75f;   // frame pipeline: see FillArgs::dense_count
     int width = 0, height = 0;
     char* slab = nullptr;
     void* tex[HRBF_FILL_COUNT] = {};
@@ -189,6 +190,7 @@ int hrbf_fillin_run(hrbf_fillin* f, hrbf_indexmap* im, hrbf_frame* fr, int passt
     a.n = f->width * f->height; a.passthrough = passthrough; a.lambda = lambda; a.curvThr = curvThr;
     a.weighting = (f->inline_weighting && !fr->p.useConfEval) ? f->inline_weighting : nullptr;
     a.cols = fr->p.width; a.rows = fr->p.height; a.cx = fr->p.cx; a.cy = fr->p.cy;
+    a.dense_count = f->skip_if_dense; a.dense_thresh = f->dense_thresh;
     HRBF_LAUNCH_PDL(fill_in_kernel, dim3(div_up(a.n, 256)), dim3(256), 0, (cudaStream_t)stream, a);
     return HRBF_OK;
 }
@@ -597,6 +599,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
     // ---- Prediction (HRBFFusion.cpp:1244-1260) ----
     if (int rc = splat(7)) return rc;
     im->dense_count_next = denseCount + (F->tick & 1);
+    F->fill->skip_if_dense = denseCount + (F->tick & 1); F->fill->dense_thresh = p.denseEnoughThresh;
     if (int rc = hrbf_indexmap_predict_hrbf(im, 0, p.predWindow, p.predMinNeighbors, p.predMaxNeighbors, p.predConfThreshold, p.icpWeightLambda, s)) return rc;
     if (int rc = hrbf_fillin_run(F->fill, im, fr, 0, p.icpWeightLambda, p.curvValidThreshold, s)) return rc;
     mark(4);

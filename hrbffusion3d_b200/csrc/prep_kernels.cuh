@@ -410,12 +410,16 @@ struct FillArgs {
     // frame pipeline: when non-null the confidence of depth_confidence_evaluation.frag is evaluated in place from this device scalar
     // instead of being read from the CONFIDENCE texture (same expression, confidence_kernel below)
     const float* weighting; int cols, rows; float cx, cy;
+    // frame pipeline: the fill-in maps are only ever read when the prediction is NOT dense enough (HRBFFusion.cpp:1069-1086); when the
+    // prediction kernel's sample count says it is, the pass is skipped (non-null dense_count)
+    const unsigned int* dense_count; float dense_thresh;
 };
 __global__ void fill_in_kernel(FillArgs f)
 {
     pdl_wait();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= f.n) return;
+    if (f.dense_count != nullptr && (float)*f.dense_count / (float)((f.cols / 20) * (f.rows / 20)) > f.dense_thresh) return;
     const bool pass = f.passthrough == 1;
     const float4 s = __ldg(f.eVertex + o);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
