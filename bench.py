@@ -201,8 +201,13 @@ def ours_arm(args):
                 F.stageFrame(rgb_dev[k], depth_dev[k])
 
         def step(i):
-            stage(i + 1)
-            F.processStaged(pose if host_inputs else None)     # host run: blocks until this frame's pose is on the host
+            if host_inputs:
+                F.processStaged(None)                          # enqueue frame i (staged by the previous step)
+                stage(i + 1)                                   # H2D + preprocess of frame i + 1 behind it, on the staging stream
+                pose[:] = F.getPose().ravel()                  # D2H of frame i's pose: blocks until frame i is done
+            else:
+                stage(i + 1)
+                F.processStaged(None)
         stage(0)
         for i in range(args.warmup):
             step(i)
