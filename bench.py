@@ -11,8 +11,12 @@ A "step" is one frame through the hot path on the workload named in `config.work
              timed live with CUDA events on its own stream (hrbf_odometry_time_kernel)
   cpu_baseline : the CPU oracle (oracle/, a restatement of the reference; kind "port") on the host cores,
              on a bounded sample of the same frames
-N > 1 : one process per GPU (torchrun), one independent sequence per rank (weak scaling), NCCL only to
-scatter the inputs' seeds and gather the trajectories; no collective inside the frame loop.
+Offline throughput (the metric): `--sequences S` (default 3) independent sequences per GPU, each a complete pipeline object on
+its own stream with a 256-thread tracker, so that one sequence's latency-bound Gauss-Newton loop shares the SMs with the
+other sequences' ALU-bound kernels; a step = one frame of every sequence.  `single_sequence` in the same line is the live
+single-camera path (one sequence, 512-thread tracker), measured the same way in the same run.
+N > 1 : one process per GPU (torchrun), S independent sequences per rank (weak scaling), NCCL only to
+scatter the .klg streams and gather the trajectories; no collective inside the frame loop.
 `--impl reference` times the oracle's CPU path (the reference itself needs OpenGL + Pangolin + Eigen and
 cannot run headless) with all host threads on the same workload.
 """
@@ -114,13 +118,15 @@ class OracleRunner:
         return time.perf_counter() - t0
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, seqs=1):
     return {"workload": "synthetic 640x480 Kinect-noise planar scene (SURVEY 8d config 2): full per-frame hot path = preprocess "
                         "(bilateral, PCA normals, HRBF curvature) + pyramid prep + RGB-D/ICP tracking (reference defaults: icpWeight 10, "
                         "SO3 pre-align, iterations 10/5/4) + splat/fuse/splat/clean + splat/HRBF predict (win 3, K 10) + fill-in",
             "width": W, "height": H, "frames_in_loop": RING,
             "l2": "inputs cycle through a closed loop of %d frames x 1.54 MB = %d MB > 126 MB L2; a frame also streams ~30 full-resolution textures" % (RING, int(RING * 1.536)),
-            "sequences": n_gpus, "parallelism": "one independent sequence per GPU (rank 0 scatters the .klg streams, trajectories are gathered back), no collective inside the frame loop"}
+            "sequences": n_gpus * seqs, "sequences_per_gpu": seqs, "tracker_threads": 256 if seqs > 1 else 512,
+            "parallelism": "%d independent sequence(s) per GPU, each a full pipeline on its own stream (rank 0 scatters the .klg streams, trajectories are "
+                           "gathered back), no collective inside the frame loop; a step = one frame of every sequence" % seqs}
 
 
 def reference_arm(args):
@@ -137,7 +143,7 @@ def reference_arm(args):
     v = args.steps / t
     print(json.dumps({"impl": "reference", "metric": "frames/sec HRBF+ICP 640x480", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus, args.sequences),
                       "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                                        "sample": "%d frames, one per step, OpenMP over %d threads" % (args.steps, cores)},
                       "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -179,36 +185,49 @@ def ours_arm(args):
     rgb = np.stack([f[2] for f in frames])
     klg_bytes = len(blob)
     del blob, frames
+    S_max = max(1, args.sequences)
+    # sequence q of rank r enters the closed loop (r * S + q) * RING / (world * S) frames after sequence 0: all distinct
     offset = (rank * RING) // world
-    poses = [poses_all[(i + offset) % RING] for i in range(RING)]
     depth_pin = torch.from_numpy(depth.view(np.int16)).pin_memory()
     rgb_pin = torch.from_numpy(rgb).pin_memory()
     depth_dev, rgb_dev = depth_pin.cuda(), rgb_pin.cuda()
     h2d_bytes = W * H * 2 + W * H * 3
 
-    def run(host_inputs):
-        """fresh pipeline: W warm-up frames (frame 1 initialises the map), then K timed frames"""
-        F = HRBFFusion(W, H, cam, capacity=1 << 22, **FUSION_KW)
-        pose = np.zeros(16, np.float32)
+    def run(host_inputs, S):
+        """S fresh pipelines on S streams: W warm-up steps (frame 1 initialises the map), then K timed steps; a step = one frame of
+        every sequence.  Returns (ms, launches, pipelines)."""
+        Fs = [HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=(256 if S > 1 else 512), **FUSION_KW) for _ in range(S)]
+        st = [torch.cuda.Stream() for _ in range(S)]
+        off = [(q * RING) // (world * S) for q in range(S)]
+        pose = np.zeros((S, 16), np.float32)
 
-        # log replay through the pipelined API: frame i+1 is staged (upload + preprocess on the library's staging stream) while
-        # frame i is tracked and fused; every frame's H2D copy and the D2H of its pose are inside the timed region of the e2e run
-        def stage(i):
-            k = i % RING
+        # log replay through the pipelined API: frame i+1 of a sequence is staged (upload + preprocess on the library's staging stream)
+        # while its frame i is tracked and fused; every frame's H2D copy and the D2H of its pose are inside the timed region of the e2e run
+        def stage(q, i):
+            k = (i + off[q]) % RING
             if host_inputs:
-                F.stageFrame(rgb_pin[k], depth_pin[k])
+                Fs[q].stageFrame(rgb_pin[k], depth_pin[k])
             else:
-                F.stageFrame(rgb_dev[k], depth_dev[k])
+                Fs[q].stageFrame(rgb_dev[k], depth_dev[k])
 
         def step(i):
-            if host_inputs:
-                F.processStaged(None)                          # enqueue frame i (staged by the previous step)
-                stage(i + 1)                                   # H2D + preprocess of frame i + 1 behind it, on the staging stream
-                pose[:] = F.getPose().ravel()                  # D2H of frame i's pose: blocks until frame i is done
-            else:
-                stage(i + 1)
-                F.processStaged(None)
-        stage(0)
+            for q in range(S):
+                with torch.cuda.stream(st[q]):
+                    if host_inputs:
+                        Fs[q].processStaged(None)                  # enqueue frame i (staged by the previous step)
+                        stage(q, i + 1)                            # H2D + preprocess of frame i + 1 behind it, on the staging stream
+                    else:
+                        stage(q, i + 1)
+                        Fs[q].processStaged(None)
+                if host_inputs:
+                    # D2H of a pose, every frame of every sequence exactly once: the oldest frame in flight (the sequence enqueued S - 1
+                    # slots ago; for S = 1 the frame just enqueued).  Blocks until that frame is done; the others keep the GPU busy.
+                    o = (q + 1) % S
+                    with torch.cuda.stream(st[o]):
+                        pose[o] = Fs[o].getPose().ravel()
+        for q in range(S):
+            with torch.cuda.stream(st[q]):
+                stage(q, 0)
         for i in range(args.warmup):
             step(i)
         torch.cuda.synchronize()
@@ -217,26 +236,32 @@ def ours_arm(args):
         torch.cuda.synchronize()
         l0 = lib().hrbf_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record()                                                # the device is idle: nothing of the timed steps can start before this
         for i in range(args.warmup, args.warmup + args.steps):
             step(i)
+        for q in range(S):                                         # e1 = when the last sequence's last frame is done
+            torch.cuda.current_stream().wait_stream(st[q])
         e1.record()
         torch.cuda.synchronize()
         launches = lib().hrbf_launch_count() - l0
-        F.processStaged(None)                                  # drain the frame staged by the last step (outside the timed region)
+        for q in range(S):
+            with torch.cuda.stream(st[q]):
+                Fs[q].processStaged(None)                          # drain the frame staged by the last step (outside the timed region)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), int(launches), F
+        return float(ms.item()), int(launches), Fs
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, F = run(False)
+    # (1) the live single-camera path: one sequence, 512-thread tracker
+    ms1_dev, launches1, Fs = run(False, 1)
+    F = Fs[0]
     count = F.globalModel.lastCount()
-    traj = F.trajectory().clone()
+    traj1 = F.trajectory().clone()
     # roofline: the level-0 ICP JTJ/JTr reduction (what hrbf_icp_step = the reference's icpStep launches), timed live with CUDA
     # events over 200 back-to-back launches on this pipeline's maps; and the same reduction in its production form, as one
     # iteration of the persistent tracker (reduction + cross-CTA exchange + fp64 solve inside ONE launch)
@@ -245,11 +270,21 @@ def ours_arm(args):
     check(lib().hrbf_odometry_time_kernel(odom, 0, 0, 0, 200, C.byref(us), stream_ptr()))
     check(lib().hrbf_odometry_time_kernel(odom, 4, 0, 0, 200, C.byref(us_iter), stream_ptr()))
     torch.cuda.synchronize()
-    del F
-    ms_e2e, _, F2 = run(True)
-    del F2
+    del F, Fs
+    ms1_e2e, _, Fs = run(True, 1)
+    del Fs
+    # (2) offline throughput: S_max sequences per GPU (the headline when S_max > 1)
+    if S_max > 1:
+        ms_dev, launches, Fs = run(False, S_max)
+        count = [f.globalModel.lastCount() for f in Fs]
+        traj = torch.cat([f.trajectory() for f in Fs]).clone()
+        del Fs
+        ms_e2e, _, Fs = run(True, S_max)
+        del Fs
+    else:
+        ms_dev, launches, ms_e2e, traj = ms1_dev, launches1, ms1_e2e, traj1
     clocks = sampler.stop() if rank == 0 else None
-    gathered = multigpu.gather_trajectories(traj)       # per-sequence trajectories back to rank 0
+    gathered = multigpu.gather_trajectories(traj)       # per-rank trajectories (S_max sequences each) back to rank 0
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,12 +292,14 @@ def ours_arm(args):
     # sanity of the measured work: absolute trajectory error of every gathered sequence against the synthetic ground truth
     ate = []
     for r, g in enumerate(gathered):
-        o_r = (r * RING) // world
-        gt = [poses_all[(i + o_r) % RING] for i in range(RING)]
-        P0inv = np.linalg.inv(np.asarray(gt[0], np.float64))
-        est_t = g.numpy()[:, 9:12].astype(np.float64)
-        gt_t = np.stack([(P0inv @ np.asarray(gt[i % RING], np.float64))[:3, 3] for i in range(est_t.shape[0])])
-        ate.append(float(np.sqrt(np.mean(np.sum((est_t - gt_t) ** 2, axis=1)))))
+        per = g.numpy().reshape(S_max, -1, 12)
+        for q in range(S_max):
+            o_r = (r * RING) // world + (q * RING) // (world * S_max)
+            gt = [poses_all[(i + o_r) % RING] for i in range(RING)]
+            P0inv = np.linalg.inv(np.asarray(gt[0], np.float64))
+            est_t = per[q][:, 9:12].astype(np.float64)
+            gt_t = np.stack([(P0inv @ np.asarray(gt[i % RING], np.float64))[:3, 3] for i in range(est_t.shape[0])])
+            ate.append(float(np.sqrt(np.mean(np.sum((est_t - gt_t) ** 2, axis=1)))))
 
     peak, peak_src = measured_peak_hbm()
     alg_bytes = ICP_BYTES_PER_PIXEL_ITER * W * H
@@ -276,12 +313,15 @@ def ours_arm(args):
         cpu_s = sum(r.step() for _ in range(n_cpu))
         cpu_baseline = {"value": n_cpu / cpu_s, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": "frames 2-%d of the same sequence (oracle pipeline, OpenMP over %d threads)" % (n_cpu + 1, cores)}
-    total_frames = args.steps * world
+    total_frames = args.steps * world * S_max
+    single = {"what": "the live single-camera path: ONE sequence per GPU, 512-thread tracker, same frames, same timing rules",
+              "value": args.steps * world / (ms1_dev * 1e-3), "e2e": args.steps * world / (ms1_e2e * 1e-3), "unit": "frames/s",
+              "ms_per_frame": ms1_dev / args.steps, "gpu_launches": launches1}
     out = {"metric": "frames/sec HRBF+ICP 640x480", "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
-           "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 48},
-           "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count, "klg_bytes_per_sequence": klg_bytes,
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, S_max),
+           "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * S_max, "d2h_bytes_per_step": 48 * S_max},
+           "single_sequence": single, "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count, "klg_bytes_per_sequence": klg_bytes,
            "trajectory_ate_rmse_m": ate,
            "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false>, level 0 (640x480): the ICP JTJ/JTr reduction as hrbf_icp_step launches it",
                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
@@ -302,6 +342,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sequences", type=int, default=3, help="independent sequences per GPU (offline throughput); 1 = the live single-camera path only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

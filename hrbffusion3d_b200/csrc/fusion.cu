@@ -644,6 +644,7 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
     if (!rc) rc = hrbf_model_set_params(F->model, fp.radiusMultiplier, p->curvValidThreshold, fp.normalPCA, p->cleanWindow, fp.useConfEval, fp.confEvalEpsilon);
     if (!rc) rc = hrbf_odometry_create(&F->odom, fp.width, fp.height, fp.cx, fp.cy, fp.fx, fp.fy, 0.10f, sinf(20.f * 3.14159265f / 180.f));
     if (!rc) rc = hrbf_odometry_set_params(F->odom, p->curvValidThreshold, 0, 2, 0);
+    if (!rc) rc = hrbf_odometry_set_tracker_threads(F->odom, p->trackerThreads);
     if (!rc) {
         F->traj_cap = 1 << 16;
         if (cudaMalloc(&F->dev, 64 * sizeof(float)) != cudaSuccess || cudaMalloc(&F->traj, (size_t)F->traj_cap * 12 * sizeof(float)) != cudaSuccess ||

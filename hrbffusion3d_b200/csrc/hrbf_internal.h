@@ -31,7 +31,7 @@ struct hrbf_odometry {
     float4* pk[4][HRBF_NUM_PYRS] = {};           // packed ICP operands: [0] curr pk0, [1] curr pk1, [2] model pk0, [3] model pk1
     bool pack_dirty_curr = false, pack_dirty_model = false;   // SoA written by a builder that does not pack (GPUTest path)
     unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
-    size_t tp_dyn_set = 0;                       // dynamic shared memory the persistent kernel is currently allowed
+    int track_threads = 512;                     // threads per CTA of the persistent tracker (256 | 512), hrbf_odometry_set_tracker_threads
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
     hrbf::ReduceWork* work = nullptr;
     unsigned long long *tp_ll_f = nullptr, *tp_ll_i = nullptr;   // persistent tracker: tagged-word exchange buffers

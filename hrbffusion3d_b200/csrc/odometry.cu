@@ -32,6 +32,7 @@ static inline int reduce_blocks(int n) { int b = div_up(n, kReduceThreads * 2); 
 
 using namespace hrbf;
 
+#include <mutex>
 #include "hrbf_internal.h"
 
 namespace hrbf {
@@ -161,12 +162,19 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     // RGB slots: one per pixel of a CTA's range and thread
     int max_slots = 1;
     for (int l = 0; l < 3; ++l)
-        if (iters[l] > 0) { const int s_l = div_up(div_up(o->rows(l) * o->cols(l), o->num_sms), kTrackThreads); if (s_l > max_slots) max_slots = s_l; }
+        if (iters[l] > 0) { const int s_l = div_up(div_up(o->rows(l) * o->cols(l), o->num_sms), o->track_threads); if (s_l > max_slots) max_slots = s_l; }
     p.max_slots = max_slots;
-    const size_t dyn = track_slots_bytes(max_slots);
-    if (dyn > o->tp_dyn_set) {
-        HRBF_CUDA(cudaFuncSetAttribute((const void*)track_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        o->tp_dyn_set = dyn;
+    const bool half = o->track_threads == 256;
+    const void* kernel = half ? (const void*)track_persistent_kernel<256> : (const void*)track_persistent_kernel<512>;
+    const size_t dyn = track_slots_bytes(max_slots, o->track_threads);
+    {   // the attribute belongs to the kernel, not to this object: only ever raise it
+        static std::mutex mu;
+        static size_t dyn_set[2] = { 0, 0 };
+        std::lock_guard<std::mutex> lock(mu);
+        if (dyn > dyn_set[half]) {
+            HRBF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            dyn_set[half] = dyn;
+        }
     }
     p.so3_last = o->lastNextImage[2]; p.so3_next = o->nextImage[2];
     p.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
@@ -184,17 +192,18 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     p.dbg = o->tp_dbg;
     {   // cooperative (all CTAs co-resident: they spin on each other's words) + programmatic stream serialization (see pdl_wait)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(o->num_sms); cfg.blockDim = dim3(kTrackThreads); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+        cfg.gridDim = dim3(o->num_sms); cfg.blockDim = dim3(o->track_threads); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = o->tp_no_pdl ? 1 : 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, track_persistent_kernel, p);
+        void* kargs[1] = { (void*)&p };
+        cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, kargs);
         if (e != cudaSuccess && !o->tp_no_pdl) {      // a driver that refuses the combination: cooperative only, from now on
             (void)cudaGetLastError();
             o->tp_no_pdl = true;
             cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, track_persistent_kernel, p);
+            e = cudaLaunchKernelExC(&cfg, kernel, kargs);
         }
         HRBF_CUDA(e);
     }
@@ -537,6 +546,14 @@ int hrbf_odometry_set_tracker(hrbf_odometry* o, int use_kernel_graph)
 {
     HRBF_CHECK_ARG(o);
     o->use_graph = use_kernel_graph != 0;
+    return HRBF_OK;
+}
+int hrbf_odometry_set_tracker_threads(hrbf_odometry* o, int threads)
+{
+    HRBF_CHECK_ARG(o);
+    if (threads == 0) threads = kTrackThreadsDefault;
+    if (threads != 256 && threads != 512) { set_error("set_tracker_threads: 256 or 512 (0 = default 512)"); return HRBF_ERR_INVALID_ARG; }
+    o->track_threads = threads;
     return HRBF_OK;
 }
 int hrbf_odometry_set_params(hrbf_odometry* o, float curvThr, int useSearch, int searchRadius, int rgbGradWeight)

@@ -13,11 +13,10 @@
 
 namespace hrbf {
 
-#ifndef HRBF_TRACK_THREADS
-#define HRBF_TRACK_THREADS 512
-#endif
-constexpr int kTrackThreads = HRBF_TRACK_THREADS;       // x 148 CTAs (one per SM)
-constexpr int kTrackWarps = kTrackThreads / 32;
+// Threads per CTA (x 148 CTAs, one per SM) are a template parameter of the tracker, chosen per odometry object at run time
+// (hrbf_odometry_set_tracker_threads): 512 x 128 registers fill an SM's register file -- the lowest latency for ONE sequence;
+// 256 leave half of every SM to the kernels of other sequences' pipelines (several fusion objects on their own streams).
+constexpr int kTrackThreadsDefault = 512;
 
 struct TrackLevel {
     IcpArgs icp;
@@ -64,8 +63,10 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
 }
 
 // 32 per-thread sums -> this CTA's partial, published by warp 0 as 32 LL words dst[0..31]
+template <int kTrackThreads>
 __device__ __forceinline__ void block_partial32(float (&acc)[32], float (*s_w)[32], unsigned long long* dst, unsigned int tag)
 {
+    constexpr int kTrackWarps = kTrackThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float r = warp_reduce32_transpose(acc);
     s_w[warp][lane] = r;
@@ -83,6 +84,7 @@ __device__ __forceinline__ void block_partial32(float (&acc)[32], float (*s_w)[3
 // Thread t owns value (t & 63) of CTA slice (t >> 6): ALL its loads are issued at once (one L2 round trip), words that
 // are not there yet are re-polled; the additions run in a fixed order -> bit-identical totals in every CTA.
 // lo / hi: whether the first / second 32 values were published in this exchange (ICP / RGB).
+template <int kTrackThreads>
 __device__ __forceinline__ void all_reduce_partials(const unsigned long long* part /* [gridDim.x][64] */, unsigned int tag, bool lo, bool hi,
                                                     double (*s_d)[64], double* out /* [64] */)
 {
@@ -160,6 +162,7 @@ constexpr int kRgbInFlight = 5;      // pixels per thread whose loads are in fli
 // computeRgbResidual over this CTA's pixel range [begin, end): pixel begin + tid + m * kTrackThreads -> slot m of this thread.
 // Same arithmetic as rgb_residual_pixel, staged so that the (dependent) loads of kRgbInFlight pixels overlap:
 // candidate byte + next depth  ->  projection, gather of last depth / last image  ->  residual.
+template <int kTrackThreads>
 __device__ __forceinline__ void rgb_residual_pass(const RgbResArgs& a, const unsigned char* cand, const float* s_k, int begin, int end,
                                                   RgbSlot* s_slots, int& cnt, int& sig)
 {
@@ -215,6 +218,7 @@ __device__ __forceinline__ void rgb_residual_pass(const RgbResArgs& a, const uns
 
 // rgbStep (reduce.cu:718-811) from the slots: the cloud point of projectToPointCloud (cudafuncs.cu:995-1013) is rebuilt
 // from d0 with the same expression, the gradients are read at the pixel itself (DataTerm.one == the pixel).
+template <int kTrackThreads>
 __device__ __forceinline__ void rgb_step_pass(const RgbStepArgs& a, float sigma, const RgbSlot* s_slots, int begin, int end,
                                               float ifx, float ify, float cx, float cy, float (&acc)[32])
 {
@@ -266,14 +270,12 @@ __device__ __forceinline__ void rgb_step_pass(const RgbStepArgs& a, float sigma,
 }
 
 // dynamic shared memory of the persistent tracker: the RGB slots, max_slots x kTrackThreads
-inline size_t track_slots_bytes(int max_slots) { return (size_t)max_slots * kTrackThreads * sizeof(RgbSlot); }
+inline size_t track_slots_bytes(int max_slots, int threads) { return (size_t)max_slots * threads * sizeof(RgbSlot); }
 
-#ifdef HRBF_TRACK_MAXNREG      // development builds: cap the registers so that other kernels can co-reside with the tracker
-__global__ void __maxnreg__(HRBF_TRACK_MAXNREG) track_persistent_kernel(const TrackParams p)
-#else
+template <int kTrackThreads>
 __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
-#endif
 {
+    constexpr int kTrackWarps = kTrackThreads / 32;
     pdl_wait();
     extern __shared__ __align__(16) unsigned char s_dyn[];
     RgbSlot* s_slots = reinterpret_cast<RgbSlot*>(s_dyn);
@@ -340,8 +342,8 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
             for (int k = gtid; k < N; k += gstride) so3_pixel(p.so3_last, p.so3_next, rows, cols, S.so3_basis, k, acc);
             unsigned long long* part = p.ll_f + (size_t)(phase & 1) * gridDim.x * 64;
             const unsigned int tag = tag_base | (phase + 1);
-            block_partial32(acc, s_w, part + (size_t)blockIdx.x * 64, tag);
-            all_reduce_partials(part, tag, true, false, s_d, s_tot);
+            block_partial32<kTrackThreads>(acc, s_w, part + (size_t)blockIdx.x * 64, tag);
+            all_reduce_partials<kTrackThreads>(part, tag, true, false, s_d, s_tot);
             if (tid < 16) S.so3_sums[tid] = s_tot[tid];
             __syncthreads();
             if (tid == 0) so3_update(&S);
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 // computeRgbResidual (reduce.cu:986-1060): the correspondence of each of this thread's pixels stays in its
                 // shared-memory slot for the step pass below (the reference's corresImg round trip through HBM is gone)
                 int cnt = 0, sig = 0;
-                rgb_residual_pass(L.res, L.cand, S.krkinv, begin, end, s_slots, cnt, sig);      // krkinv[9], kt[3] contiguous
+                rgb_residual_pass<kTrackThreads>(L.res, L.cand, S.krkinv, begin, end, s_slots, cnt, sig);      // krkinv[9], kt[3] contiguous
                 TP_STAMP(7);
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 sig = __reduce_add_sync(0xffffffffu, sig);
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 if (L.icp.use_search) for (int i = gtid; i < N; i += gstride) icp_pixel<true>(L.icp, Rc, tc, Rpi, tp, i, acc);
                 else icp_pass_nosearch<kTrackThreads>(L.icp, Rc, tc, Rpi, tp, begin, end, acc);
                 TP_STAMP(2);
-                block_partial32(acc, s_w, part + (size_t)blockIdx.x * 64, tag);
+                block_partial32<kTrackThreads>(acc, s_w, part + (size_t)blockIdx.x * 64, tag);
                 TP_STAMP(3);
             }
             if (p.rgb) {
@@ -435,12 +437,12 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 for (int k = 0; k < 32; ++k) acc[k] = 0.f;
                 const float sigma = S.sigmaVal;
                 TP_STAMP(10);
-                rgb_step_pass(L.step, sigma, s_slots, begin, end, ifx, ify, lcx, lcy, acc);
+                rgb_step_pass<kTrackThreads>(L.step, sigma, s_slots, begin, end, ifx, ify, lcx, lcy, acc);
                 TP_STAMP(11);
-                block_partial32(acc, s_w, part + (size_t)blockIdx.x * 64 + 32, tag);
+                block_partial32<kTrackThreads>(acc, s_w, part + (size_t)blockIdx.x * 64 + 32, tag);
             }
             TP_STAMP(4);
-            all_reduce_partials(part, tag, p.icp != 0, p.rgb != 0, s_d, s_tot);
+            all_reduce_partials<kTrackThreads>(part, tag, p.icp != 0, p.rgb != 0, s_d, s_tot);
             TP_STAMP(5);
             if (tid < 32) { if (p.icp) S.icp_sums[tid] = s_tot[tid]; if (p.rgb) S.rgb_sums[tid] = s_tot[32 + tid]; }
             __syncthreads();

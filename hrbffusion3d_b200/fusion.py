@@ -22,7 +22,7 @@ class FusionParams(C.Structure):
                 ("rgbOnly", C.c_int), ("pyramid", C.c_int), ("fastOdom", C.c_int), ("so3", C.c_int), ("weightedICP", C.c_int),
                 ("predWindow", C.c_int), ("predMinNeighbors", C.c_int), ("predMaxNeighbors", C.c_int), ("predConfThreshold", C.c_float),
                 ("icpWeightLambda", C.c_float), ("curvValidThreshold", C.c_float), ("denseEnoughThresh", C.c_float), ("cleanWindow", C.c_int),
-                ("capacity", C.c_uint)]
+                ("capacity", C.c_uint), ("trackerThreads", C.c_int)]
 
 
 _FT = ["RGB", "RGBA", "DEPTH_RAW", "DEPTH_FILTERED", "DEPTH_METRIC", "DEPTH_METRIC_FILTERED", "VERTEX_RAW", "VERTEX_FILTERED", "NORMAL_PCA",

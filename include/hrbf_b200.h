@@ -157,6 +157,10 @@ int hrbf_odometry_set_params(hrbf_odometry*, float curvValidThreshold, int useCo
 /* Tracker implementation: 0 (default) = the whole coarse-to-fine loop as ONE persistent cooperative kernel;
  * 1 = one kernel per reduction, replayed as a CUDA graph (kept for comparison and for the per-kernel timing hook) */
 int hrbf_odometry_set_tracker(hrbf_odometry*, int use_kernel_graph);
+/* Threads per CTA of the persistent tracker: 512 (default; 512 x 128 registers fill an SM's register file -- lowest latency
+ * for ONE sequence) or 256 (leaves half of every SM to the kernels of OTHER fusion objects running on their own streams:
+ * several sequences per GPU, offline throughput runs).  Replaces the launch-shape table of Utils/GPUConfig.h:53-78. */
+int hrbf_odometry_set_tracker_threads(hrbf_odometry*, int threads);
 /* initICP(depth) [GPUTest path], RGBDOdometry.cpp:161-181 : depth_dev = float[h][w] raw units */
 int hrbf_odometry_init_icp_depth(hrbf_odometry*, const float* depth_dev, float depthCutoff, float depthMapFactor, void* stream);
 /* initICP(vertices, normals), RGBDOdometry.cpp:183-206 */
@@ -373,6 +377,7 @@ typedef struct {
     float denseEnoughThresh;      /* globalDenseEnoughThresh (0.75)          */
     int cleanWindow;              /* fusionCleanWindowMultiplier (2)         */
     unsigned int capacity;        /* surfel capacity, 0 = reference default  */
+    int trackerThreads;           /* hrbf_odometry_set_tracker_threads: 0 = 512 (one live sequence), 256 = several sequences per GPU */
 } hrbf_fusion_params;
 void hrbf_fusion_default_params(hrbf_fusion_params* p, int width, int height, float cx, float cy, float fx, float fy);
 int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p);

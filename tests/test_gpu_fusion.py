@@ -247,3 +247,50 @@ def test_staged_pipeline_is_identical_to_process_frame(orc, cuda):
         assert g.globalModel.lastCount() == ref.globalModel.lastCount()
         assert torch.equal(g.trajectory(), ref.trajectory())
         assert g.tick == n + 1
+
+
+def test_concurrent_sequences_on_one_gpu(orc, cuda):
+    """Offline throughput mode: several fusion objects on their own streams with the 256-thread tracker
+    (hrbf_odometry_set_tracker_threads) share one GPU.  Every sequence run concurrently must be bit-identical to the same
+    sequence run alone with the same tracker shape, and within the pose tolerance of the 512-thread tracker (its per-CTA
+    partial sums are taken in another order); an invalid thread count fails loudly."""
+    torch = cuda
+    from hrbffusion3d_b200.fusion import HRBFFusion
+    from hrbffusion3d_b200._lib import HrbfError
+    W, H, n, S = 320, 240, 6, 3
+    cam, poses, fr = _frames(W, H, n + S)
+    d_dev = [torch.from_numpy(d.view(np.int16)).cuda() for d, _ in fr]
+    c_dev = [torch.from_numpy(c).cuda() for _, c in fr]
+
+    def alone(q, threads):
+        g = HRBFFusion(W, H, cam, capacity=1 << 19, trackerThreads=threads)
+        for i in range(n):
+            g.processFrameDev(c_dev[q + i], d_dev[q + i])
+        torch.cuda.synchronize()
+        return g.trajectory().clone(), g.globalModel.lastCount()
+
+    solo = [alone(q, 256) for q in range(S)]                   # sequence q = frames q .. q+n-1
+    Fs = [HRBFFusion(W, H, cam, capacity=1 << 19, trackerThreads=256) for _ in range(S)]
+    st = [torch.cuda.Stream() for _ in range(S)]
+    torch.cuda.synchronize()
+    for q in range(S):
+        with torch.cuda.stream(st[q]):
+            Fs[q].stageFrame(c_dev[q], d_dev[q])
+    for i in range(n):
+        for q in range(S):
+            with torch.cuda.stream(st[q]):
+                if i + 1 < n:
+                    Fs[q].stageFrame(c_dev[q + i + 1], d_dev[q + i + 1])
+                Fs[q].processStaged(None)
+    torch.cuda.synchronize()
+    for q in range(S):
+        assert torch.equal(Fs[q].trajectory(), solo[q][0]), q
+        assert Fs[q].globalModel.lastCount() == solo[q][1]
+    t512, c512 = alone(0, 512)
+    a, b = solo[0][0].cpu().numpy(), t512.cpu().numpy()
+    for i in range(n):
+        ang, dt = pose_err(a[i, :9].reshape(3, 3), a[i, 9:], b[i, :9].reshape(3, 3), b[i, 9:])
+        assert ang <= 3e-4 * (i + 1) and dt <= 3e-4 * (i + 1), (i, ang, dt)      # default config (RGB term): tolerance of test_process_frame_sequence
+    assert abs(solo[0][1] - c512) <= max(5, int(3e-3 * c512))
+    with pytest.raises(HrbfError):
+        HRBFFusion(W, H, cam, capacity=1 << 16, trackerThreads=384)
