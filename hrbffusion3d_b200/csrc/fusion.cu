@@ -472,6 +472,59 @@ int hrbf_model_last_count(hrbf_model* m, unsigned int* count, void* stream)
     m->bound = *count;          // exact again
     return HRBF_OK;
 }
+// GlobalModel::downloadMap (GlobalModel.cpp:775-804): the current surfel array to the host, count records of 20 floats
+int hrbf_model_download_map(hrbf_model* m, float* surfels_host, unsigned int max_count, unsigned int* count_out, void* stream)
+{
+    HRBF_CHECK_ARG(m && count_out && (surfels_host || max_count == 0));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = hrbf_model_last_count(m, count_out, stream)) return rc;
+    if (max_count == 0) return HRBF_OK;                      // size query
+    if (*count_out > max_count) { set_error("download_map: %u surfels do not fit a buffer of %u", *count_out, max_count); return HRBF_ERR_CAPACITY; }
+    if (*count_out) HRBF_CUDA(cudaMemcpyAsync(surfels_host, m->vbo[m->cur], (size_t)*count_out * 80, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    return HRBF_OK;
+}
+// HRBFFusion::savePly (HRBFFusion.cpp:1737-1853): header text for n vertices; returns its length (0 if buf is too small)
+size_t hrbf_ply_header(unsigned int n_vertices, char* buf, size_t buf_len)
+{
+    if (!buf) return 0;
+    const int n = snprintf(buf, buf_len,
+                           "ply\nformat binary_little_endian 1.0\nelement vertex %u\nproperty float x\nproperty float y\nproperty float z"
+                           "\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty float nx\nproperty float ny\nproperty float nz"
+                           "\nproperty float curvature_max\nproperty float curvature_min\nproperty float radius\nproperty float submapIndex\nend_header\n",
+                           n_vertices);
+    return (n > 0 && (size_t)n < buf_len) ? (size_t)n : 0;
+}
+// The vertex block of savePly: surfels with confidence > confThreshold packed to 43-byte records on the device (in the idle
+// ping-pong buffer), then copied to records_host.  records_host == NULL: only the vertex count is returned (size query).
+int hrbf_model_export_ply(hrbf_model* m, float confThreshold, void* records_host, size_t host_bytes, unsigned int* n_vertices_out, void* stream)
+{
+    HRBF_CHECK_ARG(m && n_vertices_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    *n_vertices_out = 0;
+    if (m->bound == 0) return HRBF_OK;
+    int nb = (int)((m->bound + kScanBlock - 1) / kScanBlock);
+    const int grid = nb < kNumSMs * 8 ? nb : kNumSMs * 8;
+    unsigned char* packed = (unsigned char*)m->vbo[m->cur ^ 1];        // 43 B <= 80 B per surfel: always fits
+    unsigned int* total = m->count[m->cur ^ 1];                        // rewritten by the next clean before it is read
+    ply_flags_kernel<<<grid, kScanBlock, 0, s>>>(m->vbo[m->cur], m->count[m->cur], confThreshold, m->flags, m->block_counts);
+    HRBF_KERNEL_CHECK();
+    scan_blocks_kernel<<<1, 1024, 0, s>>>(m->block_counts, m->block_offsets, m->count[m->cur], 0u, 0xffffffffu, total, m->overflow);
+    HRBF_KERNEL_CHECK();
+    HRBF_CUDA(cudaMemcpyAsync(m->h_count + 3, total, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    if (records_host) {
+        ply_scatter_kernel<<<grid, kScanBlock, 0, s>>>(m->vbo[m->cur], m->count[m->cur], m->flags, m->block_offsets, packed);
+        HRBF_KERNEL_CHECK();
+    }
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    const unsigned int n = m->h_count[3];
+    *n_vertices_out = n;
+    if (!records_host || n == 0) return HRBF_OK;
+    if ((size_t)n * kPlyVertexBytes > host_bytes) { set_error("export_ply: %u vertices need %zu bytes, buffer has %zu", n, (size_t)n * kPlyVertexBytes, host_bytes); return HRBF_ERR_CAPACITY; }
+    HRBF_CUDA(cudaMemcpyAsync(records_host, packed, (size_t)n * kPlyVertexBytes, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    return HRBF_OK;
+}
 int hrbf_model_overflowed(hrbf_model* m, int* flag, void* stream)
 {
     HRBF_CHECK_ARG(m && flag);

@@ -466,6 +466,62 @@ __global__ void __launch_bounds__(256) update_model_kernel(float4* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------ savePly ---
+// HRBFFusion::savePly (HRBFFusion.cpp:1737-1853): every surfel with confidence > threshold becomes one 43-byte binary PLY vertex
+// {x y z | r g b | -nx -ny -nz | curvature_max curvature_min | radius | submapIndex}, in map order.  The reference downloads the whole
+// map (80 B per surfel) and filters on the host; here the filter + packing is an order-preserving compaction on the device and only
+// the packed records cross PCIe.
+constexpr int kPlyVertexBytes = 43;
+__global__ void __launch_bounds__(kScanBlock) ply_flags_kernel(const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev, float confThreshold,
+                                                               unsigned char* __restrict__ flags, unsigned int* __restrict__ block_counts)
+{
+    const unsigned int n = *count_dev;
+    for (unsigned int blk = blockIdx.x; blk * kScanBlock < n; blk += gridDim.x) {
+        const unsigned int i = blk * kScanBlock + threadIdx.x;
+        bool f = false;
+        if (i < n) {
+            f = __ldg(&surfels[5 * (size_t)i].w) > confThreshold;
+            flags[i] = f ? 1 : 0;
+        }
+        const int cnt = __syncthreads_count(f);
+        if (threadIdx.x == 0) block_counts[blk] = cnt;
+    }
+}
+__global__ void __launch_bounds__(kScanBlock) ply_scatter_kernel(const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
+                                                                 const unsigned char* __restrict__ flags, const unsigned int* __restrict__ block_offsets,
+                                                                 unsigned char* __restrict__ out)
+{
+    __shared__ unsigned int s_warp[kScanBlock / 32];
+    __shared__ unsigned int s_n;
+    __shared__ __align__(4) unsigned char s_rec[kScanBlock * kPlyVertexBytes + 1];
+    const unsigned int n = *count_dev;
+    for (unsigned int blk = blockIdx.x; blk * kScanBlock < n; blk += gridDim.x) {
+        const unsigned int i = blk * kScanBlock + threadIdx.x;
+        const bool f = i < n && flags[i];
+        const unsigned int r = block_rank(f, s_warp);
+        if (threadIdx.x == kScanBlock - 1) s_n = r + (f ? 1u : 0u);
+        if (f) {
+            const float4* sp = surfels + 5 * (size_t)i;
+            const float4 pos = __ldg(sp), col = __ldg(sp + 1), nor = __ldg(sp + 2);
+            const float cmax = __ldg(&sp[3].w), cmin = __ldg(&sp[4].w);
+            const int c = (int)col.x;
+            const float fl[10] = { pos.x, pos.y, pos.z, -nor.x, -nor.y, -nor.z, cmax, cmin, nor.w, col.y };
+            unsigned char* d = s_rec + r * kPlyVertexBytes;
+            auto put = [&](int off, float v) { const unsigned int b = __float_as_uint(v); d[off] = b & 0xff; d[off + 1] = (b >> 8) & 0xff; d[off + 2] = (b >> 16) & 0xff; d[off + 3] = b >> 24; };
+            put(0, fl[0]); put(4, fl[1]); put(8, fl[2]);
+            d[12] = (unsigned char)(c >> 16 & 0xFF); d[13] = (unsigned char)(c >> 8 & 0xFF); d[14] = (unsigned char)(c & 0xFF);
+#pragma unroll
+            for (int k = 3; k < 10; ++k) put(15 + 4 * (k - 3), fl[k]);
+        }
+        __syncthreads();
+        // the block's records are one contiguous byte range of the output: coalesced byte stores
+        const size_t base = (size_t)block_offsets[blk] * kPlyVertexBytes;
+        const unsigned int bytes = s_n * kPlyVertexBytes;
+        for (unsigned int b = threadIdx.x; b < bytes; b += kScanBlock) out[base + b] = s_rec[b];
+        __syncthreads();       // s_warp / s_rec are reused by the next tile
+    }
+}
+
 __global__ void fill_u32_kernel(unsigned int* p, size_t n, unsigned int v)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;

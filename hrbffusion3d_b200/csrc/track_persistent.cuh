@@ -17,6 +17,9 @@ namespace hrbf {
 // (hrbf_odometry_set_tracker_threads): 512 x 128 registers fill an SM's register file -- the lowest latency for ONE sequence;
 // 256 leave half of every SM to the kernels of other sequences' pipelines (several fusion objects on their own streams).
 constexpr int kTrackThreadsDefault = 512;
+#ifndef HRBF_TRACK_POLL_SLEEP
+#define HRBF_TRACK_POLL_SLEEP 100      // ns between polling rounds of the shared-SM shape
+#endif
 
 struct TrackLevel {
     IcpArgs icp;
@@ -107,6 +110,8 @@ __device__ __forceinline__ void all_reduce_partials(const unsigned long long* pa
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if ((unsigned int)(w[u] >> 32) != tag) { w[u] = ll_load(part + (size_t)(b0 + u * kSlices) * 64 + v); all = false; }
+                // sharing the SM with other sequences' kernels (256-thread shape): do not burn their issue slots and L2 bandwidth while waiting
+                if (kTrackThreads < kTrackThreadsDefault && !all) __nanosleep(HRBF_TRACK_POLL_SLEEP);
             } while (!all);
 #pragma unroll
             for (int u = 0; u < U; ++u) a += (double)__uint_as_float((unsigned int)w[u]);

@@ -182,6 +182,30 @@ class GlobalModel:
         p = lib().hrbf_model_model(self._h)
         return alias_tensor(p, (max(n, 1), 20), torch.float32)[:n], n
 
+    def downloadMap(self):
+        """GlobalModel::downloadMap: numpy float32 [count, 20]"""
+        n = C.c_uint(0)
+        check(lib().hrbf_model_download_map(self._h, None, 0, C.byref(n), stream_ptr()))
+        out = np.zeros((n.value, 20), np.float32)
+        if n.value:
+            check(lib().hrbf_model_download_map(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n), stream_ptr()))
+        return out
+
+    def exportPly(self, confThreshold):
+        """bytes of the PLY file HRBFFusion::savePly writes (header + 43-byte vertices, packed on the device)"""
+        L = lib()
+        L.hrbf_ply_header.restype = C.c_size_t
+        n = C.c_uint(0)
+        check(L.hrbf_model_export_ply(self._h, C.c_float(confThreshold), None, C.c_size_t(0), C.byref(n), stream_ptr()))
+        rec = np.zeros(n.value * 43, np.uint8)
+        if n.value:
+            check(L.hrbf_model_export_ply(self._h, C.c_float(confThreshold), rec.ctypes.data_as(C.c_void_p), C.c_size_t(rec.size), C.byref(n), stream_ptr()))
+        buf = C.create_string_buffer(512)
+        k = L.hrbf_ply_header(n.value, buf, C.c_size_t(512))
+        if k == 0:
+            raise RuntimeError("hrbf_ply_header: buffer too small")
+        return buf.raw[:k] + rec.tobytes()
+
     def overflowed(self):
         f = C.c_int(0)
         check(lib().hrbf_model_overflowed(self._h, C.byref(f), stream_ptr()))
@@ -257,6 +281,11 @@ class HRBFFusion:
         pose = np.zeros(16, np.float32)
         check(lib().hrbf_fusion_get_pose(self._h, pose.ctypes.data_as(C.POINTER(C.c_float)), stream_ptr()))
         return pose.reshape(4, 4)
+
+    def savePly(self, filename, confThreshold=0.0):
+        """HRBFFusion::savePly (HRBFFusion.cpp:1737-1853); confThreshold = globalOutputSavePointCloudConfThreshold"""
+        with open(filename, "wb") as f:
+            f.write(self.globalModel.exportPly(confThreshold))
 
     def trajectory(self):
         n = C.c_int(0)

@@ -356,6 +356,17 @@ const unsigned int* hrbf_model_count_dev(hrbf_model*);
 int hrbf_model_last_count(hrbf_model*, unsigned int* count_host, void* stream);
 /* 1 if a compaction ever ran out of capacity (survivors beyond it were dropped) */
 int hrbf_model_overflowed(hrbf_model*, int* flag_host, void* stream);
+/* GlobalModel::downloadMap, GlobalModel.cpp:775-804: the surfel array (count x 20 floats) to surfels_host.
+ * max_count = capacity of surfels_host in surfels; 0 = size query (only *count_out is written). */
+int hrbf_model_download_map(hrbf_model*, float* surfels_host, unsigned int max_count, unsigned int* count_out, void* stream);
+/* HRBFFusion::savePly, HRBFFusion.cpp:1737-1853.  hrbf_ply_header writes the reference's header text for n vertices
+ * (returns its length, 0 if buf is too small).  hrbf_model_export_ply filters the map (confidence >
+ * globalOutputSavePointCloudConfThreshold) and packs the 43-byte binary_little_endian vertices {x y z, r g b, -n, curvature_max,
+ * curvature_min, radius, submapIndex} ON THE DEVICE, in map order, and copies them to records_host; records_host = NULL is a
+ * size query.  File = header + records. */
+#include <stddef.h>
+size_t hrbf_ply_header(unsigned int n_vertices, char* buf, size_t buf_len);
+int hrbf_model_export_ply(hrbf_model*, float confThreshold, void* records_host, size_t host_bytes, unsigned int* n_vertices_out, void* stream);
 
 /* ------------------------------------------------------------------------
  * The per-frame orchestrator: HRBFFusion::processFrame / predict (Core/src/HRBFFusion.cpp:991-1260)

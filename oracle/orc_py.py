@@ -411,3 +411,22 @@ def modelUpdate(surfels, delta):
     d = np.ascontiguousarray(delta, np.float32).reshape(-1, 16)
     lib().orc_model_update(_p(out), int(out.shape[0]), _p(d), int(d.shape[0]))
     return out
+
+
+def savePlyBytes(surfels, confThreshold=0.0):
+    """HRBFFusion::savePly (HRBFFusion.cpp:1737-1853) restated byte for byte: header (:1760-1787), then per surfel with
+    pos.w > globalOutputSavePointCloudConfThreshold (:1797) the 43-byte record x y z (:1811-1818), r g b from
+    int(col[0]) >> 16 / >> 8 / & 0xFF (:1821-1827), the NEGATED normal (:1805-1807,1829-1836), curvature_max = c_max[3],
+    curvature_min = c_min[3] (:1838-1842), radius = nor[3] (:1844), submapIndex = col[1] (:1847).  surfels: float32 [n, 20]."""
+    s = np.ascontiguousarray(surfels, np.float32).reshape(-1, 20)
+    keep = s[s[:, 3] > np.float32(confThreshold)]
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z"
+              "\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty float nx\nproperty float ny\nproperty float nz"
+              "\nproperty float curvature_max\nproperty float curvature_min\nproperty float radius\nproperty float submapIndex\nend_header\n" % keep.shape[0])
+    out = bytearray(header.encode("ascii"))
+    for v in keep:          # small maps only (test infrastructure)
+        c = int(v[4])
+        out += np.array([v[0], v[1], v[2]], "<f4").tobytes()
+        out += bytes([(c >> 16) & 0xFF, (c >> 8) & 0xFF, c & 0xFF])
+        out += np.array([-v[8], -v[9], -v[10], v[15], v[19], v[11], v[5]], "<f4").tobytes()
+    return bytes(out)
