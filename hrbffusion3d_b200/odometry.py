@@ -41,6 +41,10 @@ class RGBDOdometry:
         """False (default): one persistent cooperative kernel; True: one kernel per reduction in a CUDA graph"""
         check(lib().hrbf_odometry_set_tracker(self._h, int(use_kernel_graph)))
 
+    def setTrackerThreads(self, threads=512):
+        """512 (default): the persistent tracker fills every SM; 256: leaves half of each SM to other sequences' kernels"""
+        check(lib().hrbf_odometry_set_tracker_threads(self._h, int(threads)))
+
     def setParams(self, curvValidThreshold=300.0, useCorrespondenceSearch=False, searchRadius=2, rgbUseGradientWeight=False):
         check(lib().hrbf_odometry_set_params(self._h, C.c_float(curvValidThreshold), int(useCorrespondenceSearch), int(searchRadius), int(rgbUseGradientWeight)))
 

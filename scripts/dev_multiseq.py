@@ -6,6 +6,7 @@ import numpy as np, torch
 import bench
 from hrbffusion3d_b200.fusion import HRBFFusion
 n = 48
+STAGES = int(os.environ.get('STAGES', '0'))
 TT = int(os.environ.get('TT', '256'))      # tracker threads per CTA
 depth, rgb, poses, cam = bench.make_sequence(0, bench.RING, only=n)
 d = torch.from_numpy(depth.view(np.int16)).cuda(); c = torch.from_numpy(rgb).cuda()
@@ -16,10 +17,18 @@ def run(S, steps=150, warm=20):
     st = [torch.cuda.Stream() for _ in range(S)]
     off = [(s * n) // S for s in range(S)]
 
+    stages = []
+    pose = np.zeros(16, np.float32)
+    if STAGES: Fs[0].enableTimings(True)
+
     def step(i):
         for s in range(S):
             with torch.cuda.stream(st[s]):
-                Fs[s].stageFrame(c[(i + 1 + off[s]) % n], d[(i + 1 + off[s]) % n]); Fs[s].processStaged(None)
+                Fs[s].stageFrame(c[(i + 1 + off[s]) % n], d[(i + 1 + off[s]) % n])
+                if STAGES and s == 0:      # sequence 0 is read back every frame: its per-stage times under the others' load
+                    Fs[0].processStaged(pose); stages.append(list(Fs[0].lastTimings().values()))
+                else:
+                    Fs[s].processStaged(None)
     for s in range(S):
         with torch.cuda.stream(st[s]):
             Fs[s].stageFrame(c[off[s]], d[off[s]])
@@ -31,6 +40,9 @@ def run(S, steps=150, warm=20):
     torch.cuda.synchronize()
     t = time.perf_counter() - t0
     cnt = [F.globalModel.lastCount() for F in Fs]
+    if STAGES:
+        m = np.median(np.array(stages[warm:]), axis=0) * 1e3
+        print("   sequence 0 stage medians (us): preprocess-wait %.0f  registration %.0f  integration %.0f  prediction %.0f  (sum %.0f)" % (*m, m.sum()))
     return S * steps / t, t_host / (S * steps) * 1e6, cnt
 
 
