@@ -1,9 +1,9 @@
 // track_persistent.cuh -- the whole coarse-to-fine tracking loop of RGBDOdometry::getIncrementalTransformation
-// (Core/src/Utils/RGBDOdometry.cpp:796-1249) as ONE persistent cooperative kernel: one CTA per SM, grid-wide
-// barriers between the reduction phases, the Gauss-Newton state in shared memory.
+// (Core/src/Utils/RGBDOdometry.cpp:796-1249) as ONE persistent cooperative kernel: one CTA per SM, the Gauss-Newton
+// state in shared memory, tagged-word exchanges (no grid barrier) between the reduction phases.
 //
 // Every CTA reduces the same per-CTA partial sums in the same fixed order and runs the same fp64 solve, so all
-// CTAs hold bit-identical copies of the state and only ONE grid barrier is needed per reduction (none to
+// CTAs hold bit-identical copies of the state and only ONE exchange is needed per reduction (none to
 // broadcast the new pose).  Compared with one kernel per reduction (icp_reduce_kernel & co., kept for the
 // step-function ABI) this removes ~70 dependent kernel boundaries per frame, the ticket atomics and the
 // __threadfence of the last-block-done scheme.

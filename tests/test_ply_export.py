@@ -34,6 +34,21 @@ def test_oracle_ply_known_answer(orc):
     assert orc.savePlyBytes(np.zeros((0, 20), np.float32)).split(b"end_header\n")[1] == b""
 
 
+def test_ply_header_matches_oracle(orc):
+    """hrbf_ply_header is host code: the library's header text against the oracle's, without a GPU"""
+    import ctypes as C
+    from hrbffusion3d_b200 import lib
+    L = lib()
+    L.hrbf_ply_header.restype = C.c_size_t
+    for n in (0, 1, 305191, 4294967295):
+        buf = C.create_string_buffer(512)
+        k = L.hrbf_ply_header(C.c_uint(n), buf, C.c_size_t(512))
+        want = orc.savePlyBytes(np.zeros((0, 20), np.float32)).replace(b"element vertex 0", b"element vertex %d" % n)
+        assert buf.raw[:k] == want
+    assert L.hrbf_ply_header(C.c_uint(5), C.create_string_buffer(64), C.c_size_t(64)) == 0      # too small: 0, nothing truncated silently
+    assert L.hrbf_ply_header(C.c_uint(5), None, C.c_size_t(0)) == 0
+
+
 @pytest.mark.gpu
 def test_export_ply_and_download_map_match_oracle(orc, cuda, tmp_path):
     torch = cuda
