@@ -430,3 +430,53 @@ def savePlyBytes(surfels, confThreshold=0.0):
         out += bytes([(c >> 16) & 0xFF, (c >> 8) & 0xFF, c & 0xFF])
         out += np.array([-v[8], -v[9], -v[10], v[15], v[19], v[11], v[5]], "<f4").tobytes()
     return bytes(out)
+
+
+# ---------------------------------------------------- row 5, the remaining single kernels (cudafuncs.cu) --
+def pyrDownDepth(src):
+    rows, cols = src.shape
+    dst = np.zeros((rows // 2, cols // 2), np.float32)
+    lib().orc_pyrDownDepth(rows, cols, _p(_f(src)), _p(dst))
+    return dst
+
+
+def createVMap(cam, depth, cutoff, factor):
+    rows, cols = depth.shape
+    v = np.zeros((4 * rows, cols), np.float32)
+    lib().orc_createVMap(Cam(*cam), rows, cols, _p(_f(depth)), _p(v), C.c_float(cutoff), C.c_float(factor))
+    return v
+
+
+def createNMap(vmap):
+    rows, cols = vmap.shape[0] // 4, vmap.shape[1]
+    n = np.zeros((4 * rows, cols), np.float32)
+    lib().orc_createNMap(rows, cols, _p(_f(vmap)), _p(n))
+    return n
+
+
+def verticesToDepth(v_aos, cutoff):
+    rows, cols = v_aos.shape[:2]
+    d = np.zeros((rows, cols), np.float32)
+    lib().orc_verticesToDepth(rows, cols, _p(_f(v_aos)), _p(d), C.c_float(cutoff))
+    return d
+
+
+def pyrDownGaussF(src):
+    rows, cols = src.shape
+    dst = np.zeros((rows // 2, cols // 2), np.float32)
+    lib().orc_pyrDownGaussF(rows, cols, _p(_f(src)), _p(dst))
+    return dst
+
+
+def pyrDownUcharGauss(src):
+    rows, cols = src.shape
+    dst = np.zeros((rows // 2, cols // 2), np.uint8)
+    lib().orc_pyrDownUcharGauss(rows, cols, _p(np.ascontiguousarray(src, np.uint8), C.c_ubyte), _p(dst, C.c_ubyte))
+    return dst
+
+
+def rgbaToIntensity(rgba):
+    rows, cols = rgba.shape[:2]
+    dst = np.zeros((rows, cols), np.uint8)
+    lib().orc_rgbaToIntensity(rows, cols, _p(np.ascontiguousarray(rgba, np.uint8), C.c_ubyte), _p(dst, C.c_ubyte))
+    return dst

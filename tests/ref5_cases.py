@@ -1,0 +1,62 @@
+"""Deterministic cases for the row-5 single kernels (Core/src/Cuda/cudafuncs.cu), shared by
+  * oracle/gen_ref5_golden.py (runs the REFERENCE's own kernels on the GPU box -> tests/golden/ref_cudafuncs.npz)
+  * tests/test_oracle_vs_reference_row5.py (CPU: oracle vs those golden vectors; GPU: oracle vs the reference kernels live).
+Every stage gets its inputs from the CPU oracle (not from the module under test), so that a last-bit difference in one
+stage cannot leak into the next."""
+import numpy as np
+
+from tests.util import pair
+
+SIZES = ((96, 72), (640, 480))
+
+
+def run_all(mod, orc, W, H):
+    """mod: oracle.orc_py or oracle.ref5_py (same function names).  Returns {name: array}."""
+    m0, pose0, m1, pose1, cam = pair(W, H)
+    R, t = np.ascontiguousarray(pose0[:3, :3]), np.ascontiguousarray(pose0[:3, 3])
+    out = {}
+    out["copy_v"], out["copy_n"] = mod.copyMaps(m0["vertex"], m0["normal"])
+    out["copy_k1"] = mod.copyCurvatureMap(m0["k1"], 300.0)
+    thr = float(np.nanmedian(np.abs(m0["k1"][..., 3])))                   # a threshold that rejects about half of the pixels
+    out["copy_k1_tight"] = mod.copyCurvatureMap(m0["k1"], thr)
+    out["copy_w"] = mod.copyicpWeightMap(m0["icpw"])
+    v, n = orc.copyMaps(m0["vertex"], m0["normal"])
+    k1, k2 = orc.copyCurvatureMap(m0["k1"], 300.0), orc.copyCurvatureMap(m0["k2"], 300.0)
+    w = orc.copyicpWeightMap(m0["icpw"])
+    init = np.full((4 * (H // 2), W // 2), 3.0, np.float32)               # stale contents the kernels must leave where they do not write
+    out["resize_v"] = mod.resizeMap(v, 0, init=init)
+    out["resize_n"] = mod.resizeMap(n, 1, init=init)
+    out["resize_k1"] = mod.resizeCMap(k1)
+    out["resize_w"] = mod.resizeicpWeightMap(w)
+    out["xf_v"], out["xf_n"] = mod.tranformMaps(v, n, R, t)
+    out["xf_k1"], out["xf_k2"] = mod.transformCurvMaps(k1, k2, R, t)
+    out["v2d"] = mod.verticesToDepth(m0["vertex"], 20.0)
+    out["v2d_cut"] = mod.verticesToDepth(m0["vertex"], 2.0)               # a cut-off inside the scene
+    d = orc.verticesToDepth(m0["vertex"], 20.0)
+    out["pyr_gauss_f"] = mod.pyrDownGaussF(d)
+    out["pyr_depth"] = mod.pyrDownDepth(np.nan_to_num(d * 1000.0))          # pyrDown: raw depth in mm, 0 = invalid (sigma_color 30)
+    out["intensity"] = mod.rgbaToIntensity(m0["rgba"])
+    img = orc.rgbaToIntensity(m0["rgba"])
+    out["pyr_u8"] = mod.pyrDownUcharGauss(img)
+    out["sobel_dx"], out["sobel_dy"] = mod.sobel(img)
+    out["cloud"] = mod.projectToPointCloud(d, cam)
+    raw = np.nan_to_num(d * 5000.0).astype(np.float32)                      # TUM-style raw depth (1/5000 m), 0 = invalid
+    out["vmap"] = mod.createVMap(cam, raw, 20.0, 1.0 / 5000.0)
+    out["nmap"] = mod.createNMap(orc.createVMap(cam, raw, 20.0, 1.0 / 5000.0))
+    return out
+
+
+INTEGER = ("intensity", "pyr_u8", "sobel_dx", "sobel_dy")
+
+
+def compare(name, got, want, exact_copy=("copy_v", "copy_n", "copy_k1", "copy_k1_tight", "copy_w", "v2d", "v2d_cut")):
+    """oracle vs reference.  Copies and integer images: bit-exact.  Float arithmetic: the reference is built with
+    --ftz --prec-div=false --prec-sqrt=false and FMA contraction, the oracle is plain C: 2e-6 relative; NaN masks identical."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, name
+    if name in INTEGER or name in exact_copy:
+        assert np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), name
+        return
+    assert np.array_equal(np.isnan(got), np.isnan(want)), name + ": NaN masks differ"
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2e-6, atol=2e-6, err_msg=name)
