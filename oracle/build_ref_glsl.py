@@ -25,6 +25,12 @@ OUT = os.path.join(HERE, "_ref", "libref_glsl.so")
 # name -> shader file; the driver is oracle/glsl_drivers/<name>.inc
 SHADERS = {
     "predict_hrbf": "predict_hrbf.frag",
+    "depth_bilateral": "depth_bilateral.frag",
+    "depth_metric_raw": "depth_metric_raw.frag",
+    "depth_metric_filtered": "depth_metric_filtered.frag",
+    "depth_vertex_normal_radius": "depth_vertex_normal_radius.frag",
+    "depth_curvature_gradient": "depth_curvature_gradient.frag",
+    "depth_confidence_evaluation": "depth_confidence_evaluation.frag",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 
@@ -62,7 +68,7 @@ def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, "glsl_cpu.h"), os.path.abspath(__file__)] + [os.path.join(HERE, "glsl_drivers", n + ".inc") for n in SHADERS]
+    deps = [os.path.join(HERE, "glsl_cpu.h"), os.path.abspath(__file__)] + [os.path.join(HERE, "glsl_drivers", f) for f in os.listdir(os.path.join(HERE, "glsl_drivers"))]
     deps += [os.path.join(REF, f) for f in os.listdir(REF) if f.endswith((".glsl", ".frag", ".vert"))]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -84,7 +90,7 @@ def main():
                 f.write('#include "glsl_cpu.h"\nnamespace glsl { namespace shader_%s {\n#line 1 "%s"\n%s\n#line 1 "%s"\n#include "%s"\n} }\n'
                         % (name, fname, body, os.path.basename(driver), driver))
             tus.append(tu)
-        cmd = ["g++", "-O2", "-std=c++17", "-fsingle-precision-constant", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", HERE, "-o", OUT] + tus
+        cmd = ["g++", "-O2", "-std=c++17", "-fsingle-precision-constant", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", HERE, "-I", os.path.join(HERE, "glsl_drivers"), "-o", OUT] + tus
         subprocess.check_call(cmd)
     print("built", OUT)
     return 0

@@ -7,7 +7,7 @@
  * 6 and 10, FillIn) to the shader text itself.  What it is NOT: a GL implementation.  Arithmetic is IEEE fp32 evaluated by
  * the host compiler (-fsingle-precision-constant, no FMA contraction); a GPU's GLSL compiler may fuse and reorder, so the
  * comparison is to tolerance, never bit-for-bit.  Textures are sampled GL_NEAREST with clamp-to-edge (the reference creates
- * them with draw = false -> GL_NEAREST, GPUTexture.cpp:47 / pangolin GlTexture).
+ * them with draw = false -> GL_NEAREST, GPUTexture.cpp:47 / pangolin GlTexture); see texel() for the boundary rule.
  */
 #pragma once
 #include <cmath>
@@ -18,8 +18,16 @@ namespace glsl {
 
 typedef unsigned int uint;
 
+struct vec2;
+struct vec3;
+struct vec2_self { float x, y; inline operator vec2() const; };            // `v.xy` of a vec2
+struct vec3_self { float x, y, z; inline operator vec3() const; };         // `v.xyz` of a vec3
 struct vec2 {
-    float x, y;
+    union {
+        struct { float x, y; };
+        struct { float r, g; };
+        vec2_self xy;
+    };
     vec2() = default;
     vec2(float a, float b) : x(a), y(b) {}
     explicit vec2(float a) : x(a), y(a) {}
@@ -31,6 +39,7 @@ struct vec3 {
         struct { float x, y, z; };
         struct { float r, g, b; };
         vec2 xy;
+        vec3_self xyz;
     };
     vec3() = default;
     vec3(float a, float b, float c) : x(a), y(b), z(c) {}
@@ -55,6 +64,8 @@ struct vec4 {
     float& operator[](int i) { return (&x)[i]; }
     const float& operator[](int i) const { return (&x)[i]; }
 };
+inline vec2_self::operator vec2() const { return vec2(x, y); }
+inline vec3_self::operator vec3() const { return vec3(x, y, z); }
 struct uvec4 {
     uint x, y, z, w;
     explicit operator uint() const { return x; }
@@ -161,9 +172,15 @@ struct usampler2D {
     const uint* data = nullptr;    // [h][w]
     int w = 0, h = 0;
 };
+// Texel selection.  Several shaders sample EXACTLY on a texel boundary (u = float(cx) / cols, depth_bilateral.frag, geometry.glsl):
+// in fp32 (cx / cols) * cols lands a few ulps above or below cx, and a plain floor() would pick texel cx - 1 for about half of
+// the columns.  Texture units do not work that way: the scaled coordinate is converted to fixed point with 8 fractional bits
+// (round to nearest) before the integer part is taken, so a coordinate within 1/512 texel of a boundary selects the texel that
+// starts there.  That model is used here; it is also what the oracle's integer-offset restatement assumes (SURVEY 8a hazard iii).
 inline int texel(float u, int n)
 {
-    int i = (int)::floorf(u * (float)n);
+    const float fixed = ::floorf(u * (float)n * 256.0f + 0.5f);      // 8 fractional bits, round to nearest
+    int i = (int)::floorf(fixed / 256.0f);
     return i < 0 ? 0 : (i >= n ? n - 1 : i);
 }
 inline vec4 textureLod(const sampler2D& s, vec2 uv, float)
@@ -173,6 +190,7 @@ inline vec4 textureLod(const sampler2D& s, vec2 uv, float)
     return vec4(p[0], s.ch > 1 ? p[1] : 0.f, s.ch > 2 ? p[2] : 0.f, s.ch > 3 ? p[3] : 1.f);
 }
 inline vec4 texture(const sampler2D& s, vec2 uv) { return textureLod(s, uv, 0.f); }
+inline vec4 texture(const sampler2D& s, vec2 uv, float /* LOD bias: single-level textures */) { return textureLod(s, uv, 0.f); }
 inline vec4 texture2D(const sampler2D& s, vec2 uv) { return textureLod(s, uv, 0.f); }
 inline uvec4 textureLod(const usampler2D& s, vec2 uv, float)
 {

@@ -151,6 +151,35 @@ static void compute_roots(float m[3][3], float r[3])
     if (r[0] <= 0) roots2(c2, c1, r);
 }
 
+/* ---- shader-literal windows -------------------------------------------------------------------------------------------
+ * The window loops of geometry.glsl:198-212 and depth_curvature_gradient.frag:62-75 run on FLOAT counters in texture space:
+ *     for (float i = tx_min; i <= tx_max; i += indexXStep)      tx_min/max = clamp(texcoord.x -/+ indexXStep * winMultiply)
+ * In fp32 the accumulated i overshoots tx_max by an ulp for many columns, and the last column of the window is then never
+ * visited (e.g. 247 of the 634 interior columns at 640 px see 6 samples, not 7); the sample coordinate i * cols handed to
+ * getVertex is px + 0.5 only up to that round-off.  By default the oracle (and the CUDA kernels, which follow it) restate the
+ * INTENDED window: integer offsets -win..win, coordinates exactly qx + 0.5 (SURVEY 8a hazard iii).  orc_set_float_loops(1)
+ * switches these two passes to the literal float loops, which is what tests/test_oracle_vs_reference_glsl.py compares with the
+ * reference's own shader text compiled for the CPU; the same test measures what the idealisation changes. */
+static int g_float_loops = 0;
+void orc_set_float_loops(int on) { g_float_loops = on; }
+static int texel_of(float u, int n)      /* GL_NEAREST with 8 fractional bits of fixed point, see oracle/glsl_cpu.h texel() */
+{
+    const float fixed = floorf(u * (float)n * 256.0f + 0.5f);
+    int i = (int)floorf(fixed / 256.0f);
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+/* one axis of the window of pixel p: texel index and the float coordinate i * n of every visited sample; returns their number */
+static int float_window(int p, int n, float win, int* texels, float* coords)
+{
+    const float step = 1.0f / (float)n, tc = ((float)p + 0.5f) / (float)n;
+    float lo = tc - step * win, hi = tc + step * win;
+    if (lo < 0.0f) lo = 0.0f;
+    if (hi > 1.0f) hi = 1.0f;
+    int k = 0;
+    for (float i = lo; i <= hi && k < 16; i += step) { texels[k] = texel_of(i, n); coords[k] = i * (float)n; ++k; }
+    return k;
+}
+
 /* geometry.glsl:190-244 getNormalPCA(vPosition (z only), texCoord of pixel (px,py), win = 3, depth map) */
 void orc_getNormalPCA(const orc_prep_params* p, const float* depth, int px, int py, float vz, float n[3])
 {
@@ -163,10 +192,18 @@ void orc_getNormalPCA(const orc_prep_params* p, const float* depth, int px, int 
     float accu[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     int N = 0;
     n[0] = n[1] = n[2] = 0.0f;
-    for (int qx = x0; qx <= x1; ++qx)
-        for (int qy = y0; qy <= y1; ++qy) {
-            const float z = depth[(size_t)qy * W + qx];
-            const float fx_ = xclamped ? (float)qx : (float)qx + 0.5f, fy_ = yclamped ? (float)qy : (float)qy + 0.5f;
+    int txs[16], tys[16], nx = 0, ny = 0;
+    float cxs[16], cys[16];
+    if (g_float_loops) {
+        nx = float_window(px, W, 3.0f, txs, cxs); ny = float_window(py, H, 3.0f, tys, cys);
+    } else {
+        for (int qx = x0; qx <= x1; ++qx, ++nx) { txs[nx] = qx; cxs[nx] = xclamped ? (float)qx : (float)qx + 0.5f; }
+        for (int qy = y0; qy <= y1; ++qy, ++ny) { tys[ny] = qy; cys[ny] = yclamped ? (float)qy : (float)qy + 0.5f; }
+    }
+    for (int ix = 0; ix < nx; ++ix)
+        for (int iy = 0; iy < ny; ++iy) {
+            const float z = depth[(size_t)tys[iy] * W + txs[ix]];
+            const float fx_ = cxs[ix], fy_ = cys[iy];
             const float X = (fx_ - p->cx) * z * icx, Y = (fy_ - p->cy) * z * icy;
             if (z > 0.3f && fabsf(z - vz) < 0.05f) {
                 accu[0] += X * X; accu[1] += X * Y; accu[2] += X * z; accu[3] += Y * Y; accu[4] += Y * z; accu[5] += z * z;
@@ -338,8 +375,17 @@ void orc_computeCurvatureGradient(const orc_prep_params* p, const float* vertex_
                 int N = 0;
                 const int x0 = px - win < 0 ? 0 : px - win, x1 = px + win > W - 1 ? W - 1 : px + win;
                 const int y0 = py - win < 0 ? 0 : py - win, y1 = py + win > H - 1 ? H - 1 : py + win;
-                for (int qx = x0; qx <= x1; ++qx)
-                    for (int qy = y0; qy <= y1; ++qy) {
+                int txs[16], tys[16], nx = 0, ny = 0;
+                if (g_float_loops) {
+                    float unused[16];
+                    nx = float_window(px, W, p->curvWindow, txs, unused); ny = float_window(py, H, p->curvWindow, tys, unused);
+                } else {
+                    for (int qx = x0; qx <= x1 && nx < 16; ++qx) txs[nx++] = qx;
+                    for (int qy = y0; qy <= y1 && ny < 16; ++qy) tys[ny++] = qy;
+                }
+                for (int ix = 0; ix < nx; ++ix)
+                    for (int iy = 0; iy < ny; ++iy) {
+                        const int qx = txs[ix], qy = tys[iy];
                         const float* v = vertex_filtered + 4 * ((size_t)qy * W + qx);
                         const float* n = normal + 4 * ((size_t)qy * W + qx);
                         if (fabsf(v[2] - vf[2]) < 0.10f && v[2] > 0.3f && sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) > 0.8f && N < 100) {
@@ -374,6 +420,9 @@ void orc_computeCurvatureGradient(const orc_prep_params* p, const float* vertex_
                         const float lmax = -(M - k1 * F) / (Nn - k1 * G), lmin = -(M - k2 * F) / (Nn - k2 * G);
                         /* r_u + lambda r_v = (1, lambda, h_x + lambda h_y), normalised */
                         float a[3] = { 1.0f, lmax, h_x + lmax * h_y }, b[3] = { 1.0f, lmin, h_x + lmin * h_y };
+                        /* literal mode: the shader evaluates r_u + lambda * r_v component-wise, so an infinite lambda (degenerate
+                         * direction, y and z are NaN anyway) also turns x = 1 + lambda * 0 into NaN; the default keeps x = 1 -> 0 */
+                        if (g_float_loops) { a[0] = 1.0f + lmax * 0.0f; a[1] = 0.0f + lmax * 1.0f; b[0] = 1.0f + lmin * 0.0f; b[1] = 0.0f + lmin * 1.0f; }
                         const float la = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), lb = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
                         for (int k = 0; k < 3; ++k) { pmax[k] = a[k] / la; pmin[k] = b[k] / lb; }
                     }

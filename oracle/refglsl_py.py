@@ -52,3 +52,59 @@ def predictHRBF(idx, cam, width, height, win=3, minNeighbors=6, maxNeighbors=10,
                             int(minNeighbors), int(maxNeighbors), C.c_float(icpWeightLambda), C.c_float(confThreshold),
                             _p(image), _p(vertex), _p(normal), _p(k1), _p(k2), _p(time, C.c_uint), _p(icpw))
     return {"image": _unorm8(image), "vertex": vertex, "normal": normal, "curvk1": k1, "curvk2": k2, "time": time.astype(np.uint16), "icpw": icpw}
+
+
+def preprocess(pp, depth_u16):
+    """The reference's preprocessing shaders in the order of HRBFFusion::processFrame (HRBFFusion.cpp:1017-1021): depth_bilateral.frag ->
+    depth_metric_raw / depth_metric_filtered.frag -> depth_vertex_normal_radius.frag -> depth_curvature_gradient.frag (-> updateNormalRad).
+    pp: orc_py.prep_params(...).  Returns the dict orc_py.preprocess returns.  Like there, every pass reads the PREVIOUS pass's output of
+    the same implementation (this is the shader chain end to end)."""
+    H, W = pp.rows, pp.cols
+    raw = np.ascontiguousarray(depth_u16, np.uint16).astype(np.uint32)
+    cam4 = (C.c_float(pp.cx), C.c_float(pp.cy), C.c_float(pp.fx), C.c_float(pp.fy))
+    t = {k: np.zeros((H, W), np.float32) for k in ("filtered", "metric", "metric_filtered", "radius", "gradient_mag")}
+    for k in ("vertex_raw", "vertex_filtered", "normal_pca", "curv1", "curv2", "normal_opt"):
+        t[k] = np.zeros((H, W, 4), np.float32)
+    L = lib()
+    if pp.bilateral:
+        L.glsl_depth_bilateral(W, H, _p(raw, C.c_uint), C.c_float(pp.depthFactor), C.c_float(pp.maxD), _p(t["filtered"]))
+    else:
+        raise NotImplementedError("depth_guass.frag is not wired (preprocessingUsebilateralFilter defaults to true)")
+    L.glsl_depth_metric_raw(W, H, _p(raw, C.c_uint), C.c_float(pp.depthFactor), C.c_float(pp.maxD), _p(t["metric"]))
+    L.glsl_depth_metric_filtered(W, H, _p(t["filtered"]), C.c_float(pp.depthFactor), C.c_float(pp.maxD), _p(t["metric_filtered"]))
+    L.glsl_depth_vertex_normal_radius(W, H, _p(t["metric"]), _p(t["metric_filtered"]), *cam4, C.c_float(pp.radiusMultiplier), C.c_float(pp.pca),
+                                      _p(t["vertex_raw"]), _p(t["vertex_filtered"]), _p(t["normal_pca"]), _p(t["radius"]))
+    L.glsl_depth_curvature_gradient(W, H, _p(t["vertex_filtered"]), _p(t["normal_pca"]), *cam4, C.c_float(pp.maxD), C.c_float(pp.curvWindow),
+                                    _p(t["curv1"]), _p(t["curv2"]), _p(t["gradient_mag"]), _p(t["normal_opt"]))
+    t["normal"] = t["normal_opt"]
+    return t
+
+
+def preprocess_stage(pp, name, src):
+    """ONE shader pass on given inputs (a dict with the oracle's texture names) -> dict of that pass's outputs"""
+    H, W = pp.rows, pp.cols
+    cam4 = (C.c_float(pp.cx), C.c_float(pp.cy), C.c_float(pp.fx), C.c_float(pp.fy))
+    L = lib()
+    f1, f4 = (lambda: np.zeros((H, W), np.float32)), (lambda: np.zeros((H, W, 4), np.float32))
+    if name == "metric_filtered":
+        o = f1()
+        L.glsl_depth_metric_filtered(W, H, _p(_f(src["filtered"])), C.c_float(pp.depthFactor), C.c_float(pp.maxD), _p(o))
+        return {"metric_filtered": o}
+    if name == "vertex_normal_radius":
+        o = {"vertex_raw": f4(), "vertex_filtered": f4(), "normal_pca": f4(), "radius": f1()}
+        L.glsl_depth_vertex_normal_radius(W, H, _p(_f(src["metric"])), _p(_f(src["metric_filtered"])), *cam4, C.c_float(pp.radiusMultiplier), C.c_float(pp.pca),
+                                          _p(o["vertex_raw"]), _p(o["vertex_filtered"]), _p(o["normal_pca"]), _p(o["radius"]))
+        return o
+    if name == "curvature_gradient":
+        o = {"curv1": f4(), "curv2": f4(), "gradient_mag": f1(), "normal_opt": f4()}
+        L.glsl_depth_curvature_gradient(W, H, _p(_f(src["vertex_filtered"])), _p(_f(src["normal_pca"])), *cam4, C.c_float(pp.maxD), C.c_float(pp.curvWindow),
+                                        _p(o["curv1"]), _p(o["curv2"]), _p(o["gradient_mag"]), _p(o["normal_opt"]))
+        return o
+    raise ValueError(name)
+
+
+def vertexConfidence(pp, gradient_mag, metric, weighting, useConfEval=0, epsilon=1000.0):
+    out = np.zeros((pp.rows, pp.cols), np.float32)
+    lib().glsl_depth_confidence_evaluation(pp.cols, pp.rows, _p(_f(gradient_mag)), _p(_f(metric)), C.c_float(pp.cx), C.c_float(pp.cy), C.c_float(pp.fx),
+                                           C.c_float(pp.fy), C.c_float(weighting), C.c_float(useConfEval), C.c_float(epsilon), _p(out))
+    return out
