@@ -31,6 +31,10 @@ SHADERS = {
     "depth_vertex_normal_radius": "depth_vertex_normal_radius.frag",
     "depth_curvature_gradient": "depth_curvature_gradient.frag",
     "depth_confidence_evaluation": "depth_confidence_evaluation.frag",
+    "fill_vertex": "fill_vertex.frag",
+    "fill_normal": "fill_normal.frag",
+    "fill_curvature": "fill_curvature.frag",
+    "fill_rgb": "fill_rgb.frag",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 

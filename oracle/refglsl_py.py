@@ -108,3 +108,24 @@ def vertexConfidence(pp, gradient_mag, metric, weighting, useConfEval=0, epsilon
     lib().glsl_depth_confidence_evaluation(pp.cols, pp.rows, _p(_f(gradient_mag)), _p(_f(metric)), C.c_float(pp.cx), C.c_float(pp.cy), C.c_float(pp.fx),
                                            C.c_float(pp.fy), C.c_float(weighting), C.c_float(useConfEval), C.c_float(epsilon), _p(out))
     return out
+
+
+def fillIn(pp, pred, frame, confidence, rgb, passthrough=0, lamb=10.0, curvThr=300.0):
+    """Shaders/fill_vertex.frag, fill_normal.frag, fill_curvature.frag, fill_rgb.frag as HRBFFusion::predict runs them
+    (HRBFFusion.cpp:1253-1259); arguments and result as orc_py.fillIn"""
+    H, W = pp.rows, pp.cols
+    cam4 = (C.c_float(pp.cx), C.c_float(pp.cy), C.c_float(pp.fx), C.c_float(pp.fy))
+    f4 = lambda: np.zeros((H, W, 4), np.float32)
+    o = {"vertex": f4(), "icpw": np.zeros((H, W), np.float32), "normal": f4(), "curvk1": f4(), "curvk2": f4()}
+    L = lib()
+    L.glsl_fill_vertex(W, H, _p(_f(pred["vertex"])), _p(_f(frame["vertex_filtered"])), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])), _p(_f(pred["icpw"])),
+                       _p(_f(confidence)), *cam4, int(passthrough), C.c_float(lamb), C.c_float(curvThr), _p(o["vertex"]), _p(o["icpw"]))
+    L.glsl_fill_normal(W, H, _p(_f(pred["normal"])), _p(_f(frame["normal"])), *cam4, int(passthrough), _p(o["normal"]))
+    L.glsl_fill_curvature(W, H, _p(_f(pred["curvk1"])), _p(_f(pred["curvk2"])), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])), *cam4, int(passthrough),
+                          _p(o["curvk1"]), _p(o["curvk2"]))
+    img = f4()
+    e = np.ascontiguousarray(pred["image"], np.uint8).astype(np.float32) / np.float32(255.0)
+    r = np.ascontiguousarray(rgb, np.uint8).astype(np.float32) / np.float32(255.0)
+    L.glsl_fill_rgb(W, H, _p(_f(e)), _p(_f(r)), int(passthrough), _p(img))
+    o["image"] = _unorm8(img)
+    return o

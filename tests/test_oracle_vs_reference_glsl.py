@@ -118,3 +118,35 @@ def test_intended_vs_literal_windows_deviation_is_bounded(orc):
     assert np.median(ang) <= 0.5 and np.percentile(ang, 99) <= 3.0, (np.median(ang), np.percentile(ang, 99))
     k0, k1 = ideal["curv1"][..., 3], lit["curv1"][..., 3]
     assert np.mean((np.abs(k0) < 300) != (np.abs(k1) < 300)) <= 2e-3
+
+
+@pytest.mark.parametrize("useConfEval", [0, 1])
+def test_vertex_confidence_and_fill_in_oracle_matches_reference_shaders(orc, useConfEval):
+    """depth_confidence_evaluation.frag and the four FillIn shaders (fill_vertex / fill_normal / fill_curvature / fill_rgb.frag) on the
+    state of the oracle pipeline after a few frames: a prediction with holes (young map: confidence below the prediction threshold
+    in places) + the current frame.  Pass-through copies: bit-exact; the icp weight (exp) to fp32 round-off."""
+    from oracle import orc_pipeline as op
+    W, H = 320, 240
+    cam = synth.default_camera(W, H)
+    sc = synth.Scene("room")
+    f = op.HRBFFusion(W, H, cam, icpWeight=100.0, so3=False)
+    for i, p in enumerate(synth.circle_trajectory(6, frames_per_rev=120)):      # confidence passes the prediction threshold (3) after 4 frames
+        depth, rgb = synth.render_depth(sc, p, W, H, cam, noise=True, seed=i)
+        f.processFrame(rgb, depth)
+    fr, pred, pp = f.last["frame"], f.pred, f.pp
+    # VertexConfidence
+    for weighting in (1.0, 0.5):
+        a = orc.vertexConfidence(pp, fr["gradient_mag"], weighting, useConfEval, 1000.0)
+        b = rg.vertexConfidence(pp, fr["gradient_mag"], fr["metric"], weighting, useConfEval, 1000.0)
+        assert a.max() > 0
+        np.testing.assert_allclose(b, a, rtol=2e-6, atol=1e-12)
+    conf = orc.vertexConfidence(pp, fr["gradient_mag"], 1.0, useConfEval, 1000.0)
+    holes = pred["vertex"][..., 2] == 0
+    assert holes.sum() > 1000 and (~holes).sum() > 1000   # both branches of every fill shader are exercised
+    for passthrough in (0, 1):
+        a = orc.fillIn(pp, pred, fr, conf, rgb, passthrough, 10.0, 300.0)
+        b = rg.fillIn(pp, pred, fr, conf, rgb, passthrough, 10.0, 300.0)
+        for k in ("vertex", "normal", "curvk1", "curvk2", "image"):
+            assert _identical(a[k].astype(np.float32), b[k].astype(np.float32)) == 1.0, (k, passthrough)
+        assert np.array_equal(a["icpw"] == 0, b["icpw"] == 0)
+        np.testing.assert_allclose(b["icpw"], a["icpw"], rtol=3e-6, atol=0)
