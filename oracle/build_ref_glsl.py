@@ -35,6 +35,7 @@ SHADERS = {
     "fill_normal": "fill_normal.frag",
     "fill_curvature": "fill_curvature.frag",
     "fill_rgb": "fill_rgb.frag",
+    "index_map": "index_map.vert",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 
@@ -91,8 +92,9 @@ def main():
             driver = os.path.join(HERE, "glsl_drivers", name + ".inc")
             tu = os.path.join(tmp, name + ".cpp")
             with open(tu, "w") as f:
-                f.write('#include "glsl_cpu.h"\nnamespace glsl { namespace shader_%s {\n#line 1 "%s"\n%s\n#line 1 "%s"\n#include "%s"\n} }\n'
-                        % (name, fname, body, os.path.basename(driver), driver))
+                prelude = '#include "vertex_stage.inc"\n' if fname.endswith(".vert") else ""
+                f.write('#include "glsl_cpu.h"\nnamespace glsl { namespace shader_%s {\n%s#line 1 "%s"\n%s\n#line 1 "%s"\n#include "%s"\n} }\n'
+                        % (name, prelude, fname, body, os.path.basename(driver), driver))
             tus.append(tu)
         cmd = ["g++", "-O2", "-std=c++17", "-fsingle-precision-constant", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", HERE, "-I", os.path.join(HERE, "glsl_drivers"), "-o", OUT] + tus
         subprocess.check_call(cmd)

@@ -103,9 +103,16 @@ GLSL_VEC_OPS(vec4, 4)
 inline vec3 cross(vec3 a, vec3 b) { return vec3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 
 // column-major, m[col][row] like GLSL
+struct mat4 {
+    vec4 c[4];
+    mat4() = default;
+    vec4& operator[](int i) { return c[i]; }
+    const vec4& operator[](int i) const { return c[i]; }
+};
 struct mat3 {
     vec3 c[3];
     mat3() = default;
+    explicit mat3(const mat4& m) { c[0] = m[0].xyz; c[1] = m[1].xyz; c[2] = m[2].xyz; }      // upper-left 3x3
     explicit mat3(float d) { c[0] = vec3(d, 0, 0); c[1] = vec3(0, d, 0); c[2] = vec3(0, 0, d); }
     mat3(vec3 a, vec3 b, vec3 d) { c[0] = a; c[1] = b; c[2] = d; }
     mat3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) { c[0] = vec3(a0, a1, a2); c[1] = vec3(b0, b1, b2); c[2] = vec3(c0, c1, c2); }
@@ -121,14 +128,14 @@ inline vec3 operator*(mat3 m, vec3 v) { return m[0] * v.x + m[1] * v.y + m[2] * 
 inline vec3 operator*(vec3 v, mat3 m) { return vec3(dot(v, m[0]), dot(v, m[1]), dot(v, m[2])); }
 inline mat3 operator*(mat3 a, mat3 b) { return mat3(a * b[0], a * b[1], a * b[2]); }
 inline mat3 transpose(mat3 m) { return mat3(vec3(m[0].x, m[1].x, m[2].x), vec3(m[0].y, m[1].y, m[2].y), vec3(m[0].z, m[1].z, m[2].z)); }
-struct mat4 {
-    vec4 c[4];
-    mat4() = default;
-    vec4& operator[](int i) { return c[i]; }
-    const vec4& operator[](int i) const { return c[i]; }
-};
 inline vec4 operator*(mat4 m, vec4 v) { return m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3] * v.w; }
-inline mat3 mat3_of(mat4 m) { return mat3(m[0].xyz, m[1].xyz, m[2].xyz); }
+// a row-major host 4x4 (as the callers keep their poses) -> GLSL's column-major mat4
+inline mat4 mat4_from_row_major(const float* p)
+{
+    mat4 m;
+    for (int c = 0; c < 4; ++c) m[c] = vec4(p[0 * 4 + c], p[1 * 4 + c], p[2 * 4 + c], p[3 * 4 + c]);
+    return m;
+}
 
 // scalar built-ins, fp32 throughout
 inline float sqrt(float x) { return ::sqrtf(x); }

@@ -129,3 +129,21 @@ def fillIn(pp, pred, frame, confidence, rgb, passthrough=0, lamb=10.0, curvThr=3
     L.glsl_fill_rgb(W, H, _p(_f(e)), _p(_f(r)), int(passthrough), _p(img))
     o["image"] = _unorm8(img)
     return o
+
+
+def predictIndices(pose, surfels, cam, width, height, maxDepth=20.0, active_kf=None):
+    """Shaders/index_map.vert per surfel + the fixed-function point rasterisation restated in the driver; arguments and result as
+    orc_py.predictIndices"""
+    surfels = np.ascontiguousarray(surfels, np.float32).reshape(-1, 20)
+    if active_kf is None:
+        active_kf = np.zeros(19200, np.float32)
+        active_kf[0] = 1.0
+    active_kf = _f(active_kf)
+    pinv = np.linalg.inv(np.asarray(pose, np.float64)).astype(np.float32)          # Eigen: pose.inverse() (IndexMap.cpp:207)
+    out = {"index": np.zeros((height, width), np.uint32)}
+    for k in ("vertConf", "colorTime", "normRad", "curvMax", "curvMin"):
+        out[k] = np.zeros((height, width, 4), np.float32)
+    lib().glsl_index_map(surfels.shape[0], _p(surfels), _p(_f(pinv)), C.c_float(cam[2]), C.c_float(cam[3]), C.c_float(cam[0]), C.c_float(cam[1]),
+                         width, height, C.c_float(maxDepth), _p(active_kf), len(active_kf),
+                         _p(out["index"], C.c_uint), _p(out["vertConf"]), _p(out["colorTime"]), _p(out["normRad"]), _p(out["curvMax"]), _p(out["curvMin"]))
+    return out

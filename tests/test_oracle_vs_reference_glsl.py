@@ -150,3 +150,24 @@ def test_vertex_confidence_and_fill_in_oracle_matches_reference_shaders(orc, use
             assert _identical(a[k].astype(np.float32), b[k].astype(np.float32)) == 1.0, (k, passthrough)
         assert np.array_equal(a["icpw"] == 0, b["icpw"] == 0)
         np.testing.assert_allclose(b["icpw"], a["icpw"], rtol=3e-6, atol=0)
+
+
+@pytest.mark.parametrize("W,H,kind", [(160, 120, "room"), (640, 480, "room"), (640, 480, "plane")])
+def test_predict_indices_oracle_matches_reference_vertex_shader(orc, W, H, kind):
+    """row 7: Shaders/index_map.vert per surfel (projection, depth / sub-map culling, normal rotation); the point rasterisation and
+    the depth test are fixed-function GL, restated in the driver with the rules the oracle states.  The shader goes through
+    normalised device coordinates, the oracle projects directly: a surfel within an ulp of a pixel boundary may land next door."""
+    s, pose, cam = _scene(W, H, kind, 1)
+    s = s.copy()
+    s[::7, 5] = 3.0                                        # sub-map 3 is not active: culled by the key-frame mask
+    ak = np.zeros(19200, np.float32); ak[0] = 1.0
+    a = orc.predictIndices(pose, s, cam, W, H, maxDepth=2.5, active_kf=ak)      # a depth cut-off inside the scene
+    b = rg.predictIndices(pose, s, cam, W, H, maxDepth=2.5, active_kf=ak)
+    same = a["index"] == b["index"]
+    assert (a["index"] > 0).mean() > 0.5 and same.mean() >= 0.9999
+    assert np.array_equal(a["index"] > 0, b["index"] > 0) or np.mean((a["index"] > 0) != (b["index"] > 0)) < 1e-4
+    assert not np.isin(a["index"][a["index"] > 0], np.arange(0, len(s), 7)).any()            # none of the culled sub-map
+    for k in ("colorTime", "curvMax", "curvMin"):
+        assert np.array_equal(a[k][same], b[k][same]), k
+    for k in ("vertConf", "normRad"):
+        assert np.abs(a[k] - b[k])[same].max() <= 1e-6, k
