@@ -36,6 +36,9 @@ SHADERS = {
     "fill_curvature": "fill_curvature.frag",
     "fill_rgb": "fill_rgb.frag",
     "index_map": "index_map.vert",
+    "data_vert": "data.vert",
+    "update_vert": "update.vert",
+    "copy_unstable": "copy_unstable.vert",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 

@@ -228,6 +228,8 @@ void orc_metriciseDepth(const orc_prep_params* p, const unsigned short* raw, con
 /* geometry.glsl:190-244 (getNormalPCA, window 3) at pixel (px,py); surfels.glsl:19-34, 37-46 */
 /* 0 (default): intended integer windows; 1: the shaders' literal float-counter window loops (see orc_prep.c) */
 void orc_set_float_loops(int on);
+int orc_get_float_loops(void);
+void orc_set_uv_vbo_coords(int on);      /* per thread; used by orc_model_fuse around its PCA normal (literal mode only) */
 void orc_getNormalPCA(const orc_prep_params* p, const float* depth, int px, int py, float vz, float n[3]);
 float orc_getRadius(float icx, float icy, float depth, float norm_z);
 float orc_confidence(float cx, float cy, float x, float y, float max_dist, float w);

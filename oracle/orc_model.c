@@ -113,7 +113,7 @@ static int fuse_pixel(const orc_model_params* p, const orc_prep_params* pp, cons
     const float* k2 = curv2 + 4 * o;
     if (!(px % 2 == time % 2 && py % 2 == time % 2)) return 0;
     float n[3] = { 0, 0, 0 };
-    if (p->pca) orc_getNormalPCA(pp, depthFiltered, px, py, zf, n);
+    if (p->pca) { orc_set_uv_vbo_coords(1); orc_getNormalPCA(pp, depthFiltered, px, py, zf, n); orc_set_uv_vbo_coords(0); }
     const float nlen = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
     if (!(nlen > 0.8f && vloc[2] > 0.3f && vloc[2] <= p->maxDepth && k1[3] > -300.0f && k1[3] < 300.0f && k2[3] > -300.0f && k2[3] < 300.0f)) return 0;
 

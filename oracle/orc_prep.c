@@ -162,6 +162,11 @@ static void compute_roots(float m[3][3], float r[3])
  * reference's own shader text compiled for the CPU; the same test measures what the idealisation changes. */
 static int g_float_loops = 0;
 void orc_set_float_loops(int on) { g_float_loops = on; }
+int orc_get_float_loops(void) { return g_float_loops; }
+/* literal mode, which texcoord a pass sees for pixel p: a full-screen fragment pass gets (p + 0.5) / n; the vertex pass of
+ * GlobalModel::fuse reads it from the uv VBO, built as float(p) / n + 1.0 / (2 * n) with the sum in double (GlobalModel.cpp:87-96) */
+static _Thread_local int t_uv_vbo_coords = 0;
+void orc_set_uv_vbo_coords(int on) { t_uv_vbo_coords = on; }
 static int texel_of(float u, int n)      /* GL_NEAREST with 8 fractional bits of fixed point, see oracle/glsl_cpu.h texel() */
 {
     const float fixed = floorf(u * (float)n * 256.0f + 0.5f);
@@ -171,7 +176,8 @@ static int texel_of(float u, int n)      /* GL_NEAREST with 8 fractional bits of
 /* one axis of the window of pixel p: texel index and the float coordinate i * n of every visited sample; returns their number */
 static int float_window(int p, int n, float win, int* texels, float* coords)
 {
-    const float step = 1.0f / (float)n, tc = ((float)p + 0.5f) / (float)n;
+    const float step = 1.0f / (float)n;
+    const float tc = t_uv_vbo_coords ? (float)((double)((float)p / (float)n) + 1.0 / (double)(2 * (float)n)) : ((float)p + 0.5f) / (float)n;
     float lo = tc - step * win, hi = tc + step * win;
     if (lo < 0.0f) lo = 0.0f;
     if (hi > 1.0f) hi = 1.0f;

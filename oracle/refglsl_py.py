@@ -147,3 +147,50 @@ def predictIndices(pose, surfels, cam, width, height, maxDepth=20.0, active_kf=N
                          width, height, C.c_float(maxDepth), _p(active_kf), len(active_kf),
                          _p(out["index"], C.c_uint), _p(out["vertConf"]), _p(out["colorTime"]), _p(out["normRad"]), _p(out["curvMax"]), _p(out["curvMin"]))
     return out
+
+
+def modelFuse(mp, pose, time, rgb, frame, confidence, idx, indexSubmap, surfels):
+    """GlobalModel::fuse through the reference's own shaders: data.vert per pixel (association + candidate record), the scatter of the
+    merge candidates into the update textures (fixed function: GL_LESS at constant depth = the first fragment of a texel wins;
+    restated here), update.vert per surfel (merge).  Arguments and result as orc_py.modelFuse: (surfels after fuse, recorded vertices)."""
+    H, W = mp.rows, mp.cols
+    surfels = np.ascontiguousarray(surfels, np.float32).reshape(-1, 20)
+    count = surfels.shape[0]
+    tex = max(64, int(np.ceil(np.sqrt(count + 1))))
+    tex += tex % 2
+    rec = np.zeros((W * H, 20), np.float32)
+    uid, best = np.zeros(W * H, np.int32), np.zeros(W * H, np.uint32)
+    rgbf = np.ascontiguousarray(rgb, np.uint8).astype(np.float32) / np.float32(255.0)
+    n = lib().glsl_data_vert(W, H, _p(_f(rgbf)), _p(_f(frame["metric"])), _p(_f(frame["metric_filtered"])), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])),
+                             _p(_f(confidence)), _p(np.ascontiguousarray(idx["index"], np.uint32), C.c_uint), _p(_f(idx["vertConf"])), _p(_f(idx["colorTime"])),
+                             _p(_f(idx["normRad"])), C.c_float(mp.cx), C.c_float(mp.cy), C.c_float(mp.fx), C.c_float(mp.fy), _p(_f(pose)), C.c_float(mp.maxDepth),
+                             C.c_float(time), C.c_float(indexSubmap), C.c_float(mp.radiusMultiplier), C.c_float(mp.pca), C.c_float(tex),
+                             _p(rec), _p(uid, C.c_int), _p(best, C.c_uint))
+    rec, uid, best = rec[:n], uid[:n], best[:n]
+    # data.frag writes a merge candidate's record at its surfel's texel; all fragments have the same depth, GL_LESS keeps the first
+    upd = np.zeros((5, tex * tex, 4), np.float32)
+    cand = np.flatnonzero(uid == 1)
+    _, first = np.unique(best[cand], return_index=True)
+    win = cand[first]
+    for k in range(5):
+        upd[k, best[win]] = rec[win, 4 * k:4 * k + 4]
+    out = np.zeros((max(count, 1), 20), np.float32)
+    if count:
+        lib().glsl_update_vert(count, _p(surfels), tex, _p(upd[0]), _p(upd[1]), _p(upd[2]), _p(upd[3]), _p(upd[4]), int(time), _p(out))
+    return out[:count].copy(), rec.copy()
+
+
+def modelClean(mp, pose, time, idx, surfels, unstable, active_kf=None):
+    """GlobalModel::clean through Shaders/copy_unstable.vert / .geom: the model's surfels, then the vertices fuse recorded; as orc_py.modelClean"""
+    if active_kf is None:
+        active_kf = np.zeros(19200, np.float32)
+        active_kf[0] = 1.0
+    active_kf = _f(active_kf)
+    verts = np.ascontiguousarray(np.concatenate([np.asarray(surfels, np.float32).reshape(-1, 20), np.asarray(unstable, np.float32).reshape(-1, 20)]))
+    out = np.zeros((verts.shape[0] + 1, 20), np.float32)
+    pinv = np.linalg.inv(np.asarray(pose, np.float64)).astype(np.float32)
+    n = lib().glsl_copy_unstable(verts.shape[0], _p(verts), mp.cols, mp.rows, _p(np.ascontiguousarray(idx["index"], np.uint32), C.c_uint), _p(_f(idx["vertConf"])),
+                                 _p(_f(idx["colorTime"])), _p(_f(idx["normRad"])), _p(_f(pose)), _p(_f(pinv)), C.c_float(mp.cx), C.c_float(mp.cy),
+                                 C.c_float(mp.fx), C.c_float(mp.fy), int(time), C.c_float(mp.confThreshold), C.c_float(mp.cleanWindow), C.c_float(mp.curvThr),
+                                 C.c_float(mp.maxDepth), _p(active_kf), len(active_kf), _p(out))
+    return out[:n].copy()

@@ -171,3 +171,40 @@ def test_predict_indices_oracle_matches_reference_vertex_shader(orc, W, H, kind)
         assert np.array_equal(a[k][same], b[k][same]), k
     for k in ("vertConf", "normRad"):
         assert np.abs(a[k] - b[k])[same].max() <= 1e-6, k
+
+
+def test_fuse_and_clean_oracle_match_reference_vertex_shaders(orc, literal_windows):
+    """rows 8-9: GlobalModel::fuse = data.vert per pixel (association, candidate record) + the first-fragment-wins scatter into the
+    update textures (fixed function, restated in oracle/refglsl_py.py) + update.vert per surfel (merge); GlobalModel::clean =
+    copy_unstable.vert / .geom over the model and the recorded vertices.  On the state of the oracle pipeline after several
+    frames, with the literal window loops (the fuse pass recomputes the PCA normal): same merges, same new surfels, every
+    attribute bit-identical except the positions (the shader multiplies pose * vec4 column by column: 2 ulps), and clean
+    returns the identical surfel array."""
+    from oracle import orc_pipeline as op
+    W, H = 320, 240
+    cam = synth.default_camera(W, H)
+    sc = synth.Scene("room")
+    f = op.HRBFFusion(W, H, cam, icpWeight=100.0, so3=False)
+    poses = synth.circle_trajectory(8, frames_per_rev=120)
+    for i, p in enumerate(poses[:6]):
+        depth, rgb = synth.render_depth(sc, p, W, H, cam, noise=True, seed=i)
+        f.processFrame(rgb, depth)
+    for t in (6, 7):                                            # both parities of the 1/4-pixel candidate pattern
+        depth, rgb = synth.render_depth(sc, poses[t], W, H, cam, noise=True, seed=t)
+        fr = orc.preprocess(f.pp, depth)
+        conf = orc.vertexConfidence(f.pp, fr["gradient_mag"], 1.0)
+        pose, tick, s0 = f.currPose.copy(), f.tick + (t - 6), f.surfels.copy()
+        idx = orc.predictIndices(pose, s0, cam, W, H, f.maxDepthProcessed)
+        a_s, a_u = orc.modelFuse(f.mp, pose, tick, rgb, fr, conf, idx, 0, s0)
+        b_s, b_u = rg.modelFuse(f.mp, pose, tick, rgb, fr, conf, idx, 0, s0)
+        assert a_u.shape == b_u.shape and (a_u[:, 7] == -1).sum() > 1000 and (a_u[:, 7] == -2).sum() > 0
+        assert np.array_equal(a_u[:, 3:], b_u[:, 3:], equal_nan=True)           # confidence, colour, sub-map, times, normal, radius, curvatures
+        assert np.abs(a_u[:, :3] - b_u[:, :3]).max() <= 1e-6
+        assert (a_s != s0).any(1).sum() > 1000                                   # surfels were merged
+        assert np.array_equal(a_s[:, 3:], b_s[:, 3:], equal_nan=True)
+        assert np.abs(a_s[:, :3] - b_s[:, :3]).max() <= 1e-6
+        idx2 = orc.predictIndices(pose, a_s, cam, W, H, f.maxDepthProcessed)
+        a_c = orc.modelClean(f.mp, pose, tick, idx2, a_s, a_u)
+        b_c = rg.modelClean(f.mp, pose, tick, idx2, a_s, a_u)
+        assert len(a_c) < len(a_s) + len(a_u)                                    # something was dropped (the merged markers at least)
+        assert a_c.shape == b_c.shape and np.array_equal(a_c, b_c, equal_nan=True)
