@@ -39,6 +39,7 @@ SHADERS = {
     "data_vert": "data.vert",
     "update_vert": "update.vert",
     "copy_unstable": "copy_unstable.vert",
+    "init_unstable": "init_unstableTex.vert",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 

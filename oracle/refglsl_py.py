@@ -194,3 +194,14 @@ def modelClean(mp, pose, time, idx, surfels, unstable, active_kf=None):
                                  C.c_float(mp.fx), C.c_float(mp.fy), int(time), C.c_float(mp.confThreshold), C.c_float(mp.cleanWindow), C.c_float(mp.curvThr),
                                  C.c_float(mp.maxDepth), _p(active_kf), len(active_kf), _p(out))
     return out[:n].copy()
+
+
+def modelInitialise(mp, pose, frame, rgb, useConfEval=0, epsilon=1000.0):
+    """GlobalModel::initialise through Shaders/init_unstableTex.vert / .geom; as orc_py.modelInitialise"""
+    H, W = mp.rows, mp.cols
+    out = np.zeros((W * H, 20), np.float32)
+    rgbf = np.ascontiguousarray(rgb, np.uint8).astype(np.float32) / np.float32(255.0)
+    n = lib().glsl_init_unstable(W, H, _p(_f(frame["vertex_raw"])), _p(_f(frame["normal"])), _p(_f(rgbf)), _p(_f(frame["curv1"])), _p(_f(frame["curv2"])),
+                                 _p(_f(frame["gradient_mag"])), C.c_float(mp.cx), C.c_float(mp.cy), C.c_float(mp.fx), C.c_float(mp.fy), _p(_f(pose)),
+                                 C.c_float(mp.curvThr), C.c_float(useConfEval), C.c_float(epsilon), _p(out))
+    return out[:n].copy()

@@ -208,3 +208,20 @@ def test_fuse_and_clean_oracle_match_reference_vertex_shaders(orc, literal_windo
         b_c = rg.modelClean(f.mp, pose, tick, idx2, a_s, a_u)
         assert len(a_c) < len(a_s) + len(a_u)                                    # something was dropped (the merged markers at least)
         assert a_c.shape == b_c.shape and np.array_equal(a_c, b_c, equal_nan=True)
+
+
+@pytest.mark.parametrize("useConfEval", [0, 1])
+def test_model_initialise_oracle_matches_reference_vertex_shader(orc, useConfEval):
+    """GlobalModel::initialise = init_unstableTex.vert / .geom per pixel: same surfels in the same order, every attribute
+    bit-identical except the confidence (an exp: fp32 round-off)."""
+    W, H = 320, 240
+    cam, depth, rgb = _frame(W, H, "room", seed=0)
+    pp, mp = orc.prep_params(cam, W, H), orc.model_params(cam, W, H)
+    fr = orc.preprocess(pp, depth)
+    pose = synth.make_pose(0.02, -0.03, 0.01, (0.05, -0.02, 0.0))
+    a = orc.modelInitialise(mp, pose, fr, rgb, useConfEval, 1000.0)
+    b = rg.modelInitialise(mp, pose, fr, rgb, useConfEval, 1000.0)
+    assert a.shape == b.shape and a.shape[0] > 0.5 * W * H
+    cols = [c for c in range(20) if c != 3]
+    assert np.array_equal(a[:, cols], b[:, cols], equal_nan=True)
+    np.testing.assert_allclose(b[:, 3], a[:, 3], rtol=1e-6, atol=1e-9)
