@@ -14,10 +14,21 @@
  *     the reference's OWN CUDA kernels (Core/src/Cuda/reduce.cu compiled
  *     unmodified into oracle/_ref/, run on a B200; golden vectors in
  *     tests/golden/ref_reduce.npz, generator oracle/gen_ref_golden.py).
- *   rows 4-10 (host GN loop, pyramid prep, GLSL passes): the reference holds no
- *     golden vectors, no tests, and its GL/Eigen/Pangolin path cannot be built
- *     here -> "parity unpinned" for those rows; the oracle's own outputs on the
- *     GPUTest pair are committed as the golden vectors (tests/golden/).
+ *   rows 6-10, GlobalModel::initialise, FillIn, VertexConfidence (the GLSL passes):
+ *     pinned against the reference's OWN SHADER TEXT, compiled for the CPU
+ *     (oracle/build_ref_glsl.py + glsl_cpu.h -> oracle/_ref/libref_glsl.so) and run
+ *     per fragment / vertex on the same inputs: tests/test_oracle_vs_reference_glsl.py.
+ *     Bit-identical where the pass is not an exp / a root search, with the shaders'
+ *     float-counter window loops taken literally (orc_set_float_loops; the default
+ *     restates the intended integer windows -- DESIGN.md, stated deviation).
+ *     Fixed-function GL between the shaders (point rasterisation, depth test,
+ *     transform-feedback order, framebuffer formats) is restated, not executed.
+ *   row 5 (cudafuncs.cu map / pyramid kernels): the reference's kernels are built
+ *     (oracle/_ref/libref_cudafuncs.so, texture-reference shim) but have not run on a
+ *     GPU yet -> "parity unpinned" until tests/golden/ref_cudafuncs.npz exists.
+ *   row 4 (host Gauss-Newton loop, RGBDOdometry.cpp + Eigen ldlt): Eigen is not
+ *     installed and the class is inseparable from GL -> "parity unpinned"; the
+ *     oracle's own outputs on the reference's GPUTest pair are the golden vectors.
  *
  * Layouts (identical to the reference so buffers are interchangeable):
  *   SoA map    : float[4*rows][cols], planes x,y,z,w stacked row-wise
