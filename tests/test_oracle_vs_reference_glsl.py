@@ -225,3 +225,71 @@ def test_model_initialise_oracle_matches_reference_vertex_shader(orc, useConfEva
     cols = [c for c in range(20) if c != 3]
     assert np.array_equal(a[:, cols], b[:, cols], equal_nan=True)
     np.testing.assert_allclose(b[:, 3], a[:, 3], rtol=1e-6, atol=1e-9)
+
+
+class _ShaderOrc:
+    """oracle/orc_py with every GLSL pass replaced by the reference's own shader (the tracker, rows 1-5, stays the oracle's)"""
+
+    def __init__(self, orc):
+        self._orc, self._metric = orc, None
+
+    def __getattr__(self, k):
+        return getattr(self._orc, k)
+
+    def preprocess(self, pp, depth):
+        fr = rg.preprocess(pp, depth)
+        self._metric = fr["metric"]
+        return fr
+
+    def vertexConfidence(self, pp, gm, weighting, useConfEval=0, epsilon=1000.0):
+        return rg.vertexConfidence(pp, gm, self._metric, weighting, useConfEval, epsilon)
+
+    modelInitialise = staticmethod(rg.modelInitialise)
+    predictIndices = staticmethod(rg.predictIndices)
+    modelFuse = staticmethod(rg.modelFuse)
+    modelClean = staticmethod(rg.modelClean)
+    predictHRBF = staticmethod(rg.predictHRBF)
+    fillIn = staticmethod(rg.fillIn)
+
+
+def _run_pipeline(orc, mode, n, W=320, H=240, **kw):
+    from oracle import orc_pipeline as op
+    cam = synth.default_camera(W, H)
+    sc = synth.Scene("room")
+    saved = op.orc
+    try:
+        if mode == "shader":
+            op.orc = _ShaderOrc(orc)
+        orc.lib().orc_set_float_loops(1 if mode == "literal" else 0)
+        f = op.HRBFFusion(W, H, cam, **kw)
+        poses = []
+        for i, p in enumerate(synth.circle_trajectory(n, frames_per_rev=120)):
+            depth, rgb = synth.render_depth(sc, p, W, H, cam, noise=True, seed=i)
+            poses.append(f.processFrame(rgb, depth).copy())
+        return poses, f.surfels.shape[0]
+    finally:
+        op.orc = saved
+        orc.lib().orc_set_float_loops(0)
+
+
+def test_frame_loop_driven_by_reference_shaders_tracks_like_the_oracle(orc):
+    """The whole per-frame loop (HRBFFusion::processFrame) with every GLSL pass executed by the reference's own shader text and only
+    the tracker taken from the oracle, against the oracle pipeline, free-running over 6 frames (ICP-only: the configuration the
+    north-star tolerance is asserted on).  Two comparisons:
+      literal-window oracle vs shader loop: every pass is bit-identical or within fp32 round-off on equal inputs, what is left is
+        how the tracker amplifies that round-off (5e-7 relative in the filtered depth -> ~5e-5 in the pose at 320x240);
+      intended-window oracle (the default, what the CUDA kernels implement) vs literal: the stated deviation, in pose units."""
+    from tests.util import pose_err
+    kw = dict(icpWeight=100.0, so3=False)
+    n = 6
+    lit, n_lit = _run_pipeline(orc, "literal", n, **kw)
+    sha, n_sha = _run_pipeline(orc, "shader", n, **kw)
+    ide, n_ide = _run_pipeline(orc, "intended", n, **kw)
+    assert abs(n_lit - n_sha) <= max(5, int(1e-3 * n_lit)) and abs(n_ide - n_lit) <= max(5, int(3e-3 * n_lit))
+    worst_shader = worst_dev = 0.0
+    for i in range(1, n):
+        worst_shader = max(worst_shader, *pose_err(lit[i][:3, :3], lit[i][:3, 3], sha[i][:3, :3], sha[i][:3, 3]))
+        worst_dev = max(worst_dev, *pose_err(ide[i][:3, :3], ide[i][:3, 3], lit[i][:3, :3], lit[i][:3, 3]))
+    print(f"pose after {n} free-running frames: literal oracle vs shader loop {worst_shader:.2e}; intended vs literal windows {worst_dev:.2e}")
+    assert worst_shader <= 3e-4          # measured 7e-5
+    assert worst_dev <= 3e-3             # measured 9e-4: the price of the intended-window restatement (DESIGN.md)
