@@ -16,9 +16,10 @@ pytestmark = pytest.mark.skipif(not rg.available(), reason="oracle/_ref/libref_g
 
 
 def _scene(W, H, kind, stride):
-    """a confident map seen from a nearby pose (the helper of tests/test_gpu_indexmap.py, without the GPU)"""
-    from tests.test_gpu_indexmap import _scene as f
-    return f(W, H, kind, stride)
+    """a confident map seen from a nearby pose (the same construction as tests/test_gpu_indexmap.py)"""
+    from tests.util import pair
+    m0, pose0, m1, pose1, cam = pair(W, H, kind=kind)
+    return synth.surfels_from_maps(m0, pose0, stride=stride), pose1, cam
 
 
 @pytest.mark.parametrize("W,H,kind,stride,kw", [
