@@ -472,6 +472,41 @@ int hrbf_model_last_count(hrbf_model* m, unsigned int* count, void* stream)
     m->bound = *count;          // exact again
     return HRBF_OK;
 }
+// The window a shader's FLOAT-counter loop really visits along one axis (geometry.glsl:198-212, depth_curvature_gradient.frag:62-75):
+//     for (float i = tx_min; i <= tx_max; i += 1 / n)     tx_min/max = clamp(texcoord -/+ win / n, 0, 1)
+// For every pixel p of an axis of n texels: the first texel, the number of samples and each sample's coordinate i * n, evaluated
+// with the shader's own fp32 expressions (the accumulated counter overshoots tx_max for ~40 % of the pixels: 6 samples, not 7).
+// uv_vbo_coords: 0 = the texcoord of a full-screen fragment pass, (p + 0.5) / n; 1 = the uv VBO of GlobalModel::fuse
+// (GlobalModel.cpp:87-96), float(p) / n + 1.0 / (2 n) summed in double.  Texel selection: GL_NEAREST on a coordinate held with 8
+// fractional bits.  Host code; it builds the tables of the literal-window kernels and is tested against the
+// oracle's literal loops on the CPU.
+int hrbf_window_table(int n, float win, int uv_vbo_coords, int* first, int* count, float* coords /* [n][HRBF_WINDOW_MAX] */)
+{
+    HRBF_CHECK_ARG(n > 0 && win >= 0.f && win <= 3.5f && first && count && coords);
+    const float fn = (float)n, step = 1.0f / fn;
+    for (int p = 0; p < n; ++p) {
+        volatile float tc = uv_vbo_coords ? (float)((double)((float)p / fn) + 1.0 / (double)(2 * fn)) : ((float)p + 0.5f) / fn;
+        volatile float sw = step * win;                       // volatile: every intermediate is rounded to fp32, no contraction
+        volatile float lo = tc - sw, hi = tc + sw;
+        if (lo < 0.0f) lo = 0.0f;
+        if (hi > 1.0f) hi = 1.0f;
+        int k = 0;
+        first[p] = 0;
+        for (volatile float i = lo; i <= hi && k < HRBF_WINDOW_MAX; i = i + step) {
+            volatile float scaled = i * fn;
+            volatile float fixed = floorf(scaled * 256.0f + 0.5f);
+            int t = (int)floorf(fixed / 256.0f);
+            t = t < 0 ? 0 : (t >= n ? n - 1 : t);
+            if (k == 0) first[p] = t;
+            else if (t != first[p] + k) { set_error("window_table: samples of pixel %d are not consecutive texels", p); return HRBF_ERR_INVALID_ARG; }
+            coords[(size_t)p * HRBF_WINDOW_MAX + k] = scaled;
+            ++k;
+        }
+        count[p] = k;
+        for (int q = k; q < HRBF_WINDOW_MAX; ++q) coords[(size_t)p * HRBF_WINDOW_MAX + q] = 0.0f;
+    }
+    return HRBF_OK;
+}
 // GlobalModel::downloadMap (GlobalModel.cpp:775-804): the current surfel array to the host, count records of 20 floats
 int hrbf_model_download_map(hrbf_model* m, float* surfels_host, unsigned int max_count, unsigned int* count_out, void* stream)
 {

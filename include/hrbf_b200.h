@@ -356,6 +356,11 @@ const unsigned int* hrbf_model_count_dev(hrbf_model*);
 int hrbf_model_last_count(hrbf_model*, unsigned int* count_host, void* stream);
 /* 1 if a compaction ever ran out of capacity (survivors beyond it were dropped) */
 int hrbf_model_overflowed(hrbf_model*, int* flag_host, void* stream);
+/* The samples a shader's float-counter window loop visits along one axis of n texels (geometry.glsl:198-212,
+ * depth_curvature_gradient.frag:62-75; win = 3): per pixel the first texel, the sample count (6 or 7 in the interior) and the
+ * coordinates i * n.  uv_vbo_coords = 1: the texcoords of GlobalModel::fuse's uv VBO (GlobalModel.cpp:87-96).  Host code. */
+#define HRBF_WINDOW_MAX 8
+int hrbf_window_table(int n, float win, int uv_vbo_coords, int* first_host, int* count_host, float* coords_host /* [n][HRBF_WINDOW_MAX] */);
 /* GlobalModel::downloadMap, GlobalModel.cpp:775-804: the surfel array (count x 20 floats) to surfels_host.
  * max_count = capacity of surfels_host in surfels; 0 = size query (only *count_out is written). */
 int hrbf_model_download_map(hrbf_model*, float* surfels_host, unsigned int max_count, unsigned int* count_out, void* stream);

@@ -186,6 +186,16 @@ static int float_window(int p, int n, float win, int* texels, float* coords)
     return k;
 }
 
+/* test hook: the literal window of pixel p along an axis of n texels (uv != 0: uv-VBO texcoords) */
+int orc_float_window(int p, int n, float win, int uv, int* texels, float* coords)
+{
+    const int saved = t_uv_vbo_coords;
+    t_uv_vbo_coords = uv;
+    const int k = float_window(p, n, win, texels, coords);
+    t_uv_vbo_coords = saved;
+    return k;
+}
+
 /* geometry.glsl:190-244 getNormalPCA(vPosition (z only), texCoord of pixel (px,py), win = 3, depth map) */
 void orc_getNormalPCA(const orc_prep_params* p, const float* depth, int px, int py, float vz, float n[3])
 {

@@ -96,3 +96,30 @@ def test_compat_header_compiles_against_reference_headers(tmp_path):
     # DeviceMemory's own members (create/release) live in the reference's device_memory.cpp: allow only those to be undefined
     undefined = [l for l in r.stderr.splitlines() if "undefined reference" in l and "DeviceMemory" not in l and "DeviceArray" not in l]
     assert not undefined, "\n".join(undefined)
+
+
+def test_window_table_matches_the_oracles_literal_loops(orc):
+    """hrbf_window_table (host code of the library: the table the literal-window kernels will read) against the float-counter
+    loops as the oracle runs them in literal mode, for every pixel of every axis length the BASELINE configs use."""
+    import numpy as np
+    from hrbffusion3d_b200 import lib
+    L = lib()
+    short = 0
+    for n in (120, 160, 240, 320, 480, 640, 960, 1280):
+        for win in (3.0, 2.0):
+            for uv in (0, 1):
+                first, count = np.zeros(n, np.int32), np.zeros(n, np.int32)
+                coords = np.zeros((n, 8), np.float32)
+                assert L.hrbf_window_table(n, C.c_float(win), uv, first.ctypes.data_as(C.POINTER(C.c_int)), count.ctypes.data_as(C.POINTER(C.c_int)),
+                                           coords.ctypes.data_as(C.POINTER(C.c_float))) == 0
+                tex, co = np.zeros(16, np.int32), np.zeros(16, np.float32)
+                for p in range(n):
+                    k = orc.lib().orc_float_window(p, n, C.c_float(win), uv, tex.ctypes.data_as(C.POINTER(C.c_int)), co.ctypes.data_as(C.POINTER(C.c_float)))
+                    assert k == count[p] and first[p] == tex[0], (n, win, uv, p)
+                    assert np.array_equal(tex[:k], first[p] + np.arange(k)) and np.array_equal(co[:k], coords[p, :k]), (n, win, uv, p)
+                interior = count[int(win) + 1:n - int(win) - 1]
+                assert set(np.unique(interior)) <= {2 * int(win), 2 * int(win) + 1}
+                short += int((interior == 2 * int(win)).sum())
+    assert short > 0          # the effect exists: some interior windows lose their last sample
+    bad = np.zeros(4, np.int32)
+    assert L.hrbf_window_table(0, C.c_float(3.0), 0, bad.ctypes.data_as(C.POINTER(C.c_int)), bad.ctypes.data_as(C.POINTER(C.c_int)), None) != 0
