@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
     float3 n = make_float3(0.f, 0.f, 0.f);
     if (m.pca) {
         if (f.normal_pca != nullptr) { const float4 t = __ldg(f.normal_pca + o); n = make_float3(t.x, t.y, t.z); }
-        else n = normal_pca(pa, [&](int qx, int qy) { return __ldg(f.depthFiltered + (size_t)qy * W + qx); }, px, py, zf);
+        else n = normal_pca(pa, [&](int qx, int qy) { return __ldg(f.depthFiltered + (size_t)qy * W + qx); }, px, py, zf, /* uv-VBO texcoords */ 1);
     }
     const float nlen = norm(n);
     if (!(nlen > 0.8f)) return;

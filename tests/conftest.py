@@ -12,10 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def default_float_loops():
+    """HRBF_LITERAL=1 (development): the oracle runs the shaders' literal float-counter window loops for the
+    whole session -- to be used together with HRBF_B200_LIB=build/libhrbf_literal.so (scripts/run_literal_variant.sh)"""
+    return 1 if os.environ.get("HRBF_LITERAL") == "1" else 0
+
+
 @pytest.fixture(scope="session")
 def orc():
     from oracle import orc_py
-    orc_py.lib()
+    orc_py.lib().orc_set_float_loops(default_float_loops())
     return orc_py
 
 

@@ -66,9 +66,10 @@ def _identical(x, y):
 @pytest.fixture
 def literal_windows(orc):
     """the oracle with the shaders' literal float-counter window loops (orc_set_float_loops, oracle/orc_prep.c)"""
+    from tests.conftest import default_float_loops
     orc.lib().orc_set_float_loops(1)
     yield
-    orc.lib().orc_set_float_loops(0)
+    orc.lib().orc_set_float_loops(default_float_loops())
 
 
 @pytest.mark.parametrize("W,H,kind", [(160, 120, "room"), (320, 240, "plane"), (640, 480, "room")])
@@ -109,7 +110,8 @@ def test_intended_vs_literal_windows_deviation_is_bounded(orc):
     try:
         lit = orc.preprocess(pp, depth)
     finally:
-        orc.lib().orc_set_float_loops(0)
+        from tests.conftest import default_float_loops
+        orc.lib().orc_set_float_loops(default_float_loops())
     for k in ("filtered", "metric", "metric_filtered", "vertex_raw", "vertex_filtered"):          # no window loops of that kind there
         assert np.array_equal(ideal[k], lit[k]), k
     n0, n1 = ideal["normal_pca"][..., :3], lit["normal_pca"][..., :3]
@@ -269,8 +271,9 @@ def _run_pipeline(orc, mode, n, W=320, H=240, **kw):
             poses.append(f.processFrame(rgb, depth).copy())
         return poses, f.surfels.shape[0]
     finally:
+        from tests.conftest import default_float_loops
         op.orc = saved
-        orc.lib().orc_set_float_loops(0)
+        orc.lib().orc_set_float_loops(default_float_loops())
 
 
 def test_frame_loop_driven_by_reference_shaders_tracks_like_the_oracle(orc):
