@@ -27,8 +27,11 @@
  *     (oracle/_ref/libref_cudafuncs.so, texture-reference shim) but have not run on a
  *     GPU yet -> "parity unpinned" until tests/golden/ref_cudafuncs.npz exists.
  *   row 4 (host Gauss-Newton loop, RGBDOdometry.cpp + Eigen ldlt): Eigen is not
- *     installed and the class is inseparable from GL -> "parity unpinned"; the
- *     oracle's own outputs on the reference's GPUTest pair are the golden vectors.
+ *     installed and the class is inseparable from GL -> "parity unpinned", except the
+ *     pose update (OdometryProvider.h rodrigues / computeUpdateSE3), which is pinned to
+ *     the reference's own header compiled against oracle/eigen_mini
+ *     (tests/test_oracle_vs_reference_host.py, bit-identical); the oracle's own outputs
+ *     on the reference's GPUTest pair are the golden vectors.
  *
  * Layouts (identical to the reference so buffers are interchangeable):
  *   SoA map    : float[4*rows][cols], planes x,y,z,w stacked row-wise
@@ -168,6 +171,7 @@ const float* orc_odom_depth(const orc_odom*, int which, int level);         /* 0
 /* Utils/OdometryProvider.h:35-93 and the fp64 6x6 / fp32 3x3 LDLT standing in for Eigen's ldlt() */
 void orc_rodrigues(const double w[3], double R[9]);
 void orc_ldlt_solve6(const double A[36], const double b[6], double x[6]);
+void orc_computeUpdateSE3(double resultRt[16], const double result[6], float iso16[16]);   /* OdometryProvider.h:71-93 */
 void orc_ldlt_solve3f(const float A[9], const float b[3], float x[3]);
 
 /* ---------------------------------------------------------- rows 6-7 -- */

@@ -704,6 +704,23 @@ static void ldlt_solve_n(int n, const double* Ain, const double* bin, double* x)
 
 void orc_ldlt_solve6(const double A[36], const double b[6], double x[6]) { ldlt_solve_n(6, A, b, x); }
 
+/* OdometryProvider.h:71-93 computeUpdateSE3: resultRt (row-major 4x4, in/out) = [rodrigues(omega) | t; 0 1] * resultRt with
+ * xi = (t, omega); rgbOdom (iso16, row-major) = the float cast of its rotation and translation */
+void orc_computeUpdateSE3(double resultRt[16], const double result[6], float iso16[16])
+{
+    double Rupd[9], Rt[16] = { 0 }, nrt[16];
+    orc_rodrigues(result + 3, Rupd);
+    for (int a = 0; a < 3; ++a) { for (int b2 = 0; b2 < 3; ++b2) Rt[a * 4 + b2] = Rupd[a * 3 + b2]; Rt[a * 4 + 3] = result[a]; }
+    Rt[15] = 1;
+    for (int a = 0; a < 4; ++a) for (int b2 = 0; b2 < 4; ++b2) {
+        double s = 0; for (int k = 0; k < 4; ++k) s += Rt[a * 4 + k] * resultRt[k * 4 + b2];
+        nrt[a * 4 + b2] = s;
+    }
+    memcpy(resultRt, nrt, sizeof nrt);
+    for (int k = 0; k < 16; ++k) iso16[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    for (int a = 0; a < 3; ++a) { for (int b2 = 0; b2 < 3; ++b2) iso16[a * 4 + b2] = (float)resultRt[a * 4 + b2]; iso16[a * 4 + 3] = (float)resultRt[a * 4 + 3]; }
+}
+
 /* RGBDOdometry.cpp:900 : the 3x3 SO3 system is solved in float by Eigen; the
  * oracle solves the float-valued system in double and rounds (differences are
  * below float epsilon on a well-conditioned 3x3). */
@@ -1038,21 +1055,14 @@ void orc_odom_getIncrementalTransformation(orc_odom* o, float trans[3], float ro
             orc_ldlt_solve6(lastA, lastb, result);
             memcpy(st->lastA, lastA, sizeof lastA); memcpy(st->lastb, lastb, sizeof lastb);
 
-            /* OdometryProvider.h:71-93 : resultRt = exp(xi) * resultRt */
-            double Rupd[9], Rt[16] = { 0 }, nrt[16];
-            orc_rodrigues(result + 3, Rupd);
-            for (int a = 0; a < 3; ++a) { for (int b2 = 0; b2 < 3; ++b2) Rt[a * 4 + b2] = Rupd[a * 3 + b2]; Rt[a * 4 + 3] = result[a]; }
-            Rt[15] = 1;
-            for (int a = 0; a < 4; ++a) for (int b2 = 0; b2 < 4; ++b2) {
-                double s = 0; for (int k = 0; k < 4; ++k) s += Rt[a * 4 + k] * resultRt[k * 4 + b2];
-                nrt[a * 4 + b2] = s;
-            }
-            memcpy(resultRt, nrt, sizeof nrt);
+            /* OdometryProvider.h:71-93 : resultRt = exp(xi) * resultRt, rgbOdom = float(resultRt) */
+            float iso[16];
+            orc_computeUpdateSE3(resultRt, result, iso);
 
             /* :1196-1204 : currentT = [Rprev|tprev] * rgbOdom^-1, all in float; an
              * Isometry3f inverse is the transpose of the float-cast rotation */
             float Rf[9], tf[3];
-            for (int a = 0; a < 3; ++a) { for (int b2 = 0; b2 < 3; ++b2) Rf[a * 3 + b2] = (float)resultRt[a * 4 + b2]; tf[a] = (float)resultRt[a * 4 + 3]; }
+            for (int a = 0; a < 3; ++a) { for (int b2 = 0; b2 < 3; ++b2) Rf[a * 3 + b2] = iso[a * 4 + b2]; tf[a] = iso[a * 4 + 3]; }
             float ti[3];
             for (int a = 0; a < 3; ++a) ti[a] = -(Rf[0 * 3 + a] * tf[0] + Rf[1 * 3 + a] * tf[1] + Rf[2 * 3 + a] * tf[2]);
             for (int a = 0; a < 3; ++a) {
