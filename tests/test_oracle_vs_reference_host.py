@@ -50,3 +50,37 @@ def test_compute_update_se3_matches_reference_header(orc):
     R = Ra.reshape(4, 4)[:3, :3]
     np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-14)
     assert np.array_equal(ia.reshape(4, 4)[3], [0, 0, 0, 1])
+
+
+# ---- .klg wire format against the reference's own reader ---------------------------------------------------------
+KLG_PATH = os.path.join(ORACLE, "_ref", "libref_klg.so")
+KLG_W, KLG_H = 80, 60        # ONE size per process: the reference's Resolution singleton keeps the first size it is given
+
+
+@pytest.mark.skipif(not os.path.exists(KLG_PATH), reason="oracle/_ref/libref_klg.so not built and /root/reference absent")
+@pytest.mark.parametrize("compress", [True, False])
+def test_klg_written_here_is_read_by_the_reference_reader(tmp_path, compress):
+    """hrbffusion3d_b200.klg.write_klg -> GUI/src/Tools/RawLogReader.cpp (compiled unmodified): frame count, timestamps, zlib and raw depth,
+    raw RGB, and flipColors; and our KlgReader returns what the reference reader returns."""
+    from hrbffusion3d_b200 import klg
+    L = C.CDLL(KLG_PATH)
+    rng = np.random.default_rng(21)
+    n = 5
+    frames = [(33333 * i + 7, rng.integers(0, 9000, (KLG_H, KLG_W)).astype(np.uint16), rng.integers(0, 256, (KLG_H, KLG_W, 3)).astype(np.uint8)) for i in range(n)]
+    frames[2] = (frames[2][0], np.zeros((KLG_H, KLG_W), np.uint16), frames[2][2])      # an all-zero depth image compresses to a few bytes
+    path = tmp_path / "log.klg"
+    path.write_bytes(klg.write_klg(frames, KLG_W, KLG_H, compress_depth=compress))
+    assert L.refk_num_frames(str(path).encode(), KLG_W, KLG_H) == n
+    for flip in (0, 1):
+        ts = np.zeros(n + 2, np.int64)
+        depth = np.zeros((n + 2, KLG_H, KLG_W), np.uint16)
+        rgb = np.zeros((n + 2, KLG_H, KLG_W, 3), np.uint8)
+        got = L.refk_read_klg(str(path).encode(), KLG_W, KLG_H, flip, n + 2, ts.ctypes.data_as(C.POINTER(C.c_longlong)),
+                              depth.ctypes.data_as(C.POINTER(C.c_ushort)), rgb.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        assert got == n
+        ours = list(klg.KlgReader(str(path), KLG_W, KLG_H, flip_colors=bool(flip)))
+        assert len(ours) == n
+        for i, (t, d, c) in enumerate(frames):
+            assert ts[i] == t and np.array_equal(depth[i], d)
+            assert np.array_equal(rgb[i], c[..., ::-1] if flip else c)
+            assert ours[i][0] == ts[i] and np.array_equal(ours[i][1], depth[i]) and np.array_equal(ours[i][2], rgb[i])
