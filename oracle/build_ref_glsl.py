@@ -40,6 +40,7 @@ SHADERS = {
     "update_vert": "update.vert",
     "copy_unstable": "copy_unstable.vert",
     "init_unstable": "init_unstableTex.vert",
+    "resize": "resize.frag",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 

@@ -205,3 +205,14 @@ def modelInitialise(mp, pose, frame, rgb, useConfEval=0, epsilon=1000.0):
                                  _p(_f(frame["gradient_mag"])), C.c_float(mp.cx), C.c_float(mp.cy), C.c_float(mp.fx), C.c_float(mp.fy), _p(_f(pose)),
                                  C.c_float(mp.curvThr), C.c_float(useConfEval), C.c_float(epsilon), _p(out))
     return out[:n].copy()
+
+
+def denseEnough(vertex, thresh=0.75):
+    """Resize::vertex (resize.frag at 1/20 of the resolution) + HRBFFusion::denseEnough's count (HRBFFusion.cpp:974-987, host code restated:
+    sum of z > 0 over the sampled image, float(sum) / float(n) > thresh); as orc_py.denseEnough"""
+    H, W = vertex.shape[:2]
+    w, h = W // 20, H // 20
+    out = np.zeros((h, w, 4), np.float32)
+    lib().glsl_resize(W, H, _p(_f(vertex)), w, h, _p(out))
+    per = np.float32(int((out[..., 2] > 0).sum())) / np.float32(h * w)
+    return bool(per > np.float32(thresh)), out

@@ -297,3 +297,25 @@ def test_frame_loop_driven_by_reference_shaders_tracks_like_the_oracle(orc):
     print(f"pose after {n} free-running frames: literal oracle vs shader loop {worst_shader:.2e}; intended vs literal windows {worst_dev:.2e}")
     assert worst_shader <= 3e-4          # measured 7e-5
     assert worst_dev <= 3e-3             # measured 9e-4: the price of the intended-window restatement
+
+
+def test_dense_enough_oracle_matches_reference_resize_shader(orc):
+    """denseEnough: resize.frag over a 32x24 viewport samples texel (20 i + 10, 20 j + 10) of the predicted vertex map; the decision
+    flips exactly where the oracle's does when valid samples are removed one by one around the 75 % threshold."""
+    W, H = 640, 480
+    rng = np.random.default_rng(4)
+    v = np.zeros((H, W, 4), np.float32)
+    v[..., 2] = rng.uniform(0.5, 3.0, (H, W)).astype(np.float32)
+    flag, sampled = rg.denseEnough(v)
+    assert sampled.shape == (24, 32, 4) and np.array_equal(sampled, v[10::20, 10::20])
+    ys, xs = np.meshgrid(np.arange(24), np.arange(32), indexing="ij")
+    order = rng.permutation(24 * 32)
+    for k in range(0, 260):                                  # 768 samples: the threshold sits at 576 valid ones
+        j = order[k]
+        v[20 * ys.ravel()[j] + 10, 20 * xs.ravel()[j] + 10, 2] = 0.0
+        if k >= 180:
+            assert rg.denseEnough(v)[0] == orc.denseEnough(v), k
+    assert rg.denseEnough(v)[0] is False and orc.denseEnough(v) is False
+    # a pixel that is not a sample does not matter
+    v2 = v.copy(); v2[11::20, 11::20, 2] = 0.0
+    assert np.array_equal(rg.denseEnough(v2)[1], rg.denseEnough(v)[1])
