@@ -41,6 +41,8 @@ SHADERS = {
     "copy_unstable": "copy_unstable.vert",
     "init_unstable": "init_unstableTex.vert",
     "resize": "resize.frag",
+    "update_delta_trans": "update_delta_trans.vert",
+    "depth_update_normalrad": "depth_update_normalrad.frag",
 }
 TYPES = r"(?:float|int|uint|bool|vec[234]|mat[34]|sampler2D|usampler2D)"
 

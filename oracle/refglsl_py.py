@@ -76,7 +76,8 @@ def preprocess(pp, depth_u16):
                                       _p(t["vertex_raw"]), _p(t["vertex_filtered"]), _p(t["normal_pca"]), _p(t["radius"]))
     L.glsl_depth_curvature_gradient(W, H, _p(t["vertex_filtered"]), _p(t["normal_pca"]), *cam4, C.c_float(pp.maxD), C.c_float(pp.curvWindow),
                                     _p(t["curv1"]), _p(t["curv2"]), _p(t["gradient_mag"]), _p(t["normal_opt"]))
-    t["normal"] = t["normal_opt"]
+    t["normal"] = np.zeros((H, W, 4), np.float32)          # updateNormalRad: depth_update_normalrad.frag
+    L.glsl_depth_update_normalrad(W, H, _p(t["normal_opt"]), _p(t["vertex_filtered"]), _p(t["normal"]))
     return t
 
 
@@ -216,3 +217,12 @@ def denseEnough(vertex, thresh=0.75):
     lib().glsl_resize(W, H, _p(_f(vertex)), w, h, _p(out))
     per = np.float32(int((out[..., 2] > 0).sum())) / np.float32(h * w)
     return bool(per > np.float32(thresh)), out
+
+
+def modelUpdate(surfels, delta):
+    """GlobalModel::updateModel through Shaders/update_delta_trans.vert; as orc_py.modelUpdate (delta [n, 4, 4] row-major)"""
+    s = np.ascontiguousarray(surfels, np.float32).reshape(-1, 20)
+    d = np.ascontiguousarray(delta, np.float32).reshape(-1, 16)
+    out = np.zeros_like(s)
+    lib().glsl_update_delta_trans(s.shape[0], _p(s), _p(d), d.shape[0], _p(out))
+    return out

@@ -319,3 +319,16 @@ def test_dense_enough_oracle_matches_reference_resize_shader(orc):
     # a pixel that is not a sample does not matter
     v2 = v.copy(); v2[11::20, 11::20, 2] = 0.0
     assert np.array_equal(rg.denseEnough(v2)[1], rg.denseEnough(v)[1])
+
+
+def test_update_model_oracle_matches_reference_vertex_shader(orc):
+    """SURVEY 8f row 3: GlobalModel::updateModel = update_delta_trans.vert per surfel (rigid correction of its sub-map, read from the
+    19200 x 1 DeltaTransformKF texture): bit-identical, everything but position and normal passes through."""
+    rng = np.random.default_rng(9)
+    n, k = 5000, 7
+    s = rng.standard_normal((n, 20)).astype(np.float32)
+    s[:, 5] = rng.integers(0, k, n).astype(np.float32)
+    delta = np.stack([synth.make_pose(*rng.uniform(-0.05, 0.05, 3), tuple(rng.uniform(-0.1, 0.1, 3))) for _ in range(k)]).astype(np.float32)
+    a, b = orc.modelUpdate(s, delta), rg.modelUpdate(s, delta)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a[:, :3], s[:, :3]) and np.array_equal(a[:, [3, 4, 5, 6, 7, 11] + list(range(12, 20))], s[:, [3, 4, 5, 6, 7, 11] + list(range(12, 20))])
