@@ -16,9 +16,7 @@ using namespace hrbf;
 struct hrbf_frame {
     hrbf_frame_params p{};
     PrepArgs a{};
-#ifdef HRBF_LITERAL_WINDOWS
     char* wintab = nullptr;          // device tables of the literal window loops (PrepArgs::wx / wy point into it)
-#endif
     char* slab = nullptr;
     void* tex[HRBF_FT_COUNT] = {};
     float* weighting = nullptr;      // device scalar (VertexConfidence's uniform)
@@ -47,7 +45,6 @@ static PrepArgs prep_args(const hrbf_frame_params& p)
     return a;
 }
 
-#ifdef HRBF_LITERAL_WINDOWS
 // Builds the four window tables {x, y} x {fragment-pass texcoords, uv-VBO texcoords} with hrbf_window_table, uploads them as one
 // device block and points a.wx / a.wy at it.  Table of an axis of n pixels: first[n] (int), count[n] (int), coord[n][kWinMax] (float).
 static int build_window_tables(PrepArgs& a, float win, char** dev_out)
@@ -76,7 +73,6 @@ static int build_window_tables(PrepArgs& a, float win, char** dev_out)
     *dev_out = dev;
     return HRBF_OK;
 }
-#endif
 
 extern "C" {
 
@@ -88,10 +84,8 @@ int hrbf_frame_create(hrbf_frame** out, const hrbf_frame_params* p)
     hrbf_frame* f = new (std::nothrow) hrbf_frame();
     HRBF_CHECK_ARG(f != nullptr);
     f->p = *p; f->a = prep_args(*p);
-#ifdef HRBF_LITERAL_WINDOWS
     if (p->curvWindow != 3) { set_error("literal-window build: preprocessingCurvEstimationWindow must be 3"); delete f; return HRBF_ERR_INVALID_ARG; }
     if (int rc = build_window_tables(f->a, 3.0f, &f->wintab)) { delete f; return rc; }
-#endif
     const size_t P = (size_t)p->width * p->height;
     size_t off = 0, o[HRBF_FT_COUNT];
     auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
@@ -115,9 +109,7 @@ int hrbf_frame_destroy(hrbf_frame* f)
     if (!f) return HRBF_OK;
     if (f->h_w) cudaFreeHost(f->h_w);
     if (f->slab) cudaFree(f->slab);
-#ifdef HRBF_LITERAL_WINDOWS
     if (f->wintab) cudaFree(f->wintab);
-#endif
     delete f;
     return HRBF_OK;
 }
@@ -285,9 +277,7 @@ struct hrbf_model {
     int staged_time = -1;        // time of the fuse whose staging buffer clean() must append
     float* delta = nullptr;      // updateModel: device copy of the per-sub-map corrections
     size_t delta_bytes = 0;
-#ifdef HRBF_LITERAL_WINDOWS
     char* wintab = nullptr;      // device tables of the literal window loops (pa.wx / pa.wy point into it)
-#endif
 };
 
 static int model_upload_pose(hrbf_model* m, const float* pose16, cudaStream_t s, const float** pose_dev, const float** inv_dev)
@@ -386,9 +376,7 @@ int hrbf_model_create(hrbf_model** out, int width, int height, float cx, float c
     hrbf_frame_params fp{};
     fp.width = width; fp.height = height; fp.cx = cx; fp.cy = cy; fp.fx = fx; fp.fy = fy; fp.depthFactor = 1.f; fp.normalPCA = 1; fp.curvWindow = 3;
     m->pa = prep_args(fp);
-#ifdef HRBF_LITERAL_WINDOWS
     if (int rc = build_window_tables(m->pa, 3.0f, &m->wintab)) { delete m; return rc; }
-#endif
     m->n_slots = fuse_slots_x(width) * fuse_slots_y(height);
     const size_t P = (size_t)width * height;
     const size_t items = (size_t)capacity + (size_t)m->n_slots > P ? (size_t)capacity + (size_t)m->n_slots : P;
@@ -426,9 +414,7 @@ int hrbf_model_destroy(hrbf_model* m)
     if (m->h_count) cudaFreeHost(m->h_count);
     if (m->delta) cudaFree(m->delta);
     if (m->slab) cudaFree(m->slab);
-#ifdef HRBF_LITERAL_WINDOWS
     if (m->wintab) cudaFree(m->wintab);
-#endif
     delete m;
     return HRBF_OK;
 }
@@ -726,11 +712,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
                                         (const float*)FT(HRBF_FT_DEPTH_METRIC_FILTERED), (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2),
                                         (const float*)FT(HRBF_FT_CONFIDENCE), (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                         (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s, inline_w,
-#ifdef HRBF_LITERAL_WINDOWS      // data.vert's PCA normal sees the uv VBO's texcoords: another window than the fragment pass's, recompute
                                         nullptr)) return rc;
-#else
-                                        p.frame.normalPCA ? (const float*)FT(HRBF_FT_NORMAL_PCA) : nullptr)) return rc;
-#endif
             if (int rc = splat(1)) return rc;                  // clean reads index, vertConf, colorTime (copy_unstable.vert)
             if (int rc = model_clean_dev(M, invPose, F->tick, (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                          (const float*)IT(HRBF_TEX_COLORTIME), p.confidenceThreshold, p.maxDepthProcessed, s)) return rc;

@@ -127,7 +127,7 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
         const int nb = reduce_blocks(rows * cols);
         for (int j = 0; j < iters[l]; ++j) {
             const int next_level = (j + 1 < iters[l]) ? l : next_lower;
-            if (rgb) { rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, wk, 1, l, j == 0); ++n; }
+            if (rgb) { rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, wk, 1, l, j == 0, next_lower); ++n; }
             if (icp) {
                 if (o->useSearch) icp_reduce_kernel<true><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
                 else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
@@ -402,7 +402,7 @@ int hrbf_compute_rgb_residual(float minScale, const short* dIdx, const short* dI
     RgbResArgs ra;
     ra.minScale = minScale; ra.maxDepthDelta = maxDepthDelta; ra.dIdx = dIdx; ra.dIdy = dIdy; ra.lastDepth = lastDepth; ra.nextDepth = nextDepth;
     ra.lastImage = lastImage; ra.nextImage = nextImage; ra.corres = corresImg; ra.rows = rows; ra.cols = cols;
-    rgb_residual_kernel<<<reduce_blocks(rows * cols), 256, 0, s>>>(ra, wk, 0, 0, 1);
+    rgb_residual_kernel<<<reduce_blocks(rows * cols), 256, 0, s>>>(ra, wk, 0, 0, 1, -1);
     HRBF_KERNEL_CHECK();
     int out[2];
     HRBF_CUDA(cudaMemcpyAsync(out, &wk->st.rgb_count, sizeof out, cudaMemcpyDeviceToHost, s));
@@ -856,7 +856,7 @@ int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_u
     auto launch_once = [&](cudaStream_t q) {
         switch (which) {
         case 0: icp_reduce_kernel<false><<<nb, kReduceThreads, 0, q>>>(ia, o->work, with_update ? 1 : 0, level, -1); break;
-        case 1: rgb_residual_kernel<<<nb, 256, 0, q>>>(ra, o->work, 1, level, 0); break;
+        case 1: rgb_residual_kernel<<<nb, 256, 0, q>>>(ra, o->work, 1, level, 0, -1); break;
         case 2: rgb_step_kernel<<<nb, kReduceThreads, 0, q>>>(sa, -2.0f, o->work, with_update ? 1 : 0, level, -1); break;
         default: so3_reduce_kernel<<<reduce_blocks(o->rows(2) * o->cols(2)), kReduceThreads, 0, q>>>(o->lastNextImage[2], o->nextImage[2], o->rows(2), o->cols(2), o->work, 0); break;
         }

@@ -854,7 +854,7 @@ __device__ __forceinline__ void rgb_residual_pixel(const RgbResArgs& a, const fl
 // reduce.cu:986-1060; the int2 {count, sum diff^2} goes through redux + one atomic per warp.
 // When the caller is the tracking loop, the last block also evaluates sigma / the rgbOnly break
 // (RGBDOdometry.cpp:1017-1032).
-__global__ void __launch_bounds__(256) rgb_residual_kernel(RgbResArgs a, ReduceWork* wk, int finalize, int cur_level, int first_iter)
+__global__ void __launch_bounds__(256) rgb_residual_kernel(RgbResArgs a, ReduceWork* wk, int finalize, int cur_level, int first_iter, int next_lower)
 {
     TrackState* st = &wk->st;
     __shared__ float s_k[12];
@@ -887,8 +887,16 @@ __global__ void __launch_bounds__(256) rgb_residual_kernel(RgbResArgs a, ReduceW
             float sigmaVal = sqrtf(((float)sigma / (float)rgbSize == 0.f) ? 1.f : (float)rgbSize);
             const float rgbError = sqrtf((float)sigma) / (float)(rgbSize == 0 ? 1 : rgbSize);
             const float lastErr = first_iter ? FLT_MAX : st->lastRGBError;   // RGBDOdometry.cpp:962
-            if (st->rgbOnly && rgbError > lastErr) st->done_level = cur_level;
-            else {
+            if (st->rgbOnly && rgbError > lastErr) {
+                st->done_level = cur_level;
+                // the next level's first iteration warps with ITS camera matrix (RGBDOdometry.cpp:983-992 rebuilds K R K^-1, K t
+                // at the top of every iteration): the last gn_update prepared them for cur_level
+                if (next_lower >= 0) {
+                    double Rt[16];
+                    for (int k = 0; k < 16; ++k) Rt[k] = st->resultRt[k];
+                    update_krk(st, Rt, next_lower);
+                }
+            } else {
                 st->lastRGBError = rgbError;
                 st->lastRGBCount = (float)rgbSize;
                 if (st->rgbOnly) sigmaVal = -1.f;

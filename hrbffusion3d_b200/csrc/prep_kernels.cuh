@@ -13,22 +13,20 @@
 
 namespace hrbf {
 
-#ifdef HRBF_LITERAL_WINDOWS
-// Development variant (stated deviation; round 2): the 7x7 windows of the PCA normal and of the curvature
-// pass as the shaders' float-counter loops really visit them, from host-built tables (hrbf_window_table): per pixel of an axis
-// the first texel, the sample count and the sample coordinates.  The default build does not contain any of this.
+// The 7x7 windows of the PCA normal (geometry.glsl:198-212) and of the curvature pass (depth_curvature_gradient.frag:62-75) as
+// the shaders' float-counter loops really visit them: `for (float i = tx_min; i <= tx_max; i += step)` overshoots tx_max by an
+// ulp for ~40 % of the columns / rows and then never visits the window's last column / row, and the sample coordinate i * cols
+// is px + 0.5 only up to that round-off.  Host-built tables (hrbf_window_table) give, per pixel of an axis, the first texel,
+// the sample count and the sample coordinates the shader's fp32 expressions produce.
 struct WinTab { const int* first; const int* count; const float* coord; };      // coord[p * kWinMax + k]
 constexpr int kWinMax = 8;
-#endif
 struct PrepArgs {
     int cols, rows;
     float cx, cy, icx, icy;          // cam = (cx, cy, 1/fx, 1/fy)
     float depthFactor, maxD;         // metres per raw unit, globalDepthCutoff
     float radiusMultiplier;
     int pca, curvWin, bilateral;
-#ifdef HRBF_LITERAL_WINDOWS
     WinTab wx[2], wy[2];             // [0]: texcoords of a full-screen fragment pass, [1]: of the uv VBO (GlobalModel::fuse)
-#endif
 };
 
 // exp() of the bilateral weights as a fixed sequence of IEEE fp32 operations (explicit FMAs in the Horner scheme), identical to the oracle's
@@ -199,17 +197,11 @@ __device__ __forceinline__ void compute_roots(float m00, float m10, float m20, f
 template <typename DepthAt>
 __device__ __forceinline__ float3 normal_pca(const PrepArgs& a, DepthAt depth_at, int px, int py, float vz, int coord_variant = 0)
 {
-    (void)coord_variant;
-    const int W = a.cols, H = a.rows, win = 3;
-    const int x0 = max(px - win, 0), x1 = min(px + win, W - 1), y0 = max(py - win, 0), y1 = min(py + win, H - 1);
-    const bool xcl = px - win < 0, ycl = py - win < 0;     // clamped windows start at texture coordinate 0.0: integer coords
     // The covariance is a difference of nearly equal numbers (E[x^2] - E[x]^2 with |x| ~ 1 m and a spread of
     // centimetres), so the normal inherits ~1e-3 of relative round-off: only a bit-identical evaluation order
     // reproduces the oracle.  Hence explicit _rn arithmetic (no FMA contraction) for the sums and the covariance.
     float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
     int N = 0;
-#ifdef HRBF_LITERAL_WINDOWS
-    (void)x0; (void)x1; (void)y0; (void)y1; (void)xcl; (void)ycl; (void)W; (void)H;
     const WinTab tx = a.wx[coord_variant], ty = a.wy[coord_variant];
     const int lx0 = __ldg(tx.first + px), lnx = __ldg(tx.count + px), ly0 = __ldg(ty.first + py), lny = __ldg(ty.count + py);
     for (int ix = 0; ix < lnx; ++ix)
@@ -217,12 +209,6 @@ __device__ __forceinline__ float3 normal_pca(const PrepArgs& a, DepthAt depth_at
             const int qx = lx0 + ix, qy = ly0 + iy;
             const float z = depth_at(qx, qy);
             const float fx_ = __ldg(tx.coord + px * kWinMax + ix), fy_ = __ldg(ty.coord + py * kWinMax + iy);
-#else
-    for (int qx = x0; qx <= x1; ++qx)
-        for (int qy = y0; qy <= y1; ++qy) {
-            const float z = depth_at(qx, qy);
-            const float fx_ = xcl ? (float)qx : (float)qx + 0.5f, fy_ = ycl ? (float)qy : (float)qy + 0.5f;
-#endif
             const float X = __fmul_rn(__fmul_rn(__fsub_rn(fx_, a.cx), z), a.icx), Y = __fmul_rn(__fmul_rn(__fsub_rn(fy_, a.cy), z), a.icy);
             if (z > 0.3f && fabsf(__fsub_rn(z, vz)) < 0.05f) {
                 a0 = __fadd_rn(a0, __fmul_rn(X, X)); a1 = __fadd_rn(a1, __fmul_rn(X, Y)); a2 = __fadd_rn(a2, __fmul_rn(X, z));
@@ -328,12 +314,8 @@ __global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, con
     if (vf.z > 0.3f && sqrtf(vn.x * vn.x + vn.y * vn.y + vn.z * vn.z) > 0.5f) {
         float k1 = 1000.0f, k2 = 1000.0f;
         float3 pmax = make_float3(0.f, 0.f, 0.f), pmin = pmax;
-#ifdef HRBF_LITERAL_WINDOWS
         (void)win;       // the tables are built for curvWin (hrbf_frame_create)
         const int qx0 = __ldg(a.wx[0].first + px), qx1 = qx0 + __ldg(a.wx[0].count + px) - 1, qy0 = __ldg(a.wy[0].first + py), qy1 = qy0 + __ldg(a.wy[0].count + py) - 1;
-#else
-        const int qx0 = max(px - win, 0), qx1 = min(px + win, W - 1), qy0 = max(py - win, 0), qy1 = min(py + win, H - 1);
-#endif
         int N = 0;
         float gx = 0.f, gy = 0.f, gz = 0.f;                               // gradient
         float h0 = 0.f, h1 = 0.f, h2 = 0.f, h4 = 0.f, h5 = 0.f, h8 = 0.f;   // "Hessian" entries g[0], g[1], g[2], g[4], g[5], g[8]
@@ -402,11 +384,7 @@ __global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, con
                 if (delta < 0.0f) delta = 0.0f;
                 k1 = cm + sqrtf(delta); k2 = cm - sqrtf(delta);
                 const float lmax = -(M - k1 * F) / (Nn - k1 * G), lmin = -(M - k2 * F) / (Nn - k2 * G);
-#ifdef HRBF_LITERAL_WINDOWS      // r_u + lambda r_v component-wise, as the shader evaluates it: an infinite lambda also turns x = 1 + lambda * 0 into NaN
                 const float3 A = make_float3(__fadd_rn(1.0f, __fmul_rn(lmax, 0.0f)), lmax, h_x + lmax * h_y), B = make_float3(__fadd_rn(1.0f, __fmul_rn(lmin, 0.0f)), lmin, h_x + lmin * h_y);
-#else
-                const float3 A = make_float3(1.0f, lmax, h_x + lmax * h_y), B = make_float3(1.0f, lmin, h_x + lmin * h_y);
-#endif
                 const float la = norm(A), lb = norm(B);
                 pmax = make_float3(A.x / la, A.y / la, A.z / la);
                 pmin = make_float3(B.x / lb, B.y / lb, B.z / lb);

@@ -427,8 +427,15 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                     float sigmaVal = sqrtf(((float)sigma / (float)rgbSize == 0.f) ? 1.f : (float)rgbSize);
                     const float rgbError = sqrtf((float)sigma) / (float)(rgbSize == 0 ? 1 : rgbSize);
                     const float lastErr = (j == 0) ? FLT_MAX : S.lastRGBError;
-                    if (S.rgbOnly && rgbError > lastErr) S.done_level = l;
-                    else {
+                    if (S.rgbOnly && rgbError > lastErr) {
+                        S.done_level = l;
+                        if (next_lower >= 0) {      // the next level warps with ITS camera matrix (RGBDOdometry.cpp:983-992)
+                            double Rt[16];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) Rt[k] = S.resultRt[k];
+                            update_krk(&S, Rt, next_lower);
+                        }
+                    } else {
                         S.lastRGBError = rgbError;
                         S.lastRGBCount = (float)rgbSize;
                         if (S.rgbOnly) sigmaVal = -1.f;

@@ -19,13 +19,14 @@
  *     (oracle/build_ref_glsl.py + glsl_cpu.h -> oracle/_ref/libref_glsl.so) and run
  *     per fragment / vertex on the same inputs: tests/test_oracle_vs_reference_glsl.py.
  *     Bit-identical where the pass is not an exp / a root search, with the shaders'
- *     float-counter window loops taken literally (orc_set_float_loops; the default
- *     restates the intended integer windows -- DESIGN.md, stated deviation).
+ *     float-counter window loops taken literally (the default; orc_set_float_loops(0)
+ *     = the intended integer windows round 1 restated -- DESIGN.md).
  *     Fixed-function GL between the shaders (point rasterisation, depth test,
  *     transform-feedback order, framebuffer formats) is restated, not executed.
  *   row 5 (cudafuncs.cu map / pyramid kernels): the reference's kernels are built
- *     (oracle/_ref/libref_cudafuncs.so, texture-reference shim) but have not run on a
- *     GPU yet -> "parity unpinned" until tests/golden/ref_cudafuncs.npz exists.
+ *     (oracle/_ref/libref_cudafuncs.so, texture-reference shim), ran on a B200:
+ *     golden vectors tests/golden/ref_cudafuncs.npz (oracle/gen_ref5_golden.py), live
+ *     comparison in tests/test_oracle_vs_reference_row5.py.
  *   row 4 (host Gauss-Newton loop, RGBDOdometry.cpp + Eigen ldlt): Eigen is not
  *     installed and the class is inseparable from GL -> "parity unpinned", except the
  *     pose update (OdometryProvider.h rodrigues / computeUpdateSE3), which is pinned to

@@ -156,11 +156,11 @@ static void compute_roots(float m[3][3], float r[3])
  *     for (float i = tx_min; i <= tx_max; i += indexXStep)      tx_min/max = clamp(texcoord.x -/+ indexXStep * winMultiply)
  * In fp32 the accumulated i overshoots tx_max by an ulp for many columns, and the last column of the window is then never
  * visited (e.g. 247 of the 634 interior columns at 640 px see 6 samples, not 7); the sample coordinate i * cols handed to
- * getVertex is px + 0.5 only up to that round-off.  By default the oracle (and the CUDA kernels, which follow it) restate the
- * INTENDED window: integer offsets -win..win, coordinates exactly qx + 0.5 (SURVEY 8a hazard iii).  orc_set_float_loops(1)
- * switches these two passes to the literal float loops, which is what tests/test_oracle_vs_reference_glsl.py compares with the
- * reference's own shader text compiled for the CPU; the same test measures what the idealisation changes. */
-static int g_float_loops = 0;
+ * getVertex is px + 0.5 only up to that round-off.  The oracle (and the CUDA kernels, which follow it) run these LITERAL float
+ * loops: that is what tests/test_oracle_vs_reference_glsl.py compares bit for bit with the reference's own shader text compiled
+ * for the CPU.  orc_set_float_loops(0) switches to the INTENDED window (integer offsets -win..win, coordinates exactly qx + 0.5;
+ * round 1's restatement) -- kept only so that the same test can measure what that idealisation changed (3.7e-5 of pose per frame). */
+static int g_float_loops = 1;
 void orc_set_float_loops(int on) { g_float_loops = on; }
 int orc_get_float_loops(void) { return g_float_loops; }
 /* literal mode, which texcoord a pass sees for pixel p: a full-screen fragment pass gets (p + 0.5) / n; the vertex pass of

@@ -13,9 +13,9 @@ def pytest_configure(config):
 
 
 def default_float_loops():
-    """HRBF_LITERAL=1 (development): the oracle runs the shaders' literal float-counter window loops for the
-    whole session -- to be used together with HRBF_B200_LIB=build/libhrbf_literal.so (scripts/run_literal_variant.sh)"""
-    return 1 if os.environ.get("HRBF_LITERAL") == "1" else 0
+    """The oracle runs the shaders' literal float-counter window loops (geometry.glsl:198-212, depth_curvature_gradient.frag:62-75),
+    like the CUDA kernels; 0 (round 1's intended integer windows) is only set locally by the test that measures the difference."""
+    return 1
 
 
 @pytest.fixture(scope="session")

@@ -54,6 +54,16 @@ def compare(name, got, want, exact_copy=("copy_v", "copy_n", "copy_k1", "copy_k1
     --ftz --prec-div=false --prec-sqrt=false and FMA contraction, the oracle is plain C: 2e-6 relative; NaN masks identical."""
     got, want = np.asarray(got), np.asarray(want)
     assert got.shape == want.shape, name
+    if name == "pyr_u8":
+        # pyrDownKernelIntensityGauss truncates sum / count to u8 (cudafuncs.cu:847).  The reference is BUILT with --prec-div=false
+        # (Core/src/CMakeLists.txt:74): div.approx lands an ulp below the exact quotient for some counts, so where the quotient is
+        # an exact integer N the reference build stores N - 1.  The oracle (and the CUDA path) keep the IEEE division the source
+        # states.  Measured on a B200 (oracle/gen_ref5_golden.py): 3 of 1728 pixels at 96x72, all three with an exact-integer
+        # quotient.  Pinned as: oracle - reference in {0, +1}, at most 0.5 % of the pixels.
+        d = got.astype(np.int32) - want.astype(np.int32)
+        assert d.min() >= 0 and d.max() <= 1, (name, d.min(), d.max())
+        assert (d != 0).mean() <= 5e-3, (name, float((d != 0).mean()))
+        return
     if name in INTEGER or name in exact_copy:
         assert np.array_equal(got, want, equal_nan=got.dtype.kind == "f"), name
         return

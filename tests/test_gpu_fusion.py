@@ -119,12 +119,31 @@ def test_model_initialise_fuse_clean_match_oracle(orc, cuda):
     new_ref = int((unstable_ref[:, 7] == -2).sum())
     assert new_ref > 50
     assert abs(n2 - cleaned_ref.shape[0]) <= max(3, int(2e-3 * cleaned_ref.shape[0])), (n2, cleaned_ref.shape)
-    if n2 == cleaned_ref.shape[0]:
-        _close(c_gpu, cleaned_ref, "clean", rtol=1e-4, atol=1e-5, max_bad=2e-3)
+    # same surfels in the same order; where the counts differ (a surfel on the edge of a cull test) the extra rows are skipped
+    ia, ib = _align_rows(c_gpu[:n2], cleaned_ref)
+    assert len(ia) >= min(n2, cleaned_ref.shape[0]) - 3
+    _close(c_gpu[ia], cleaned_ref[ib], "clean", rtol=1e-4, atol=1e-5, max_bad=2e-3)
     assert not gm.overflowed()
     # a clean without a preceding fuse of the same frame only compacts
     gm.clean(pose1, time + 1, im.tex("index"), im.tex("vertConf"), im.tex("colorTime"), im.tex("normRad"))
     assert gm.lastCount() <= n2
+
+
+def _align_rows(a, b, look=4, tol=1e-3):
+    """indices (ia, ib) of the rows two order-preserving surfel arrays have in common: rows match when their positions agree;
+    a row missing on one side (up to `look` in a row) is skipped"""
+    ia, ib, i, j = [], [], 0, 0
+    same = lambda x, y: np.abs(x[:3] - y[:3]).max() <= tol
+    while i < len(a) and j < len(b):
+        if same(a[i], b[j]):
+            ia.append(i); ib.append(j); i += 1; j += 1
+            continue
+        for k in range(1, look + 1):
+            if i + k < len(a) and same(a[i + k], b[j]): i += k; break
+            if j + k < len(b) and same(a[i], b[j + k]): j += k; break
+        else:
+            i += 1; j += 1
+    return np.array(ia, np.int64), np.array(ib, np.int64)
 
 
 def test_model_capacity_overflow_is_reported(orc, cuda):
@@ -140,7 +159,7 @@ def test_model_capacity_overflow_is_reported(orc, cuda):
     _close(gm.model()[0].cpu().numpy(), s_ref[:1000], "first 1000 survive in order", max_bad=0)
 
 
-@pytest.mark.parametrize("W,H,kw", [(320, 240, dict(icpWeight=100.0, so3=0)), (320, 240, {}), (640, 480, dict(icpWeight=100.0, so3=0))])
+@pytest.mark.parametrize("W,H,kw", [(320, 240, dict(icpWeight=100.0, so3=0)), (320, 240, {}), (640, 480, dict(icpWeight=100.0, so3=0)), (640, 480, {})])
 def test_process_frame_sequence_matches_oracle(orc, cuda, W, H, kw):
     """HRBFFusion::processFrame over a short sequence, frame by frame against the oracle pipeline."""
     from hrbffusion3d_b200.fusion import HRBFFusion

@@ -186,6 +186,7 @@ def test_rgb_and_so3_steps_match_oracle(orc, cuda):
     (640, 480, dict(icpWeight=10.0, so3=True)),                   # reference default: joint RGB-D + SO3 pre-alignment
     (640, 480, dict(icpWeight=10.0, so3=False, pyramid=False)),
     (320, 240, dict(rgbOnly=True, so3=False, pyramid=False, fastOdom=True)),
+    (320, 240, dict(rgbOnly=True, so3=False, pyramid=True, fastOdom=True)),      # early break at a coarse level (RGBDOdometry.cpp:1020-1023): the next level must warp with its own K
     (640, 480, dict(icpWeight=100.0, so3=False, fastOdom=True, if_curvature_info=False)),
     (1280, 960, dict(icpWeight=100.0, so3=False)),
 ])

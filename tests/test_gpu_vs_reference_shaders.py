@@ -1,0 +1,57 @@
+"""The CUDA frame pipeline against a frame loop whose every GLSL pass is the REFERENCE's own shader text
+(Core/src/Shaders/*.{vert,frag,glsl} compiled for the CPU into oracle/_ref/libref_glsl.so by oracle/build_ref_glsl.py and driven
+by oracle/refglsl_py.py + oracle/glsl_drivers/) -- preprocessing, initialise, splat, fuse, clean, HRBF prediction, fill-in,
+vertex confidence -- with only the tracker (rows 1-5, pinned to the reference's CUDA kernels elsewhere) taken from the oracle.
+This is the test that closes the chain  CUDA == oracle  and  oracle == reference shaders  in ONE comparison, at the BASELINE
+resolution, free-running over several frames.  north_star bound: pose 1e-5 (rad, m) per frame, vertices 1e-4 m RMSE."""
+import numpy as np
+import pytest
+
+from hrbffusion3d_b200 import synth
+from oracle import refglsl_py as rg
+from tests.util import pose_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not rg.available(), reason="oracle/_ref/libref_glsl.so not shipped")]
+
+
+@pytest.mark.parametrize("kw,pose_tol", [
+    (dict(icpWeight=100.0, so3=False), 1e-5),      # ICP + HRBF: the configuration the north-star tolerance is stated on
+    ({}, 1e-5),                                    # reference defaults: joint RGB-D + SO3 pre-alignment
+])
+def test_cuda_pipeline_matches_reference_shader_loop_640x480(orc, cuda, kw, pose_tol):
+    from hrbffusion3d_b200.fusion import HRBFFusion
+    from oracle import orc_pipeline as op
+    from tests.test_oracle_vs_reference_glsl import _ShaderOrc
+    W, H, n = 640, 480, 5
+    cam = synth.default_camera(W, H)
+    sc = synth.Scene("room")
+    frames = [synth.render_depth(sc, p, W, H, cam, noise=True, seed=i) for i, p in enumerate(synth.circle_trajectory(n, frames_per_rev=120))]
+    gkw = dict(kw)
+    if "so3" in gkw:
+        gkw["so3"] = int(gkw["so3"])
+    gpu = HRBFFusion(W, H, cam, capacity=1 << 20, **gkw)
+    saved = op.orc
+    op.orc = _ShaderOrc(orc)
+    try:
+        ref = op.HRBFFusion(W, H, cam, **kw)
+        worst = 0.0
+        for i, (depth, rgb) in enumerate(frames):
+            To, Tg = ref.processFrame(rgb, depth), gpu.processFrame(rgb, depth)
+            ang, dt = pose_err(To[:3, :3], To[:3, 3], Tg[:3, :3], Tg[:3, 3])
+            worst = max(worst, ang, dt)
+            cnt = gpu.globalModel.lastCount()
+            print(f"frame {i}: CUDA vs reference-shader loop: pose diff ang {ang:.2e} t {dt:.2e}; surfels {cnt} vs {ref.surfels.shape[0]}")
+            assert ang <= pose_tol and dt <= pose_tol, (i, ang, dt)
+            assert abs(cnt - ref.surfels.shape[0]) <= max(5, int(1e-3 * ref.surfels.shape[0]))
+            # the HRBF prediction the next frame is tracked against: vertices within 1e-4 m RMSE where both found a surface
+            pv = gpu.indexMap.tex("vertexHRBF").cpu().numpy()
+            fg, fo = pv[..., 2] > 0, ref.pred["vertex"][..., 2] > 0
+            assert np.mean(fg != fo) < 2e-3
+            both = fg & fo
+            if both.sum() > 1000:
+                d = (pv[..., :3].astype(np.float64) - ref.pred["vertex"][..., :3])[both]
+                bad = np.linalg.norm(d, axis=-1) > 1e-3       # depth-discontinuity pixels where another crossing of f is picked (stated)
+                assert bad.mean() < 1e-3
+                assert np.sqrt((d[~bad] ** 2).sum(-1).mean()) <= 1e-4
+    finally:
+        op.orc = saved

@@ -105,9 +105,10 @@ def test_intended_vs_literal_windows_deviation_is_bounded(orc):
     W, H = 320, 240
     cam, depth, _ = _frame(W, H, "room")
     pp = orc.prep_params(cam, W, H)
-    ideal = orc.preprocess(pp, depth)
-    orc.lib().orc_set_float_loops(1)
+    orc.lib().orc_set_float_loops(0)
     try:
+        ideal = orc.preprocess(pp, depth)
+        orc.lib().orc_set_float_loops(1)
         lit = orc.preprocess(pp, depth)
     finally:
         from tests.conftest import default_float_loops

@@ -2,9 +2,9 @@
 kernels: Core/src/Cuda/cudafuncs.cu compiled unmodified into oracle/_ref/libref_cudafuncs.so (oracle/build_ref.sh).
 
   * CPU: oracle vs the golden vectors the reference kernels produced on a B200 (tests/golden/ref_cudafuncs.npz, written by
-    oracle/gen_ref5_golden.py).  The reference library was first built after this round's GPU budget was spent, so the file
-    does not exist yet: until it is generated (next GPU session) both tests SKIP and row 5 stays "parity unpinned".
-  * GPU: oracle vs the reference kernels live, same cases -- enabled once the golden file exists (or with HRBF_REF5_LIVE=1)."""
+    oracle/gen_ref5_golden.py; generated in round 2).  Every output agrees under tests/ref5_cases.compare; the one stated
+    difference is the u8 truncation of pyrDownUcharGauss under the reference build's approximate division (see compare()).
+  * GPU: oracle vs the reference kernels live, same cases."""
 import os
 
 import numpy as np
