@@ -11,6 +11,13 @@
 
 namespace hrbf {
 
+// (a0 b0 + a1 b1) + a2 b2 with every product and sum rounded separately: the float pose compositions of the host code
+// (RGBDOdometry.cpp:902, 1196-1204) are plain C++ / Eigen fixed-size products, no FMA
+__device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
+
 // Slow path: LDL^T with symmetric diagonal pivoting; a vanishing pivot contributes 0 (what
 // Eigen's ldlt().solve() does for a singular system, e.g. no correspondences at all).
 template <int N>
@@ -161,11 +168,13 @@ __device__ __forceinline__ void inv3(const double (&m)[9], double (&o)[9])
 }
 __device__ __forceinline__ void inv3f(const float* m, float* o)
 {
-    const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
-    const float det = m[0] * c00 + m[1] * c01 + m[2] * c02, id = 1.0f / det;
-    o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
-    o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
-    o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    // Rprev.inverse() on the host (RGBDOdometry.cpp:920): cofactors / determinant in float, every operation rounded separately
+    auto d2 = [](float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); };
+    const float c00 = d2(m[4], m[8], m[5], m[7]), c01 = d2(m[5], m[6], m[3], m[8]), c02 = d2(m[3], m[7], m[4], m[6]);
+    const float det = dot3_rn(m[0], c00, m[1], c01, m[2], c02), id = __fdiv_rn(1.0f, det);
+    o[0] = __fmul_rn(c00, id); o[1] = __fmul_rn(d2(m[2], m[7], m[1], m[8]), id); o[2] = __fmul_rn(d2(m[1], m[5], m[2], m[4]), id);
+    o[3] = __fmul_rn(c01, id); o[4] = __fmul_rn(d2(m[0], m[8], m[2], m[6]), id); o[5] = __fmul_rn(d2(m[2], m[3], m[0], m[5]), id);
+    o[6] = __fmul_rn(c02, id); o[7] = __fmul_rn(d2(m[1], m[6], m[0], m[7]), id); o[8] = __fmul_rn(d2(m[0], m[4], m[1], m[3]), id);
 }
 __device__ __forceinline__ void mul3(const double (&a)[9], const double (&b)[9], double (&o)[9])
 {
@@ -292,12 +301,12 @@ __device__ __forceinline__ void gn_update(TrackState* st, int cur_level, int nex
         tp[a] = st->tprev[a];
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) ti[a] = -(Rf[0 * 3 + a] * tf[0] + Rf[1 * 3 + a] * tf[1] + Rf[2 * 3 + a] * tf[2]);
+    for (int a = 0; a < 3; ++a) ti[a] = -dot3_rn(Rf[0 * 3 + a], tf[0], Rf[1 * 3 + a], tf[1], Rf[2 * 3 + a], tf[2]);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
-        for (int b = 0; b < 3; ++b) st->Rcurr[a * 3 + b] = Rp[a * 3] * Rf[b * 3] + Rp[a * 3 + 1] * Rf[b * 3 + 1] + Rp[a * 3 + 2] * Rf[b * 3 + 2];
-        st->tcurr[a] = Rp[a * 3] * ti[0] + Rp[a * 3 + 1] * ti[1] + Rp[a * 3 + 2] * ti[2] + tp[a];
+        for (int b = 0; b < 3; ++b) st->Rcurr[a * 3 + b] = dot3_rn(Rp[a * 3], Rf[b * 3], Rp[a * 3 + 1], Rf[b * 3 + 1], Rp[a * 3 + 2], Rf[b * 3 + 2]);
+        st->tcurr[a] = __fadd_rn(dot3_rn(Rp[a * 3], ti[0], Rp[a * 3 + 1], ti[1], Rp[a * 3 + 2], ti[2]), tp[a]);
     }
     if (next_level >= 0 && rgb) update_krk(st, nrt, next_level);
 }
@@ -373,13 +382,13 @@ __device__ __forceinline__ void gn_update_warps(TrackState* st, int next_level, 
             }
             if (lane < 9) {
                 const int a = lane / 3, b = lane - 3 * a;
-                st->Rcurr[lane] = st->Rprev[a * 3] * Rf[b * 3] + st->Rprev[a * 3 + 1] * Rf[b * 3 + 1] + st->Rprev[a * 3 + 2] * Rf[b * 3 + 2];
+                st->Rcurr[lane] = dot3_rn(st->Rprev[a * 3], Rf[b * 3], st->Rprev[a * 3 + 1], Rf[b * 3 + 1], st->Rprev[a * 3 + 2], Rf[b * 3 + 2]);
             } else {
                 const int a = lane - 9;
                 float ti[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) ti[k] = -(Rf[0 * 3 + k] * tf[0] + Rf[1 * 3 + k] * tf[1] + Rf[2 * 3 + k] * tf[2]);
-                st->tcurr[a] = st->Rprev[a * 3] * ti[0] + st->Rprev[a * 3 + 1] * ti[1] + st->Rprev[a * 3 + 2] * ti[2] + st->tprev[a];
+                for (int k = 0; k < 3; ++k) ti[k] = -dot3_rn(Rf[0 * 3 + k], tf[0], Rf[1 * 3 + k], tf[1], Rf[2 * 3 + k], tf[2]);
+                st->tcurr[a] = __fadd_rn(dot3_rn(st->Rprev[a * 3], ti[0], st->Rprev[a * 3 + 1], ti[1], st->Rprev[a * 3 + 2], ti[2]), st->tprev[a]);
             }
         }
     } else if (lane == 0 && next_level >= 0 && rgb) {
@@ -434,7 +443,8 @@ __device__ __forceinline__ void so3_update(TrackState* st)
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const float v = (float)upd[i * 3] * Rl[j] + (float)upd[i * 3 + 1] * Rl[3 + j] + (float)upd[i * 3 + 2] * Rl[6 + j];
+            // R_lr = rotUpdate.cast<float>() * R_lr (RGBDOdometry.cpp:902): products and sums rounded one by one, as the host code does
+            const float v = __fadd_rn(__fadd_rn(__fmul_rn((float)upd[i * 3], Rl[j]), __fmul_rn((float)upd[i * 3 + 1], Rl[3 + j])), __fmul_rn((float)upd[i * 3 + 2], Rl[6 + j]));
             st->R_lr[i * 3 + j] = v;
             nrd[i * 3 + j] = (double)v;
             st->resultR[i * 3 + j] = (double)v;

@@ -333,7 +333,7 @@ __device__ __forceinline__ float gauss_down_f32(int srows, int scols, int x, int
             const float s = src_at(cx, cy);
             if (!isnan(s)) {
                 const float g = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
-                sum += s * g;
+                sum = fmaf(s, g, sum);      // what nvcc makes of the reference's `sum += src * gauss` (cudafuncs.cu:516); the oracle does the same
                 count = (int)((float)count + g);
             }
         }

@@ -285,7 +285,7 @@ void orc_pyrDownGaussF(int srows, int scols, const float* src, float* dst)
                     float s = src[(size_t)cy * scols + cx];
                     if (!isnan(s)) {
                         float g = kGauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
-                        sum += s * g;
+                        sum = fmaf(s, g, sum);   /* nvcc contracts the reference's `sum += src * gauss` into one FMA (cudafuncs.cu:516) */
                         count = (int)((float)count + g);
                     }
                 }

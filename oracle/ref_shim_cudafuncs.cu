@@ -119,6 +119,10 @@ int ref5_createVMap(float fx, float fy, float cx, float cy, int rows, int cols, 
 {
     DeviceArray2D<float> dp, v;
     up(dp, depth, rows, cols);
+    // computeVmapKernel writes only plane 0 (NaN) of an invalid pixel: the other planes keep what the allocation held.  Defined here
+    // (and in the oracle) as 0: create + clear first, createVMap's own create() of the same size is then a no-op.
+    v.create(4 * rows, cols);
+    cudaMemset2D(v.ptr(), v.step(), 0, (size_t)cols * sizeof(float), 4 * rows);
     createVMap(CameraModel(fx, fy, cx, cy), dp, v, cutoff, factor);
     cudaDeviceSynchronize();
     down(v, vmap, cols);
@@ -128,6 +132,8 @@ int ref5_createNMap(int rows, int cols, const float* vmap, float* nmap)
 {
     DeviceArray2D<float> v, n;
     up(v, vmap, 4 * rows, cols);
+    n.create(4 * rows, cols);      // same convention: planes the kernel leaves unwritten read 0
+    cudaMemset2D(n.ptr(), n.step(), 0, (size_t)cols * sizeof(float), 4 * rows);
     createNMap(v, n);
     cudaDeviceSynchronize();
     down(n, nmap, cols);

@@ -262,3 +262,67 @@ def test_invalid_arguments_fail_loudly(cuda):
     h = C.c_void_p()
     assert lib().hrbf_odometry_create(None, 640, 480, C.c_float(1), C.c_float(1), C.c_float(1), C.c_float(1), C.c_float(.1), C.c_float(.3)) == -1
     assert b"invalid argument" in lib().hrbf_last_error()
+
+
+def _pipeline_frame1_inputs(orc, W, H):
+    """the tracker inputs of the SECOND frame of the oracle pipeline (the first tracked one): model maps = fill-in of frame 0"""
+    from oracle import orc_pipeline as op
+    from hrbffusion3d_b200 import synth
+    cam = synth.default_camera(W, H)
+    sc = synth.Scene("room")
+    frames = [synth.render_depth(sc, p, W, H, cam, noise=True, seed=i) for i, p in enumerate(synth.circle_trajectory(2, frames_per_rev=120))]
+    f = op.HRBFFusion(W, H, cam)
+    f.processFrame(frames[0][1], frames[0][0])
+    depth, rgb = frames[1]
+    fr = orc.preprocess(f.pp, depth)
+    src = f.fill if not orc.denseEnough(f.pred["vertex"]) else f.pred
+    return cam, f.currPose.copy(), dict(first=f.rgba(frames[0][1]), rgba=f.rgba(rgb), src=src, fr=fr)
+
+
+def _init_tracker(o, up, pose, d):
+    o.initFirstRGB(up(d["first"]))
+    o.initICPModel(up(d["src"]["vertex"]), up(d["src"]["normal"]), 20.0, pose)
+    o.initRGBModel(up(d["src"]["image"]))
+    o.initCurvatureModel(up(d["src"]["curvk1"]), up(d["src"]["curvk2"]), pose)
+    o.initICP(up(d["fr"]["vertex_filtered"]), up(d["fr"]["normal"]), 20.0)
+    o.initRGB(up(d["rgba"]))
+    o.initCurvature(up(d["fr"]["curv1"]), up(d["fr"]["curv2"]))
+    o.initICPweight(up(d["src"]["icpw"]))
+    return o
+
+
+def test_default_config_frame_agrees_iteration_by_iteration(orc, cuda):
+    """The benchmarked configuration (reference defaults: RGB-D + ICP + SO3 pre-alignment, 640x480) pinned reduction by reduction.
+    The Gauss-Newton loop of RGBDOdometry.cpp:796-1249 is driven from Python over the oracle's step functions
+    (tests/gn_loop_py.py) and, at the SAME pose in every one of its 3 SO3 + 19 SE3 iterations, the CUDA step functions are
+    evaluated beside them: the integer outputs of computeRgbResidual (sigma, count) and the SO3 counts must be identical, the ICP
+    inlier count may move by a correspondence on the edge of a threshold, the 27 + 27 + 9 float sums agree to that one
+    correspondence.  Then both trackers run free on these (bit-identical) inputs."""
+    from hrbffusion3d_b200 import odometry as od
+    from tests import gn_loop_py as gn
+    W, H = 640, 480
+    cam, pose, d = _pipeline_frame1_inputs(orc, W, H)
+    mk_o = lambda: _init_tracker(orc.Odometry(W, H, cam[2], cam[3], cam[0], cam[1]), lambda a: a, pose, d)
+    mk_g = lambda: _init_tracker(od.RGBDOdometry(W, H, cam[2], cam[3], cam[0], cam[1]), lambda a: dev(cuda, a), pose, d)
+    t, R, log = gn.run(gn.OracleBackend(orc, mk_o()), cam, pose[:3, 3], pose[:3, :3], shadow=gn.CudaBackend(od, mk_g(), orc, cuda))
+    to, Ro, sto = mk_o().getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
+    ang, dt = pose_err(R, t, Ro, to)
+    assert ang <= 2e-6 and dt <= 2e-6, "the Python restatement of the loop left the oracle's C loop"      # fp64 solve: numpy vs the oracle's LDLT
+    n_so3 = sum(r["kind"] == "so3" for r in log)
+    assert n_so3 >= 2 and len(log) - n_so3 == 19
+    rel = lambda a, b, n: float(np.abs(a[:n] - b[:n]).max() / np.abs(a[:n]).max())
+    for r in log:
+        where = (r["kind"], r["level"], r["it"])
+        if r["kind"] == "so3":
+            assert r["d_res"][1] == r["s_res"][1], where
+            assert rel(r["d_sums"], r["s_sums"], 9) <= 1e-6, where
+            continue
+        assert (r["d_sigma"], r["d_count"]) == (r["s_sigma"], r["s_count"]), where               # integer sums: bit-exact
+        assert abs(r["d_icp_res"][1] - r["s_icp_res"][1]) <= 2, where
+        assert rel(r["d_icp_sums"], r["s_icp_sums"], 27) <= 1e-4, where                            # one of ~50 000 (level 1) correspondences
+        assert rel(r["d_rgb_sums"], r["s_rgb_sums"], 27) <= 1e-5, where
+    tg, Rg, stg = mk_g().getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
+    ang, dt = pose_err(Ro, to, Rg, tg)
+    print(f"default configuration, free-running on identical inputs: CUDA vs oracle ang {ang:.2e} t {dt:.2e}")
+    assert (stg.lastSO3Count, stg.lastRGBCount) == (sto.lastSO3Count, sto.lastRGBCount)
+    assert ang <= POSE_TOL and dt <= POSE_TOL, (ang, dt)
