@@ -7,6 +7,7 @@
 // pre-alignment, every ICP/RGB reduction of the three levels and the fp64 solves -- zero host
 // round trips inside the Gauss-Newton loop (the reference makes ~67 per frame).
 #include "track_persistent.cuh"
+#include "icp_tile.cuh"
 #include <map>
 #include <new>
 #include <stdarg.h>
@@ -91,6 +92,30 @@ static RgbStepArgs rgbstep_args(const hrbf_odometry* o, int l)
     return sa;
 }
 
+
+// The TMA-staged tile form of the ICP reduction (icp_tile.cuh) on the object's packed pyramids; pdl: programmatic stream serialization
+static cudaError_t launch_icp_tile(hrbf_odometry* o, const IcpArgs& ia, int mode, int level, int next_level, cudaStream_t s, bool pdl)
+{
+    const IcpTileGeom g = icp_tile_geom(ia.rows, ia.cols, o->num_sms);
+    const size_t dyn = icp_tile_smem_bytes(g);
+    {
+        static std::mutex mu;
+        static size_t dyn_set = 0;
+        std::lock_guard<std::mutex> lock(mu);
+        if (dyn > dyn_set) {
+            cudaError_t e = cudaFuncSetAttribute(icp_tile_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+            dyn_set = dyn;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.ctas); cfg.blockDim = dim3(g.threads); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, icp_tile_reduce_kernel, ia, g, o->work, mode, level, next_level);
+}
+
 // Enqueue the whole tracking loop on `s` (used under stream capture).  Returns kernel count.
 static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
                          bool so3, bool use_weight, bool host_io)
@@ -130,7 +155,7 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
             if (rgb) { rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, wk, 1, l, j == 0, next_lower); ++n; }
             if (icp) {
                 if (o->useSearch) icp_reduce_kernel<true><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
-                else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
+                else (void)launch_icp_tile(o, ia, rgb ? 0 : 1, l, next_level, s, false);
                 ++n;
             }
             if (rgb) { rgb_step_kernel<<<nb, kReduceThreads, 0, s>>>(sa, -2.0f, wk, 1, l, next_level); ++n; }
@@ -821,9 +846,35 @@ int hrbf_odometry_track_async(hrbf_odometry* o, const float* prev_pose_dev, floa
     return HRBF_OK;
 }
 
+
+int hrbf_odometry_icp_step(hrbf_odometry* o, int level, const float* Rcurr, const float* tcurr, const float* Rprev_inv, const float* tprev,
+                           int use_weight, int tiled, float* A, float* b, float* residual, double* sums29, void* stream)
+{
+    HRBF_CHECK_ARG(o && level >= 0 && level <= 2 && Rcurr && tcurr && Rprev_inv && tprev && A && b && residual);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = repack_if_dirty(o, s)) return rc;
+    TrackState h;
+    HRBF_CUDA(cudaMemcpyAsync(&h, &o->work->st, sizeof h, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    memcpy(h.Rcurr, Rcurr, 36); memcpy(h.tcurr, tcurr, 12); memcpy(h.Rprev_inv, Rprev_inv, 36); memcpy(h.tprev, tprev, 12);
+    h.done_level = -1; h.icp = 1; h.ticket = 0u;
+    if (int rc = init_work_state(o->work, s, h)) return rc;
+    const IcpArgs ia = icp_args(o, level, use_weight != 0);
+    if (tiled && !o->useSearch) HRBF_CUDA(launch_icp_tile(o, ia, 0, level, -1, s, false));
+    else if (o->useSearch) icp_reduce_kernel<true><<<reduce_blocks(ia.rows * ia.cols), kReduceThreads, 0, s>>>(ia, o->work, 0, level, -1);
+    else icp_reduce_kernel<false><<<reduce_blocks(ia.rows * ia.cols), kReduceThreads, 0, s>>>(ia, o->work, 0, level, -1);
+    HRBF_KERNEL_CHECK();
+    double sums[32];
+    HRBF_CUDA(cudaMemcpyAsync(sums, o->work->st.icp_sums, sizeof sums, cudaMemcpyDeviceToHost, s));
+    HRBF_CUDA(cudaStreamSynchronize(s));
+    unpack_host_se3(sums, A, b, residual);
+    if (sums29) memcpy(sums29, sums, 29 * sizeof(double));
+    return HRBF_OK;
+}
+
 int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_update, int reps, float* avg_us, void* stream)
 {
-    HRBF_CHECK_ARG(o && avg_us && which >= 0 && which <= 4 && level >= 0 && level <= 2 && reps > 0 && reps <= 2000);
+    HRBF_CHECK_ARG(o && avg_us && which >= 0 && which <= 7 && level >= 0 && level <= 2 && reps > 0 && reps <= 2000);
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = repack_if_dirty(o, s)) return rc;
     cudaEvent_t e0, e1;
@@ -851,10 +902,36 @@ int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_u
         *avg_us = ms * 1000.f / (float)reps;
         return HRBF_OK;
     }
+    if (which == 6 || which == 7) {
+        // COLD: before every launch a buffer larger than L2 is overwritten (so the maps come from HBM), and every launch is timed
+        // alone between its own pair of events; avg_us = mean over `reps` launches.  6: tile kernel, 7: the per-pixel-gather kernel.
+        const size_t flush_bytes = (size_t)256 << 20;
+        void* flush = nullptr;
+        HRBF_CUDA(cudaMalloc(&flush, flush_bytes));
+        double total = 0.0;
+        for (int r = 0; r < reps + 2; ++r) {
+            HRBF_CUDA(cudaMemsetAsync(flush, r & 0xff, flush_bytes, s));
+            HRBF_CUDA(cudaEventRecord(e0, s));
+            if (which == 6) HRBF_CUDA(launch_icp_tile(o, ia, with_update ? 1 : 0, level, -1, s, false));
+            else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, o->work, with_update ? 1 : 0, level, -1);
+            HRBF_CUDA(cudaEventRecord(e1, s));
+            HRBF_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            HRBF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 2) total += ms;
+            count_launch();
+        }
+        cudaFree(flush);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        HRBF_CUDA(cudaGetLastError());
+        *avg_us = (float)(total * 1000.0 / reps);
+        return HRBF_OK;
+    }
     // `reps` back-to-back launches captured into ONE graph (so the host's launch rate is not what is measured), replayed once
     // untimed and once between two events on `s`
     auto launch_once = [&](cudaStream_t q) {
         switch (which) {
+        case 5: (void)launch_icp_tile(o, ia, with_update ? 1 : 0, level, -1, q, true); break;
         case 0: icp_reduce_kernel<false><<<nb, kReduceThreads, 0, q>>>(ia, o->work, with_update ? 1 : 0, level, -1); break;
         case 1: rgb_residual_kernel<<<nb, 256, 0, q>>>(ra, o->work, 1, level, 0, -1); break;
         case 2: rgb_step_kernel<<<nb, kReduceThreads, 0, q>>>(sa, -2.0f, o->work, with_update ? 1 : 0, level, -1); break;

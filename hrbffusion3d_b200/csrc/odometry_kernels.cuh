@@ -823,6 +823,14 @@ __device__ __forceinline__ bool rgb_static_candidate(const RgbResArgs& a, int k,
     return !isnan(__ldg(a.nextDepth + k));
 }
 
+// row r of the photometric warp d1 * (K.x * x + K.y * y + K.z) + kt (reduce.cu:1029-1032), with the FMA contraction nvcc applies to
+// that expression spelled out -- FMUL y K.y, FFMA x K.x + ., FADD + K.z, FFMA d1 . + kt -- so that the rounding of u0 / v0 does
+// not depend on the compiler's mood; s_k = krkinv[9], kt[3]
+__device__ __forceinline__ float rgb_warp_row(const float* s_k, int r, int x, int y, float d1)
+{
+    return fmaf(d1, __fadd_rn(fmaf((float)x, s_k[3 * r], __fmul_rn((float)y, s_k[3 * r + 1])), s_k[3 * r + 2]), s_k[9 + r]);
+}
+
 // one pixel of computeRgbResidual (reduce.cu:986-1060); s_k = krkinv[9], kt[3]
 __device__ __forceinline__ void rgb_residual_pixel(const RgbResArgs& a, const float* s_k, int k, int& cnt, int& sig)
 {
@@ -833,9 +841,9 @@ __device__ __forceinline__ void rgb_residual_pixel(const RgbResArgs& a, const fl
     if (rgb_static_candidate(a, k, __ldg(a.dIdx + k), __ldg(a.dIdy + k))) {
         const int y = i, x = j0;
         const float d1 = __ldg(a.nextDepth + k);
-        const float td1 = d1 * (s_k[6] * x + s_k[7] * y + s_k[8]) + s_k[11];
-        const int u0 = __float2int_rn((d1 * (s_k[0] * x + s_k[1] * y + s_k[2]) + s_k[9]) / td1);
-        const int v0 = __float2int_rn((d1 * (s_k[3] * x + s_k[4] * y + s_k[5]) + s_k[10]) / td1);
+        const float td1 = rgb_warp_row(s_k, 2, x, y, d1);
+        const int u0 = __float2int_rn(rgb_warp_row(s_k, 0, x, y, d1) / td1);
+        const int v0 = __float2int_rn(rgb_warp_row(s_k, 1, x, y, d1) / td1);
         if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
             const float d0 = __ldg(a.lastDepth + (size_t)v0 * cols + u0);
             const unsigned char li = __ldg(a.lastImage + (size_t)v0 * cols + u0);

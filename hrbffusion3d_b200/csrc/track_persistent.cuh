@@ -191,9 +191,9 @@ __device__ __forceinline__ void rgb_residual_pass(const RgbResArgs& a, const uns
             uv[u] = -1; d0[u] = 0.f; td1[u] = 0.f; li[u] = 0; ni[u] = 0;
             if (c[u]) {
                 const int y = k / cols, x = k - y * cols;
-                td1[u] = d1[u] * (s_k[6] * x + s_k[7] * y + s_k[8]) + s_k[11];
-                const int u0 = __float2int_rn((d1[u] * (s_k[0] * x + s_k[1] * y + s_k[2]) + s_k[9]) / td1[u]);
-                const int v0 = __float2int_rn((d1[u] * (s_k[3] * x + s_k[4] * y + s_k[5]) + s_k[10]) / td1[u]);
+                td1[u] = rgb_warp_row(s_k, 2, x, y, d1[u]);
+                const int u0 = __float2int_rn(rgb_warp_row(s_k, 0, x, y, d1[u]) / td1[u]);
+                const int v0 = __float2int_rn(rgb_warp_row(s_k, 1, x, y, d1[u]) / td1[u]);
                 if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
                     uv[u] = (v0 << 16) | u0;
                     d0[u] = __ldg(a.lastDepth + (size_t)v0 * cols + u0);

@@ -95,6 +95,18 @@ class RGBDOdometry:
         check(lib().hrbf_odometry_track_async(self._h, ptr(prev_pose_dev), ptr(pose_out_dev), int(rgbOnly), C.c_float(icpWeight), int(pyramid),
                                               int(fastOdom), int(so3), int(if_curvature_info), stream_ptr()))
 
+    def icpStepLevel(self, level, Rcurr, tcurr, Rprev_inv, tprev, use_weight=True, tiled=True):
+        """icpStep (reduce.cu:580-693) on this object's own pyramid level; tiled = the TMA-staged tile form of the reduction"""
+        A, b, res, sums = np.zeros(36, np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32), np.zeros(29, np.float64)
+        check(lib().hrbf_odometry_icp_step(self._h, int(level), _hp(_f32(Rcurr)), _hp(_f32(tcurr)), _hp(_f32(Rprev_inv)), _hp(_f32(tprev)), int(use_weight),
+                                           int(tiled), _hp(A), _hp(b), _hp(res), _hp(sums, C.c_double), stream_ptr()))
+        return A.reshape(6, 6), b, res, sums
+
+    def timeKernel(self, which, level, with_update=0, reps=200):
+        us = C.c_float()
+        check(lib().hrbf_odometry_time_kernel(self._h, int(which), int(level), int(with_update), int(reps), C.byref(us), stream_ptr()))
+        return us.value
+
     # ---- test / chaining views (copies) ----
     def map(self, which, level):
         idx = MAP_NAMES.index(which) if isinstance(which, str) else which

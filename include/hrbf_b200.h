@@ -207,6 +207,13 @@ int hrbf_odometry_track_async(hrbf_odometry*, const float* prev_pose_dev, float*
  * iterations at `level` (reduction + cross-CTA exchange + fp64 solve); avg_us is the time per iteration.
  * Needs initialised pyramids and one prior tracking call. */
 int hrbf_odometry_time_kernel(hrbf_odometry*, int which, int level, int with_update, int reps, float* avg_us, void* stream);
+/* icpStep (reduce.cu:580-693) on the object's OWN pyramid level (the maps the init* calls built) for a caller-given pose:
+ * tiled != 0 runs the TMA-staged tile form of the reduction (the one the tracking loop uses when correspondence search is off),
+ * 0 the per-pixel-gather form.  Outputs as hrbf_icp_step.  which = 5 / 6 / 7 of hrbf_odometry_time_kernel time these two:
+ * 5 = tile form, back-to-back launches (L2-hot); 6 = tile form, 7 = gather form, each launch timed alone after an L2 flush (cold). */
+int hrbf_odometry_icp_step(hrbf_odometry*, int level, const float* Rcurr_host, const float* tcurr_host, const float* Rprev_inv_host,
+                           const float* tprev_host, int use_weight, int tiled, float* A_host, float* b_host, float* residual_host,
+                           double* sums29_host, void* stream);
 /* device views of the internal pyramid maps (tests, chaining):
  * which = 0..8 -> vmap_g_prev,nmap_g_prev,ck1_g_prev,ck2_g_prev,vmap_curr,nmap_curr,ck1_curr,ck2_curr,icpWeight */
 const float* hrbf_odometry_map(const hrbf_odometry*, int which, int level, size_t* step_bytes);

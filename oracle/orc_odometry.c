@@ -538,9 +538,14 @@ void orc_computeRgbResidual(int rows, int cols, float minScale,
                         int y = i, x = j0;
                         float d1 = nextDepth[k];
                         if (!isnan(d1)) {
-                            float td1 = (float)(d1 * (K[6] * x + K[7] * y + K[8]) + kt[2]);
-                            int u0 = f2i_rn((d1 * (K[0] * x + K[1] * y + K[2]) + kt[0]) / td1);
-                            int v0 = f2i_rn((d1 * (K[3] * x + K[4] * y + K[5]) + kt[1]) / td1);
+                            /* the warp d1 * (K.x * x + K.y * y + K.z) + kt as nvcc contracts it in the reference's build (read off the
+                             * SASS of residualKernel in oracle/_ref/libref_reduce.so): FMUL y*K.y, FFMA x*K.x + ., FADD + K.z, FFMA d1 * . + kt.
+                             * The division stays IEEE (the reference build's MUFU.RCP cannot be restated) */
+#define ORC_WARP_ROW(r, t) fmaf(d1, fmaf((float)x, K[3 * (r)], (float)y * K[3 * (r) + 1]) + K[3 * (r) + 2], (t))
+                            float td1 = ORC_WARP_ROW(2, kt[2]);
+                            int u0 = f2i_rn(ORC_WARP_ROW(0, kt[0]) / td1);
+                            int v0 = f2i_rn(ORC_WARP_ROW(1, kt[1]) / td1);
+#undef ORC_WARP_ROW
                             if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
                                 float d0 = lastDepth[(size_t)v0 * cols + u0];
                                 if (d0 > 0 && fabsf(td1 - d0) <= maxDepthDelta && lastImage[(size_t)v0 * cols + u0] != 0) {

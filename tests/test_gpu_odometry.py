@@ -131,6 +131,37 @@ def test_icp_step_matches_oracle(orc, cuda, W, H, use_weight):
         np.testing.assert_allclose(A, Ao, rtol=1e-3, atol=SUM_RTOL * np.abs(Ao).max())
 
 
+@pytest.mark.parametrize("W,H", [(96, 72), (160, 120), (640, 480), (1280, 960)])
+def test_icp_tile_reduction_matches_oracle(orc, cuda, W, H):
+    """The TMA-staged tile form of the ICP reduction (csrc/icp_tile.cuh: bulk-copied current-frame rows, bounding box of the
+    associations, bulk-copied model window, gather from shared memory, __ldg for associations outside the window) against the
+    oracle's icpStep and against the per-pixel-gather kernel, on every pyramid level, for the pose tracking starts from (shift 0),
+    the true pose (a few pixels), and a pose far outside the window (3 degrees / 5 cm: every association takes the fallback)."""
+    from hrbffusion3d_b200 import synth
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
+    Rp, tp = pose0[:3, :3], pose0[:3, 3]
+    Rpi = np.linalg.inv(Rp).astype(np.float32)
+    far = (pose0.astype(np.float64) @ synth.make_pose(0.05, -0.03, 0.02, (0.05, -0.03, 0.02)).astype(np.float64)).astype(np.float32)
+    names = ("vmap_curr", "nmap_curr", "ck1_curr", "ck2_curr")
+    gnames = ("vmap_g_prev", "nmap_g_prev", "ck1_g_prev", "ck2_g_prev", "icpWeight")
+    for pose in (pose0, pose1, far):
+        Rc, tc = np.ascontiguousarray(pose[:3, :3]), np.ascontiguousarray(pose[:3, 3])
+        for lvl in range(3):
+            if (H >> lvl) < 16:
+                continue
+            camL = tuple(np.float32(c) / np.float32(1 << lvl) for c in cam)
+            for use_weight in (1, 0):
+                Ao, bo, reso, sumso, _ = orc.icpStep(Rc, tc, *[oo.map(k, lvl) for k in names], Rpi, tp, camL, *[oo.map(k, lvl) for k in gnames], use_weight=use_weight)
+                At, bt, rest, sumst = go.icpStepLevel(lvl, Rc, tc, Rpi, tp, use_weight=bool(use_weight), tiled=True)
+                Ag, bg, resg, sumsg = go.icpStepLevel(lvl, Rc, tc, Rpi, tp, use_weight=bool(use_weight), tiled=False)
+                assert rest[1] == resg[1], (lvl, rest[1], resg[1])                           # same associations as the gather kernel, exactly
+                assert abs(rest[1] - reso[1]) <= max(2.0, 2e-4 * reso[1])
+                scale = np.abs(sumso[:27]).max()
+                np.testing.assert_allclose(sumst[:27], sumsg[:27], rtol=1e-4, atol=1e-6 * scale)     # fp32 partial sums grouped differently
+                np.testing.assert_allclose(sumst[:27], sumso[:27], rtol=SUM_RTOL * 50, atol=SUM_RTOL * scale)
+    assert reso[1] > 0
+
+
 def test_icp_step_search_window(orc, cuda):
     from hrbffusion3d_b200 import odometry as od
     oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, 160, 120)
@@ -268,27 +299,16 @@ def _pipeline_frame1_inputs(orc, W, H):
     """the tracker inputs of the SECOND frame of the oracle pipeline (the first tracked one): model maps = fill-in of frame 0"""
     from oracle import orc_pipeline as op
     from hrbffusion3d_b200 import synth
+    from tests.util import pipeline_tracker_inputs
     cam = synth.default_camera(W, H)
     sc = synth.Scene("room")
     frames = [synth.render_depth(sc, p, W, H, cam, noise=True, seed=i) for i, p in enumerate(synth.circle_trajectory(2, frames_per_rev=120))]
     f = op.HRBFFusion(W, H, cam)
     f.processFrame(frames[0][1], frames[0][0])
-    depth, rgb = frames[1]
-    fr = orc.preprocess(f.pp, depth)
-    src = f.fill if not orc.denseEnough(f.pred["vertex"]) else f.pred
-    return cam, f.currPose.copy(), dict(first=f.rgba(frames[0][1]), rgba=f.rgba(rgb), src=src, fr=fr)
+    return cam, f.currPose.copy(), pipeline_tracker_inputs(orc, f, frames[0][1], frames[1][1], frames[1][0])
 
 
-def _init_tracker(o, up, pose, d):
-    o.initFirstRGB(up(d["first"]))
-    o.initICPModel(up(d["src"]["vertex"]), up(d["src"]["normal"]), 20.0, pose)
-    o.initRGBModel(up(d["src"]["image"]))
-    o.initCurvatureModel(up(d["src"]["curvk1"]), up(d["src"]["curvk2"]), pose)
-    o.initICP(up(d["fr"]["vertex_filtered"]), up(d["fr"]["normal"]), 20.0)
-    o.initRGB(up(d["rgba"]))
-    o.initCurvature(up(d["fr"]["curv1"]), up(d["fr"]["curv2"]))
-    o.initICPweight(up(d["src"]["icpw"]))
-    return o
+from tests.util import init_tracker as _init_tracker  # noqa: E402
 
 
 def test_default_config_frame_agrees_iteration_by_iteration(orc, cuda):
@@ -297,7 +317,9 @@ def test_default_config_frame_agrees_iteration_by_iteration(orc, cuda):
     (tests/gn_loop_py.py) and, at the SAME pose in every one of its 3 SO3 + 19 SE3 iterations, the CUDA step functions are
     evaluated beside them: the integer outputs of computeRgbResidual (sigma, count) and the SO3 counts must be identical, the ICP
     inlier count may move by a correspondence on the edge of a threshold, the 27 + 27 + 9 float sums agree to that one
-    correspondence.  Then both trackers run free on these (bit-identical) inputs."""
+    correspondence.  Then both trackers run free on these (bit-identical) inputs: what separates them is bounded by what a change of
+    the inputs in the last place does to the ORACLE itself (tests/util.tracker_noise_floor) -- the hard roundings of the photometric
+    correspondences make this configuration sensitive (~5e-6 per unit in the last place with ~4 800 correspondences at level 0)."""
     from hrbffusion3d_b200 import odometry as od
     from tests import gn_loop_py as gn
     W, H = 640, 480
@@ -324,5 +346,8 @@ def test_default_config_frame_agrees_iteration_by_iteration(orc, cuda):
     tg, Rg, stg = mk_g().getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
     ang, dt = pose_err(Ro, to, Rg, tg)
     print(f"default configuration, free-running on identical inputs: CUDA vs oracle ang {ang:.2e} t {dt:.2e}")
-    assert (stg.lastSO3Count, stg.lastRGBCount) == (sto.lastSO3Count, sto.lastRGBCount)
-    assert ang <= POSE_TOL and dt <= POSE_TOL, (ang, dt)
+    from tests.util import tracker_noise_floor
+    floor = tracker_noise_floor(orc, W, H, cam, pose, d, {}, n=4)
+    print(f"the oracle's own sensitivity to one unit in the last place of its inputs: {floor:.2e}")
+    assert stg.lastSO3Count == sto.lastSO3Count and abs(stg.lastRGBCount - sto.lastRGBCount) <= 2
+    assert ang <= max(POSE_TOL, 4 * floor) and dt <= max(POSE_TOL, 4 * floor), (ang, dt, floor)
