@@ -31,6 +31,7 @@ struct hrbf_odometry {
     float4* pk[4][HRBF_NUM_PYRS] = {};           // packed ICP operands: [0] curr pk0, [1] curr pk1, [2] model pk0, [3] model pk1
     bool pack_dirty_curr = false, pack_dirty_model = false;   // SoA written by a builder that does not pack (GPUTest path)
     unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
+    bool tile_resident = true;                   // persistent tracker: keep each level's ICP tile in shared memory (hrbf_odometry_set_tracker_tiles)
     int track_threads = 512;                     // threads per CTA of the persistent tracker (256 | 512), hrbf_odometry_set_tracker_threads
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
     hrbf::ReduceWork* work = nullptr;

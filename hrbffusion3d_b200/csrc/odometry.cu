@@ -96,6 +96,10 @@ static RgbStepArgs rgbstep_args(const hrbf_odometry* o, int l)
 // The TMA-staged tile form of the ICP reduction (icp_tile.cuh) on the object's packed pyramids; pdl: programmatic stream serialization
 static cudaError_t launch_icp_tile(hrbf_odometry* o, const IcpArgs& ia, int mode, int level, int next_level, cudaStream_t s, bool pdl)
 {
+    if (ia.cols % 4 != 0 || ia.pc0 == nullptr) {      // rows of the weight map must start 16-byte aligned for the bulk copies
+        icp_reduce_kernel<false><<<reduce_blocks(ia.rows * ia.cols), kReduceThreads, 0, s>>>(ia, o->work, mode, level, next_level);
+        return cudaGetLastError();
+    }
     const IcpTileGeom g = icp_tile_geom(ia.rows, ia.cols, o->num_sms);
     const size_t dyn = icp_tile_smem_bytes(g);
     {
@@ -191,7 +195,32 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     p.max_slots = max_slots;
     const bool half = o->track_threads == 256;
     const void* kernel = half ? (const void*)track_persistent_kernel<256> : (const void*)track_persistent_kernel<512>;
-    const size_t dyn = track_slots_bytes(max_slots, o->track_threads);
+    // resident ICP tiles (icp_tile.cuh): a level keeps its tile in shared memory when slots + tile fit beside the kernel's static
+    // shared memory (the 256-thread shape shares the SM with another CTA: half the budget)
+    size_t dyn = track_slots_bytes(max_slots, o->track_threads);
+    {
+        static std::mutex mu;
+        static size_t budget[2] = { 0, 0 };
+        std::lock_guard<std::mutex> lock(mu);
+        if (budget[half] == 0) {
+            cudaFuncAttributes fa;
+            HRBF_CUDA(cudaFuncGetAttributes(&fa, kernel));
+            int dev = 0, optin = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            size_t total = (size_t)optin;
+            if (half) total = total / 2 - 1024;      // two CTAs per SM, 1 KB reserved each
+            budget[half] = total > fa.sharedSizeBytes + 1024 ? total - fa.sharedSizeBytes - 512 : 1;
+        }
+        size_t tile_bytes = 0;
+        for (int l = 0; l < 3; ++l) {
+            p.tile[l] = track_tile_geom(o->rows(l), o->cols(l), o->num_sms);
+            const size_t need = icp_tile_smem_bytes(p.tile[l]);
+            p.resident[l] = (iters[l] > 0 && o->tile_resident && !o->useSearch && o->cols(l) % 4 == 0 && dyn + need <= budget[half]) ? 1 : 0;
+            if (p.resident[l] && need > tile_bytes) tile_bytes = need;
+        }
+        dyn += tile_bytes;
+    }
     {   // the attribute belongs to the kernel, not to this object: only ever raise it
         static std::mutex mu;
         static size_t dyn_set[2] = { 0, 0 };
@@ -579,6 +608,12 @@ int hrbf_odometry_set_tracker_threads(hrbf_odometry* o, int threads)
     if (threads == 0) threads = kTrackThreadsDefault;
     if (threads != 256 && threads != 512) { set_error("set_tracker_threads: 256 or 512 (0 = default 512)"); return HRBF_ERR_INVALID_ARG; }
     o->track_threads = threads;
+    return HRBF_OK;
+}
+int hrbf_odometry_set_tracker_tiles(hrbf_odometry* o, int resident)
+{
+    HRBF_CHECK_ARG(o);
+    o->tile_resident = resident != 0;
     return HRBF_OK;
 }
 int hrbf_odometry_set_params(hrbf_odometry* o, float curvThr, int useSearch, int searchRadius, int rgbGradWeight)

@@ -9,7 +9,7 @@
 // __threadfence of the last-block-done scheme.
 #pragma once
 #define GN_STAMP(k) do { if (dbg && dbg_n_ptr && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); dbg[*dbg_n_ptr < 500 ? (*dbg_n_ptr)++ : 499] = ((long long)(k) << 56) | (t_ & 0x00ffffffffffffffll); } } while (0)
-#include "odometry_kernels.cuh"
+#include "icp_tile.cuh"
 
 namespace hrbf {
 
@@ -41,7 +41,9 @@ struct TrackParams {
     float* weighting_out; float weight_multiplier; // fusion weight from the inter-frame motion
     float* traj_out;                               // this frame's row of the trajectory
     TrackState* st_global;                         // camera in, statistics out
-    int max_slots;                                 // dynamic shared memory holds max_slots x kTrackThreads RgbSlots
+    int max_slots;                                 // dynamic shared memory holds max_slots x kTrackThreads RgbSlots ...
+    IcpTileGeom tile[3];                           // ... followed by the resident ICP tile of the level being worked on (icp_tile.cuh):
+    int resident[3];                               // level l keeps its tile of packed records + model window in shared memory for all its iterations
     unsigned long long* ll_f;                      // [2][gridDim.x][64] (float, tag) words: the per-CTA partial sums
     unsigned long long* ll_i;                      // [2][gridDim.x][kIntStride] (int, tag) words: {count, sum diff^2} of computeRgbResidual in words 0-1
     unsigned int epoch;                            // launch counter (20 bits, never 0): tags of older launches never match
@@ -274,8 +276,22 @@ __device__ __forceinline__ void rgb_step_pass(const RgbStepArgs& a, float sigma,
     }
 }
 
-// dynamic shared memory of the persistent tracker: the RGB slots, max_slots x kTrackThreads
-inline size_t track_slots_bytes(int max_slots, int threads) { return (size_t)max_slots * threads * sizeof(RgbSlot); }
+// dynamic shared memory of the persistent tracker: the RGB slots, max_slots x kTrackThreads (rounded up to 128 B), then the resident ICP tile
+inline size_t track_slots_bytes(int max_slots, int threads) { return ((size_t)max_slots * threads * sizeof(RgbSlot) + 127) & ~(size_t)127; }
+// one tile per CTA: 4 x (ctas / 4) tiles when the CTA count allows, a narrower window than the stand-alone kernel's (the bounding box is
+// taken under the pose the level starts with; 2 pixels of margin on the low side, the rest of the slack on the high side)
+inline IcpTileGeom track_tile_geom(int rows, int cols, int ctas)
+{
+    IcpTileGeom g;
+    g.ncol = (ctas % 4 == 0) ? 4 : (ctas % 2 == 0) ? 2 : 1;
+    g.nrow = ctas / g.ncol;
+    g.tw = (div_up(cols, g.ncol) + 3) & ~3;
+    g.th = div_up(rows, g.nrow);
+    g.mw = g.tw + 8;
+    g.mh = g.th + 6;
+    g.ctas = ctas; g.threads = 0;
+    return g;
+}
 
 template <int kTrackThreads>
 __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
@@ -284,6 +300,13 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
     pdl_wait();
     extern __shared__ __align__(16) unsigned char s_dyn[];
     RgbSlot* s_slots = reinterpret_cast<RgbSlot*>(s_dyn);
+    unsigned char* s_tile = s_dyn + (((size_t)p.max_slots * kTrackThreads * sizeof(RgbSlot) + 127) & ~(size_t)127);
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_box[4];
+    __shared__ int s_win[4];
+    __shared__ IcpTileView s_tv;
+    uint32_t par0 = 0, par1 = 0;                         // phase parities of the two mbarriers (uniform over the CTA)
+    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     int dbg_n = 0;
     __shared__ TrackState S;
     __shared__ float s_w[kTrackWarps][32];
@@ -377,6 +400,54 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
         const int N = L.icp.rows * L.icp.cols;
         const int begin = (int)(((long long)N * blockIdx.x) / gridDim.x), end = (int)(((long long)N * (blockIdx.x + 1)) / gridDim.x);
         const float ifx = 1.0f / L.step.fx, ify = 1.0f / L.step.fy, lcx = L.icp.cx, lcy = L.icp.cy;     // projectToPointCloud's 1/fx, 1/fy, cx, cy of this level
+        // ---- resident ICP tile: this CTA's tile of current-frame records and the model window its associations fall into are
+        // staged ONCE per level by the TMA unit (icp_tile.cuh) and serve all iterations of the level from shared memory; the window
+        // is the associations' bounding box under the pose the level starts with, plus a margin for the pose to move; an
+        // association that leaves it is served from global memory with identical arithmetic ----
+        IcpTileView& tv = s_tv;                          // shared: the view costs no registers across the iteration loop
+        const bool tile_res = p.resident[l] && p.icp && !L.icp.use_search;
+        if (tile_res) {
+            const IcpTileGeom& g = p.tile[l];
+            float4* s_c0 = reinterpret_cast<float4*>(s_tile);
+            float4* s_c1 = s_c0 + g.tw * g.th;
+            float4* s_g0 = s_c1 + g.tw * g.th;
+            float4* s_g1 = s_g0 + g.mw * g.mh;
+            float* s_gw = reinterpret_cast<float*>(s_g1 + g.mw * g.mh);
+            __syncthreads();      // nobody still reads the previous level's view
+            if (tid == 0) {
+                const int tcx = (int)blockIdx.x % g.ncol, try_ = (int)blockIdx.x / g.ncol;
+                tv.x0 = min(tcx * g.tw, L.icp.cols); tv.w = min(g.tw, L.icp.cols - tv.x0);
+                tv.y0 = (int)(((long long)L.icp.rows * try_) / g.nrow); tv.h = (int)(((long long)L.icp.rows * (try_ + 1)) / g.nrow) - tv.y0;
+                if (try_ >= g.nrow) tv.w = tv.h = 0;
+                tv.c0 = s_c0; tv.c1 = s_c1; tv.g0 = s_g0; tv.g1 = s_g1; tv.gw = s_gw; tv.tw = g.tw; tv.mw = g.mw;
+                tv.mx0 = tv.my0 = tv.mwa = tv.mha = 0;
+            }
+            __syncthreads();      // nobody still reads the previous level's tile
+            if (tv.w > 0 && tv.h > 0) {
+                if (tid < 32) icp_tile_issue_curr(L.icp, s_c0, s_c1, g.tw, tv.x0, tv.y0, tv.w, tv.h, &s_bar[0]);
+                if (tid == 32) { s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1; }
+                __syncthreads();
+                mbar_wait(&s_bar[0], par0); par0 ^= 1u;
+                float Rc[9], tc[3], Rpi[9], tp[3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { Rc[k] = S.Rcurr[k]; Rpi[k] = S.Rprev_inv[k]; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { tc[k] = S.tcurr[k]; tp[k] = S.tprev[k]; }
+                icp_tile_bbox<kTrackThreads>(L.icp, tv, Rc, tc, Rpi, tp, s_box);
+                __syncthreads();
+                if (tid < 32) {
+                    int mx0, my0, mwa, mha;
+                    icp_tile_window(s_box, L.icp.rows, L.icp.cols, g.mw, g.mh, 2, mx0, my0, mwa, mha);
+                    if (tid == 0) { s_win[0] = mx0; s_win[1] = my0; s_win[2] = mwa; s_win[3] = mha; }
+                    if (mwa > 0 && mha > 0) icp_tile_issue_model(L.icp, s_g0, s_g1, s_gw, g.mw, mx0, my0, mwa, mha, &s_bar[1]);
+                }
+                __syncthreads();
+                const bool staged = s_win[2] > 0 && s_win[3] > 0;
+                if (tid == 0 && staged) { tv.mx0 = s_win[0]; tv.my0 = s_win[1]; tv.mwa = s_win[2]; tv.mha = s_win[3]; }
+                if (staged) { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
+                __syncthreads();
+            }
+        }
         for (int j = 0; j < L.iters; ++j) {
             if (S.done_level == l) break;
             const int next_level = (j + 1 < L.iters) ? l : next_lower;
@@ -412,6 +483,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { tc[k] = S.tcurr[k]; tp[k] = S.tprev[k]; }
                 if (L.icp.use_search) for (int i = gtid; i < N; i += gstride) icp_pixel<true>(L.icp, Rc, tc, Rpi, tp, i, acc);
+                else if (tile_res) icp_tile_pass<kTrackThreads>(L.icp, tv, Rc, tc, Rpi, tp, acc);
                 else icp_pass_nosearch<kTrackThreads>(L.icp, Rc, tc, Rpi, tp, begin, end, acc);
                 TP_STAMP(2);
                 block_partial32<kTrackThreads>(acc, s_w, part + (size_t)blockIdx.x * 64, tag);

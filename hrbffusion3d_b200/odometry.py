@@ -41,6 +41,10 @@ class RGBDOdometry:
         """False (default): one persistent cooperative kernel; True: one kernel per reduction in a CUDA graph"""
         check(lib().hrbf_odometry_set_tracker(self._h, int(use_kernel_graph)))
 
+    def setTrackerTiles(self, resident=True):
+        """persistent tracker: keep every level's ICP tile in shared memory across its iterations (default) or re-read the maps"""
+        check(lib().hrbf_odometry_set_tracker_tiles(self._h, int(resident)))
+
     def setTrackerThreads(self, threads=512):
         """512 (default): the persistent tracker fills every SM; 256: leaves half of each SM to other sequences' kernels"""
         check(lib().hrbf_odometry_set_tracker_threads(self._h, int(threads)))

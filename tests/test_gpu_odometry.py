@@ -259,6 +259,42 @@ def test_persistent_and_graph_trackers_agree(orc, cuda):
         assert res[0][2].kernel_launches == 1 and res[1][2].kernel_launches > 1
 
 
+@pytest.mark.parametrize("W,H", [(96, 72), (320, 240), (640, 480), (1280, 960)])
+def test_resident_tile_tracker_matches_streaming_tracker(orc, cuda, W, H):
+    """The persistent tracker with its ICP tiles resident in shared memory (TMA-staged once per level, csrc/icp_tile.cuh) against the
+    same kernel re-reading the maps every iteration, and against the oracle: same associations, fp32 partial sums grouped by tile
+    instead of by pixel range.  1280x960: level 0 does not fit and streams, levels 1-2 are resident.  Also with the 256-thread
+    shape (half the shared-memory budget) and with a start pose far from the solution (associations outside the staged window)."""
+    from hrbffusion3d_b200 import synth
+    for kw in (dict(icpWeight=100.0, so3=False), dict(icpWeight=10.0, so3=True)):
+        for threads in (512, 256):
+            res = {}
+            for resident in (True, False):
+                oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
+                go.setTrackerTiles(resident)
+                go.setTrackerThreads(threads)
+                res[resident] = go.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **kw)
+            to, Ro, sto = oo.getIncrementalTransformation(pose0[:3, 3], pose0[:3, :3], **kw)
+            ang, dt = pose_err(res[True][1], res[True][0], res[False][1], res[False][0])
+            tol = 1e-6 if kw["icpWeight"] >= 100 else 2e-5
+            assert ang <= tol and dt <= tol, (kw, threads, ang, dt)
+            assert res[True][2].icp_iterations_run == res[False][2].icp_iterations_run == sto.icp_iterations_run
+            assert abs(res[True][2].lastICPCount - res[False][2].lastICPCount) <= 2
+            if W >= 320:
+                ang, dt = pose_err(res[True][1], res[True][0], Ro, to)
+                assert ang <= (POSE_TOL if W >= 640 else 1e-4) and dt <= (POSE_TOL if W >= 640 else 1e-4), (kw, threads, ang, dt)
+    # far start: 2 degrees / 3 cm off -> most associations leave the window staged for the level's first pose
+    oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
+    far = (pose0.astype(np.float64) @ synth.make_pose(0.03, -0.02, 0.02, (0.03, -0.02, 0.01)).astype(np.float64)).astype(np.float32)
+    out = {}
+    for resident in (True, False):
+        go.setTrackerTiles(resident)
+        out[resident] = go.getIncrementalTransformation(far[:3, 3], far[:3, :3], icpWeight=100.0, so3=False)
+    ang, dt = pose_err(out[True][1], out[True][0], out[False][1], out[False][0])
+    assert ang <= 1e-5 and dt <= 1e-5, (ang, dt)
+    assert abs(out[True][2].lastICPCount - out[False][2].lastICPCount) <= 3
+
+
 def test_tracking_two_frames_so3_swap(orc, cuda):
     """Second call exercises the lastNextImage/nextImage swap (RGBDOdometry.cpp:1239-1245)."""
     oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, 320, 240)
