@@ -180,9 +180,9 @@ def test_process_frame_sequence_matches_oracle(orc, cuda, W, H, kw):
         ang, dt = pose_err(To[:3, :3], To[:3, 3], Tg[:3, :3], Tg[:3, 3])
         cnt = gpu.globalModel.lastCount()
         print(f"frame {i}: pose diff ang {ang:.2e} t {dt:.2e} (oracle's own 1-ulp sensitivity {floors[i]:.1e}); surfels gpu {cnt} oracle {ref.surfels.shape[0]}")
-        # north_star bound 1e-5 per frame, or 4 x what one unit in the last place of the tracker's inputs does to the oracle itself on this
+        # north_star bound 1e-5 per frame, or 8 x what one unit in the last place of the tracker's inputs does to the oracle itself on this
         # frame (tests/util.tracker_noise_floor), whichever is larger; free-running, so the allowances of the frames so far add up
-        tol_sum += max(1e-5, 4 * floors[i])
+        tol_sum += max(1e-5, 8 * floors[i])
         tol = tol_sum
         assert ang <= tol and dt <= tol, (i, ang, dt)
         assert abs(cnt - ref.surfels.shape[0]) <= max(5, int(3e-3 * ref.surfels.shape[0]))
