@@ -117,6 +117,28 @@ __device__ __forceinline__ float velocity_weighting_dev(const float* curr, const
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Guard of an 8-slot staging ring (a pinned host buffer + its device twin per slot) that asynchronous copies and kernels read after
+// the API call has returned: a slot is taken again only when the work enqueued by its previous user has completed.
+struct SlotRing {
+    cudaEvent_t ev[8] = {};
+    bool used[8] = {};
+    int next = 0;
+    int acquire()      // returns the slot; blocks only if the call 8 uses ago is still in flight
+    {
+        const int k = next++ & 7;
+        if (used[k]) cudaEventSynchronize(ev[k]);
+        return k;
+    }
+    void release(int k, cudaStream_t s)      // call after the last enqueue that reads the slot
+    {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { (void)cudaGetLastError(); used[k] = false; return; }
+        if (!ev[k] && cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ev[k] = nullptr; used[k] = false; return; }
+        used[k] = cudaEventRecord(ev[k], s) == cudaSuccess;
+    }
+    void destroy() { for (int k = 0; k < 8; ++k) if (ev[k]) { cudaEventDestroy(ev[k]); ev[k] = nullptr; used[k] = false; } }
+};
+
 // SoA map view: plane k, row y, col x -> p[(k*rows + y)*pitch + x]   (pitch in elements)
 struct SoA {
     float* p;

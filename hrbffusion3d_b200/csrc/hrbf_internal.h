@@ -31,6 +31,7 @@ struct hrbf_odometry {
     float4* pk[4][HRBF_NUM_PYRS] = {};           // packed ICP operands: [0] curr pk0, [1] curr pk1, [2] model pk0, [3] model pk1
     bool pack_dirty_curr = false, pack_dirty_model = false;   // SoA written by a builder that does not pack (GPUTest path)
     unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
+    void* tmaps_dev = nullptr;                   // device: CUtensorMap[2 geometries][3 levels][5 arrays] for the TMA-staged ICP tiles (icp_tile.cuh); null = unavailable
     bool tile_resident = true;                   // persistent tracker: keep each level's ICP tile in shared memory (hrbf_odometry_set_tracker_tiles)
     int track_threads = 512;                     // threads per CTA of the persistent tracker (256 | 512), hrbf_odometry_set_tracker_threads
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
@@ -46,7 +47,7 @@ struct hrbf_odometry {
     float* h_pose = nullptr;         // [0..11] in, [12..23] out
     hrbf::TrackState* h_state = nullptr;
     float* h_model_pose = nullptr;   // staging ring for init_*_model poses
-    int h_model_pose_slot = 0;
+    hrbf::SlotRing model_pose_ring;   // guards h_model_pose
     int so3_parity = 0;
 
     cudaStream_t cap_stream = nullptr;
@@ -68,7 +69,7 @@ struct hrbf_indexmap {
     unsigned int* count_slot = nullptr;  // device ring of 8 counts (host-count API)
     float* h_stage = nullptr;            // pinned ring: 8 x 16 floats
     float* h_kf = nullptr;               // pinned keyframe mask
-    int slot = 0;
+    hrbf::SlotRing ring;                 // guards h_stage / inv_pose / count_slot
     unsigned long long* row_lut = nullptr;      // device: make_pred_row_lut()
     unsigned int* dense_count_next = nullptr;   // frame pipeline: where the next ACTIVE prediction counts its dense-enough samples (or null)
 };

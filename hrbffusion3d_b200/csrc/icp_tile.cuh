@@ -1,8 +1,9 @@
 // icp_tile.cuh -- the ICP JtJ / Jtr reduction (Core/src/Cuda/reduce.cu:317-573) over TMA-staged tiles.
 //
 // The image is cut into tiles (about 80 x 13 pixels, one or a few per CTA).  A tile's packed current-frame records are
-// contiguous rows: they are brought into shared memory by the TMA unit (cp.async.bulk, one bulk copy per row and array,
-// completion on an mbarrier) without passing through registers.  Under the inter-frame motions the tracker sees (<= 1 cm,
+// a 2-D box of the image: they are brought into shared memory by the TMA unit (cp.async.bulk.tensor.2d through a tensor map
+// per array and pyramid level, one request per box, completion on an mbarrier) without passing through registers; parts of a
+// box that fall outside the image are zero-filled by the unit and never read.  Under the inter-frame motions the tracker sees (<= 1 cm,
 // <= 0.5 degrees) the projective association is a near-constant shift over a tile, so the model records a tile needs lie in a
 // window only a few pixels larger than the tile: its bounding box is computed from the staged current-frame records, and the
 // window (model pk0 / pk1 / icp-weight rows) is staged by a second round of bulk copies.  The dependent gather of the
@@ -17,9 +18,17 @@ namespace hrbf {
 struct IcpTileGeom {
     int ncol, nrow;      // tile grid over the image
     int tw, th;          // largest tile (pixels); tw is a multiple of 4
-    int mw, mh;          // model window capacity (pixels); mw is a multiple of 4
+    int mw, mh;          // model window (pixels); mw is a multiple of 4
+    int cnb, cbx;        // a tile row is fetched as cnb boxes of cbx pixels (a TMA box is at most 256 elements = 128 float4 wide) ...
+    int mnb, mbx;        // ... a window row as mnb boxes of mbx pixels; shared-memory layout [box][row][pixel in box]
     int ctas, threads;   // launch shape
 };
+inline void icp_tile_boxes(IcpTileGeom& g)
+{
+    g.cnb = div_up(g.tw, 128); g.cbx = (div_up(g.tw, g.cnb) + 3) & ~3;
+    g.mnb = div_up(g.mw, 128); g.mbx = (div_up(g.mw, g.mnb) + 3) & ~3;
+    g.mw = g.mnb * g.mbx;
+}
 constexpr int kTileHaloX = 4, kTileHaloY = 4;      // window = tile + 2 x halo (+ 4 pixels of alignment slack in x)
 
 // tiles ~ (cols / 8a) x (rows / 37b) so that 296 = 8 x 37 CTAs (2 per SM) get 1 (640x480), 4 (1280x960) ... tiles each
@@ -38,16 +47,25 @@ inline IcpTileGeom icp_tile_geom(int rows, int cols, int num_sms)
     g.th = div_up(rows, g.nrow);
     g.mw = g.tw + 2 * kTileHaloX + 4;
     g.mh = g.th + 2 * kTileHaloY;
+    icp_tile_boxes(g);
     g.threads = kReduceThreads;
     const int tiles = g.ncol * g.nrow;
     g.ctas = tiles < num_sms * 2 ? tiles : num_sms * 2;
     if (g.ctas > kMaxReduceBlocks) g.ctas = kMaxReduceBlocks;
     return g;
 }
+// every array's boxes start 128-byte aligned
+__host__ __device__ inline size_t icp_tile_curr_bytes(const IcpTileGeom& g) { return ((size_t)g.cnb * g.cbx * g.th * sizeof(float4) + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t icp_tile_model_bytes(const IcpTileGeom& g) { return ((size_t)g.mnb * g.mbx * g.mh * sizeof(float4) + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t icp_tile_weight_bytes(const IcpTileGeom& g) { return ((size_t)g.mnb * g.mbx * g.mh * sizeof(float) + 127) & ~(size_t)127; }
 inline size_t icp_tile_smem_bytes(const IcpTileGeom& g)
 {
-    return (size_t)g.tw * g.th * 2 * sizeof(float4) + (size_t)g.mw * g.mh * (2 * sizeof(float4) + sizeof(float)) + 16;
+    return 2 * icp_tile_curr_bytes(g) + 2 * icp_tile_model_bytes(g) + icp_tile_weight_bytes(g) + 128;
 }
+// the five tensor maps of one pyramid level and geometry (device memory, written by the host at create time): packed records of the
+// current frame (pk0, pk1) and of the model (pk0, pk1) as [rows][cols] arrays of 16-byte pixels (encoded as 2 x 64-bit elements), and
+// the model's icp-weight map as [rows][cols] floats
+struct IcpTileMaps { const void *pc0, *pc1, *pg0, *pg1, *w; };
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,14 +98,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// one box of a 2-D tensor (tensor map in global memory) -> shared memory; (cx, cy) = element coordinates of the box's low corner,
+// may lie outside the tensor (zero fill); dst 128-byte aligned
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int cx, int cy, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst_smem)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(cx), "r"(cy)
+                 : "memory");
+}
+
 // A staged tile: where its pieces sit in shared memory and which part of the image they hold
 struct IcpTileView {
-    const float4 *c0, *c1;       // current-frame records, [th][tw] (row pitch tw)
-    const float4 *g0, *g1;       // model window, [mh][mw] (row pitch mw)
-    const float* gw;             // icp-weight window
+    const float4 *c0, *c1;       // current-frame records, [cnb][th][cbx]
+    const float4 *g0, *g1;       // model window, [mnb][mh][mbx]
+    const float* gw;             // icp-weight window, same layout
     int x0, y0, w, h;            // tile rectangle in the image
-    int mx0, my0, mwa, mha;      // model window rectangle actually staged (mwa == 0: nothing staged)
-    int tw, mw;                  // row pitches
+    int mx0, my0, mwa, mha;      // model window rectangle staged (mwa == 0: nothing staged); may stick out of the image (zero fill)
+    int cbx, th, mbx, mh;        // box widths and heights of the layouts above
+    __device__ __forceinline__ int cidx(int x, int y) const { const int b = x / cbx; return (b * th + y) * cbx + (x - b * cbx); }
+    __device__ __forceinline__ int midx(int x, int y) const { const int b = x / mbx; return (b * mh + y) * mbx + (x - b * mbx); }
 };
 
 // projection half of icp_gather_model (odometry_kernels.cuh): everything but the loads
@@ -112,33 +141,24 @@ __device__ __forceinline__ void icp_model_from(IcpModel& m, const float4 p0, con
     m.vx = p0.x; m.vy = p0.y; m.vz = p0.z; m.nx = p0.w; m.ny = p1.x; m.nz = p1.y; m.k1 = p1.z; m.k2 = p1.w; m.w = w;
 }
 
-// stage 1: the tile's current-frame rows (issued by warp 0; one thread arms the barrier with the byte count)
-__device__ __forceinline__ void icp_tile_issue_curr(const IcpArgs& a, float4* s_c0, float4* s_c1, int tw, int x0, int y0, int w, int h, uint64_t* bar)
+// stage 1: the tile's current-frame records, one TMA request per array and box (issued by one thread, which also arms the barrier)
+__device__ __forceinline__ void icp_tile_issue_curr(const IcpTileMaps& m, const IcpTileGeom& g, float4* s_c0, float4* s_c1, int x0, int y0, uint64_t* bar)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t row_bytes = (uint32_t)w * sizeof(float4);
-    if (lane == 0) mbar_expect_tx(bar, 2u * row_bytes * (uint32_t)h);
-    __syncwarp();
-    for (int r = lane; r < 2 * h; r += 32) {
-        const int y = r >> 1;
-        const size_t src = (size_t)(y0 + y) * a.cols + x0;
-        if (r & 1) bulk_g2s(s_c1 + y * tw, a.pc1 + src, row_bytes, bar);
-        else bulk_g2s(s_c0 + y * tw, a.pc0 + src, row_bytes, bar);
+    mbar_expect_tx(bar, 2u * (uint32_t)(g.cnb * g.cbx * g.th) * (uint32_t)sizeof(float4));
+    for (int b = 0; b < g.cnb; ++b) {
+        tma_load_2d(s_c0 + b * g.th * g.cbx, m.pc0, 2 * (x0 + b * g.cbx), y0, bar);      // x in 64-bit elements: 2 per pixel
+        tma_load_2d(s_c1 + b * g.th * g.cbx, m.pc1, 2 * (x0 + b * g.cbx), y0, bar);
     }
 }
-// stage 2: the model window rows
-__device__ __forceinline__ void icp_tile_issue_model(const IcpArgs& a, float4* s_g0, float4* s_g1, float* s_gw, int mw, int mx0, int my0, int mwa, int mha, uint64_t* bar)
+// stage 2: the model window
+__device__ __forceinline__ void icp_tile_issue_model(const IcpTileMaps& m, const IcpTileGeom& g, bool use_weight, float4* s_g0, float4* s_g1, float* s_gw,
+                                                     int mx0, int my0, uint64_t* bar)
 {
-    const int lane = threadIdx.x & 31;
-    const int per_row = a.use_weight ? 3 : 2;
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)mha * (uint32_t)mwa * (a.use_weight ? 36u : 32u));
-    __syncwarp();
-    for (int r = lane; r < per_row * mha; r += 32) {
-        const int y = r / per_row, k = r - y * per_row;
-        const size_t src = (size_t)(my0 + y) * a.cols + mx0;
-        if (k == 0) bulk_g2s(s_g0 + y * mw, a.pg0 + src, (uint32_t)mwa * 16u, bar);
-        else if (k == 1) bulk_g2s(s_g1 + y * mw, a.pg1 + src, (uint32_t)mwa * 16u, bar);
-        else bulk_g2s(s_gw + y * mw, a.w + src, (uint32_t)mwa * 4u, bar);
+    mbar_expect_tx(bar, (uint32_t)(g.mnb * g.mbx * g.mh) * (use_weight ? 36u : 32u));
+    for (int b = 0; b < g.mnb; ++b) {
+        tma_load_2d(s_g0 + b * g.mh * g.mbx, m.pg0, 2 * (mx0 + b * g.mbx), my0, bar);
+        tma_load_2d(s_g1 + b * g.mh * g.mbx, m.pg1, 2 * (mx0 + b * g.mbx), my0, bar);
+        if (use_weight) tma_load_2d(s_gw + b * g.mh * g.mbx, m.w, mx0 + b * g.mbx, my0, bar);
     }
 }
 
@@ -150,7 +170,8 @@ __device__ __forceinline__ void icp_tile_bbox(const IcpArgs& a, const IcpTileVie
     const int n = t.w * t.h;
     for (int i = threadIdx.x; i < n; i += kThreads) {
         const int y = i / t.w, x = i - y * t.w;
-        const IcpCurr c = icp_curr_from(t.c0[y * t.tw + x], t.c1[y * t.tw + x]);
+        const int ci = t.cidx(x, y);
+        const IcpCurr c = icp_curr_from(t.c0[ci], t.c1[ci]);
         IcpModel m;
         icp_project(a, c, Rc, tc, Rpi, tp, m);
         if (m.ok) { lo_x = min(lo_x, m.ux); lo_y = min(lo_y, m.uy); hi_x = max(hi_x, m.ux); hi_y = max(hi_y, m.uy); }
@@ -159,19 +180,14 @@ __device__ __forceinline__ void icp_tile_bbox(const IcpArgs& a, const IcpTileVie
     hi_x = __reduce_max_sync(0xffffffffu, hi_x); hi_y = __reduce_max_sync(0xffffffffu, hi_y);
     if ((threadIdx.x & 31) == 0 && hi_x >= 0) { atomicMin(&s_box[0], lo_x); atomicMin(&s_box[1], lo_y); atomicMax(&s_box[2], hi_x); atomicMax(&s_box[3], hi_y); }
 }
-// the window to stage for a bounding box: anchored at its low corner (x aligned down to 4 pixels), clipped to the image and to the
-// capacity; `margin` pixels are left free on the low side for the pose to move during the iterations that reuse the window
-__device__ __forceinline__ void icp_tile_window(const int* s_box, int rows, int cols, int mw, int mh, int margin, int& mx0, int& my0, int& mwa, int& mha)
+// the window to stage for a bounding box: anchored `margin` pixels (or, when the box is small, half of the slack) below its low
+// corner; it may stick out of the image, the TMA unit zero-fills what is not there
+__device__ __forceinline__ void icp_tile_window(const int* s_box, int mw, int mh, int margin, int& mx0, int& my0, bool& any)
 {
-    mwa = mha = 0; mx0 = my0 = 0;
-    if (s_box[2] < 0) return;
+    any = s_box[2] >= 0;
     const int bw = s_box[2] - s_box[0] + 1, bh = s_box[3] - s_box[1] + 1;
-    int sx = min(margin, max(0, (mw - 4 - bw) / 2)), sy = min(margin, max(0, (mh - bh) / 2));      // slack split evenly when the box is small
-    mx0 = max(0, (s_box[0] - sx) & ~3);
-    my0 = max(0, s_box[1] - sy);
-    mwa = min(mw, cols - mx0);
-    mha = min(mh, rows - my0);
-    mwa &= ~3;
+    mx0 = s_box[0] - min(margin, max(0, (mw - bw) / 2));
+    my0 = s_box[1] - min(margin, max(0, (mh - bh) / 2));
 }
 
 // stage 3: the pass over a staged tile: same arithmetic as icp_pass_nosearch_t (odometry_kernels.cuh), gathers from shared memory
@@ -181,13 +197,14 @@ __device__ __forceinline__ void icp_tile_pass(const IcpArgs& a, const IcpTileVie
     const int n = t.w * t.h;
     for (int i = threadIdx.x; i < n; i += kThreads) {
         const int y = i / t.w, x = i - y * t.w;
-        const IcpCurr c = icp_curr_from(t.c0[y * t.tw + x], t.c1[y * t.tw + x]);
+        const int ci = t.cidx(x, y);
+        const IcpCurr c = icp_curr_from(t.c0[ci], t.c1[ci]);
         IcpModel m;
         icp_project(a, c, Rc, tc, Rpi, tp, m);
         if (m.ok) {
             const int lx = m.ux - t.mx0, ly = m.uy - t.my0;
             if ((unsigned)lx < (unsigned)t.mwa && (unsigned)ly < (unsigned)t.mha) {
-                const int q = ly * t.mw + lx;
+                const int q = t.midx(lx, ly);
                 icp_model_from(m, t.g0[q], t.g1[q], a.use_weight ? t.gw[q] : 1.f);
             } else {
                 const int q = m.uy * a.cols + m.ux;
@@ -199,19 +216,19 @@ __device__ __forceinline__ void icp_tile_pass(const IcpArgs& a, const IcpTileVie
 }
 
 // mode as icp_reduce_kernel: 0 = store the 29 sums in st->icp_sums, 1 = store and run the Gauss-Newton update in the last block
-__global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpArgs a, IcpTileGeom g, ReduceWork* wk, int mode, int cur_level, int next_level)
+__global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpArgs a, IcpTileGeom g, IcpTileMaps maps, ReduceWork* wk, int mode, int cur_level, int next_level)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     float4* s_c0 = reinterpret_cast<float4*>(s_dyn);
-    float4* s_c1 = s_c0 + g.tw * g.th;
-    float4* s_g0 = s_c1 + g.tw * g.th;
-    float4* s_g1 = s_g0 + g.mw * g.mh;
-    float* s_gw = reinterpret_cast<float*>(s_g1 + g.mw * g.mh);
+    float4* s_c1 = reinterpret_cast<float4*>(s_dyn + icp_tile_curr_bytes(g));
+    float4* s_g0 = reinterpret_cast<float4*>(s_dyn + 2 * icp_tile_curr_bytes(g));
+    float4* s_g1 = reinterpret_cast<float4*>(s_dyn + 2 * icp_tile_curr_bytes(g) + icp_tile_model_bytes(g));
+    float* s_gw = reinterpret_cast<float*>(s_dyn + 2 * icp_tile_curr_bytes(g) + 2 * icp_tile_model_bytes(g));
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_total[32];
     __shared__ float s_pose[24];
     __shared__ int s_box[4];
-    __shared__ int s_win[4];
+    __shared__ int s_win[3];
 
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     pdl_wait();      // the maps and the pose may come from the previous kernel of the stream
@@ -219,7 +236,14 @@ __global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpA
     if (threadIdx.x < 9) { s_pose[threadIdx.x] = st->Rcurr[threadIdx.x]; s_pose[12 + threadIdx.x] = st->Rprev_inv[threadIdx.x]; }
     if (threadIdx.x < 3) { s_pose[9 + threadIdx.x] = st->tcurr[threadIdx.x]; s_pose[21 + threadIdx.x] = st->tprev[threadIdx.x]; }
     const bool level_done = (st->done_level == cur_level);
+    const int tiles = g.ncol * g.nrow;
+    // the first tile's current-frame records are requested before anything else
+    if (threadIdx.x == 0) { s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1; }
     __syncthreads();
+    if (!level_done && (int)blockIdx.x < tiles && threadIdx.x == 0) {
+        const int tcx = (int)blockIdx.x % g.ncol, try_ = (int)blockIdx.x / g.ncol;
+        icp_tile_issue_curr(maps, g, s_c0, s_c1, tcx * g.tw, (int)(((long long)a.rows * try_) / g.nrow), &s_bar[0]);
+    }
     float Rc[9], tc[3], Rpi[9], tp[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { Rc[k] = s_pose[k]; Rpi[k] = s_pose[12 + k]; }
@@ -229,43 +253,34 @@ __global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpA
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-    const int tiles = g.ncol * g.nrow;
-    uint32_t parity = 0;
+    uint32_t par0 = 0, par1 = 0;
     if (!level_done) {
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             IcpTileView t;
             const int tcx = tile % g.ncol, try_ = tile / g.ncol;
             t.x0 = tcx * g.tw; t.w = min(g.tw, a.cols - t.x0);
             t.y0 = (int)(((long long)a.rows * try_) / g.nrow); t.h = (int)(((long long)a.rows * (try_ + 1)) / g.nrow) - t.y0;
-            t.c0 = s_c0; t.c1 = s_c1; t.g0 = s_g0; t.g1 = s_g1; t.gw = s_gw; t.tw = g.tw; t.mw = g.mw;
-            if (threadIdx.x < 32) icp_tile_issue_curr(a, s_c0, s_c1, g.tw, t.x0, t.y0, t.w, t.h, &s_bar[0]);
-            if (threadIdx.x == 32) { s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1; }
-            __syncthreads();
-            mbar_wait(&s_bar[0], parity);
+            t.c0 = s_c0; t.c1 = s_c1; t.g0 = s_g0; t.g1 = s_g1; t.gw = s_gw; t.cbx = g.cbx; t.th = g.th; t.mbx = g.mbx; t.mh = g.mh;
+            mbar_wait(&s_bar[0], par0); par0 ^= 1u;
             icp_tile_bbox<kReduceThreads>(a, t, Rc, tc, Rpi, tp, s_box);
             __syncthreads();
-            if (threadIdx.x < 32) {
-                int mx0, my0, mwa, mha;
-                icp_tile_window(s_box, a.rows, a.cols, g.mw, g.mh, kTileHaloX, mx0, my0, mwa, mha);
-                if (threadIdx.x == 0) { s_win[0] = mx0; s_win[1] = my0; s_win[2] = mwa; s_win[3] = mha; }
-                if (mwa > 0 && mha > 0) icp_tile_issue_model(a, s_g0, s_g1, s_gw, g.mw, mx0, my0, mwa, mha, &s_bar[1]);
+            if (threadIdx.x == 0) {
+                int mx0, my0; bool any;
+                icp_tile_window(s_box, g.mw, g.mh, kTileHaloX, mx0, my0, any);
+                s_win[0] = mx0; s_win[1] = my0; s_win[2] = any ? 1 : 0;
+                if (any) icp_tile_issue_model(maps, g, a.use_weight != 0, s_g0, s_g1, s_gw, mx0, my0, &s_bar[1]);
+                s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1;      // for the next tile
             }
             __syncthreads();
-            t.mx0 = s_win[0]; t.my0 = s_win[1]; t.mwa = s_win[2]; t.mha = s_win[3];
-            if (t.mwa > 0 && t.mha > 0) mbar_wait(&s_bar[1], parity);
+            t.mx0 = s_win[0]; t.my0 = s_win[1];
+            if (s_win[2]) { t.mwa = g.mw; t.mha = g.mh; mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
             else t.mwa = t.mha = 0;
             icp_tile_pass<kReduceThreads>(a, t, Rc, tc, Rpi, tp, acc);
-            // both barriers complete one phase per tile only if the model stage ran: re-arm by re-initialising when it did not
-            if (!(t.mwa > 0 && t.mha > 0)) {
-                __syncthreads();
-                if (threadIdx.x == 0) { mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-                // keep the parities of the two barriers in step: barrier 1 restarts at phase 0, so must barrier 0
-                if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_fence_init(); }
-                parity = 0;
-                __syncthreads();
-            } else {
-                parity ^= 1u;
-                __syncthreads();      // the tile's buffers are free for the next one
+            __syncthreads();      // the tile's buffers are free: request the next tile's records
+            const int next = tile + gridDim.x;
+            if (next < tiles && threadIdx.x == 0) {
+                const int ncx = next % g.ncol, nry = next / g.ncol;
+                icp_tile_issue_curr(maps, g, s_c0, s_c1, ncx * g.tw, (int)(((long long)a.rows * nry) / g.nrow), &s_bar[0]);
             }
         }
     }

@@ -93,7 +93,7 @@ int hrbf_indexmap_predict_indices(hrbf_indexmap* m, const float* pose16, int tim
     (void)time; (void)maxTime; (void)insertSubmap; (void)indexSubmap;     // uniforms the shader declares but never reads
     HRBF_CHECK_ARG(m && pose16 && (surfels_dev || count == 0));
     cudaStream_t s = (cudaStream_t)stream;
-    const int k = m->slot++ & 7;
+    const int k = m->ring.acquire();
     float* h = m->h_stage + 16 * k;
     // pose.inverse() of a rigid transform: R^T, -R^T t (float)
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) h[i * 3 + j] = pose16[j * 4 + i];
@@ -101,7 +101,9 @@ int hrbf_indexmap_predict_indices(hrbf_indexmap* m, const float* pose16, int tim
     memcpy(h + 12, &count, 4);
     HRBF_CUDA(cudaMemcpyAsync(m->inv_pose + 12 * k, h, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     HRBF_CUDA(cudaMemcpyAsync(m->count_slot + k, h + 12, 4, cudaMemcpyHostToDevice, s));
-    return indexmap_splat(m, m->inv_pose + 12 * k, surfels_dev, m->count_slot + k, count, depthCutoff, s);
+    const int rc = indexmap_splat(m, m->inv_pose + 12 * k, surfels_dev, m->count_slot + k, count, depthCutoff, s);
+    m->ring.release(k, s);      // after the kernels that read the slot's device twin
+    return rc;
 }
 
 int hrbf_indexmap_predict_indices_dev(hrbf_indexmap* m, const float* inv_pose_dev, const float* surfels_dev, const unsigned int* count_dev,

@@ -8,6 +8,8 @@
 // round trips inside the Gauss-Newton loop (the reference makes ~67 per frame).
 #include "track_persistent.cuh"
 #include "icp_tile.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <map>
 #include <new>
 #include <stdarg.h>
@@ -53,9 +55,11 @@ static PyrOut pyr_out(hrbf_odometry* o, int which)
 static int upload_pose(hrbf_odometry* o, const float* pose16, cudaStream_t s, float** dev_out)
 {
     // row-major 4x4 -> R[9], t[3]; staged through a small pinned ring so the copy is truly async
-    float* h = o->h_model_pose + 12 * (o->h_model_pose_slot++ & 7);
+    const int k = o->model_pose_ring.acquire();
+    float* h = o->h_model_pose + 12 * k;
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) h[i * 3 + j] = pose16[i * 4 + j]; h[9 + i] = pose16[i * 4 + 3]; }
     HRBF_CUDA(cudaMemcpyAsync(o->pose_scratch, h, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    o->model_pose_ring.release(k, s);      // only the host slot is per-use here: the copy is its last reader
     *dev_out = o->pose_scratch;
     return HRBF_OK;
 }
@@ -93,14 +97,63 @@ static RgbStepArgs rgbstep_args(const hrbf_odometry* o, int l)
 }
 
 
+// ---- tensor maps of the packed ICP records (icp_tile.cuh).  cuTensorMapEncodeTiled is fetched through the runtime, so the library
+// does not link against libcuda.  geometry 0 = stand-alone tile kernel, 1 = persistent tracker (one tile per CTA)
+static IcpTileGeom tile_geom_of(const hrbf_odometry* o, int which, int l)
+{
+    return which == 0 ? icp_tile_geom(o->rows(l), o->cols(l), o->num_sms) : track_tile_geom(o->rows(l), o->cols(l), o->num_sms);
+}
+static IcpTileMaps tile_maps_of(const hrbf_odometry* o, int which, int l)
+{
+    const CUtensorMap* m = (const CUtensorMap*)o->tmaps_dev + (which * 3 + l) * 5;
+    IcpTileMaps r;
+    r.pc0 = m + 0; r.pc1 = m + 1; r.pg0 = m + 2; r.pg1 = m + 3; r.w = m + 4;
+    return r;
+}
+static int build_tile_tensor_maps(hrbf_odometry* o)
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return HRBF_OK;      // no TMA tensor maps on this driver: the gather kernels serve every path
+    }
+    auto encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    std::vector<CUtensorMap> host(2 * 3 * 5);
+    for (int which = 0; which < 2; ++which)
+        for (int l = 0; l < 3; ++l) {
+            const IcpTileGeom g = tile_geom_of(o, which, l);
+            const cuuint64_t rows = (cuuint64_t)o->rows(l), cols = (cuuint64_t)o->cols(l);
+            for (int k = 0; k < 5; ++k) {
+                const bool weight = k == 4, curr = k < 2;
+                void* base = weight ? (void*)o->maps[M_W][l] : (void*)o->pk[k][l];
+                // 16-byte pixels as 2 x 64-bit elements (a box is at most 256 elements wide); the weight map as floats
+                const cuuint64_t dims[2] = { weight ? cols : 2 * cols, rows };
+                const cuuint64_t strides[1] = { cols * (weight ? sizeof(float) : sizeof(float4)) };
+                const cuuint32_t bx = (cuuint32_t)(curr ? g.cbx : g.mbx), by = (cuuint32_t)(curr ? g.th : g.mh);
+                const cuuint32_t box[2] = { weight ? bx : 2 * bx, by };
+                const cuuint32_t estr[2] = { 1, 1 };
+                if (box[0] > 256 || box[1] > 256 || strides[0] % 16 != 0) return HRBF_OK;
+                const CUresult r = encode(&host[(which * 3 + l) * 5 + k], weight ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, base, dims, strides,
+                                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return HRBF_OK;
+            }
+        }
+    HRBF_CUDA(cudaMalloc(&o->tmaps_dev, host.size() * sizeof(CUtensorMap)));
+    HRBF_CUDA(cudaMemcpy(o->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return HRBF_OK;
+}
+
 // The TMA-staged tile form of the ICP reduction (icp_tile.cuh) on the object's packed pyramids; pdl: programmatic stream serialization
 static cudaError_t launch_icp_tile(hrbf_odometry* o, const IcpArgs& ia, int mode, int level, int next_level, cudaStream_t s, bool pdl)
 {
-    if (ia.cols % 4 != 0 || ia.pc0 == nullptr) {      // rows of the weight map must start 16-byte aligned for the bulk copies
+    if (o->tmaps_dev == nullptr || ia.cols % 4 != 0 || ia.pc0 == nullptr) {      // no tensor maps (driver), or weight-map rows not 16-byte aligned
         icp_reduce_kernel<false><<<reduce_blocks(ia.rows * ia.cols), kReduceThreads, 0, s>>>(ia, o->work, mode, level, next_level);
         return cudaGetLastError();
     }
-    const IcpTileGeom g = icp_tile_geom(ia.rows, ia.cols, o->num_sms);
+    const IcpTileGeom g = tile_geom_of(o, 0, level);
+    const IcpTileMaps maps = tile_maps_of(o, 0, level);
     const size_t dyn = icp_tile_smem_bytes(g);
     {
         static std::mutex mu;
@@ -117,7 +170,7 @@ static cudaError_t launch_icp_tile(hrbf_odometry* o, const IcpArgs& ia, int mode
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, icp_tile_reduce_kernel, ia, g, o->work, mode, level, next_level);
+    return cudaLaunchKernelEx(&cfg, icp_tile_reduce_kernel, ia, g, maps, o->work, mode, level, next_level);
 }
 
 // Enqueue the whole tracking loop on `s` (used under stream capture).  Returns kernel count.
@@ -214,9 +267,11 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
         }
         size_t tile_bytes = 0;
         for (int l = 0; l < 3; ++l) {
-            p.tile[l] = track_tile_geom(o->rows(l), o->cols(l), o->num_sms);
+            p.tile[l] = tile_geom_of(o, 1, l);
+            if (o->tmaps_dev) p.tmaps[l] = tile_maps_of(o, 1, l);
+            else p.tmaps[l] = IcpTileMaps{ nullptr, nullptr, nullptr, nullptr, nullptr };
             const size_t need = icp_tile_smem_bytes(p.tile[l]);
-            p.resident[l] = (iters[l] > 0 && o->tile_resident && !o->useSearch && o->cols(l) % 4 == 0 && dyn + need <= budget[half]) ? 1 : 0;
+            p.resident[l] = (iters[l] > 0 && o->tile_resident && o->tmaps_dev && !o->useSearch && o->cols(l) % 4 == 0 && dyn + need <= budget[half]) ? 1 : 0;
             if (p.resident[l] && need > tile_bytes) tile_bytes = need;
         }
         dyn += tile_bytes;
@@ -560,6 +615,7 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
     o->work = (ReduceWork*)(o->slab + o_work);
     o->pose_scratch = (float*)(o->slab + o_pose);
     o->tp_ll_f = (unsigned long long*)(o->slab + o_tpp); o->tp_ll_i = (unsigned long long*)(o->slab + o_tpi);      // zeroed with the slab: tag 0 never matches
+    if (int rc = build_tile_tensor_maps(o)) { hrbf_odometry_destroy(o); return rc; }
     cudaMallocHost(&o->h_pose, 24 * sizeof(float));
     cudaMallocHost(&o->h_state, sizeof(TrackState));
     cudaMallocHost(&o->h_model_pose, 8 * 12 * sizeof(float));
@@ -582,7 +638,9 @@ int hrbf_odometry_destroy(hrbf_odometry* o)
     if (o->h_pose) cudaFreeHost(o->h_pose);
     if (o->h_state) cudaFreeHost(o->h_state);
     if (o->h_model_pose) cudaFreeHost(o->h_model_pose);
+    o->model_pose_ring.destroy();
     if (o->slab) cudaFree(o->slab);
+    if (o->tmaps_dev) cudaFree(o->tmaps_dev);
     if (o->tp_dbg) cudaFree(o->tp_dbg);
     delete o;
     return HRBF_OK;

@@ -43,6 +43,7 @@ struct TrackParams {
     TrackState* st_global;                         // camera in, statistics out
     int max_slots;                                 // dynamic shared memory holds max_slots x kTrackThreads RgbSlots ...
     IcpTileGeom tile[3];                           // ... followed by the resident ICP tile of the level being worked on (icp_tile.cuh):
+    IcpTileMaps tmaps[3];                          // tensor maps of the level's packed records for that geometry
     int resident[3];                               // level l keeps its tile of packed records + model window in shared memory for all its iterations
     unsigned long long* ll_f;                      // [2][gridDim.x][64] (float, tag) words: the per-CTA partial sums
     unsigned long long* ll_i;                      // [2][gridDim.x][kIntStride] (int, tag) words: {count, sum diff^2} of computeRgbResidual in words 0-1
@@ -289,6 +290,7 @@ inline IcpTileGeom track_tile_geom(int rows, int cols, int ctas)
     g.th = div_up(rows, g.nrow);
     g.mw = g.tw + 8;
     g.mh = g.th + 6;
+    icp_tile_boxes(g);
     g.ctas = ctas; g.threads = 0;
     return g;
 }
@@ -298,12 +300,11 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
 {
     constexpr int kTrackWarps = kTrackThreads / 32;
     pdl_wait();
-    extern __shared__ __align__(16) unsigned char s_dyn[];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     RgbSlot* s_slots = reinterpret_cast<RgbSlot*>(s_dyn);
     unsigned char* s_tile = s_dyn + (((size_t)p.max_slots * kTrackThreads * sizeof(RgbSlot) + 127) & ~(size_t)127);
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_box[4];
-    __shared__ int s_win[4];
     __shared__ IcpTileView s_tv;
     uint32_t par0 = 0, par1 = 0;                         // phase parities of the two mbarriers (uniform over the CTA)
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
@@ -409,24 +410,23 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
         if (tile_res) {
             const IcpTileGeom& g = p.tile[l];
             float4* s_c0 = reinterpret_cast<float4*>(s_tile);
-            float4* s_c1 = s_c0 + g.tw * g.th;
-            float4* s_g0 = s_c1 + g.tw * g.th;
-            float4* s_g1 = s_g0 + g.mw * g.mh;
-            float* s_gw = reinterpret_cast<float*>(s_g1 + g.mw * g.mh);
-            __syncthreads();      // nobody still reads the previous level's view
+            float4* s_c1 = reinterpret_cast<float4*>(s_tile + icp_tile_curr_bytes(g));
+            float4* s_g0 = reinterpret_cast<float4*>(s_tile + 2 * icp_tile_curr_bytes(g));
+            float4* s_g1 = reinterpret_cast<float4*>(s_tile + 2 * icp_tile_curr_bytes(g) + icp_tile_model_bytes(g));
+            float* s_gw = reinterpret_cast<float*>(s_tile + 2 * icp_tile_curr_bytes(g) + 2 * icp_tile_model_bytes(g));
+            __syncthreads();      // nobody still reads the previous level's view or tile
             if (tid == 0) {
                 const int tcx = (int)blockIdx.x % g.ncol, try_ = (int)blockIdx.x / g.ncol;
                 tv.x0 = min(tcx * g.tw, L.icp.cols); tv.w = min(g.tw, L.icp.cols - tv.x0);
                 tv.y0 = (int)(((long long)L.icp.rows * try_) / g.nrow); tv.h = (int)(((long long)L.icp.rows * (try_ + 1)) / g.nrow) - tv.y0;
                 if (try_ >= g.nrow) tv.w = tv.h = 0;
-                tv.c0 = s_c0; tv.c1 = s_c1; tv.g0 = s_g0; tv.g1 = s_g1; tv.gw = s_gw; tv.tw = g.tw; tv.mw = g.mw;
+                tv.c0 = s_c0; tv.c1 = s_c1; tv.g0 = s_g0; tv.g1 = s_g1; tv.gw = s_gw; tv.cbx = g.cbx; tv.th = g.th; tv.mbx = g.mbx; tv.mh = g.mh;
                 tv.mx0 = tv.my0 = tv.mwa = tv.mha = 0;
+                s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1;
+                if (tv.w > 0 && tv.h > 0) icp_tile_issue_curr(p.tmaps[l], g, s_c0, s_c1, tv.x0, tv.y0, &s_bar[0]);
             }
-            __syncthreads();      // nobody still reads the previous level's tile
+            __syncthreads();
             if (tv.w > 0 && tv.h > 0) {
-                if (tid < 32) icp_tile_issue_curr(L.icp, s_c0, s_c1, g.tw, tv.x0, tv.y0, tv.w, tv.h, &s_bar[0]);
-                if (tid == 32) { s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1; }
-                __syncthreads();
                 mbar_wait(&s_bar[0], par0); par0 ^= 1u;
                 float Rc[9], tc[3], Rpi[9], tp[3];
 #pragma unroll
@@ -435,17 +435,16 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 for (int k = 0; k < 3; ++k) { tc[k] = S.tcurr[k]; tp[k] = S.tprev[k]; }
                 icp_tile_bbox<kTrackThreads>(L.icp, tv, Rc, tc, Rpi, tp, s_box);
                 __syncthreads();
-                if (tid < 32) {
-                    int mx0, my0, mwa, mha;
-                    icp_tile_window(s_box, L.icp.rows, L.icp.cols, g.mw, g.mh, 2, mx0, my0, mwa, mha);
-                    if (tid == 0) { s_win[0] = mx0; s_win[1] = my0; s_win[2] = mwa; s_win[3] = mha; }
-                    if (mwa > 0 && mha > 0) icp_tile_issue_model(L.icp, s_g0, s_g1, s_gw, g.mw, mx0, my0, mwa, mha, &s_bar[1]);
+                if (tid == 0) {
+                    int mx0, my0; bool any;
+                    icp_tile_window(s_box, g.mw, g.mh, 2, mx0, my0, any);
+                    if (any) {
+                        tv.mx0 = mx0; tv.my0 = my0; tv.mwa = g.mw; tv.mha = g.mh;
+                        icp_tile_issue_model(p.tmaps[l], g, L.icp.use_weight != 0, s_g0, s_g1, s_gw, mx0, my0, &s_bar[1]);
+                    }
                 }
                 __syncthreads();
-                const bool staged = s_win[2] > 0 && s_win[3] > 0;
-                if (tid == 0 && staged) { tv.mx0 = s_win[0]; tv.my0 = s_win[1]; tv.mwa = s_win[2]; tv.mha = s_win[3]; }
-                if (staged) { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
-                __syncthreads();
+                if (tv.mwa > 0) { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
             }
         }
         for (int j = 0; j < L.iters; ++j) {

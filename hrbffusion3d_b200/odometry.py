@@ -35,7 +35,12 @@ class RGBDOdometry:
             lib().hrbf_odometry_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        # at interpreter exit module globals (lib, C) may already be gone: nothing to release then, the process is ending
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def setTracker(self, use_kernel_graph=False):
         """False (default): one persistent cooperative kernel; True: one kernel per reduction in a CUDA graph"""
