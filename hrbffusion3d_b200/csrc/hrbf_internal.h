@@ -31,7 +31,7 @@ struct hrbf_odometry {
     float4* pk[4][HRBF_NUM_PYRS] = {};           // packed ICP operands: [0] curr pk0, [1] curr pk1, [2] model pk0, [3] model pk1
     bool pack_dirty_curr = false, pack_dirty_model = false;   // SoA written by a builder that does not pack (GPUTest path)
     unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
-    void* tmaps_dev = nullptr;                   // device: CUtensorMap[2 geometries][3 levels][5 arrays] for the TMA-staged ICP tiles (icp_tile.cuh); null = unavailable
+    void* tmaps_host = nullptr;                  // host: CUtensorMap[2 geometries][3 levels][5 arrays] for the TMA-staged ICP tiles (icp_tile.cuh), copied into kernel parameters; null = unavailable
     bool tile_resident = true;                   // persistent tracker: keep each level's ICP tile in shared memory (hrbf_odometry_set_tracker_tiles)
     int track_threads = 512;                     // threads per CTA of the persistent tracker (256 | 512), hrbf_odometry_set_tracker_threads
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};

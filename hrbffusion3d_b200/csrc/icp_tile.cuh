@@ -11,6 +11,7 @@
 // tile in flight, and the per-pixel gather reads shared memory.  An association that leaves the window (depth edges, large
 // motion) is served by the same __ldg path as before: same arithmetic, same result.
 #pragma once
+#include <cuda.h>      // CUtensorMap (type only: the encoder is fetched through the runtime, nothing links against libcuda)
 #include "odometry_kernels.cuh"
 
 namespace hrbf {
@@ -23,7 +24,7 @@ struct IcpTileGeom {
     int mnb, mbx;        // ... a window row as mnb boxes of mbx pixels; shared-memory layout [box][row][pixel in box]
     int ctas, threads;   // launch shape
 };
-inline void icp_tile_boxes(IcpTileGeom& g)
+inline void icp_tile_boxes(IcpTileGeom& g)      // tw, mw <= 256
 {
     g.cnb = div_up(g.tw, 128); g.cbx = (div_up(g.tw, g.cnb) + 3) & ~3;
     g.mnb = div_up(g.mw, 128); g.mbx = (div_up(g.mw, g.mnb) + 3) & ~3;
@@ -62,10 +63,10 @@ inline size_t icp_tile_smem_bytes(const IcpTileGeom& g)
 {
     return 2 * icp_tile_curr_bytes(g) + 2 * icp_tile_model_bytes(g) + icp_tile_weight_bytes(g) + 128;
 }
-// the five tensor maps of one pyramid level and geometry (device memory, written by the host at create time): packed records of the
-// current frame (pk0, pk1) and of the model (pk0, pk1) as [rows][cols] arrays of 16-byte pixels (encoded as 2 x 64-bit elements), and
-// the model's icp-weight map as [rows][cols] floats
-struct IcpTileMaps { const void *pc0, *pc1, *pg0, *pg1, *w; };
+// the five tensor maps of one pyramid level and geometry, passed BY VALUE inside __grid_constant__ kernel parameters (the TMA unit
+// reads the descriptor from parameter space): packed records of the current frame (pk0, pk1) and of the model (pk0, pk1) as
+// [rows][cols] arrays of 16-byte pixels (encoded as 2 x 64-bit elements), and the model's icp-weight map as [rows][cols] floats
+struct alignas(64) IcpTileMaps { CUtensorMap pc0, pc1, pg0, pg1, w; };
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,8 +116,9 @@ struct IcpTileView {
     int x0, y0, w, h;            // tile rectangle in the image
     int mx0, my0, mwa, mha;      // model window rectangle staged (mwa == 0: nothing staged); may stick out of the image (zero fill)
     int cbx, th, mbx, mh;        // box widths and heights of the layouts above
-    __device__ __forceinline__ int cidx(int x, int y) const { const int b = x / cbx; return (b * th + y) * cbx + (x - b * cbx); }
-    __device__ __forceinline__ int midx(int x, int y) const { const int b = x / mbx; return (b * mh + y) * mbx + (x - b * mbx); }
+    // at most two boxes per row (tiles and windows are at most 256 pixels wide): no integer division
+    __device__ __forceinline__ int cidx(int x, int y) const { const int b = x >= cbx ? 1 : 0; return (b * th + y) * cbx + (x - b * cbx); }
+    __device__ __forceinline__ int midx(int x, int y) const { const int b = x >= mbx ? 1 : 0; return (b * mh + y) * mbx + (x - b * mbx); }
 };
 
 // projection half of icp_gather_model (odometry_kernels.cuh): everything but the loads
@@ -146,8 +148,8 @@ __device__ __forceinline__ void icp_tile_issue_curr(const IcpTileMaps& m, const 
 {
     mbar_expect_tx(bar, 2u * (uint32_t)(g.cnb * g.cbx * g.th) * (uint32_t)sizeof(float4));
     for (int b = 0; b < g.cnb; ++b) {
-        tma_load_2d(s_c0 + b * g.th * g.cbx, m.pc0, 2 * (x0 + b * g.cbx), y0, bar);      // x in 64-bit elements: 2 per pixel
-        tma_load_2d(s_c1 + b * g.th * g.cbx, m.pc1, 2 * (x0 + b * g.cbx), y0, bar);
+        tma_load_2d(s_c0 + b * g.th * g.cbx, &m.pc0, 2 * (x0 + b * g.cbx), y0, bar);      // x in 64-bit elements: 2 per pixel
+        tma_load_2d(s_c1 + b * g.th * g.cbx, &m.pc1, 2 * (x0 + b * g.cbx), y0, bar);
     }
 }
 // stage 2: the model window
@@ -156,9 +158,9 @@ __device__ __forceinline__ void icp_tile_issue_model(const IcpTileMaps& m, const
 {
     mbar_expect_tx(bar, (uint32_t)(g.mnb * g.mbx * g.mh) * (use_weight ? 36u : 32u));
     for (int b = 0; b < g.mnb; ++b) {
-        tma_load_2d(s_g0 + b * g.mh * g.mbx, m.pg0, 2 * (mx0 + b * g.mbx), my0, bar);
-        tma_load_2d(s_g1 + b * g.mh * g.mbx, m.pg1, 2 * (mx0 + b * g.mbx), my0, bar);
-        if (use_weight) tma_load_2d(s_gw + b * g.mh * g.mbx, m.w, mx0 + b * g.mbx, my0, bar);
+        tma_load_2d(s_g0 + b * g.mh * g.mbx, &m.pg0, 2 * (mx0 + b * g.mbx), my0, bar);
+        tma_load_2d(s_g1 + b * g.mh * g.mbx, &m.pg1, 2 * (mx0 + b * g.mbx), my0, bar);
+        if (use_weight) tma_load_2d(s_gw + b * g.mh * g.mbx, &m.w, mx0 + b * g.mbx, my0, bar);
     }
 }
 
@@ -167,9 +169,11 @@ template <int kThreads>
 __device__ __forceinline__ void icp_tile_bbox(const IcpArgs& a, const IcpTileView& t, const float* Rc, const float* tc, const float* Rpi, const float* tp, int* s_box)
 {
     int lo_x = 1 << 30, lo_y = 1 << 30, hi_x = -1, hi_y = -1;
-    const int n = t.w * t.h;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const int y = i / t.w, x = i - y * t.w;
+    const int w = t.w, n = w * t.h;
+    const int dy = kThreads / w, dx = kThreads - dy * w;      // pixel i + kThreads from pixel i without a division per pixel
+    int y = (int)threadIdx.x / w, x = (int)threadIdx.x - y * w;
+    for (int i = threadIdx.x; i < n; i += kThreads, x += dx, y += dy) {
+        if (x >= w) { x -= w; ++y; }
         const int ci = t.cidx(x, y);
         const IcpCurr c = icp_curr_from(t.c0[ci], t.c1[ci]);
         IcpModel m;
@@ -190,33 +194,48 @@ __device__ __forceinline__ void icp_tile_window(const int* s_box, int mw, int mh
     my0 = s_box[1] - min(margin, max(0, (mh - bh) / 2));
 }
 
-// stage 3: the pass over a staged tile: same arithmetic as icp_pass_nosearch_t (odometry_kernels.cuh), gathers from shared memory
+// stage 3: the pass over a staged tile: same arithmetic as icp_pass_nosearch_t (odometry_kernels.cuh), gathers from shared memory.
+// Two pixels per thread are worked on together (pixel i and i + kThreads): the pass is bound by instruction issue and dependent
+// fp32 chains, not by memory, and two independent chains per thread keep the schedulers busy.
+__device__ __forceinline__ void icp_tile_fetch(const IcpArgs& a, const IcpTileView& t, IcpModel& m)
+{
+    if (!m.ok) return;
+    const int lx = m.ux - t.mx0, ly = m.uy - t.my0;
+    if ((unsigned)lx < (unsigned)t.mwa && (unsigned)ly < (unsigned)t.mha) {
+        const int q = t.midx(lx, ly);
+        icp_model_from(m, t.g0[q], t.g1[q], a.use_weight ? t.gw[q] : 1.f);
+    } else {
+        const int q = m.uy * a.cols + m.ux;
+        icp_model_from(m, __ldg(a.pg0 + q), __ldg(a.pg1 + q), a.use_weight ? __ldg(a.w + q) : 1.f);
+    }
+}
 template <int kThreads>
 __device__ __forceinline__ void icp_tile_pass(const IcpArgs& a, const IcpTileView& t, const float* Rc, const float* tc, const float* Rpi, const float* tp, float (&acc)[32])
 {
-    const int n = t.w * t.h;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const int y = i / t.w, x = i - y * t.w;
-        const int ci = t.cidx(x, y);
-        const IcpCurr c = icp_curr_from(t.c0[ci], t.c1[ci]);
-        IcpModel m;
-        icp_project(a, c, Rc, tc, Rpi, tp, m);
-        if (m.ok) {
-            const int lx = m.ux - t.mx0, ly = m.uy - t.my0;
-            if ((unsigned)lx < (unsigned)t.mwa && (unsigned)ly < (unsigned)t.mha) {
-                const int q = t.midx(lx, ly);
-                icp_model_from(m, t.g0[q], t.g1[q], a.use_weight ? t.gw[q] : 1.f);
-            } else {
-                const int q = m.uy * a.cols + m.ux;
-                icp_model_from(m, __ldg(a.pg0 + q), __ldg(a.pg1 + q), a.use_weight ? __ldg(a.w + q) : 1.f);
-            }
-        }
-        icp_finish(a, m, Rpi, tp, (t.y0 + y) * a.cols + t.x0 + x, acc);
+    const int w = t.w, n = w * t.h;
+    const int dy = kThreads / w, dx = kThreads - dy * w;      // pixel i + kThreads from pixel i without a division per pixel
+    int y0 = (int)threadIdx.x / w, x0 = (int)threadIdx.x - y0 * w;
+    for (int i = threadIdx.x; i < n; i += 2 * kThreads) {
+        int x1 = x0 + dx, y1 = y0 + dy;
+        if (x1 >= w) { x1 -= w; ++y1; }
+        const bool two = i + kThreads < n;
+        const int c0i = t.cidx(x0, y0), c1i = two ? t.cidx(x1, y1) : c0i;
+        const IcpCurr ca = icp_curr_from(t.c0[c0i], t.c1[c0i]), cb = icp_curr_from(t.c0[c1i], t.c1[c1i]);
+        IcpModel ma, mb;
+        icp_project(a, ca, Rc, tc, Rpi, tp, ma);
+        icp_project(a, cb, Rc, tc, Rpi, tp, mb);
+        mb.ok = mb.ok && two;
+        icp_tile_fetch(a, t, ma);
+        icp_tile_fetch(a, t, mb);
+        icp_finish(a, ma, Rpi, tp, (t.y0 + y0) * a.cols + t.x0 + x0, acc);
+        if (two) icp_finish(a, mb, Rpi, tp, (t.y0 + y1) * a.cols + t.x0 + x1, acc);
+        x0 = x1 + dx; y0 = y1 + dy;
+        if (x0 >= w) { x0 -= w; ++y0; }
     }
 }
 
 // mode as icp_reduce_kernel: 0 = store the 29 sums in st->icp_sums, 1 = store and run the Gauss-Newton update in the last block
-__global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpArgs a, IcpTileGeom g, IcpTileMaps maps, ReduceWork* wk, int mode, int cur_level, int next_level)
+__global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpArgs a, IcpTileGeom g, const __grid_constant__ IcpTileMaps maps, ReduceWork* wk, int mode, int cur_level, int next_level)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     float4* s_c0 = reinterpret_cast<float4*>(s_dyn);

@@ -105,9 +105,9 @@ static IcpTileGeom tile_geom_of(const hrbf_odometry* o, int which, int l)
 }
 static IcpTileMaps tile_maps_of(const hrbf_odometry* o, int which, int l)
 {
-    const CUtensorMap* m = (const CUtensorMap*)o->tmaps_dev + (which * 3 + l) * 5;
+    const CUtensorMap* m = (const CUtensorMap*)o->tmaps_host + (which * 3 + l) * 5;
     IcpTileMaps r;
-    r.pc0 = m + 0; r.pc1 = m + 1; r.pg0 = m + 2; r.pg1 = m + 3; r.w = m + 4;
+    r.pc0 = m[0]; r.pc1 = m[1]; r.pg0 = m[2]; r.pg1 = m[3]; r.w = m[4];
     return r;
 }
 static int build_tile_tensor_maps(hrbf_odometry* o)
@@ -119,7 +119,9 @@ static int build_tile_tensor_maps(hrbf_odometry* o)
         return HRBF_OK;      // no TMA tensor maps on this driver: the gather kernels serve every path
     }
     auto encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-    std::vector<CUtensorMap> host(2 * 3 * 5);
+    CUtensorMap* host = new (std::nothrow) CUtensorMap[2 * 3 * 5];
+    if (!host) return HRBF_OK;
+    auto fail = [&]() { delete[] host; return (int)HRBF_OK; };
     for (int which = 0; which < 2; ++which)
         for (int l = 0; l < 3; ++l) {
             const IcpTileGeom g = tile_geom_of(o, which, l);
@@ -133,22 +135,21 @@ static int build_tile_tensor_maps(hrbf_odometry* o)
                 const cuuint32_t bx = (cuuint32_t)(curr ? g.cbx : g.mbx), by = (cuuint32_t)(curr ? g.th : g.mh);
                 const cuuint32_t box[2] = { weight ? bx : 2 * bx, by };
                 const cuuint32_t estr[2] = { 1, 1 };
-                if (box[0] > 256 || box[1] > 256 || strides[0] % 16 != 0) return HRBF_OK;
+                if (box[0] > 256 || box[1] > 256 || strides[0] % 16 != 0) return fail();
                 const CUresult r = encode(&host[(which * 3 + l) * 5 + k], weight ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, base, dims, strides,
                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) return HRBF_OK;
+                if (r != CUDA_SUCCESS) return fail();
             }
         }
-    HRBF_CUDA(cudaMalloc(&o->tmaps_dev, host.size() * sizeof(CUtensorMap)));
-    HRBF_CUDA(cudaMemcpy(o->tmaps_dev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    o->tmaps_host = host;
     return HRBF_OK;
 }
 
 // The TMA-staged tile form of the ICP reduction (icp_tile.cuh) on the object's packed pyramids; pdl: programmatic stream serialization
 static cudaError_t launch_icp_tile(hrbf_odometry* o, const IcpArgs& ia, int mode, int level, int next_level, cudaStream_t s, bool pdl)
 {
-    if (o->tmaps_dev == nullptr || ia.cols % 4 != 0 || ia.pc0 == nullptr) {      // no tensor maps (driver), or weight-map rows not 16-byte aligned
+    if (o->tmaps_host == nullptr || ia.cols % 4 != 0 || ia.pc0 == nullptr) {      // no tensor maps (driver), or weight-map rows not 16-byte aligned
         icp_reduce_kernel<false><<<reduce_blocks(ia.rows * ia.cols), kReduceThreads, 0, s>>>(ia, o->work, mode, level, next_level);
         return cudaGetLastError();
     }
@@ -268,10 +269,10 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
         size_t tile_bytes = 0;
         for (int l = 0; l < 3; ++l) {
             p.tile[l] = tile_geom_of(o, 1, l);
-            if (o->tmaps_dev) p.tmaps[l] = tile_maps_of(o, 1, l);
-            else p.tmaps[l] = IcpTileMaps{ nullptr, nullptr, nullptr, nullptr, nullptr };
+            if (o->tmaps_host) p.tmaps[l] = tile_maps_of(o, 1, l);
+            else memset(&p.tmaps[l], 0, sizeof p.tmaps[l]);
             const size_t need = icp_tile_smem_bytes(p.tile[l]);
-            p.resident[l] = (iters[l] > 0 && o->tile_resident && o->tmaps_dev && !o->useSearch && o->cols(l) % 4 == 0 && dyn + need <= budget[half]) ? 1 : 0;
+            p.resident[l] = (iters[l] > 0 && o->tile_resident && o->tmaps_host && !o->useSearch && o->cols(l) % 4 == 0 && dyn + need <= budget[half]) ? 1 : 0;
             if (p.resident[l] && need > tile_bytes) tile_bytes = need;
         }
         dyn += tile_bytes;
@@ -640,7 +641,7 @@ int hrbf_odometry_destroy(hrbf_odometry* o)
     if (o->h_model_pose) cudaFreeHost(o->h_model_pose);
     o->model_pose_ring.destroy();
     if (o->slab) cudaFree(o->slab);
-    if (o->tmaps_dev) cudaFree(o->tmaps_dev);
+    delete[] (CUtensorMap*)o->tmaps_host;
     if (o->tp_dbg) cudaFree(o->tp_dbg);
     delete o;
     return HRBF_OK;

@@ -542,12 +542,13 @@ struct IcpArgs {
 // acc[0..27] += w*row_i*row_j (i<=j<7), acc[28] += inlier  (reduce.cu:511-545)
 __device__ __forceinline__ void accumulate_row7(float (&acc)[32], const float (&row)[7], float weight, bool found)
 {
+    if (!found) return;      // every caller passes an all-zero row then: 28 FMAs that add exactly 0 (pixels are spatially coherent: little divergence)
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 7; ++i)
 #pragma unroll
         for (int j = i; j < 7; ++j) acc[k++] += weight * row[i] * row[j];
-    acc[28] += found ? 1.f : 0.f;
+    acc[28] += 1.f;
 }
 
 // Per-pixel projective association + point-to-plane row (reduce.cu:317-509).

@@ -296,7 +296,7 @@ inline IcpTileGeom track_tile_geom(int rows, int cols, int ctas)
 }
 
 template <int kTrackThreads>
-__global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const TrackParams p)
+__global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const __grid_constant__ TrackParams p)
 {
     constexpr int kTrackWarps = kTrackThreads / 32;
     pdl_wait();
