@@ -190,7 +190,9 @@ __device__ __forceinline__ void icp_tile_window(const int* s_box, int mw, int mh
 {
     any = s_box[2] >= 0;
     const int bw = s_box[2] - s_box[0] + 1, bh = s_box[3] - s_box[1] + 1;
-    mx0 = s_box[0] - min(margin, max(0, (mw - bw) / 2));
+    // x is aligned down to 4 pixels: the TMA unit wants a box to start on a 16-byte boundary in global memory, and the icp-weight
+    // map has 4-byte pixels (an unaligned start traps as "illegal instruction")
+    mx0 = (s_box[0] - min(margin, max(0, (mw - bw) / 2))) & ~3;
     my0 = s_box[1] - min(margin, max(0, (mh - bh) / 2));
 }
 
