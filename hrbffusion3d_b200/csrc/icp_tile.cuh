@@ -22,6 +22,8 @@ struct IcpTileGeom {
     int mw, mh;          // model window (pixels); mw is a multiple of 4
     int cnb, cbx;        // a tile row is fetched as cnb boxes of cbx pixels (a TMA box is at most 256 elements = 128 float4 wide) ...
     int mnb, mbx;        // ... a window row as mnb boxes of mbx pixels; shared-memory layout [box][row][pixel in box]
+    int cbs, mbs, wbs;   // distance between consecutive boxes in PIXELS of the array (every box starts 128-byte aligned): records of the
+                         // tile, records of the window, weights of the window
     int ctas, threads;   // launch shape
 };
 inline void icp_tile_boxes(IcpTileGeom& g)      // tw, mw <= 256
@@ -29,6 +31,9 @@ inline void icp_tile_boxes(IcpTileGeom& g)      // tw, mw <= 256
     g.cnb = div_up(g.tw, 128); g.cbx = (div_up(g.tw, g.cnb) + 3) & ~3;
     g.mnb = div_up(g.mw, 128); g.mbx = (div_up(g.mw, g.mnb) + 3) & ~3;
     g.mw = g.mnb * g.mbx;
+    g.cbs = (g.cbx * g.th + 7) & ~7;        // x 16 B = multiple of 128 B
+    g.mbs = (g.mbx * g.mh + 7) & ~7;
+    g.wbs = (g.mbx * g.mh + 31) & ~31;      // x 4 B
 }
 constexpr int kTileHaloX = 4, kTileHaloY = 4;      // window = tile + 2 x halo (+ 4 pixels of alignment slack in x)
 
@@ -56,9 +61,9 @@ inline IcpTileGeom icp_tile_geom(int rows, int cols, int num_sms)
     return g;
 }
 // every array's boxes start 128-byte aligned
-__host__ __device__ inline size_t icp_tile_curr_bytes(const IcpTileGeom& g) { return ((size_t)g.cnb * g.cbx * g.th * sizeof(float4) + 127) & ~(size_t)127; }
-__host__ __device__ inline size_t icp_tile_model_bytes(const IcpTileGeom& g) { return ((size_t)g.mnb * g.mbx * g.mh * sizeof(float4) + 127) & ~(size_t)127; }
-__host__ __device__ inline size_t icp_tile_weight_bytes(const IcpTileGeom& g) { return ((size_t)g.mnb * g.mbx * g.mh * sizeof(float) + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t icp_tile_curr_bytes(const IcpTileGeom& g) { return (size_t)g.cnb * g.cbs * sizeof(float4); }
+__host__ __device__ inline size_t icp_tile_model_bytes(const IcpTileGeom& g) { return (size_t)g.mnb * g.mbs * sizeof(float4); }
+__host__ __device__ inline size_t icp_tile_weight_bytes(const IcpTileGeom& g) { return (size_t)g.mnb * g.wbs * sizeof(float); }
 inline size_t icp_tile_smem_bytes(const IcpTileGeom& g)
 {
     return 2 * icp_tile_curr_bytes(g) + 2 * icp_tile_model_bytes(g) + icp_tile_weight_bytes(g) + 128;
@@ -115,10 +120,11 @@ struct IcpTileView {
     const float* gw;             // icp-weight window, same layout
     int x0, y0, w, h;            // tile rectangle in the image
     int mx0, my0, mwa, mha;      // model window rectangle staged (mwa == 0: nothing staged); may stick out of the image (zero fill)
-    int cbx, th, mbx, mh;        // box widths and heights of the layouts above
+    int cbx, cbs, mbx, mbs, wbs; // box widths and box-to-box distances of the layouts above
     // at most two boxes per row (tiles and windows are at most 256 pixels wide): no integer division
-    __device__ __forceinline__ int cidx(int x, int y) const { const int b = x >= cbx ? 1 : 0; return (b * th + y) * cbx + (x - b * cbx); }
-    __device__ __forceinline__ int midx(int x, int y) const { const int b = x >= mbx ? 1 : 0; return (b * mh + y) * mbx + (x - b * mbx); }
+    __device__ __forceinline__ int cidx(int x, int y) const { return x >= cbx ? cbs + y * cbx + (x - cbx) : y * cbx + x; }
+    __device__ __forceinline__ int midx(int x, int y) const { return x >= mbx ? mbs + y * mbx + (x - mbx) : y * mbx + x; }
+    __device__ __forceinline__ int widx(int x, int y) const { return x >= mbx ? wbs + y * mbx + (x - mbx) : y * mbx + x; }
 };
 
 // projection half of icp_gather_model (odometry_kernels.cuh): everything but the loads
@@ -148,8 +154,8 @@ __device__ __forceinline__ void icp_tile_issue_curr(const IcpTileMaps& m, const 
 {
     mbar_expect_tx(bar, 2u * (uint32_t)(g.cnb * g.cbx * g.th) * (uint32_t)sizeof(float4));
     for (int b = 0; b < g.cnb; ++b) {
-        tma_load_2d(s_c0 + b * g.th * g.cbx, &m.pc0, 2 * (x0 + b * g.cbx), y0, bar);      // x in 64-bit elements: 2 per pixel
-        tma_load_2d(s_c1 + b * g.th * g.cbx, &m.pc1, 2 * (x0 + b * g.cbx), y0, bar);
+        tma_load_2d(s_c0 + b * g.cbs, &m.pc0, 2 * (x0 + b * g.cbx), y0, bar);      // x in 64-bit elements: 2 per pixel
+        tma_load_2d(s_c1 + b * g.cbs, &m.pc1, 2 * (x0 + b * g.cbx), y0, bar);
     }
 }
 // stage 2: the model window
@@ -158,9 +164,9 @@ __device__ __forceinline__ void icp_tile_issue_model(const IcpTileMaps& m, const
 {
     mbar_expect_tx(bar, (uint32_t)(g.mnb * g.mbx * g.mh) * (use_weight ? 36u : 32u));
     for (int b = 0; b < g.mnb; ++b) {
-        tma_load_2d(s_g0 + b * g.mh * g.mbx, &m.pg0, 2 * (mx0 + b * g.mbx), my0, bar);
-        tma_load_2d(s_g1 + b * g.mh * g.mbx, &m.pg1, 2 * (mx0 + b * g.mbx), my0, bar);
-        if (use_weight) tma_load_2d(s_gw + b * g.mh * g.mbx, &m.w, mx0 + b * g.mbx, my0, bar);
+        tma_load_2d(s_g0 + b * g.mbs, &m.pg0, 2 * (mx0 + b * g.mbx), my0, bar);
+        tma_load_2d(s_g1 + b * g.mbs, &m.pg1, 2 * (mx0 + b * g.mbx), my0, bar);
+        if (use_weight) tma_load_2d(s_gw + b * g.wbs, &m.w, mx0 + b * g.mbx, my0, bar);
     }
 }
 
@@ -205,7 +211,7 @@ __device__ __forceinline__ void icp_tile_fetch(const IcpArgs& a, const IcpTileVi
     const int lx = m.ux - t.mx0, ly = m.uy - t.my0;
     if ((unsigned)lx < (unsigned)t.mwa && (unsigned)ly < (unsigned)t.mha) {
         const int q = t.midx(lx, ly);
-        icp_model_from(m, t.g0[q], t.g1[q], a.use_weight ? t.gw[q] : 1.f);
+        icp_model_from(m, t.g0[q], t.g1[q], a.use_weight ? t.gw[t.widx(lx, ly)] : 1.f);
     } else {
         const int q = m.uy * a.cols + m.ux;
         icp_model_from(m, __ldg(a.pg0 + q), __ldg(a.pg1 + q), a.use_weight ? __ldg(a.w + q) : 1.f);
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpA
             const int tcx = tile % g.ncol, try_ = tile / g.ncol;
             t.x0 = tcx * g.tw; t.w = min(g.tw, a.cols - t.x0);
             t.y0 = (int)(((long long)a.rows * try_) / g.nrow); t.h = (int)(((long long)a.rows * (try_ + 1)) / g.nrow) - t.y0;
-            t.c0 = s_c0; t.c1 = s_c1; t.g0 = s_g0; t.g1 = s_g1; t.gw = s_gw; t.cbx = g.cbx; t.th = g.th; t.mbx = g.mbx; t.mh = g.mh;
+            t.c0 = s_c0; t.c1 = s_c1; t.g0 = s_g0; t.g1 = s_g1; t.gw = s_gw; t.cbx = g.cbx; t.cbs = g.cbs; t.mbx = g.mbx; t.mbs = g.mbs; t.wbs = g.wbs;
             mbar_wait(&s_bar[0], par0); par0 ^= 1u;
             icp_tile_bbox<kReduceThreads>(a, t, Rc, tc, Rpi, tp, s_box);
             __syncthreads();

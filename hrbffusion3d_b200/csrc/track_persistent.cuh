@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_pers
                 tv.x0 = min(tcx * g.tw, L.icp.cols); tv.w = min(g.tw, L.icp.cols - tv.x0);
                 tv.y0 = (int)(((long long)L.icp.rows * try_) / g.nrow); tv.h = (int)(((long long)L.icp.rows * (try_ + 1)) / g.nrow) - tv.y0;
                 if (try_ >= g.nrow) tv.w = tv.h = 0;
-                tv.c0 = s_c0; tv.c1 = s_c1; tv.g0 = s_g0; tv.g1 = s_g1; tv.gw = s_gw; tv.cbx = g.cbx; tv.th = g.th; tv.mbx = g.mbx; tv.mh = g.mh;
+                tv.c0 = s_c0; tv.c1 = s_c1; tv.g0 = s_g0; tv.g1 = s_g1; tv.gw = s_gw; tv.cbx = g.cbx; tv.cbs = g.cbs; tv.mbx = g.mbx; tv.mbs = g.mbs; tv.wbs = g.wbs;
                 tv.mx0 = tv.my0 = tv.mwa = tv.mha = 0;
                 s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -1;
                 if (tv.w > 0 && tv.h > 0) icp_tile_issue_curr(p.tmaps[l], g, s_c0, s_c1, tv.x0, tv.y0, &s_bar[0]);
