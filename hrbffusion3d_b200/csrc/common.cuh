@@ -45,6 +45,9 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 // the first statement of every such kernel -- blocks until that previous kernel has completed and its writes are visible,
 // so the stream-order semantics are unchanged.  A no-op in a kernel launched the ordinary way.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the NEXT kernel of the stream (if launched with programmatic serialization) be scheduled as soon as SM resources free up,
+// instead of after this grid has drained; it still blocks in its own pdl_wait() until this grid has completed
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
 {

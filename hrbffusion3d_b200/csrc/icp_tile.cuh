@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kReduceThreads, 2) icp_tile_reduce_kernel(IcpA
     __shared__ int s_box[4];
     __shared__ int s_win[3];
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     pdl_wait();      // the maps and the pose may come from the previous kernel of the stream
     TrackState* st = &wk->st;

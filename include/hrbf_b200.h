@@ -161,9 +161,10 @@ int hrbf_odometry_set_tracker(hrbf_odometry*, int use_kernel_graph);
  * for ONE sequence) or 256 (leaves half of every SM to the kernels of OTHER fusion objects running on their own streams:
  * several sequences per GPU, offline throughput runs).  Replaces the launch-shape table of Utils/GPUConfig.h:53-78. */
 int hrbf_odometry_set_tracker_threads(hrbf_odometry*, int threads);
-/* persistent tracker: resident != 0 (default) keeps, per pyramid level, every CTA's tile of packed ICP records and the model window its
- * associations fall into in shared memory for all Gauss-Newton iterations of the level (staged by TMA bulk copies); 0 = every
- * iteration re-reads the maps through L2 (round 1's form; kept for A/B measurements and as the path for images whose tiles do not fit). */
+/* persistent tracker: resident != 0 keeps, per pyramid level, every CTA's tile of packed ICP records and the model window its
+ * associations fall into in shared memory for all Gauss-Newton iterations of the level (staged by 2-D tensor-map TMA loads); 0 (default)
+ * = every iteration re-reads the maps through L2.  Measured on a B200 (profiles/r2_*): the pass is bound by instruction issue, not by
+ * the L2 round trips the streaming form already overlaps, and the resident form's extra index arithmetic makes it ~20 % slower. */
 int hrbf_odometry_set_tracker_tiles(hrbf_odometry*, int resident);
 /* initICP(depth) [GPUTest path], RGBDOdometry.cpp:161-181 : depth_dev = float[h][w] raw units */
 int hrbf_odometry_init_icp_depth(hrbf_odometry*, const float* depth_dev, float depthCutoff, float depthMapFactor, void* stream);
