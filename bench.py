@@ -40,8 +40,7 @@ from hrbffusion3d_b200 import synth  # noqa: E402
 W, H = 640, 480
 RING = 96                    # frames of one closed camera loop, cycled (96 x 1.54 MB of inputs = 147 MB > 126 MB L2)
 ICP_BYTES_PER_PIXEL_ITER = 68.0
-ICP_NCU_TRAFFIC = 20.9e6          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, cold cache
-ICP_NCU_TRAFFIC_SRC = "ncu --set full, profiles/r1_final_icp_reduce_ncu_full.txt"
+ICP_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "icp_reduce_dram_traffic.json")      # written from the ncu --set full capture of this kernel (scripts/ncu_icp_traffic.py)
 FUSION_KW = {}               # reference defaults: RGB+ICP (weight 10), SO3 pre-alignment, iterations 10/5/4, HRBF win 3 / K 10
 
 
@@ -49,10 +48,9 @@ def make_sequence(seed, n=RING, only=None):
     """plane z = 1.5 m tilted 15 deg, camera on a 5 cm circle with 2 deg yaw wobble, Kinect-style
     noise.  One closed loop of n frames (3.3 mm / 0.13 deg per frame), replayed for as many steps as asked.
     only = k: render just the first k frames of that loop."""
-    sc = synth.Scene("plane")
     cam = synth.default_camera(W, H)
     poses = synth.circle_trajectory(n, frames_per_rev=n)[:only]
-    frames = [synth.render_depth(sc, p, W, H, cam, noise=True, seed=seed * 100000 + i) for i, p in enumerate(poses)]
+    frames = synth.render_sequence("plane", poses, W, H, cam, seed0=seed * 100000)      # host process pool (before CUDA is touched)
     depth = np.stack([f[0] for f in frames])
     rgb = np.stack([f[1] for f in frames])
     return depth, rgb, poses, cam
@@ -88,6 +86,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def icp_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the reduction kernel, from the committed ncu --set full capture
+    (per launch like `achieved`); None when no capture has been summarised"""
+    try:
+        d = json.load(open(ICP_TRAFFIC_FILE))
+        return float(d["dram_bytes_per_launch"]), d.get("source", ICP_TRAFFIC_FILE)
+    except Exception:
+        return None, "no ncu capture summarised (profiles/icp_reduce_dram_traffic.json missing)"
 
 
 def measured_peak_hbm():
@@ -159,6 +167,9 @@ def ours_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_job0 = time.perf_counter()
+    rendered = make_sequence(0) if rank == 0 else None      # host-side synthetic data, rendered by a process pool before CUDA is initialised
+    t_render = time.perf_counter() - t_job0
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
@@ -170,16 +181,22 @@ def ours_arm(args):
     blobs = None
     cam = synth.default_camera(W, H)
     poses_all = synth.circle_trajectory(RING, frames_per_rev=RING)
+    t_io0 = time.perf_counter()
     if rank == 0:
-        depth0, rgb0, _, _ = make_sequence(0)
+        depth0, rgb0, _, _ = rendered
+        del rendered
         blobs = []
         for r in range(world):
             o = (r * RING) // world
             blobs.append(klg.write_klg(((33333 * i, depth0[(i + o) % RING], rgb0[(i + o) % RING]) for i in range(RING)), W, H))
         del depth0, rgb0
+    t_io1 = time.perf_counter()
     blob = multigpu.scatter_blobs(blobs, device="cuda")
     del blobs
+    torch.cuda.synchronize()
+    t_io2 = time.perf_counter()
     frames = list(klg.KlgReader(blob, W, H))
+    t_io3 = time.perf_counter()
     assert len(frames) == RING
     depth = np.stack([f[1] for f in frames])
     rgb = np.stack([f[2] for f in frames])
@@ -237,12 +254,14 @@ def ours_arm(args):
         l0 = lib().hrbf_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()                                                # the device is idle: nothing of the timed steps can start before this
+        t_w0 = time.perf_counter()
         for i in range(args.warmup, args.warmup + args.steps):
             step(i)
         for q in range(S):                                         # e1 = when the last sequence's last frame is done
             torch.cuda.current_stream().wait_stream(st[q])
         e1.record()
         torch.cuda.synchronize()
+        run.wall_s = time.perf_counter() - t_w0                    # the same region on the host's clock (enqueue + completion)
         launches = lib().hrbf_launch_count() - l0
         for q in range(S):
             with torch.cuda.stream(st[q]):
@@ -259,30 +278,35 @@ def ours_arm(args):
         sampler.start()
     # (1) the live single-camera path: one sequence, 512-thread tracker
     ms1_dev, launches1, Fs = run(False, 1)
+    wall1_dev = run.wall_s
     F = Fs[0]
     count = F.globalModel.lastCount()
     traj1 = F.trajectory().clone()
     # roofline: the level-0 ICP JTJ/JTr reduction (what hrbf_icp_step = the reference's icpStep launches), timed live with CUDA
     # events over 200 back-to-back launches on this pipeline's maps; and the same reduction in its production form, as one
     # iteration of the persistent tracker (reduction + cross-CTA exchange + fp64 solve inside ONE launch)
-    us, us_iter = C.c_float(), C.c_float()
+    us, us_iter, us_cold = C.c_float(), C.c_float(), C.c_float()
     odom = C.c_void_p(lib().hrbf_fusion_odometry(F._h))
     check(lib().hrbf_odometry_time_kernel(odom, 0, 0, 0, 200, C.byref(us), stream_ptr()))
     check(lib().hrbf_odometry_time_kernel(odom, 4, 0, 0, 200, C.byref(us_iter), stream_ptr()))
+    check(lib().hrbf_odometry_time_kernel(odom, 7, 0, 0, 30, C.byref(us_cold), stream_ptr()))      # every launch alone, after an L2 flush
     torch.cuda.synchronize()
     del F, Fs
     ms1_e2e, _, Fs = run(True, 1)
+    wall1_e2e = run.wall_s
     del Fs
     # (2) offline throughput: S_max sequences per GPU (the headline when S_max > 1)
     if S_max > 1:
         ms_dev, launches, Fs = run(False, S_max)
+        wall_dev = run.wall_s
         count = [f.globalModel.lastCount() for f in Fs]
         traj = torch.cat([f.trajectory() for f in Fs]).clone()
         del Fs
         ms_e2e, _, Fs = run(True, S_max)
+        wall_e2e = run.wall_s
         del Fs
     else:
-        ms_dev, launches, ms_e2e, traj = ms1_dev, launches1, ms1_e2e, traj1
+        ms_dev, launches, ms_e2e, traj, wall_dev, wall_e2e = ms1_dev, launches1, ms1_e2e, traj1, wall1_dev, wall1_e2e
     clocks = sampler.stop() if rank == 0 else None
     gathered = multigpu.gather_trajectories(traj)       # per-rank trajectories (S_max sequences each) back to rank 0
     if rank != 0:
@@ -328,25 +352,55 @@ def ours_arm(args):
                 big["frac"] = big["achieved"] / peak
         except Exception as e:
             big = {"error": repr(e)[:200]}
+    # BASELINE configs 3 (room with loop, map growing to ~1 M surfels) and 4 (1280x960, K = 16) through the full pipeline: extra keys,
+    # measured by scripts/bench_extra.py in a subprocess after this process has released the GPU's memory
+    extras = None
+    if world == 1 and args.extras:
+        torch.cuda.empty_cache()
+        try:
+            pr = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_extra.py"), "--frames3", str(args.extras_frames3), "--frames4", str(args.extras_frames4)],
+                                capture_output=True, text=True, timeout=600)
+            extras = [json.loads(l) for l in pr.stdout.splitlines() if l.startswith("{")]
+            if not extras:
+                extras = {"error": ((pr.stderr or "no output").strip().splitlines() or ["no output"])[-1][:300]}
+        except Exception as e:
+            extras = {"error": repr(e)[:300]}
     total_frames = args.steps * world * S_max
+    traffic, traffic_src = icp_traffic()
     single = {"what": "the live single-camera path: ONE sequence per GPU, 512-thread tracker, same frames, same timing rules",
               "value": args.steps * world / (ms1_dev * 1e-3), "e2e": args.steps * world / (ms1_e2e * 1e-3), "unit": "frames/s",
-              "ms_per_frame": ms1_dev / args.steps, "gpu_launches": launches1}
+              "ms_per_frame": ms1_dev / args.steps, "gpu_launches": launches1,
+              "host_wall_clock": {"value": args.steps / wall1_dev, "e2e": args.steps / wall1_e2e, "unit": "frames/s per GPU (time.perf_counter around the same region, this rank)"}}
     out = {"metric": "frames/sec HRBF+ICP 640x480", "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, S_max),
-           "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * S_max, "d2h_bytes_per_step": 48 * S_max},
+           "timed_region_s": ms_dev * 1e-3,
+           "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * S_max, "d2h_bytes_per_step": 48 * S_max,
+                   "timed_region_s": ms_e2e * 1e-3,
+                   "host_wall_clock": {"value": args.steps * S_max / wall_e2e, "unit": "frames/s per GPU",
+                                       "what": "the same e2e region measured with time.perf_counter on rank 0 (enqueue of every frame + H2D + D2H of every pose + completion)"}},
+           "host_wall_clock": {"value": args.steps * S_max / wall_dev, "unit": "frames/s per GPU", "what": "the timed region of `value` on rank 0's host clock"},
+           "offline_batch_io": {"what": "what the timed region leaves out of an offline batch run, measured in this run: rank 0 packs one .klg stream per rank, "
+                                        "scatters them (NCCL for N > 1), every rank decodes (zlib) its stream of %d frames" % RING,
+                                "host_render_s": t_render, "klg_pack_s": t_io1 - t_io0, "klg_scatter_s": t_io2 - t_io1, "klg_decode_s": t_io3 - t_io2,
+                                "frames_per_s_of_one_pass_over_the_log_including_scatter_and_decode":
+                                    world * RING / ((t_io3 - t_io1) + RING / (total_frames / (ms_e2e * 1e-3) / world))},
            "single_sequence": single, "gpu_launches": launches, "clocks": clocks, "surfels_at_end": count, "klg_bytes_per_sequence": klg_bytes,
            "trajectory_ate_rmse_m": ate,
            "roofline": {"bound": "hbm", "kernel": "icp_reduce_kernel<false>, level 0 (640x480): the ICP JTJ/JTr reduction as hrbf_icp_step launches it",
                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                        "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": ICP_NCU_TRAFFIC,
-                        "traffic_source": ICP_NCU_TRAFFIC_SRC,
+                        "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us.value, "traffic": traffic, "traffic_source": traffic_src,
+                        "l2_state": "hot: 200 back-to-back launches over the same 20.9 MB (resident in the 126 MB L2)",
+                        "cold": {"what": "the same launch timed ALONE right after a 256 MB memset has flushed L2 (30 launches, CUDA events around each): the maps come from HBM",
+                                 "us_per_launch": us_cold.value, "achieved": alg_bytes / (us_cold.value * 1e-6) / 1e9, "frac": alg_bytes / (us_cold.value * 1e-6) / 1e9 / peak},
+                        "bound_note": "at 640x480 a launch is bound by its fixed cost (launch + grid-wide last-block reduction: 5 us for a 160x120 level) and by "
+                                      "instruction issue (~290 instructions per pixel: 7.5 ps/pixel at one instruction per scheduler and clock, against 10.5 ps/pixel "
+                                      "of HBM time at the measured peak), not by HBM: see DESIGN.md section 3",
                         "in_tracker": {"what": "the same reduction as one Gauss-Newton iteration of track_persistent_kernel (reduction + cross-CTA exchange "
                                                "+ fp64 solve; 200 iterations in one launch, CUDA events)",
                                        "us_per_iteration": us_iter.value, "achieved": alg_bytes / (us_iter.value * 1e-6) / 1e9, "unit": "GB/s"},
                         "at_1280x960": big},
-           "cpu_baseline": cpu_baseline}
+           "cpu_baseline": cpu_baseline, "extra_configs": extras}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -359,6 +413,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sequences", type=int, default=3, help="independent sequences per GPU (offline throughput); 1 = the live single-camera path only")
+    ap.add_argument("--extras", type=int, default=1, help="also run BASELINE configs 3 and 4 (scripts/bench_extra.py) and attach them as extra_configs (N = 1 only)")
+    ap.add_argument("--extras-frames3", type=int, default=1000)
+    ap.add_argument("--extras-frames4", type=int, default=120)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

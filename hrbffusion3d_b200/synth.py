@@ -40,8 +40,9 @@ class Scene:
             self.spheres = []
         else:
             # 4 x 3 x 2.5 m box seen from the inside, camera near the middle looking at +z
+            # (the wall behind the start pose, z = -1.8, is only ever seen by the room loop of SURVEY 8d config 3)
             self.planes = [(np.array([0, 0, 1.0]), 2.2), (np.array([1.0, 0, 0]), 2.0), (np.array([-1.0, 0, 0]), 2.0),
-                           (np.array([0, 1.0, 0]), 1.2), (np.array([0, -1.0, 0]), 1.3)]
+                           (np.array([0, 1.0, 0]), 1.2), (np.array([0, -1.0, 0]), 1.3), (np.array([0, 0, -1.0]), 1.8)]
             self.spheres = [(np.array([0.3, 0.6, 1.7]), 0.45), (np.array([-0.8, 0.2, 1.9]), 0.35)]
 
     def raycast(self, o, D):
@@ -163,6 +164,35 @@ def circle_trajectory(n_frames, radius=0.05, yaw_deg=2.0, frames_per_rev=200):
         poses.append(make_pose(0.0, np.deg2rad(yaw_deg) * np.sin(a), 0.0,
                                (radius * np.cos(a) - radius, radius * np.sin(a), 0.0)))
     return poses
+
+
+def room_loop_trajectory(n_frames, radius=0.05):
+    """a closed loop inside the room -- the camera turns once about the vertical axis (360 / n degrees per
+    frame: 0.36 degrees at n = 1000) while it moves on a small circle (<= 1 cm per frame); the last frame closes onto the first,
+    so the map first grows around the whole room and then the start of the loop is seen again."""
+    poses = []
+    for i in range(n_frames):
+        a = 2 * np.pi * i / n_frames
+        poses.append(make_pose(0.0, a, 0.0, (radius * np.sin(3 * a), 0.02 * np.sin(2 * a), radius * (1 - np.cos(3 * a)))))
+    return poses
+
+
+def _render_one(args):
+    kind, pose, W, H, cam, seed = args
+    return render_depth(Scene(kind), pose, W, H, cam, noise=True, seed=seed)
+
+
+def render_sequence(kind, poses, W, H, cam, seed0=0, workers=None):
+    """[(depth u16, rgb u8)] for every pose, rendered on `workers` processes (host-side data generation only; call before CUDA is
+    initialised in this process -- the pool forks)."""
+    import multiprocessing as mp
+    import os
+    jobs = [(kind, p, W, H, cam, seed0 + i) for i, p in enumerate(poses)]
+    workers = workers or min(len(jobs), max(1, (os.cpu_count() or 2) - 1))
+    if workers <= 1 or len(jobs) < 4:
+        return [_render_one(j) for j in jobs]
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_render_one, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
 
 
 def surfels_from_maps(maps, pose, time=1, submap=0, stride=1):
