@@ -1026,7 +1026,7 @@ int hrbf_odometry_time_kernel(hrbf_odometry* o, int which, int level, int with_u
     auto launch_once = [&](cudaStream_t q) {
         switch (which) {
         case 5: (void)launch_icp_tile(o, ia, with_update ? 1 : 0, level, -1, q, true); break;
-        case 0: (void)launch_pdl(icp_reduce_kernel<false>, dim3(nb), dim3(kReduceThreads), 0, q, ia, o->work, with_update ? 1 : 0, level, -1, 1); break;
+        case 0: icp_reduce_kernel<false><<<nb, kReduceThreads, 0, q>>>(ia, o->work, with_update ? 1 : 0, level, -1); break;
         case 1: rgb_residual_kernel<<<nb, 256, 0, q>>>(ra, o->work, 1, level, 0, -1); break;
         case 2: rgb_step_kernel<<<nb, kReduceThreads, 0, q>>>(sa, -2.0f, o->work, with_update ? 1 : 0, level, -1); break;
         default: so3_reduce_kernel<<<reduce_blocks(o->rows(2) * o->cols(2)), kReduceThreads, 0, q>>>(o->lastNextImage[2], o->nextImage[2], o->rows(2), o->cols(2), o->work, 0); break;

@@ -714,7 +714,7 @@ __device__ __forceinline__ void icp_finish(const IcpArgs& a, const IcpModel& m, 
 constexpr int kIcpInFlight = HRBF_ICP_INFLIGHT;
 template <int kThreads, bool PACKED>
 __device__ __forceinline__ void icp_pass_nosearch_t(const IcpArgs& a, const float* Rc, const float* tc, const float* Rpi, const float* tp,
-                                                    int begin, int end, float (&acc)[32], const IcpCurr* pre = nullptr)
+                                                    int begin, int end, float (&acc)[32])
 {
     constexpr int kTrackThreads = kThreads;
     for (int i0 = begin + (int)threadIdx.x; i0 < end; i0 += kIcpInFlight * kTrackThreads) {
@@ -722,8 +722,7 @@ __device__ __forceinline__ void icp_pass_nosearch_t(const IcpArgs& a, const floa
 #pragma unroll
         for (int u = 0; u < kIcpInFlight; ++u) {
             const int i = i0 + u * kTrackThreads;
-            // pre: the records of the first trip, loaded by the caller before it waited for the previous kernel (icp_reduce_kernel)
-            c[u] = (pre != nullptr && i0 == begin + (int)threadIdx.x) ? pre[u] : icp_load_curr<PACKED>(a, i < end ? i : i0);
+            c[u] = icp_load_curr<PACKED>(a, i < end ? i : i0);
         }
         IcpModel m[kIcpInFlight];
 #pragma unroll
@@ -756,28 +755,13 @@ __global__ void pack_maps_kernel(int n, const float* __restrict__ v, const float
 
 // mode 0: store the 29 sums in st->icp_sums only (hrbf_icp_step, or RGB still to come)
 // mode 1: store and run the Gauss-Newton update in the last block
-// early != 0: the maps are not written by the previous kernel of the stream (only the pose state may be): the first trip's
-// current-frame records are requested BEFORE waiting for that kernel, so that launch latency and the first memory round trip
-// overlap its tail (programmatic dependent launch; back-to-back reductions of the kernel-graph tracker and of the probe)
 template <bool SEARCH>
-__global__ void __launch_bounds__(kReduceThreads, 2) icp_reduce_kernel(IcpArgs a, ReduceWork* wk, int mode, int cur_level, int next_level, int early = 0)
+__global__ void __launch_bounds__(kReduceThreads, 2) icp_reduce_kernel(IcpArgs a, ReduceWork* wk, int mode, int cur_level, int next_level)
 {
     TrackState* st = &wk->st;
     __shared__ double s_total[32];
     __shared__ float s_pose[24];
-    pdl_launch_dependents();
-    const int N_ = a.rows * a.cols;
-    const int begin_ = (int)(((long long)N_ * blockIdx.x) / gridDim.x), end_ = (int)(((long long)N_ * (blockIdx.x + 1)) / gridDim.x);
-    IcpCurr pre[kIcpInFlight];
-    const bool use_pre = !SEARCH && early && a.pc0 != nullptr;
-    if (use_pre) {
-#pragma unroll
-        for (int u = 0; u < kIcpInFlight; ++u) {
-            const int i0 = begin_ + (int)threadIdx.x, i = i0 + u * kReduceThreads;
-            pre[u] = icp_load_curr<true>(a, i < end_ ? i : (i0 < end_ ? i0 : begin_));
-        }
-    }
-    pdl_wait();
+    pdl_wait();      // (no-op unless launched with programmatic stream serialization)
     if (threadIdx.x < 9) { s_pose[threadIdx.x] = st->Rcurr[threadIdx.x]; s_pose[12 + threadIdx.x] = st->Rprev_inv[threadIdx.x]; }
     if (threadIdx.x < 3) { s_pose[9 + threadIdx.x] = st->tcurr[threadIdx.x]; s_pose[21 + threadIdx.x] = st->tprev[threadIdx.x]; }
     __syncthreads();
@@ -796,8 +780,8 @@ __global__ void __launch_bounds__(kReduceThreads, 2) icp_reduce_kernel(IcpArgs a
         if (SEARCH) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) icp_pixel<true>(a, Rc, tc, Rpi, tp, i, acc);
         else {
             // contiguous pixel range per CTA, several pixels per thread in flight (same pass as the persistent tracker)
-            if (use_pre) icp_pass_nosearch_t<kReduceThreads, true>(a, Rc, tc, Rpi, tp, begin_, end_, acc, pre);
-            else icp_pass_nosearch<kReduceThreads>(a, Rc, tc, Rpi, tp, begin_, end_, acc);
+            const int begin = (int)(((long long)N * blockIdx.x) / gridDim.x), end = (int)(((long long)N * (blockIdx.x + 1)) / gridDim.x);
+            icp_pass_nosearch<kReduceThreads>(a, Rc, tc, Rpi, tp, begin, end, acc);
         }
     }
 

@@ -66,7 +66,7 @@ def run(W, H, kind, poses, n_frames, name, capacity, **kw):
         i = n_frames + j
         F.processStaged(None)
         F.stageFrame(rgb[(i + 1) % n_in], depth[(i + 1) % n_in])
-        acc += np.asarray(F.lastTimings(), np.float64)
+        acc += np.asarray(list(F.lastTimings().values()), np.float64)
     F.enableTimings(False)
     out = {"config": name, "width": W, "height": H, "frames": n_frames - 1, "frames_per_s": (n_frames - 1) / (ms * 1e-3), "ms_per_frame": ms / (n_frames - 1),
            "frames_per_s_host_wall_clock": (n_frames - 1) / wall, "surfels": checkpoints, "surfels_at_end": int(F.globalModel.lastCount()),
