@@ -213,7 +213,8 @@ def ours_arm(args):
     def run(host_inputs, S):
         """S fresh pipelines on S streams: W warm-up steps (frame 1 initialises the map), then K timed steps; a step = one frame of
         every sequence.  Returns (ms, launches, pipelines)."""
-        Fs = [HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=(256 if S > 1 else 512), **FUSION_KW) for _ in range(S)]
+        tthreads = int(os.environ.get("HRBF_BENCH_TRACKER_THREADS", "0")) or (256 if S > 1 else 512)      # (development override)
+        Fs = [HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=tthreads, **FUSION_KW) for _ in range(S)]
         st = [torch.cuda.Stream() for _ in range(S)]
         off = [(q * RING) // (world * S) for q in range(S)]
         pose = np.zeros((S, 16), np.float32)
