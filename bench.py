@@ -341,6 +341,46 @@ def ours_arm(args):
                             "sample": "frames 2-%d of the same sequence (oracle pipeline, OpenMP over %d threads)" % (n_cpu + 1, cores)}
         except Exception as e:      # the reported baseline must never cost the measured line
             cpu_baseline = {"value": None, "unit": "frames/s", "cores": cores, "kind": "port", "sample": "failed: %r" % (e,)}
+    # the tracking stage against the REFERENCE'S OWN tracking loop on this GPU (reported baseline, like cpu_baseline): the reference's
+    # RGBDOdometry.cpp compiled verbatim on its own CUDA kernels (oracle/_ref/libref_odometry.so, oracle/build_ref_odometry.py) and this
+    # library's tracker, on the same inputs -- the tracker inputs of the next frame of the oracle pipeline used for cpu_baseline
+    ref_tracker = None
+    if world == 1 and cpu_baseline is not None and cpu_baseline.get("value"):
+        try:
+            from oracle import orc_py, refodom_py
+            from tests.util import init_tracker, pipeline_tracker_inputs, pose_err
+            from hrbffusion3d_b200 import odometry as od
+            if refodom_py.available():
+                k = r.i % RING
+                d = pipeline_tracker_inputs(orc_py, r.f, rgb[(k - 1) % RING], rgb[k], depth[k])
+                pose = r.f.currPose.copy()
+                us_ref = []
+                for _ in range(5):
+                    ro = init_tracker(refodom_py.Odometry(W, H, cam[2], cam[3], cam[0], cam[1]), lambda a: a, pose, d)
+                    tr_, Rr_, st_ = ro.getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
+                    us_ref.append(st_["wall_us"])
+                    del ro
+                up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+                go = init_tracker(od.RGBDOdometry(W, H, cam[2], cam[3], cam[0], cam[1]), up, pose, d)
+                tg_, Rg_, _ = go.getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
+                pin = torch.from_numpy(np.concatenate([pose[:3, :3].reshape(-1), pose[:3, 3]]).astype(np.float32)).cuda()
+                pout = torch.zeros(12, device="cuda")
+                us_ours = []
+                for _ in range(12):
+                    go.initRGB(up(d["rgba"]))      # the SO3 step swaps the image pyramids: restore them (untimed)
+                    torch.cuda.synchronize()
+                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record(); go.trackAsync(pin, pout); eb.record(); torch.cuda.synchronize()
+                    us_ours.append(ea.elapsed_time(eb) * 1e3)
+                ang, dt = pose_err(Rr_, tr_, Rg_, tg_)
+                ref_tracker = {"what": "RGBDOdometry::getIncrementalTransformation, reference defaults (RGB-D + ICP + SO3, 10/5/4), 640x480, one frame of this workload: the "
+                                       "reference's own RGBDOdometry.cpp + reduce.cu + cudafuncs.cu (compiled unmodified for sm_100a with the reference's nvcc flags; Eigen and "
+                                       "GL textures are stand-ins) against track_persistent_kernel, same inputs, same GPU",
+                               "reference_us": float(np.median(us_ref)), "reference_timing": "host wall clock around the synchronous call (median of 5)",
+                               "ours_us": float(np.median(us_ours[2:])), "ours_timing": "CUDA events around hrbf_odometry_track_async (median of 10)",
+                               "speedup": float(np.median(us_ref) / np.median(us_ours[2:])), "pose_difference": {"angle_rad": ang, "translation_m": dt}}
+        except Exception as e:
+            ref_tracker = {"error": repr(e)[:300]}
     # the same reduction probe at BASELINE config 4's image size, where the fixed cost of a launch is amortised over 4x the bytes; in a
     # subprocess with a timeout, so that nothing in it can cost this line
     big = None
@@ -401,7 +441,7 @@ def ours_arm(args):
                                                "+ fp64 solve; 200 iterations in one launch, CUDA events)",
                                        "us_per_iteration": us_iter.value, "achieved": alg_bytes / (us_iter.value * 1e-6) / 1e9, "unit": "GB/s"},
                         "at_1280x960": big},
-           "cpu_baseline": cpu_baseline, "extra_configs": extras}
+           "cpu_baseline": cpu_baseline, "reference_tracker_on_this_gpu": ref_tracker, "extra_configs": extras}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
