@@ -1073,3 +1073,5 @@ const float* hrbf_odometry_depth(const hrbf_odometry* o, int which, int level)
 }
 
 }  // extern "C"
+
+#include "cudafuncs_api.inl"

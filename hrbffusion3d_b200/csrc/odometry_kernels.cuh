@@ -271,27 +271,32 @@ __global__ void transform_kernel(int rows, int cols, const float* a_src, int asp
 }
 
 // ---- GPUTest path (initICP(depth)): cudafuncs.cu:57-94, 109-136, 154-195 ----
+// pyrDown of the raw depth (cudafuncs.cu:57-94): 5x5 binomial taps (6, 4, 1) / 16 per axis around source pixel (2x, 2y), clipped to
+// the image, a tap counting only when it is within 3 sigma_color (= 90 raw units) of the centre; src_at(cx, cy) reads the source level
+template <typename At>
+__device__ __forceinline__ float depth_down_gated(int srows, int scols, int x, int y, At src_at)
+{
+    const float tap[3] = { 0.375f, 0.25f, 0.0625f };      // by distance from the centre
+    const int sx = 2 * x, sy = 2 * y;
+    const float mid = src_at(sx, sy), gate = 3.f * 30.f;
+    float acc = 0.f, norm = 0.f;
+    for (int cy = max(sy - 2, 0); cy < min(sy + 3, srows); ++cy)
+        for (int cx = max(sx - 2, 0); cx < min(sx + 3, scols); ++cx) {
+            const float d = src_at(cx, cy);
+            if (fabsf(d - mid) < gate) {
+                const float w = tap[abs(cx - sx)] * tap[abs(cy - sy)];
+                acc += d * w;
+                norm += w;
+            }
+        }
+    return acc / norm;
+}
 __global__ void pyrdown_depth_kernel(int srows, int scols, const float* __restrict__ src, float* dst)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const int drows = srows / 2, dcols = scols / 2;
     if (x >= dcols || y >= drows) return;
-    const int D = 5;
-    const float sigma_color = 30.f;
-    const float center = src[(size_t)(2 * y) * scols + 2 * x];
-    const int x_mi = max(0, 2 * x - D / 2) - 2 * x, y_mi = max(0, 2 * y - D / 2) - 2 * y;
-    const int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x, y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
-    const float weights[3] = { 0.375f, 0.25f, 0.0625f };
-    float sum = 0, wall = 0;
-    for (int yi = y_mi; yi < y_ma; ++yi)
-        for (int xi = x_mi; xi < x_ma; ++xi) {
-            const float val = src[(size_t)(2 * y + yi) * scols + 2 * x + xi];
-            if (fabsf(val - center) < 3 * sigma_color) {
-                const float w = weights[abs(xi)] * weights[abs(yi)];
-                sum += val * w; wall += w;
-            }
-        }
-    dst[(size_t)y * dcols + x] = sum / wall;
+    dst[(size_t)y * dcols + x] = depth_down_gated(srows, scols, x, y, [&](int cx, int cy) { return src[(size_t)cy * scols + cx]; });
 }
 __global__ void create_vmap_kernel(int rows, int cols, const float* __restrict__ depth, float* vmap, int vp,
                                    float fx_inv, float fy_inv, float cx, float cy, float cutoff, float factor)

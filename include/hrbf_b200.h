@@ -89,6 +89,28 @@ int hrbf_transform_curv_maps(const float* k1src_dev, size_t k1sstep, const float
                              float* k1dst_dev, size_t k1dstep, float* k2dst_dev, size_t k2dstep,
                              int rows, int cols, void* stream);
 
+/* The RGB-branch / GPUTest-branch preparation functions of the same seam, one to one, on pitched arrays (step in bytes):
+ *   pyrDown               Cuda/cudafuncs.cuh:177 (cudafuncs.cu:57-107)     depth pyramid level with a 3-sigma colour gate
+ *   createVMap / NMap     cudafuncs.cuh:140-145 (cudafuncs.cu:109-211)     depth -> SoA vertex map, forward-difference normals
+ *   verticesToDepth       cudafuncs.cuh:218 (cudafuncs.cu:874-894)         z of an RGBA32F vertex texture, NaN beyond maxDepth
+ *   pyrDownGaussF         cudafuncs.cuh:181 (cudafuncs.cu:493-524,794-816) 5x5 Gaussian pyramid level of a float image
+ *   pyrDownUcharGauss     cudafuncs.cuh:183 (cudafuncs.cu:818-871)         the same on u8 intensities
+ *   imageBGRToIntensity   cudafuncs.cuh:213 (cudafuncs.cu:896-928)         RGBA8 texture -> u8 intensity (0.114 / 0.299 / 0.587)
+ *   computeDerivativeImages cudafuncs.cuh:185 (cudafuncs.cu:930-993)       3x3 Sobel pair -> short dIdx, dIdy
+ *   projectToPointCloud   cudafuncs.cuh:216 (cudafuncs.cu:995-1028)        depth -> float3 cloud with K of pyramid `level` */
+int hrbf_pyr_down(const float* src_dev, size_t src_step, float* dst_dev, size_t dst_step, int src_rows, int src_cols, void* stream);
+int hrbf_create_vmap(hrbf_camera intr, const float* depth_dev, size_t depth_step /* dense: cols * 4 */, float* vmap_dev, size_t vmap_step,
+                     int rows, int cols, float depthCutoff, float depthMapFactor, void* stream);
+int hrbf_create_nmap(const float* vmap_dev, size_t vmap_step, float* nmap_dev, size_t nmap_step, int rows, int cols, void* stream);
+int hrbf_vertices_to_depth(const float* vert_aos_dev, float* depth_dev, size_t depth_step, int rows, int cols, float maxDepth, void* stream);
+int hrbf_pyr_down_gauss_f(const float* src_dev, size_t src_step, float* dst_dev, size_t dst_step, int src_rows, int src_cols, void* stream);
+int hrbf_pyr_down_uchar_gauss(const unsigned char* src_dev, size_t src_step, unsigned char* dst_dev, size_t dst_step, int src_rows, int src_cols, void* stream);
+int hrbf_image_bgr_to_intensity(const unsigned char* rgba8_dev, unsigned char* dst_dev, size_t dst_step, int rows, int cols, void* stream);
+int hrbf_compute_derivative_images(const unsigned char* src_dev, size_t src_step, short* dIdx_dev, size_t dx_step, short* dIdy_dev, size_t dy_step,
+                                   int rows, int cols, void* stream);
+int hrbf_project_to_point_cloud(const float* depth_dev, size_t depth_step, float* cloud3_dev, size_t cloud_step, hrbf_camera intr, int level,
+                                int rows, int cols, void* stream);
+
 /* ------------------------------------------------------------------------
  * Rows 1-3 : Jacobian-product reductions  (replaces Cuda/cudafuncs.cuh:82-147)
  * Synchronous like the reference: results are on the host when the call returns.

@@ -195,4 +195,69 @@ HRBF_COMPAT_RESIZE(resizeCMap, hrbf_resize_cmap, 4)
 HRBF_COMPAT_RESIZE(resizeicpWeightMap, hrbf_resize_icpweight_map, 1)
 #undef HRBF_COMPAT_RESIZE
 
+/* ---- the GPUTest- and RGB-branch preparation functions (Cuda/cudafuncs.cuh:140-239), pitched arrays throughout ---- */
+/* pyrDown, cudafuncs.cuh:177 (cudafuncs.cu:96-107): dst is (re)created at half size like the reference does */
+template <class MapF>
+inline void pyrDown(const MapF& src, MapF& dst)
+{
+    dst.create(src.rows() / 2, src.cols() / 2);
+    hrbf_compat::check(hrbf_pyr_down(src.ptr(), src.step(), dst.ptr(), dst.step(), src.rows(), src.cols(), nullptr), "pyrDown");
+}
+/* createVMap / createNMap, cudafuncs.cuh:140-145 (cudafuncs.cu:138-211) */
+template <class Cam, class MapF>
+inline void createVMap(const Cam& intr, const MapF& depth, MapF& vmap, const float depthCutoff, const float mDepthMapFactor)
+{
+    vmap.create(depth.rows() * 4, depth.cols());
+    if (depth.step() != (size_t)depth.cols() * sizeof(float)) throw std::runtime_error("createVMap: dense (unpitched) depth expected");
+    const hrbf_camera cam = { intr.fx, intr.fy, intr.cx, intr.cy };
+    hrbf_compat::check(hrbf_create_vmap(cam, depth.ptr(), depth.step(), vmap.ptr(), vmap.step(), depth.rows(), depth.cols(), depthCutoff, mDepthMapFactor, nullptr), "createVMap");
+}
+template <class MapF>
+inline void createNMap(const MapF& vmap, MapF& nmap)
+{
+    nmap.create(vmap.rows(), vmap.cols());
+    hrbf_compat::check(hrbf_create_nmap(vmap.ptr(), vmap.step(), nmap.ptr(), nmap.step(), vmap.rows() / 4, vmap.cols(), nullptr), "createNMap");
+}
+/* verticesToDepth, cudafuncs.cuh:218 (cudafuncs.cu:887-894): dst already created (rows x cols) */
+template <class Map1F, class MapF>
+inline void verticesToDepth(Map1F& vmap_src, MapF& dst, float cutOff)
+{
+    hrbf_compat::check(hrbf_vertices_to_depth(vmap_src.ptr(), dst.ptr(), dst.step(), dst.rows(), dst.cols(), cutOff, nullptr), "verticesToDepth");
+}
+/* pyrDownGaussF / pyrDownUcharGauss, cudafuncs.cuh:181-183 (cudafuncs.cu:794-871) */
+template <class MapF>
+inline void pyrDownGaussF(const MapF& src, MapF& dst)
+{
+    dst.create(src.rows() / 2, src.cols() / 2);
+    hrbf_compat::check(hrbf_pyr_down_gauss_f(src.ptr(), src.step(), dst.ptr(), dst.step(), src.rows(), src.cols(), nullptr), "pyrDownGaussF");
+}
+template <class MapU8>
+inline void pyrDownUcharGauss(const MapU8& src, MapU8& dst)
+{
+    dst.create(src.rows() / 2, src.cols() / 2);
+    hrbf_compat::check(hrbf_pyr_down_uchar_gauss(src.ptr(), src.step(), dst.ptr(), dst.step(), src.rows(), src.cols(), nullptr), "pyrDownUcharGauss");
+}
+/* imageBGRToIntensity, cudafuncs.cuh:213 (cudafuncs.cu:913-928).  The reference reads a cudaArray through a texture reference; a
+ * GL-free caller holds the RGBA8 image in linear device memory, which is what this overload takes. */
+template <class MapU8>
+inline void imageBGRToIntensity(const unsigned char* rgba8_dev, MapU8& dst)
+{
+    hrbf_compat::check(hrbf_image_bgr_to_intensity(rgba8_dev, dst.ptr(), dst.step(), dst.rows(), dst.cols(), nullptr), "imageBGRToIntensity");
+}
+/* computeDerivativeImages, cudafuncs.cuh:185 (cudafuncs.cu:956-993) */
+template <class MapU8, class MapS>
+inline void computeDerivativeImages(MapU8& src, MapS& dx, MapS& dy)
+{
+    hrbf_compat::check(hrbf_compute_derivative_images(src.ptr(), src.step(), dx.ptr(), dx.step(), dy.ptr(), dy.step(), src.rows(), src.cols(), nullptr),
+                       "computeDerivativeImages");
+}
+/* projectToPointCloud, cudafuncs.cuh:216 (cudafuncs.cu:1015-1028) */
+template <class MapF, class MapF3, class Cam>
+inline void projectToPointCloud(const MapF& depth, const MapF3& cloud, Cam& intrinsics, const int& level)
+{
+    const hrbf_camera cam = { intrinsics.fx, intrinsics.fy, intrinsics.cx, intrinsics.cy };
+    hrbf_compat::check(hrbf_project_to_point_cloud(depth.ptr(), depth.step(), (float*)cloud.ptr(), cloud.step(), cam, level, depth.rows(), depth.cols(), nullptr),
+                       "projectToPointCloud");
+}
+
 #endif /* HRBF_CUDAFUNCS_COMPAT_HPP_ */

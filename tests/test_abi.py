@@ -77,6 +77,16 @@ void use_all(mat33& R, float3& t, CameraModel& intr, DeviceArray2D<float>& m, De
     copyCurvatureMap(lin, m, 300.f);
     copyicpWeightMap(lin, m);
     resizeVMap(m, m); resizeNMap(m, m); resizeCMap(m, m); resizeicpWeightMap(m, m);
+    // the GPUTest- and RGB-branch preparation functions (Cuda/cudafuncs.cuh:140-239)
+    pyrDown(m, m);
+    createVMap(intr(1), m, m, 20.0f, 0.001f);
+    createNMap(m, m);
+    verticesToDepth(lin, m, 6.0f);
+    pyrDownGaussF(m, m);
+    pyrDownUcharGauss(img, img);
+    imageBGRToIntensity((const unsigned char*)nullptr, img);
+    computeDerivativeImages(img, s, s);
+    projectToPointCloud(m, f3, intr, 1);
 }
 """
 

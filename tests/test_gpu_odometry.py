@@ -407,3 +407,65 @@ def test_default_config_frame_agrees_iteration_by_iteration(orc, cuda):
     print(f"the oracle's own sensitivity to one unit in the last place of its inputs: {floor:.2e}")
     assert stg.lastSO3Count == sto.lastSO3Count and abs(stg.lastRGBCount - sto.lastRGBCount) <= 2
     assert ang <= max(POSE_TOL, 4 * floor) and dt <= max(POSE_TOL, 4 * floor), (ang, dt, floor)
+
+
+def test_rgb_prep_single_functions_match_oracle(orc, cuda):
+    """The GPUTest- and RGB-branch preparation functions of cudafuncs.cuh as one-to-one C-ABI calls on PITCHED arrays (pyrDown, createVMap,
+    createNMap, verticesToDepth, pyrDownGaussF, pyrDownUcharGauss, imageBGRToIntensity, computeDerivativeImages, projectToPointCloud)
+    against the oracle functions that tests/test_oracle_vs_reference_row5.py pins to the reference's own kernels."""
+    import ctypes as C
+    from hrbffusion3d_b200._lib import lib, check, ptr, stream_ptr, Camera
+    torch = cuda
+    W, H = 160, 120
+    m0, pose0, m1, pose1, cam = pair(W, H)
+    L = lib()
+    camS = Camera(*cam)
+    pitched = lambda rows, cols, dt, fill: torch.full((rows, cols + 24), fill, dtype=dt, device="cuda")      # 24 elements of padding per row
+    step = lambda t: C.c_size_t(t.shape[1] * t.element_size())
+    d_v = dev(torch, m0["vertex"])
+    # verticesToDepth
+    d = pitched(H, W, torch.float32, 7.0)
+    check(L.hrbf_vertices_to_depth(ptr(d_v), ptr(d), step(d), H, W, C.c_float(2.0), stream_ptr()))
+    ref_d = orc.verticesToDepth(m0["vertex"], 2.0)
+    np.testing.assert_array_equal(d[:, :W].cpu().numpy(), ref_d)
+    assert float(d[:, W:].min()) == 7.0
+    ref_d = orc.verticesToDepth(m0["vertex"], 20.0)
+    check(L.hrbf_vertices_to_depth(ptr(d_v), ptr(d), step(d), H, W, C.c_float(20.0), stream_ptr()))
+    # pyrDownGaussF
+    g = pitched(H // 2, W // 2, torch.float32, 0.0)
+    check(L.hrbf_pyr_down_gauss_f(ptr(d), step(d), ptr(g), step(g), H, W, stream_ptr()))
+    np.testing.assert_array_equal(g[:, :W // 2].cpu().numpy(), orc.pyrDownGaussF(ref_d))
+    # pyrDown (raw depth in mm, 0 = invalid)
+    raw = np.nan_to_num(ref_d * 1000.0).astype(np.float32)
+    d_raw = pitched(H, W, torch.float32, 0.0); d_raw[:, :W] = dev(torch, raw)
+    pd = pitched(H // 2, W // 2, torch.float32, 0.0)
+    check(L.hrbf_pyr_down(ptr(d_raw), step(d_raw), ptr(pd), step(pd), H, W, stream_ptr()))
+    np.testing.assert_allclose(pd[:, :W // 2].cpu().numpy(), orc.pyrDownDepth(raw), rtol=1e-6, atol=1e-4)
+    # imageBGRToIntensity, pyrDownUcharGauss, computeDerivativeImages
+    img = pitched(H, W, torch.uint8, 0)
+    check(L.hrbf_image_bgr_to_intensity(ptr(dev(torch, m0["rgba"])), ptr(img), step(img), H, W, stream_ptr()))
+    ref_img = orc.rgbaToIntensity(m0["rgba"])
+    np.testing.assert_array_equal(img[:, :W].cpu().numpy(), ref_img)
+    img2 = pitched(H // 2, W // 2, torch.uint8, 0)
+    check(L.hrbf_pyr_down_uchar_gauss(ptr(img), step(img), ptr(img2), step(img2), H, W, stream_ptr()))
+    np.testing.assert_array_equal(img2[:, :W // 2].cpu().numpy(), orc.pyrDownUcharGauss(ref_img))
+    dx, dy = pitched(H, W, torch.int16, 0), pitched(H, W, torch.int16, 0)
+    check(L.hrbf_compute_derivative_images(ptr(img), step(img), ptr(dx), step(dx), ptr(dy), step(dy), H, W, stream_ptr()))
+    rdx, rdy = orc.sobel(ref_img)
+    np.testing.assert_array_equal(dx[:, :W].cpu().numpy(), rdx)
+    np.testing.assert_array_equal(dy[:, :W].cpu().numpy(), rdy)
+    # projectToPointCloud at pyramid level 1 of a dense half-size depth
+    g_dense = g[:, :W // 2].contiguous()
+    cloud = torch.zeros((H // 2, W // 2, 3), device="cuda")
+    check(L.hrbf_project_to_point_cloud(ptr(g_dense), C.c_size_t(W // 2 * 4), ptr(cloud), C.c_size_t(W // 2 * 12), camS, 1, H // 2, W // 2, stream_ptr()))
+    camL = tuple(np.float32(c) / np.float32(2) for c in cam)
+    np.testing.assert_allclose(cloud.cpu().numpy(), orc.projectToPointCloud(orc.pyrDownGaussF(ref_d), camL), rtol=1e-6, atol=1e-7, equal_nan=True)
+    # createVMap / createNMap (TUM-style raw depth, 1/5000 m)
+    raw5 = np.nan_to_num(ref_d * 5000.0).astype(np.float32)
+    vm, nm = pitched(4 * H, W, torch.float32, 0.0), pitched(4 * H, W, torch.float32, 0.0)
+    d5 = dev(torch, raw5)
+    check(L.hrbf_create_vmap(camS, ptr(d5), C.c_size_t(W * 4), ptr(vm), step(vm), H, W, C.c_float(20.0), C.c_float(1.0 / 5000.0), stream_ptr()))
+    check(L.hrbf_create_nmap(ptr(vm), step(vm), ptr(nm), step(nm), H, W, stream_ptr()))
+    rv = orc.createVMap(cam, raw5, 20.0, 1.0 / 5000.0)
+    nan_eq_planes(vm[:, :W].cpu().numpy(), rv, H, atol=1e-6)
+    nan_eq_planes(nm[:, :W].cpu().numpy(), orc.createNMap(rv), H, atol=1e-5)
