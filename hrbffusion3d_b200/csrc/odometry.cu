@@ -349,11 +349,21 @@ static int get_graph(hrbf_odometry* o, bool rgbOnly, float icpWeight, bool pyram
     if (it == o->graphs.end()) {
         cudaGraph_t g = nullptr;
         HRBF_CUDA(cudaStreamBeginCapture(o->cap_stream, cudaStreamCaptureModeThreadLocal));
+        (void)cudaGetLastError();
         const int n = enqueue_track(o, o->cap_stream, rgbOnly, icpWeight, pyramid, fastOdom, so3, use_weight, host_io);
-        HRBF_CUDA(cudaStreamEndCapture(o->cap_stream, &g));
+        // a launch that failed during capture (bad configuration, ...) must not leave a half-built graph in the cache
+        const cudaError_t launch_err = cudaGetLastError();
+        const cudaError_t end_err = cudaStreamEndCapture(o->cap_stream, &g);
+        if (launch_err != cudaSuccess || end_err != cudaSuccess || g == nullptr) {
+            if (g) cudaGraphDestroy(g);
+            set_error("capture of the tracking graph failed: %s", cudaGetErrorString(launch_err != cudaSuccess ? launch_err : end_err));
+            (void)cudaGetLastError();
+            return HRBF_ERR_CUDA;
+        }
         cudaGraphExec_t e = nullptr;
-        HRBF_CUDA(cudaGraphInstantiate(&e, g, 0));
+        const cudaError_t inst_err = cudaGraphInstantiate(&e, g, 0);
         cudaGraphDestroy(g);
+        if (inst_err != cudaSuccess) { set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(inst_err)); return HRBF_ERR_CUDA; }
         it = o->graphs.emplace(key, std::make_pair(e, n)).first;
     }
     *exec = it->second.first;

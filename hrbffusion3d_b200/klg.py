@@ -14,8 +14,10 @@ import zlib
 import numpy as np
 
 
-def write_klg(frames, width, height, compress_depth=True):
-    """frames: iterable of (timestamp_us, depth uint16 [h,w], rgb uint8 [h,w,3]).  Returns the log as bytes."""
+def write_klg(frames, width, height, compress_depth=True, jpeg_quality=None):
+    """frames: iterable of (timestamp_us, depth uint16 [h,w], rgb uint8 [h,w,3]).  Returns the log as bytes.
+    jpeg_quality = 1..100: the image is stored as a JPEG stream (what the reference's Logger writes for live captures and its
+    RawLogReader hands to libjpeg, RawLogReader.cpp:103-105 / JPEGLoader.h); None: raw RGB8."""
     body = io.BytesIO()
     n = 0
     for ts, depth, rgb in frames:
@@ -28,9 +30,17 @@ def write_klg(frames, width, height, compress_depth=True):
             z = zlib.compress(d, 1)
             if len(z) != len(d):                # a stream of exactly w*h*2 bytes would be read back as raw
                 d = z
-        body.write(struct.pack("<qii", int(ts), len(d), rgb.size))
+        img = rgb.tobytes()
+        if jpeg_quality is not None:
+            import cv2
+            ok, enc = cv2.imencode(".jpg", rgb[..., ::-1], [int(cv2.IMWRITE_JPEG_QUALITY), int(jpeg_quality)])
+            if not ok:
+                raise RuntimeError("frame %d: JPEG encoding failed" % n)
+            if enc.size != rgb.size:            # a stream of exactly w*h*3 bytes would be read back as raw
+                img = enc.tobytes()
+        body.write(struct.pack("<qii", int(ts), len(d), len(img)))
         body.write(d)
-        body.write(rgb.tobytes())
+        body.write(img)
         n += 1
     return struct.pack("<i", n) + body.getvalue()
 

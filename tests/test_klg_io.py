@@ -73,3 +73,42 @@ def test_tum_trajectory_format():
         q = klg.rotation_to_quaternion(R)
         e = [0, 0, 0, 0]; e[axis] = 1
         np.testing.assert_allclose(np.abs(q), e, atol=1e-12)
+
+
+def test_klg_jpeg_image_branch_round_trip():
+    """The JPEG branch of the .klg image payload (GUI/src/Tools/RawLogReader.cpp:103-105: imageSize != w*h*3 -> jpeg.readData): frames
+    written with JPEG-compressed images read back as the decoder's RGB output (exactly what cv2.imdecode gives for the stored stream),
+    depth stays lossless, a raw frame in the same log is still recognised by its size, flipColors swaps channels.  (libjpeg's headers
+    are not installed, so this branch cannot be pinned to the reference's own reader like the raw / zlib branches are.)"""
+    cv2 = pytest.importorskip("cv2")
+    import struct
+    W, H = 96, 64
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames = []
+    for i in range(3):
+        rgb = np.stack([(xx * 2 + 10 * i) % 256, (yy * 3) % 256, (xx + yy) % 256], -1).astype(np.uint8)
+        depth = rng.integers(0, 20000, (H, W)).astype(np.uint16)
+        frames.append((1000 * i, depth, rgb))
+    blob = klg.write_klg(frames, W, H, jpeg_quality=90)
+    assert len(blob) < sum(f[2].size for f in frames)                       # the images really are compressed
+    out = list(klg.KlgReader(blob, W, H))
+    assert len(out) == 3
+    pos = 4
+    for (ts, depth, rgb), (ts2, d2, r2) in zip(frames, out):
+        assert ts2 == ts and np.array_equal(d2, depth)
+        _, dsz, isz = struct.unpack_from("<qii", blob, pos)
+        stream = np.frombuffer(blob, np.uint8, isz, pos + 16 + dsz)
+        pos += 16 + dsz + isz
+        assert isz != W * H * 3
+        assert np.array_equal(r2, cv2.imdecode(stream, cv2.IMREAD_COLOR)[..., ::-1])      # the decoder's output, channel order RGB
+        err = r2.astype(np.float64) - rgb
+        assert 10 * np.log10(255.0 ** 2 / np.mean(err ** 2)) > 30.0                      # and close to what was stored (lossy codec)
+    flipped = list(klg.KlgReader(blob, W, H, flip_colors=True))
+    assert np.array_equal(flipped[0][2], out[0][2][..., ::-1])
+    # a truncated JPEG stream is an error, not a black frame
+    with pytest.raises(ValueError):
+        bad = bytearray(klg.write_klg(frames[:1], W, H, jpeg_quality=90))
+        _, dsz, isz = struct.unpack_from("<qii", bad, 4)
+        bad[4 + 16 + dsz:4 + 16 + dsz + isz] = bytes(isz)
+        list(klg.KlgReader(bytes(bad), W, H))
