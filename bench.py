@@ -88,6 +88,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+class quiet_stdout:
+    """the reference's GPUConfig prints to std::cout ("Your GPU ... isn't in the ... database"): keep fd 1 clean, this program prints ONE line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
 def icp_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the reduction kernel, from the committed ncu --set full capture
     (per launch like `achieved`); None when no capture has been summarised"""
@@ -355,11 +370,12 @@ def ours_arm(args):
                 d = pipeline_tracker_inputs(orc_py, r.f, rgb[(k - 1) % RING], rgb[k], depth[k])
                 pose = r.f.currPose.copy()
                 us_ref = []
-                for _ in range(5):
-                    ro = init_tracker(refodom_py.Odometry(W, H, cam[2], cam[3], cam[0], cam[1]), lambda a: a, pose, d)
-                    tr_, Rr_, st_ = ro.getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
-                    us_ref.append(st_["wall_us"])
-                    del ro
+                with quiet_stdout():
+                    for _ in range(5):
+                        ro = init_tracker(refodom_py.Odometry(W, H, cam[2], cam[3], cam[0], cam[1]), lambda a: a, pose, d)
+                        tr_, Rr_, st_ = ro.getIncrementalTransformation(pose[:3, 3], pose[:3, :3])
+                        us_ref.append(st_["wall_us"])
+                        del ro
                 up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
                 go = init_tracker(od.RGBDOdometry(W, H, cam[2], cam[3], cam[0], cam[1]), up, pose, d)
                 tg_, Rg_, _ = go.getIncrementalTransformation(pose[:3, 3], pose[:3, :3])

@@ -16,6 +16,6 @@ echo "== tracker stamps"
 timeout -s KILL 300 python scripts/dev_track_stamps.py 2>&1 | grep -v "Traceback\|^  File\|TypeError\|Exception ignored"
 timeout -s KILL 300 python scripts/dev_bench_track.py 2>&1 | grep -E "^track|^trackAsync|^prep"
 echo "== bench, one sequence"
-timeout -s KILL 600 python bench.py --sequences 1 --steps 100 2>/dev/null | cut -c1-600
+timeout -s KILL 900 python bench.py --steps 100 > gpurun_out/${1:-gpu_check}_bench.json 2>/dev/null; python scripts/show_bench.py gpurun_out/${1:-gpu_check}_bench.json
 } > $out 2>&1
 cat $out
