@@ -213,7 +213,7 @@ static int enqueue_track(hrbf_odometry* o, cudaStream_t s, bool rgbOnly, float i
             if (rgb) { rgb_residual_kernel<<<nb, 256, 0, s>>>(ra, wk, 1, l, j == 0, next_lower); ++n; }
             if (icp) {
                 if (o->useSearch) icp_reduce_kernel<true><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
-                else (void)launch_icp_tile(o, ia, rgb ? 0 : 1, l, next_level, s, false);
+                else icp_reduce_kernel<false><<<nb, kReduceThreads, 0, s>>>(ia, wk, rgb ? 0 : 1, l, next_level);
                 ++n;
             }
             if (rgb) { rgb_step_kernel<<<nb, kReduceThreads, 0, s>>>(sa, -2.0f, wk, 1, l, next_level); ++n; }
