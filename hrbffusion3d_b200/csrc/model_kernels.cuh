@@ -337,50 +337,67 @@ __device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& 
                 }
             }
         };
+        // copy_unstable.vert:106-108 walks the window with FLOAT counters in texture space:
+        //     for (float i = x / cols - (scale * indexXStep * windowMultiplier); i < x / cols + (...); i += indexXStep),  indexXStep = (1 / (cols * scale)) * 0.5
+        // nominally 2 * windowMultiplier samples half a pixel apart, GL_NEAREST; the accumulated counter can stay an ulp below the end
+        // value (one more sample) and a sample within round-off of a texel boundary falls on either side, both depending on the
+        // texture size.  The loops are run as written, every operation rounded separately like the shader's.
+        const float wm = (float)m.cleanWindow;
+        const float stepx = __fmul_rn(__fdiv_rn(1.0f, (float)W), 0.5f), stepy = __fmul_rn(__fdiv_rn(1.0f, (float)H), 0.5f);
+        const float ux = __fdiv_rn(x, (float)W), uy = __fdiv_rn(y, (float)H);
+        const float i0 = __fsub_rn(ux, __fmul_rn(stepx, wm)), i1 = __fadd_rn(ux, __fmul_rn(stepx, wm));
+        const float j0 = __fsub_rn(uy, __fmul_rn(stepy, wm)), j1 = __fadd_rn(uy, __fmul_rn(stepy, wm));
+        auto texel = [](float u, int n) {      // GL_NEAREST with 8 fractional bits of fixed point
+            const float fixed = floorf(__fadd_rn(__fmul_rn(__fmul_rn(u, (float)n), 256.0f), 0.5f));
+            return min(max((int)floorf(__fdiv_rn(fixed, 256.0f)), 0), n - 1);
+        };
         if (m.cleanWindow == 2) {
-            // the reference default: 4 x 4 half-pixel offsets {-1, -1/2, 0, +1/2}, GL_NEAREST.  Per axis they hit only the texels
-            // floor(x - 1), floor(x - 1/2), floor(x), floor(x + 1/2): each DISTINCT texel is fetched once and counted with its
-            // multiplicity (the tests only count), and all index loads are issued before the first dependent texture read.
-            int tx[4], ty[4];
+            // the reference default: per axis the (4, rarely 5) samples hit at most 3 distinct texels: each DISTINCT texel is fetched once
+            // and counted with its multiplicity (the tests only count)
+            constexpr int kS = 5;     // 2 * windowMultiplier nominal samples + the one round-off can add
+            int tx[kS], ty[kS], nx = 0, ny = 0;
+            {
+                float i = i0, j = j0;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                tx[a] = min(max((int)floorf(x + 0.5f * (float)(a - 2)), 0), W - 1);
-                ty[a] = min(max((int)floorf(y + 0.5f * (float)(a - 2)), 0), H - 1);
+                for (int a = 0; a < kS; ++a) {
+                    const bool inx = i < i1, iny = j < j1;
+                    tx[a] = inx ? texel(i, W) : -1; ty[a] = iny ? texel(j, H) : -1;
+                    nx += inx ? 1 : 0; ny += iny ? 1 : 0;
+                    i = __fadd_rn(i, stepx); j = __fadd_rn(j, stepy);
+                }
             }
-            int mx[4], my[4];        // multiplicity of sample a if it is the first of a run of equal texels, else 0
+            (void)nx; (void)ny;
+            int mx[kS], my[kS];        // multiplicity of sample a if it is the first of a run of equal texels, else 0
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < kS; ++a) {
                 int cx_ = 0, cy_ = 0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) { cx_ += (tx[b] == tx[a]) ? 1 : 0; cy_ += (ty[b] == ty[a]) ? 1 : 0; }
-                bool fx = true, fy = true;
+                for (int b = 0; b < kS; ++b) { cx_ += (tx[b] == tx[a]) ? 1 : 0; cy_ += (ty[b] == ty[a]) ? 1 : 0; }
+                bool fx = tx[a] >= 0, fy = ty[a] >= 0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) if (b < a) { fx = fx && tx[b] != tx[a]; fy = fy && ty[b] != ty[a]; }
+                for (int b = 0; b < kS; ++b) if (b < a) { fx = fx && tx[b] != tx[a]; fy = fy && ty[b] != ty[a]; }
                 mx[a] = fx ? cx_ : 0; my[a] = fy ? cy_ : 0;
             }
-            unsigned int idx[16];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < kS; ++a) {
+                if (mx[a] == 0) continue;
+                unsigned int idx[kS];          // one window column: its index loads are issued before the first dependent read
 #pragma unroll
-                for (int b = 0; b < 4; ++b) idx[a * 4 + b] = (mx[a] * my[b] > 0) ? __ldg(c.index + (size_t)ty[b] * W + tx[a]) : 0u;
+                for (int b = 0; b < kS; ++b) idx[b] = (my[b] > 0) ? __ldg(c.index + (size_t)ty[b] * W + tx[a]) : 0u;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
+                for (int b = 0; b < kS; ++b) {
                     const int mult = mx[a] * my[b];
-                    if (mult > 0 && idx[a * 4 + b] > 0u) {
+                    if (mult > 0 && idx[b] > 0u) {
                         const int c0 = count, z0 = zCount;
-                        sample(idx[a * 4 + b], (size_t)ty[b] * W + tx[a]);
+                        sample(idx[b], (size_t)ty[b] * W + tx[a]);
                         count = c0 + (count - c0) * mult; zCount = z0 + (zCount - z0) * mult;
                     }
                 }
+            }
         } else {
-            const int ns = 2 * m.cleanWindow;
-            for (int a = 0; a < ns; ++a)
-                for (int b = 0; b < ns; ++b) {
-                    const float ox = 0.5f * (float)(a - m.cleanWindow), oy = 0.5f * (float)(b - m.cleanWindow);
-                    const int sx = min(max((int)floorf(x + ox), 0), W - 1), sy = min(max((int)floorf(y + oy), 0), H - 1);
-                    const size_t q = (size_t)sy * W + sx;
+            for (float i = i0; i < i1; i = __fadd_rn(i, stepx))
+                for (float j = j0; j < j1; j = __fadd_rn(j, stepy)) {
+                    const size_t q = (size_t)texel(j, H) * W + texel(i, W);
                     sample(__ldg(c.index + q), q);
                 }
         }

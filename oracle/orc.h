@@ -245,6 +245,7 @@ void orc_metriciseDepth(const orc_prep_params* p, const unsigned short* raw, con
 /* 0 (default): intended integer windows; 1: the shaders' literal float-counter window loops (see orc_prep.c) */
 void orc_set_float_loops(int on);
 int orc_get_float_loops(void);
+int orc_texel_of(float u, int n);      /* GL_NEAREST texel of texture coordinate u on an axis of n texels (8 fractional bits of fixed point) */
 int orc_float_window(int p, int n, float win, int uv, int* texels /*[16]*/, float* coords /*[16]*/);   /* test hook */
 void orc_set_uv_vbo_coords(int on);      /* per thread; used by orc_model_fuse around its PCA normal (literal mode only) */
 void orc_getNormalPCA(const orc_prep_params* p, const float* depth, int px, int py, float vz, float n[3]);

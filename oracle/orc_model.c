@@ -227,12 +227,31 @@ static int clean_test(const orc_model_params* p, const float inv[16], int time,
     const int kf = (sub >= 0.0f && sub < (float)kf_dim) ? (int)sub : -1;
     const float active = kf >= 0 ? active_kf[kf] : 0.0f;
     if (lp[2] < p->maxDepth && lp[2] > 0 && x > 0 && y > 0 && x < (float)W && y < (float)H) {
-        const int ns = 2 * p->cleanWindow;
-        for (int a = 0; a < ns; ++a)
-            for (int b = 0; b < ns; ++b) {
-                const float ox = 0.5f * (float)(a - p->cleanWindow), oy = 0.5f * (float)(b - p->cleanWindow);
-                const int sx = clampi((int)floorf(x + ox), 0, W - 1), sy = clampi((int)floorf(y + oy), 0, H - 1);
-                const size_t q = (size_t)sy * W + sx;
+        /* copy_unstable.vert:106-108 walks the window with FLOAT counters in texture space,
+         *     for (float i = x / cols - (scale * indexXStep * windowMultiplier); i < x / cols + (...); i += indexXStep)
+         * with indexXStep = (1 / (cols * scale)) * 0.5: nominally 2 * windowMultiplier samples per axis half a pixel apart, but the
+         * accumulated counter can stay an ulp below the end value and then a further sample is taken (and a sample within round-off of
+         * a texel boundary falls on either side).  Literal mode runs these loops as written with GL_NEAREST texels (orc_texel_of);
+         * the intended-window mode keeps round 1's integer offsets. */
+        const int literal = orc_get_float_loops();
+        const float scale = 1.0f, wm = (float)p->cleanWindow;
+        const float stepx = (1.0f / ((float)W * scale)) * 0.5f, stepy = (1.0f / ((float)H * scale)) * 0.5f;
+        int sxs[16], sys[16], nx = 0, ny = 0;
+        if (literal) {
+            const float i0 = x / (float)W - (scale * stepx * wm), i1 = x / (float)W + (scale * stepx * wm);
+            const float j0 = y / (float)H - (scale * stepy * wm), j1 = y / (float)H + (scale * stepy * wm);
+            for (float i = i0; i < i1 && nx < 16; i += stepx) sxs[nx++] = orc_texel_of(i, W);
+            for (float j = j0; j < j1 && ny < 16; j += stepy) sys[ny++] = orc_texel_of(j, H);
+        } else {
+            const int ns = 2 * p->cleanWindow;
+            for (int a = 0; a < ns; ++a) {
+                sxs[nx++] = clampi((int)floorf(x + 0.5f * (float)(a - p->cleanWindow)), 0, W - 1);
+                sys[ny++] = clampi((int)floorf(y + 0.5f * (float)(a - p->cleanWindow)), 0, H - 1);
+            }
+        }
+        for (int a = 0; a < nx; ++a)
+            for (int b = 0; b < ny; ++b) {
+                const size_t q = (size_t)sys[b] * W + sxs[a];
                 if (index[q] > 0u) {
                     const float* vc = vertConf + 4 * q;
                     const float* ct = colorTime + 4 * q;

@@ -173,6 +173,7 @@ static int texel_of(float u, int n)      /* GL_NEAREST with 8 fractional bits of
     int i = (int)floorf(fixed / 256.0f);
     return i < 0 ? 0 : (i >= n ? n - 1 : i);
 }
+int orc_texel_of(float u, int n) { return texel_of(u, n); }
 /* one axis of the window of pixel p: texel index and the float coordinate i * n of every visited sample; returns their number */
 static int float_window(int p, int n, float win, int* texels, float* coords)
 {

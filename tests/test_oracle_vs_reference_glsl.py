@@ -177,19 +177,21 @@ def test_predict_indices_oracle_matches_reference_vertex_shader(orc, W, H, kind)
         assert np.abs(a[k] - b[k])[same].max() <= 1e-6, k
 
 
-def test_fuse_and_clean_oracle_match_reference_vertex_shaders(orc, literal_windows):
+@pytest.mark.parametrize("W,H", [(320, 240), (640, 480), (1280, 960)])
+def test_fuse_and_clean_oracle_match_reference_vertex_shaders(orc, literal_windows, W, H):
     """rows 8-9: GlobalModel::fuse = data.vert per pixel (association, candidate record) + the first-fragment-wins scatter into the
     update textures (fixed function, restated in oracle/refglsl_py.py) + update.vert per surfel (merge); GlobalModel::clean =
     copy_unstable.vert / .geom over the model and the recorded vertices.  On the state of the oracle pipeline after several
     frames, with the literal window loops (the fuse pass recomputes the PCA normal): same merges, same new surfels, every
     attribute bit-identical except the positions (the shader multiplies pose * vec4 column by column: 2 ulps), and clean
-    returns the identical surfel array."""
+    returns the identical surfel array.  Run at every BASELINE image width: the float-counter loops of data.vert:137-138 and
+    copy_unstable.vert:106-108 overshoot depending on the texture size (the effect that bit row 10 at 640 pixels)."""
     from oracle import orc_pipeline as op
-    W, H = 320, 240
     cam = synth.default_camera(W, H)
     sc = synth.Scene("room")
     f = op.HRBFFusion(W, H, cam, icpWeight=100.0, so3=False)
     poses = synth.circle_trajectory(8, frames_per_rev=120)
+    n_warm = 6 if W <= 640 else 5       # (1280x960: one frame less of the slow CPU pipeline; confidence still passes the thresholds)
     for i, p in enumerate(poses[:6]):
         depth, rgb = synth.render_depth(sc, p, W, H, cam, noise=True, seed=i)
         f.processFrame(rgb, depth)
