@@ -14,7 +14,7 @@ A "step" is one frame through the hot path on the workload named in `config.work
 Offline throughput (the metric): `--sequences S` (default 3) independent sequences per GPU, each a complete pipeline object on
 its own stream with a 256-thread tracker, so that one sequence's latency-bound Gauss-Newton loop shares the SMs with the
 other sequences' ALU-bound kernels; a step = one frame of every sequence.  `single_sequence` in the same line is the live
-single-camera path (one sequence, 512-thread tracker), measured the same way in the same run.
+single-camera path (one sequence, 384-thread tracker: the staged preprocessing of frame t+1 runs beside the tracker of frame t), measured the same way in the same run.
 N > 1 : one process per GPU (torchrun), S independent sequences per rank (weak scaling), NCCL only to
 scatter the .klg streams and gather the trajectories; no collective inside the frame loop.
 `--impl reference` times the oracle's CPU path (the reference itself needs OpenGL + Pangolin + Eigen and
@@ -147,7 +147,7 @@ def config_dict(n_gpus, seqs=1):
                         "SO3 pre-align, iterations 10/5/4) + splat/fuse/splat/clean + splat/HRBF predict (win 3, K 10) + fill-in",
             "width": W, "height": H, "frames_in_loop": RING,
             "l2": "inputs cycle through a closed loop of %d frames x 1.54 MB = %d MB > 126 MB L2; a frame also streams ~30 full-resolution textures" % (RING, int(RING * 1.536)),
-            "sequences": n_gpus * seqs, "sequences_per_gpu": seqs, "tracker_threads": 256 if seqs > 1 else 512,
+            "sequences": n_gpus * seqs, "sequences_per_gpu": seqs, "tracker_threads": 256 if seqs > 1 else 384,
             "parallelism": "%d independent sequence(s) per GPU, each a full pipeline on its own stream (rank 0 scatters the .klg streams, trajectories are "
                            "gathered back), no collective inside the frame loop; a step = one frame of every sequence" % seqs}
 
@@ -228,7 +228,7 @@ def ours_arm(args):
     def run(host_inputs, S):
         """S fresh pipelines on S streams: W warm-up steps (frame 1 initialises the map), then K timed steps; a step = one frame of
         every sequence.  Returns (ms, launches, pipelines)."""
-        tthreads = int(os.environ.get("HRBF_BENCH_TRACKER_THREADS", "0")) or (256 if S > 1 else 512)      # (development override)
+        tthreads = int(os.environ.get("HRBF_BENCH_TRACKER_THREADS", "0")) or (256 if S > 1 else 384)      # (development override)
         Fs = [HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=tthreads, **FUSION_KW) for _ in range(S)]
         st = [torch.cuda.Stream() for _ in range(S)]
         off = [(q * RING) // (world * S) for q in range(S)]
@@ -292,7 +292,7 @@ def ours_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # (1) the live single-camera path: one sequence, 512-thread tracker
+    # (1) the live single-camera path: one sequence, 384-thread tracker
     ms1_dev, launches1, Fs = run(False, 1)
     wall1_dev = run.wall_s
     F = Fs[0]
@@ -424,7 +424,7 @@ def ours_arm(args):
             extras = {"error": repr(e)[:300]}
     total_frames = args.steps * world * S_max
     traffic, traffic_src = icp_traffic()
-    single = {"what": "the live single-camera path: ONE sequence per GPU, 512-thread tracker, same frames, same timing rules",
+    single = {"what": "the live single-camera path: ONE sequence per GPU, 384-thread tracker, same frames, same timing rules",
               "value": args.steps * world / (ms1_dev * 1e-3), "e2e": args.steps * world / (ms1_e2e * 1e-3), "unit": "frames/s",
               "ms_per_frame": ms1_dev / args.steps, "gpu_launches": launches1,
               "host_wall_clock": {"value": args.steps / wall1_dev, "e2e": args.steps / wall1_e2e, "unit": "frames/s per GPU (time.perf_counter around the same region, this rank)"}}

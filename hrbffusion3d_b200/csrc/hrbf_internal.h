@@ -33,7 +33,7 @@ struct hrbf_odometry {
     unsigned char* cand[HRBF_NUM_PYRS] = {};     // persistent tracker: pose-independent candidate mask of computeRgbResidual
     void* tmaps_host = nullptr;                  // host: CUtensorMap[2 geometries][3 levels][5 arrays] for the TMA-staged ICP tiles (icp_tile.cuh), copied into kernel parameters; null = unavailable
     bool tile_resident = false;                  // persistent tracker: keep each level's ICP tile in shared memory (hrbf_odometry_set_tracker_tiles; measured slower, off)
-    int track_threads = 512;                     // threads per CTA of the persistent tracker (256 | 512), hrbf_odometry_set_tracker_threads
+    int track_threads = 512;                     // threads per CTA of the persistent tracker (256 | 384 | 512), hrbf_odometry_set_tracker_threads
     hrbf_dataterm* corresImg[HRBF_NUM_PYRS] = {};
     hrbf::ReduceWork* work = nullptr;
     unsigned long long *tp_ll_f = nullptr, *tp_ll_i = nullptr;   // persistent tracker: tagged-word exchange buffers

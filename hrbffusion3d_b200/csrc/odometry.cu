@@ -247,14 +247,16 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     for (int l = 0; l < 3; ++l)
         if (iters[l] > 0) { const int s_l = div_up(div_up(o->rows(l) * o->cols(l), o->num_sms), o->track_threads); if (s_l > max_slots) max_slots = s_l; }
     p.max_slots = max_slots;
-    const bool half = o->track_threads == 256;
-    const void* kernel = half ? (const void*)track_persistent_kernel<256> : (const void*)track_persistent_kernel<512>;
+    // shape 0: 512 threads (the whole register file: nothing co-resides), 1: 256 threads (two CTAs, or a CTA and other kernels, per SM),
+    // 2: 384 threads (three quarters of the register file; the staging stream's kernels fit beside it)
+    const int half = o->track_threads == 256 ? 1 : o->track_threads == 384 ? 2 : 0;
+    const void* kernel = half == 1 ? (const void*)track_persistent_kernel<256> : half == 2 ? (const void*)track_persistent_kernel<384> : (const void*)track_persistent_kernel<512>;
     // resident ICP tiles (icp_tile.cuh): a level keeps its tile in shared memory when slots + tile fit beside the kernel's static
     // shared memory (the 256-thread shape shares the SM with another CTA: half the budget)
     size_t dyn = track_slots_bytes(max_slots, o->track_threads);
     {
         static std::mutex mu;
-        static size_t budget[2] = { 0, 0 };
+        static size_t budget[3] = { 0, 0, 0 };
         std::lock_guard<std::mutex> lock(mu);
         if (budget[half] == 0) {
             cudaFuncAttributes fa;
@@ -263,7 +265,8 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
             size_t total = (size_t)optin;
-            if (half) total = total / 2 - 1024;      // two CTAs per SM, 1 KB reserved each
+            if (half == 1) total = total / 2 - 1024;      // two CTAs per SM, 1 KB reserved each
+            if (half == 2) total = total * 3 / 4 - 1024;  // a quarter of the SM is left to co-resident kernels
             budget[half] = total > fa.sharedSizeBytes + 1024 ? total - fa.sharedSizeBytes - 512 : 1;
         }
         size_t tile_bytes = 0;
@@ -279,7 +282,7 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
     }
     {   // the attribute belongs to the kernel, not to this object: only ever raise it
         static std::mutex mu;
-        static size_t dyn_set[2] = { 0, 0 };
+        static size_t dyn_set[3] = { 0, 0, 0 };
         std::lock_guard<std::mutex> lock(mu);
         if (dyn > dyn_set[half]) {
             HRBF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -675,7 +678,7 @@ int hrbf_odometry_set_tracker_threads(hrbf_odometry* o, int threads)
 {
     HRBF_CHECK_ARG(o);
     if (threads == 0) threads = kTrackThreadsDefault;
-    if (threads != 256 && threads != 512) { set_error("set_tracker_threads: 256 or 512 (0 = default 512)"); return HRBF_ERR_INVALID_ARG; }
+    if (threads != 256 && threads != 384 && threads != 512) { set_error("set_tracker_threads: 256, 384 or 512 (0 = default 512)"); return HRBF_ERR_INVALID_ARG; }
     o->track_threads = threads;
     return HRBF_OK;
 }

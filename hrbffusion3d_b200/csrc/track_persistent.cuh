@@ -94,7 +94,7 @@ template <int kTrackThreads>
 __device__ __forceinline__ void all_reduce_partials(const unsigned long long* part /* [gridDim.x][64] */, unsigned int tag, bool lo, bool hi,
                                                     double (*s_d)[64], double* out /* [64] */)
 {
-    constexpr int kSlices = kTrackThreads / 64, U = 20;      // up to 160 CTAs per batch
+    constexpr int kSlices = kTrackThreads / 64, U = kTrackThreads == 256 ? 20 : (160 + kSlices - 1) / kSlices;      // up to 160 CTAs per batch (80 for 256 threads)
     static_assert(kTrackThreads % 64 == 0, "slice layout");
     const int v = threadIdx.x & 63, q = threadIdx.x >> 6;
     const bool active = v < 32 ? lo : hi;
@@ -296,7 +296,7 @@ inline IcpTileGeom track_tile_geom(int rows, int cols, int ctas)
 }
 
 template <int kTrackThreads>
-__global__ void __launch_bounds__(kTrackThreads, 512 / kTrackThreads) track_persistent_kernel(const __grid_constant__ TrackParams p)
+__global__ void __maxnreg__(128) track_persistent_kernel(const __grid_constant__ TrackParams p)
 {
     constexpr int kTrackWarps = kTrackThreads / 32;
     pdl_wait();

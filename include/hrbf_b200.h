@@ -427,7 +427,8 @@ typedef struct {
     float denseEnoughThresh;      /* globalDenseEnoughThresh (0.75)          */
     int cleanWindow;              /* fusionCleanWindowMultiplier (2)         */
     unsigned int capacity;        /* surfel capacity, 0 = reference default  */
-    int trackerThreads;           /* hrbf_odometry_set_tracker_threads: 0 = 512 (one live sequence), 256 = several sequences per GPU */
+    int trackerThreads;           /* hrbf_odometry_set_tracker_threads: 0 = 512 (one-shot calls), 384 = one sequence replayed through stage_frame (the staged
+                                     preprocessing of frame t+1 co-resides with the tracker of frame t), 256 = several sequences per GPU */
 } hrbf_fusion_params;
 void hrbf_fusion_default_params(hrbf_fusion_params* p, int width, int height, float cx, float cy, float fx, float fy);
 int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p);

@@ -268,7 +268,7 @@ def test_resident_tile_tracker_matches_streaming_tracker(orc, cuda, W, H):
     from hrbffusion3d_b200 import synth
     floor = None
     for kw in (dict(icpWeight=100.0, so3=False), dict(icpWeight=10.0, so3=True)):
-        for threads in (512, 256):
+        for threads in (512, 384, 256):
             res = {}
             for resident in (True, False):
                 oo, go, (m0, pose0, m1, pose1, cam) = build_both(orc, cuda, W, H)
