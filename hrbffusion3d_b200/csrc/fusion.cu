@@ -619,8 +619,10 @@ struct hrbf_fusion {
     int cur = 0;                     // buffer the next processed frame uses
     bool staged[2] = { false, false };
     cudaStream_t pre_stream = nullptr;              // staging stream (lowest priority)
-    cudaEvent_t ev_staged[2] = {}, ev_free[2] = {};
-    bool ev_free_valid[2] = { false, false };
+    // tracker-input banks of the odometry (CurrBank): frame number k (1-based) uses bank k & 1, whichever frame buffer it sits in.
+    // ev_curr[k]: bank k is built (the next frame's SO3 pre-alignment reads its image); ev_bank_free[k]: the frame that used it is done
+    cudaEvent_t ev_staged[2] = {}, ev_free[2] = {}, ev_curr[2] = {}, ev_bank_free[2] = {};
+    bool ev_free_valid[2] = { false, false }, ev_curr_valid[2] = { false, false }, ev_bank_free_valid[2] = { false, false };
     hrbf_fillin* fill = nullptr;
     int tick = 1;
     int indexSubmap = 0;
@@ -636,6 +638,26 @@ struct hrbf_fusion {
 __global__ void set_identity_pose_kernel(float* p)
 {
     if (threadIdx.x < 12) p[threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.f : 0.f;
+}
+
+// Everything the tracker needs from the camera frame in buffer b alone (current-frame pyramids, Sobel + candidates, SO3 pre-alignment
+// against the previous camera image = the other bank), on stream s: the staging stream for staged frames, else the main stream.
+static int stage_current(hrbf_fusion* F, int b, int frame_number, cudaStream_t s)
+{
+    hrbf_frame* fr = F->frames[b];
+    const int k = frame_number & 1;
+    const bool first = frame_number == 1;
+    OdomPrepInputs in;
+    memset(&in, 0, sizeof in);
+    in.vc = (const float*)fr->tex[HRBF_FT_VERTEX_FILTERED]; in.nc = (const float*)fr->tex[HRBF_FT_NORMAL];
+    in.k1c = (const float*)fr->tex[HRBF_FT_PRINCIPAL_CURV1]; in.k2c = (const float*)fr->tex[HRBF_FT_PRINCIPAL_CURV2];
+    in.rgba_c = (const unsigned char*)fr->tex[HRBF_FT_RGBA]; in.rgb8_c = (const unsigned char*)fr->tex[HRBF_FT_RGB];
+    if (F->ev_bank_free_valid[k]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_bank_free[k], 0));   // frame_number - 2 tracked from this bank
+    if (F->ev_curr_valid[k ^ 1]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_curr[k ^ 1], 0));      // the SO3 pre-alignment reads the other bank's image
+    if (int rc = odom_stage_current_dev(F->odom, k, in, F->p.so3 != 0, !first, s)) return rc;
+    HRBF_CUDA(cudaEventRecord(F->ev_curr[k], s));
+    F->ev_curr_valid[k] = true;
+    return HRBF_OK;
 }
 
 // preprocessed = true: frames[cur] was uploaded and preprocessed by hrbf_fusion_stage_frame (on the staging stream)
@@ -655,7 +677,11 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
     auto splat = [&](int out_mask) { return indexmap_splat(im, invPose, (const float*)M->vbo[M->cur], M->count[M->cur], M->bound, p.maxDepthProcessed, s, out_mask); };
 
     mark(0);
-    if (!preprocessed) { if (int rc = hrbf_frame_preprocess(fr, s)) return rc; }
+    if (!preprocessed) {
+        if (int rc = hrbf_frame_preprocess(fr, s)) return rc;
+        if (int rc = stage_current(F, F->cur, F->tick, s)) return rc;
+    }
+    odom_select_bank(F->odom, F->tick & 1);
     mark(1);
     if (F->tick == 1) {
         set_identity_pose_kernel<<<1, 32, 0, s>>>(currPose);
@@ -663,7 +689,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
         if (int rc = model_initialise_dev(M, (const float*)FT(HRBF_FT_VERTEX_RAW), (const float*)FT(HRBF_FT_NORMAL), (const unsigned char*)FT(HRBF_FT_RGB),
                                           (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2), (const float*)FT(HRBF_FT_GRADIENT_MAG),
                                           currPose, s)) return rc;
-        if (int rc = hrbf_odometry_init_first_rgb(F->odom, (const unsigned char*)FT(HRBF_FT_RGBA), s)) return rc;
+        // (initFirstRGB, HRBFFusion.cpp:1058: this frame's image pyramid is in its bank, where the next frame's SO3 pre-alignment reads it)
         // VertexConfidence is not run on the first frame (HRBFFusion.cpp:1028-1126): CONFIDENCE keeps its initial zeros
         mark(2); mark(3);
     } else {
@@ -729,8 +755,10 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
     mark(4);
     if (F->tick == 1 && F->traj_n < F->traj_cap) HRBF_CUDA(cudaMemcpyAsync(F->traj + 12 * (size_t)F->traj_n, currPose, 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ++F->traj_n;
+    // the buffer and the bank are free for the frame after next once everything above has run
+    HRBF_CUDA(cudaEventRecord(F->ev_bank_free[F->tick & 1], s));
+    F->ev_bank_free_valid[F->tick & 1] = true;
     ++F->tick;
-    // the buffer is free for the frame after next once everything above has run
     HRBF_CUDA(cudaEventRecord(F->ev_free[F->cur], s));
     F->ev_free_valid[F->cur] = true;
     return HRBF_OK;
@@ -769,6 +797,7 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
     if (!rc) rc = hrbf_odometry_create(&F->odom, fp.width, fp.height, fp.cx, fp.cy, fp.fx, fp.fy, 0.10f, sinf(20.f * 3.14159265f / 180.f));
     if (!rc) rc = hrbf_odometry_set_params(F->odom, p->curvValidThreshold, 0, 2, 0);
     if (!rc) rc = hrbf_odometry_set_tracker_threads(F->odom, p->trackerThreads);
+    if (!rc) rc = odom_enable_banks(F->odom);
     if (!rc) {
         F->traj_cap = 1 << 16;
         if (cudaMalloc(&F->dev, 64 * sizeof(float)) != cudaSuccess || cudaMalloc(&F->traj, (size_t)F->traj_cap * 12 * sizeof(float)) != cudaSuccess ||
@@ -776,7 +805,7 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
         else {
             cudaMemset(F->dev, 0, 64 * sizeof(float));
             for (auto& e : F->ev) cudaEventCreate(&e);
-            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); }
+            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_curr[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_bank_free[k], cudaEventDisableTiming); }
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             if (cudaStreamCreateWithPriority(&F->pre_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { set_error("fusion_create: stream creation failed"); rc = HRBF_ERR_CUDA; }
@@ -791,7 +820,7 @@ int hrbf_fusion_destroy(hrbf_fusion* F)
     if (!F) return HRBF_OK;
     hrbf_odometry_destroy(F->odom); hrbf_model_destroy(F->model); hrbf_indexmap_destroy(F->im); hrbf_fillin_destroy(F->fill); hrbf_frame_destroy(F->frames[0]); hrbf_frame_destroy(F->frames[1]);
     if (F->pre_stream) cudaStreamDestroy(F->pre_stream);
-    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); }
+    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); if (F->ev_curr[k]) cudaEventDestroy(F->ev_curr[k]); if (F->ev_bank_free[k]) cudaEventDestroy(F->ev_bank_free[k]); }
     if (F->dev) cudaFree(F->dev);
     if (F->traj) cudaFree(F->traj);
     if (F->h_pose) cudaFreeHost(F->h_pose);
@@ -845,6 +874,7 @@ int hrbf_fusion_stage_frame(hrbf_fusion* F, const unsigned char* rgb8, const uns
     if (F->ev_free_valid[b]) HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_free[b], 0));
     if (int rc = frame_upload(F->frames[b], rgb8, depth16, host, first, F->pre_stream)) return rc;
     if (int rc = hrbf_frame_preprocess(F->frames[b], F->pre_stream)) return rc;
+    if (int rc = stage_current(F, b, F->tick + (b != F->cur ? 1 : 0), F->pre_stream)) return rc;
     HRBF_CUDA(cudaEventRecord(F->ev_staged[b], F->pre_stream));
     F->staged[b] = true;
     return HRBF_OK;

@@ -9,6 +9,21 @@ namespace hrbf {
 struct ReduceWork;
 struct TrackState;
 enum { M_VG = 0, M_NG, M_K1G, M_K2G, M_VC, M_NC, M_K1C, M_K2C, M_W, M_COUNT };
+struct So3Pre;
+// Everything the tracker needs that depends on the CURRENT camera frame alone: the outputs of initICP / initRGB / initCurvature
+// (RGBDOdometry.cpp:183-247, 689-794), the Sobel images and candidate mask of computeRgbResidual, and the SO3 pre-alignment
+// (RGBDOdometry.cpp:827-914: it compares two CAMERA images).  Two banks: the frame pipeline builds bank (t+1) & 1 on its staging
+// stream while frame t is tracked from bank t & 1 (odom_stage_current_dev); the stand-alone API only ever uses bank 0.
+struct CurrBank {
+    float* maps[4][HRBF_NUM_PYRS] = {};          // M_VC, M_NC, M_K1C, M_K2C
+    float4* pk[2][HRBF_NUM_PYRS] = {};           // packed current records
+    unsigned char* nextImage[HRBF_NUM_PYRS] = {}; float* nextDepth[HRBF_NUM_PYRS] = {};
+    short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
+    unsigned char* cand[HRBF_NUM_PYRS] = {};
+    So3Pre* so3 = nullptr;                       // device: result of the staged SO3 pre-alignment
+    void* tmaps = nullptr;                       // host tensor maps over this bank's records
+    bool cand_ready = false, so3_ready = false;  // staged for the frame this bank holds
+};
 }
 
 struct hrbf_odometry {
@@ -49,6 +64,10 @@ struct hrbf_odometry {
     float* h_model_pose = nullptr;   // staging ring for init_*_model poses
     hrbf::SlotRing model_pose_ring;   // guards h_model_pose
     int so3_parity = 0;
+    hrbf::CurrBank bank[2];          // bank[0] = the buffers of the slab; bank[1] allocated by odom_enable_banks
+    char* bank1_slab = nullptr;
+    int cur_bank = 0;
+    bool banked = false;
 
     cudaStream_t cap_stream = nullptr;
     std::map<uint64_t, std::pair<cudaGraphExec_t, int>> graphs;   // key -> (exec, kernel nodes)
@@ -104,6 +123,12 @@ struct OdomPrepInputs {
     const unsigned char* rgb8_c;                     // current image as RGB8 (used instead of rgba_c when non-null)
 };
 int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s);
+// Frame pipeline: two CurrBanks (see above).  odom_stage_current_dev builds bank `b` from a preprocessed frame's textures -- the
+// current-frame jobs of prep_all, Sobel + candidates, and (so3 and not the first frame) the SO3 pre-alignment against the OTHER bank's
+// image -- on any stream; odom_select_bank makes a bank the one the tracker and the init* calls use.
+int odom_enable_banks(hrbf_odometry* o);
+void odom_select_bank(hrbf_odometry* o, int b);
+int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, bool so3, bool has_previous, cudaStream_t s);
 struct OdomFrameEpilogue { float* last_pose_out; float* inv_pose_out; float* weighting_out; float weight_multiplier; float* traj_out; };
 int odom_track_frame_dev(hrbf_odometry* o, float* pose_inout, const OdomFrameEpilogue& ep, bool rgbOnly, float icpWeight, bool pyramid,
                          bool fastOdom, bool so3, bool use_weight, cudaStream_t s);

@@ -143,6 +143,7 @@ static int build_tile_tensor_maps(hrbf_odometry* o)
             }
         }
     o->tmaps_host = host;
+    o->bank[o->cur_bank].tmaps = host;
     return HRBF_OK;
 }
 
@@ -290,6 +291,11 @@ static int launch_track_persistent(hrbf_odometry* o, cudaStream_t s, bool rgbOnl
         }
     }
     p.so3_last = o->lastNextImage[2]; p.so3_next = o->nextImage[2];
+    {   // a staged frame (odom_stage_current_dev) brings its Sobel images, candidate masks and SO3 pre-alignment along
+        const CurrBank& cb = o->bank[o->cur_bank];
+        p.cand_ready = (o->banked && cb.cand_ready) ? 1 : 0;
+        p.so3_pre = (o->banked && so3 && cb.so3_ready) ? cb.so3 : nullptr;
+    }
     p.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
     p.rgb = (rgbOnly || icpWeight < 100) ? 1 : 0;
     p.rgbOnly = rgbOnly; p.so3 = so3; p.icpWeight = icpWeight;
@@ -347,7 +353,7 @@ static int get_graph(hrbf_odometry* o, bool rgbOnly, float icpWeight, bool pyram
     uint32_t wbits;
     memcpy(&wbits, &icpWeight, 4);
     const uint64_t key = ((uint64_t)wbits << 32) | (uint64_t)(rgbOnly | pyramid << 1 | fastOdom << 2 | so3 << 3 | use_weight << 4 | host_io << 5 |
-                                                             (o->useSearch ? 1 : 0) << 6 | (o->rgbGradWeight ? 1 : 0) << 7 | (uint64_t)(o->searchRadius & 0xff) << 8 | (uint64_t)(o->so3_parity & 1) << 16);
+                                                             (o->useSearch ? 1 : 0) << 6 | (o->rgbGradWeight ? 1 : 0) << 7 | (uint64_t)(o->searchRadius & 0xff) << 8 | (uint64_t)(o->so3_parity & 1) << 16 | (uint64_t)(o->cur_bank & 1) << 17);
     auto it = o->graphs.find(key);
     if (it == o->graphs.end()) {
         cudaGraph_t g = nullptr;
@@ -628,6 +634,12 @@ int hrbf_odometry_create(hrbf_odometry** out, int width, int height, float cx, f
     o->vdepth_tmp = (float*)(o->slab + o_vd);
     o->work = (ReduceWork*)(o->slab + o_work);
     o->pose_scratch = (float*)(o->slab + o_pose);
+    for (int l = 0; l < 3; ++l) {
+        CurrBank& b0 = o->bank[0];
+        for (int m = 0; m < 4; ++m) b0.maps[m][l] = o->maps[M_VC + m][l];
+        b0.pk[0][l] = o->pk[0][l]; b0.pk[1][l] = o->pk[1][l];
+        b0.nextImage[l] = o->nextImage[l]; b0.nextDepth[l] = o->nextDepth[l]; b0.dIdx[l] = o->dIdx[l]; b0.dIdy[l] = o->dIdy[l]; b0.cand[l] = o->cand[l];
+    }
     o->tp_ll_f = (unsigned long long*)(o->slab + o_tpp); o->tp_ll_i = (unsigned long long*)(o->slab + o_tpi);      // zeroed with the slab: tag 0 never matches
     if (int rc = build_tile_tensor_maps(o)) { hrbf_odometry_destroy(o); return rc; }
     cudaMallocHost(&o->h_pose, 24 * sizeof(float));
@@ -654,7 +666,9 @@ int hrbf_odometry_destroy(hrbf_odometry* o)
     if (o->h_model_pose) cudaFreeHost(o->h_model_pose);
     o->model_pose_ring.destroy();
     if (o->slab) cudaFree(o->slab);
-    delete[] (CUtensorMap*)o->tmaps_host;
+    if (o->bank1_slab) cudaFree(o->bank1_slab);
+    delete[] (CUtensorMap*)o->bank[0].tmaps;
+    delete[] (CUtensorMap*)o->bank[1].tmaps;
     if (o->tp_dbg) cudaFree(o->tp_dbg);
     delete o;
     return HRBF_OK;
@@ -757,16 +771,96 @@ int odom_track_frame_dev(hrbf_odometry* o, float* pose_inout, const OdomFrameEpi
     if (o->use_graph) return 1;
     if (int rc = repack_if_dirty(o, s)) return rc;
     if (int rc = launch_track_persistent(o, s, rgbOnly, icpWeight, pyramid, fastOdom, so3, use_weight, pose_inout, pose_inout, nullptr, &ep)) return rc;
-    if (so3) {      // RGBDOdometry.cpp:1239-1245 (swap_so3_images)
+    if (so3 && !o->banked) {      // RGBDOdometry.cpp:1239-1245 (swap_so3_images); with banks the other bank IS the last camera image
         for (int i = 0; i < 3; ++i) std::swap(o->lastNextImage[i], o->nextImage[i]);
         o->so3_parity ^= 1;
     }
     return HRBF_OK;
 }
 
+// ---- current-frame banks (hrbf_internal.h: CurrBank) ----
+int odom_enable_banks(hrbf_odometry* o)
+{
+    if (o->banked) return HRBF_OK;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+    size_t o_maps[4][3], o_pk[2][3], o_ni[3], o_nd[3], o_dx[3], o_dy[3], o_cd[3];
+    for (int l = 0; l < 3; ++l) {
+        const size_t P = (size_t)o->rows(l) * o->cols(l);
+        for (int m = 0; m < 4; ++m) o_maps[m][l] = take(4 * P * sizeof(float));
+        for (int k = 0; k < 2; ++k) o_pk[k][l] = take(P * sizeof(float4));
+        o_ni[l] = take(P); o_nd[l] = take(P * 4); o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cd[l] = take(P);
+    }
+    const size_t o_so3 = take(2 * sizeof(So3Pre));
+    if (cudaMalloc(&o->bank1_slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); return HRBF_ERR_CUDA; }
+    HRBF_CUDA(cudaMemset(o->bank1_slab, 0, off));
+    CurrBank& b1 = o->bank[1];
+    for (int l = 0; l < 3; ++l) {
+        for (int m = 0; m < 4; ++m) b1.maps[m][l] = (float*)(o->bank1_slab + o_maps[m][l]);
+        for (int k = 0; k < 2; ++k) b1.pk[k][l] = (float4*)(o->bank1_slab + o_pk[k][l]);
+        b1.nextImage[l] = (unsigned char*)(o->bank1_slab + o_ni[l]); b1.nextDepth[l] = (float*)(o->bank1_slab + o_nd[l]);
+        b1.dIdx[l] = (short*)(o->bank1_slab + o_dx[l]); b1.dIdy[l] = (short*)(o->bank1_slab + o_dy[l]); b1.cand[l] = (unsigned char*)(o->bank1_slab + o_cd[l]);
+    }
+    o->bank[0].so3 = (So3Pre*)(o->bank1_slab + o_so3); b1.so3 = o->bank[0].so3 + 1;
+    o->banked = true;
+    if (o->tmaps_host) {      // tensor maps over bank 1's records
+        odom_select_bank(o, 1);
+        o->tmaps_host = nullptr;
+        const int rc = build_tile_tensor_maps(o);
+        if (rc || o->tmaps_host == nullptr) {      // all or nothing: without maps for both banks the gather kernels serve every path
+            delete[] (CUtensorMap*)o->bank[0].tmaps; o->bank[0].tmaps = nullptr; b1.tmaps = nullptr;
+        }
+        odom_select_bank(o, 0);
+    }
+    return HRBF_OK;
+}
+void odom_select_bank(hrbf_odometry* o, int b)
+{
+    const CurrBank& cb = o->bank[b];
+    for (int l = 0; l < 3; ++l) {
+        for (int m = 0; m < 4; ++m) o->maps[M_VC + m][l] = cb.maps[m][l];
+        o->pk[0][l] = cb.pk[0][l]; o->pk[1][l] = cb.pk[1][l];
+        o->nextImage[l] = cb.nextImage[l]; o->nextDepth[l] = cb.nextDepth[l];
+        o->dIdx[l] = cb.dIdx[l]; o->dIdy[l] = cb.dIdy[l]; o->cand[l] = cb.cand[l];
+        if (o->banked) o->lastNextImage[l] = o->bank[b ^ 1].nextImage[l];
+    }
+    o->tmaps_host = cb.tmaps;
+    o->cur_bank = b;
+}
+static int launch_prep_all(hrbf_odometry* o, const OdomPrepInputs& in, const int* jobs, int njobs, cudaStream_t s);
+int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, bool so3, bool has_previous, cudaStream_t s)
+{
+    if (!o->banked) { set_error("odom_stage_current_dev: banks not enabled"); return HRBF_ERR_INVALID_ARG; }
+    const int before = o->cur_bank;
+    odom_select_bank(o, b);          // the argument builders read the active pointers; kernel arguments are captured at launch
+    static const int jobs[3] = { 1, 3, 5 };      // RGB-D pyramids of the camera frame, its vertex / normal maps, its curvature maps
+    if (int rc = launch_prep_all(o, in, jobs, 3, s)) { odom_select_bank(o, before); return rc; }
+    SobelCandArgs sc;
+    for (int l = 0; l < 3; ++l) { sc.r[l] = rgbres_args(o, l); sc.cand[l] = o->cand[l]; }
+    HRBF_LAUNCH_PDL(sobel_cand_kernel, dim3(div_up(o->width * o->height, 256), 3), dim3(256), 0, s, sc);
+    CurrBank& cb = o->bank[b];
+    cb.cand_ready = true;
+    cb.so3_ready = false;
+    if (so3 && has_previous) {
+        HRBF_LAUNCH_PDL(so3_prealign_kernel, dim3(1), dim3(kSo3Threads), 0, s, (const unsigned char*)o->lastNextImage[2], (const unsigned char*)o->nextImage[2],
+                        o->rows(2), o->cols(2), o->intr.fx, o->intr.fy, o->intr.cx, o->intr.cy, cb.so3);
+        cb.so3_ready = true;
+    }
+    o->pack_dirty_curr = false;
+    odom_select_bank(o, before);
+    return HRBF_OK;
+}
+
 int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s)
 {
+    // grid z order: the (heavier) RGB-D pyramid jobs first; with banks the camera-frame jobs were run by odom_stage_current_dev
+    static const int all[7] = { 0, 1, 2, 3, 4, 5, 6 }, model[4] = { 0, 2, 4, 6 };
+    return o->banked ? launch_prep_all(o, in, model, 4, s) : launch_prep_all(o, in, all, 7, s);
+}
+static int launch_prep_all(hrbf_odometry* o, const OdomPrepInputs& in, const int* jobs, int njobs, cudaStream_t s)
+{
     PrepAllArgs A;
+    for (int k = 0; k < 7; ++k) A.jobs[k] = k < njobs ? jobs[k] : 0;
     A.rows = o->height; A.cols = o->width; A.sel = in.sel; A.pose = in.pose_dev;
     A.dense_count = in.dense_count; A.dense_count_reset = in.dense_count_reset; A.dense_thresh = in.dense_thresh; A.curv_thr = o->curvThr; A.depth_cutoff = o->maxDepthRGB;
     A.vm = (const float4*)in.vm; A.nm = (const float4*)in.nm; A.vm_alt = (const float4*)in.vm_alt; A.nm_alt = (const float4*)in.nm_alt;
@@ -788,7 +882,7 @@ int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s
     }
     A.pyr_bx = div_up(o->width, 32); A.pyr_by = div_up(o->height, 8);
     A.rgbd_bx = div_up(o->cols(2), 8); A.rgbd_by = div_up(o->rows(2), 8);
-    const dim3 grid(A.pyr_bx > A.rgbd_bx ? A.pyr_bx : A.rgbd_bx, A.pyr_by > A.rgbd_by ? A.pyr_by : A.rgbd_by, 7);
+    const dim3 grid(A.pyr_bx > A.rgbd_bx ? A.pyr_bx : A.rgbd_bx, A.pyr_by > A.rgbd_by ? A.pyr_by : A.rgbd_by, njobs);
     HRBF_LAUNCH_PDL(prep_all_kernel, dim3(grid), dim3(256), 0, s, A);
     return HRBF_OK;
 }

@@ -418,6 +418,7 @@ struct PrepAllArgs {
     float* o_w[3]; int w_pitch[3];
     RgbdJob rgbd[2];                             // [0] model ("last"), [1] current ("next")
     int pyr_bx, pyr_by, rgbd_bx, rgbd_by;        // tiles per job
+    int jobs[7];                                 // blockIdx.z -> job (gridDim.z = number of jobs): 0, 1 RGB-D pyramids (model, current), 2..5 map pairs, 6 weight
 };
 
 constexpr int kRgbdL0 = 41, kRgbdL1 = 19;        // tile edge at level 0 / 1 for an 8x8 level-2 tile
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
     pdl_wait();
     // grid = (tiles x, tiles y, 7 jobs): z = 0, 1 are the (heavier) RGB-D pyramid jobs -- lowest block indices, scheduled first --
     // z = 2..6 the map jobs; no index arithmetic beyond blockIdx
-    const int job_z = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;
+    const int job_z = A.jobs[blockIdx.z], bx = blockIdx.x, by = blockIdx.y;
     if (job_z < 2 ? (bx >= A.rgbd_bx || by >= A.rgbd_by) : (bx >= A.pyr_bx || by >= A.pyr_by)) return;
     // HRBFFusion::denseEnough (HRBFFusion.cpp:974-987): fill-in textures replace the prediction when <= thresh of the 1/20 samples are set
     bool alt;

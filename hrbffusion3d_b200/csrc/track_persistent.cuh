@@ -17,6 +17,8 @@ namespace hrbf {
 // (hrbf_odometry_set_tracker_threads): 512 x 128 registers fill an SM's register file -- the lowest latency for ONE sequence;
 // 256 leave half of every SM to the kernels of other sequences' pipelines (several fusion objects on their own streams).
 constexpr int kTrackThreadsDefault = 512;
+// result of the SO3 pre-alignment when it runs ahead of the tracking call (so3_prealign_kernel)
+struct So3Pre { double resultR[9]; float lastSO3Error, lastSO3Count; };
 #ifndef HRBF_TRACK_POLL_SLEEP
 #define HRBF_TRACK_POLL_SLEEP 100      // ns between polling rounds of the shared-SM shape
 #endif
@@ -41,6 +43,8 @@ struct TrackParams {
     float* weighting_out; float weight_multiplier; // fusion weight from the inter-frame motion
     float* traj_out;                               // this frame's row of the trajectory
     TrackState* st_global;                         // camera in, statistics out
+    int cand_ready;                                // the Sobel images and candidate masks were built by sobel_cand_kernel (staged frame)
+    const So3Pre* so3_pre;                         // non-null: the SO3 pre-alignment was run by so3_prealign_kernel (staged frame), this is its result
     int max_slots;                                 // dynamic shared memory holds max_slots x kTrackThreads RgbSlots ...
     IcpTileGeom tile[3];                           // ... followed by the resident ICP tile of the level being worked on (icp_tile.cuh):
     IcpTileMaps tmaps[3];                          // tensor maps of the level's packed records for that geometry
@@ -338,14 +342,18 @@ __global__ void __maxnreg__(128) track_persistent_kernel(const __grid_constant__
         for (int k = 0; k < 6; ++k) S.lastb[k] = 0;
         const double I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
         const double I4[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
-        if (p.so3) update_so3_mats(&S, I3);
+        if (p.so3 && p.so3_pre != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) S.resultR[k] = p.so3_pre->resultR[k];
+            S.lastSO3Error = p.so3_pre->lastSO3Error; S.lastSO3Count = p.so3_pre->lastSO3Count;
+        } else if (p.so3) update_so3_mats(&S, I3);
         else if (p.rgb) update_krk(&S, I4, first_level);
     }
 
     // ---- RGB branch prep: Sobel of the next image + the pose-independent part of computeRgbResidual, all levels.
     // Pixel k of a level belongs to CTA range [begin, end) and, inside it, to thread (k - begin) % kTrackThreads: the SAME
     // mapping as the residual / step passes below, so every thread only ever re-reads what it wrote itself (no barrier).
-    if (p.rgb) {
+    if (p.rgb && !p.cand_ready) {
         for (int l = 0; l < 3; ++l) {
             const RgbResArgs& r = p.lvl[l].res;
             const int N = r.rows * r.cols;
@@ -362,7 +370,7 @@ __global__ void __maxnreg__(128) track_persistent_kernel(const __grid_constant__
     // ---- SO3 pre-alignment (RGBDOdometry.cpp:827-914), level 2 ----
     if (p.so3) {
         const int rows = p.lvl[2].res.rows, cols = p.lvl[2].res.cols, N = rows * cols;
-        for (int it = 0; it < 10; ++it) {
+        for (int it = 0; it < 10 && p.so3_pre == nullptr; ++it) {
             if (S.so3_done) break;
             float acc[32];
 #pragma unroll
@@ -564,6 +572,65 @@ __global__ void __maxnreg__(128) track_persistent_kernel(const __grid_constant__
         for (int k = 0; k < 9; ++k) { g->krkinv[k] = S.krkinv[k]; g->so3_basis[k] = S.so3_basis[k]; g->so3_kinv[k] = S.so3_kinv[k]; g->so3_krlr[k] = S.so3_krlr[k]; }
         for (int k = 0; k < 3; ++k) g->kt[k] = S.kt[k];
     }
+}
+
+// ---- the parts of a tracking call that depend on the camera images alone, as kernels of their own: the frame pipeline runs them on
+// its staging stream, one frame ahead of the tracker (hrbf_internal.h: CurrBank) ----
+
+// Sobel of the next image + the pose-independent candidate mask of computeRgbResidual, all three levels (grid.y = level): the
+// per-pixel code of the tracker's own prologue
+struct SobelCandArgs { RgbResArgs r[3]; unsigned char* cand[3]; };
+__global__ void __launch_bounds__(256) sobel_cand_kernel(const SobelCandArgs a)
+{
+    pdl_wait();
+    const RgbResArgs& r = a.r[blockIdx.y];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= r.rows * r.cols) return;
+    const int y = k / r.cols, x = k - y * r.cols;
+    sobel_pixel(r.rows, r.cols, r.nextImage, const_cast<short*>(r.dIdx), const_cast<short*>(r.dIdy), x, y);
+    a.cand[blockIdx.y][k] = rgb_static_candidate(r, k, r.dIdx[k], r.dIdy[k]) ? 1 : 0;      // plain loads of this thread's own stores
+}
+
+// The SO3 pre-alignment loop (RGBDOdometry.cpp:827-914) on the level-2 images of two consecutive camera frames: ONE CTA (4 800 pixels
+// at 640x480; the loop is a chain of <= 10 dependent reductions, and it runs off the critical path), fp32 per-thread and per-warp
+// sums, fp64 across warps, the same so3_pixel / so3_update as the tracker's in-kernel loop.
+constexpr int kSo3Threads = 1024;
+__global__ void __launch_bounds__(kSo3Threads) so3_prealign_kernel(const unsigned char* __restrict__ lastImage, const unsigned char* __restrict__ nextImage,
+                                                                   int rows, int cols, float fx, float fy, float cx, float cy, So3Pre* __restrict__ out)
+{
+    pdl_wait();
+    __shared__ TrackState S;
+    __shared__ float s_w[kSo3Threads / 32][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, N = rows * cols;
+    if (tid == 0) {
+        S.fx = fx; S.fy = fy; S.cx = cx; S.cy = cy;
+        for (int k = 0; k < 9; ++k) { S.resultR[k] = S.lastResultR[k] = (k % 4 == 0) ? 1.0 : 0.0; S.R_lr[k] = (k % 4 == 0) ? 1.f : 0.f; }
+        S.so3_lastError = FLT_MAX / 2; S.so3_lastCount = FLT_MAX / 2; S.so3_done = 0;
+        S.lastSO3Error = 0; S.lastSO3Count = 0;
+        const double I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+        update_so3_mats(&S, I3);
+    }
+    __syncthreads();
+    for (int it = 0; it < 10; ++it) {
+        if (S.so3_done) break;
+        float acc[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+        for (int k = tid; k < N; k += kSo3Threads) so3_pixel(lastImage, nextImage, rows, cols, S.so3_basis, k, acc);
+        s_w[warp][lane] = warp_reduce32_transpose(acc);
+        __syncthreads();
+        if (tid < 16) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kSo3Threads / 32; ++w) t += (double)s_w[w][tid];
+            S.so3_sums[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) so3_update(&S);
+        __syncthreads();
+    }
+    if (tid < 9) out->resultR[tid] = S.resultR[tid];
+    if (tid == 0) { out->lastSO3Error = S.lastSO3Error; out->lastSO3Count = S.lastSO3Count; }
 }
 
 }  // namespace hrbf
