@@ -230,7 +230,9 @@ def ours_arm(args):
         every sequence.  Returns (ms, launches, pipelines)."""
         tthreads = int(os.environ.get("HRBF_BENCH_TRACKER_THREADS", "0")) or (256 if S > 1 else 384)      # (development override)
         Fs = [HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=tthreads, **FUSION_KW) for _ in range(S)]
-        st = [torch.cuda.Stream() for _ in range(S)]
+        # the pipelines' own streams get a higher priority than the library's staging streams (created at the lowest one): the staged work
+        # of frame t+1 then only takes what frame t leaves free
+        st = [torch.cuda.Stream(priority=-1) for _ in range(S)]
         off = [(q * RING) // (world * S) for q in range(S)]
         pose = np.zeros((S, 16), np.float32)
 

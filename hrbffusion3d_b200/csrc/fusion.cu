@@ -619,6 +619,9 @@ struct hrbf_fusion {
     int cur = 0;                     // buffer the next processed frame uses
     bool staged[2] = { false, false };
     cudaStream_t pre_stream = nullptr;              // staging stream (lowest priority)
+    cudaStream_t so3_stream = nullptr;              // the staged SO3 pre-alignment, beside the preprocessing (lowest priority)
+    cudaEvent_t ev_up = nullptr, ev_so3[2] = {};    // upload done (forks so3_stream) / SO3 pre-alignment of bank k done (joins)
+    bool ev_so3_valid[2] = { false, false };
     // tracker-input banks of the odometry (CurrBank): frame number k (1-based) uses bank k & 1, whichever frame buffer it sits in.
     // ev_curr[k]: bank k is built (the next frame's SO3 pre-alignment reads its image); ev_bank_free[k]: the frame that used it is done
     cudaEvent_t ev_staged[2] = {}, ev_free[2] = {}, ev_curr[2] = {}, ev_bank_free[2] = {};
@@ -642,19 +645,28 @@ __global__ void set_identity_pose_kernel(float* p)
 
 // Everything the tracker needs from the camera frame in buffer b alone (current-frame pyramids, Sobel + candidates, SO3 pre-alignment
 // against the previous camera image = the other bank), on stream s: the staging stream for staged frames, else the main stream.
+// the SO3 pre-alignment of the frame in buffer b (frame_number) against the previous camera frame, on stream s
+static int stage_so3(hrbf_fusion* F, int b, int frame_number, cudaStream_t s)
+{
+    const int k = frame_number & 1;
+    if (F->ev_bank_free_valid[k]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_bank_free[k], 0));   // frame_number - 2 read this bank's result
+    if (F->ev_so3_valid[k ^ 1]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_so3[k ^ 1], 0));        // the other bank's image: written, and no longer compared with this bank's old one
+    if (int rc = odom_stage_so3_dev(F->odom, k, (const unsigned char*)F->frames[b]->tex[HRBF_FT_RGB], F->p.so3 != 0, frame_number != 1, s)) return rc;
+    HRBF_CUDA(cudaEventRecord(F->ev_so3[k], s));
+    F->ev_so3_valid[k] = true;
+    return HRBF_OK;
+}
 static int stage_current(hrbf_fusion* F, int b, int frame_number, cudaStream_t s)
 {
     hrbf_frame* fr = F->frames[b];
     const int k = frame_number & 1;
-    const bool first = frame_number == 1;
     OdomPrepInputs in;
     memset(&in, 0, sizeof in);
     in.vc = (const float*)fr->tex[HRBF_FT_VERTEX_FILTERED]; in.nc = (const float*)fr->tex[HRBF_FT_NORMAL];
     in.k1c = (const float*)fr->tex[HRBF_FT_PRINCIPAL_CURV1]; in.k2c = (const float*)fr->tex[HRBF_FT_PRINCIPAL_CURV2];
     in.rgba_c = (const unsigned char*)fr->tex[HRBF_FT_RGBA]; in.rgb8_c = (const unsigned char*)fr->tex[HRBF_FT_RGB];
     if (F->ev_bank_free_valid[k]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_bank_free[k], 0));   // frame_number - 2 tracked from this bank
-    if (F->ev_curr_valid[k ^ 1]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_curr[k ^ 1], 0));      // the SO3 pre-alignment reads the other bank's image
-    if (int rc = odom_stage_current_dev(F->odom, k, in, F->p.so3 != 0, !first, s)) return rc;
+    if (int rc = odom_stage_current_dev(F->odom, k, in, s)) return rc;
     HRBF_CUDA(cudaEventRecord(F->ev_curr[k], s));
     F->ev_curr_valid[k] = true;
     return HRBF_OK;
@@ -678,6 +690,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
 
     mark(0);
     if (!preprocessed) {
+        if (int rc = stage_so3(F, F->cur, F->tick, s)) return rc;
         if (int rc = hrbf_frame_preprocess(fr, s)) return rc;
         if (int rc = stage_current(F, F->cur, F->tick, s)) return rc;
     }
@@ -796,7 +809,7 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
     if (!rc) rc = hrbf_model_set_params(F->model, fp.radiusMultiplier, p->curvValidThreshold, fp.normalPCA, p->cleanWindow, fp.useConfEval, fp.confEvalEpsilon);
     if (!rc) rc = hrbf_odometry_create(&F->odom, fp.width, fp.height, fp.cx, fp.cy, fp.fx, fp.fy, 0.10f, sinf(20.f * 3.14159265f / 180.f));
     if (!rc) rc = hrbf_odometry_set_params(F->odom, p->curvValidThreshold, 0, 2, 0);
-    if (!rc) rc = hrbf_odometry_set_tracker_threads(F->odom, p->trackerThreads);
+    if (!rc) rc = hrbf_odometry_set_tracker_threads(F->odom, p->trackerThreads ? p->trackerThreads : 384);
     if (!rc) rc = odom_enable_banks(F->odom);
     if (!rc) {
         F->traj_cap = 1 << 16;
@@ -805,10 +818,12 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
         else {
             cudaMemset(F->dev, 0, 64 * sizeof(float));
             for (auto& e : F->ev) cudaEventCreate(&e);
-            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_curr[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_bank_free[k], cudaEventDisableTiming); }
+            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_curr[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_bank_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_so3[k], cudaEventDisableTiming); }
+            cudaEventCreateWithFlags(&F->ev_up, cudaEventDisableTiming);
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            if (cudaStreamCreateWithPriority(&F->pre_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { set_error("fusion_create: stream creation failed"); rc = HRBF_ERR_CUDA; }
+            if (cudaStreamCreateWithPriority(&F->pre_stream, cudaStreamNonBlocking, lo) != cudaSuccess ||
+                cudaStreamCreateWithPriority(&F->so3_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { set_error("fusion_create: stream creation failed"); rc = HRBF_ERR_CUDA; }
         }
     }
     if (rc) { hrbf_fusion_destroy(F); return rc; }
@@ -820,7 +835,9 @@ int hrbf_fusion_destroy(hrbf_fusion* F)
     if (!F) return HRBF_OK;
     hrbf_odometry_destroy(F->odom); hrbf_model_destroy(F->model); hrbf_indexmap_destroy(F->im); hrbf_fillin_destroy(F->fill); hrbf_frame_destroy(F->frames[0]); hrbf_frame_destroy(F->frames[1]);
     if (F->pre_stream) cudaStreamDestroy(F->pre_stream);
-    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); if (F->ev_curr[k]) cudaEventDestroy(F->ev_curr[k]); if (F->ev_bank_free[k]) cudaEventDestroy(F->ev_bank_free[k]); }
+    if (F->so3_stream) cudaStreamDestroy(F->so3_stream);
+    if (F->ev_up) cudaEventDestroy(F->ev_up);
+    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); if (F->ev_curr[k]) cudaEventDestroy(F->ev_curr[k]); if (F->ev_bank_free[k]) cudaEventDestroy(F->ev_bank_free[k]); if (F->ev_so3[k]) cudaEventDestroy(F->ev_so3[k]); }
     if (F->dev) cudaFree(F->dev);
     if (F->traj) cudaFree(F->traj);
     if (F->h_pose) cudaFreeHost(F->h_pose);
@@ -873,8 +890,13 @@ int hrbf_fusion_stage_frame(hrbf_fusion* F, const unsigned char* rgb8, const uns
     const bool first = F->tick + (b != F->cur ? 1 : 0) == 1;
     if (F->ev_free_valid[b]) HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_free[b], 0));
     if (int rc = frame_upload(F->frames[b], rgb8, depth16, host, first, F->pre_stream)) return rc;
+    const int frame_number = F->tick + (b != F->cur ? 1 : 0);
+    HRBF_CUDA(cudaEventRecord(F->ev_up, F->pre_stream));
+    HRBF_CUDA(cudaStreamWaitEvent(F->so3_stream, F->ev_up, 0));
+    if (int rc = stage_so3(F, b, frame_number, F->so3_stream)) return rc;
     if (int rc = hrbf_frame_preprocess(F->frames[b], F->pre_stream)) return rc;
-    if (int rc = stage_current(F, b, F->tick + (b != F->cur ? 1 : 0), F->pre_stream)) return rc;
+    if (int rc = stage_current(F, b, frame_number, F->pre_stream)) return rc;
+    HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_so3[frame_number & 1], 0));
     HRBF_CUDA(cudaEventRecord(F->ev_staged[b], F->pre_stream));
     F->staged[b] = true;
     return HRBF_OK;

@@ -20,6 +20,7 @@ struct CurrBank {
     unsigned char* nextImage[HRBF_NUM_PYRS] = {}; float* nextDepth[HRBF_NUM_PYRS] = {};
     short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
     unsigned char* cand[HRBF_NUM_PYRS] = {};
+    unsigned char* so3img = nullptr;             // level-2 intensity image of the camera frame (= nextImage[2]), built straight from the upload
     So3Pre* so3 = nullptr;                       // device: result of the staged SO3 pre-alignment
     void* tmaps = nullptr;                       // host tensor maps over this bank's records
     bool cand_ready = false, so3_ready = false;  // staged for the frame this bank holds
@@ -124,11 +125,14 @@ struct OdomPrepInputs {
 };
 int odom_prep_all_dev(hrbf_odometry* o, const OdomPrepInputs& in, cudaStream_t s);
 // Frame pipeline: two CurrBanks (see above).  odom_stage_current_dev builds bank `b` from a preprocessed frame's textures -- the
-// current-frame jobs of prep_all, Sobel + candidates, and (so3 and not the first frame) the SO3 pre-alignment against the OTHER bank's
-// image -- on any stream; odom_select_bank makes a bank the one the tracker and the init* calls use.
+// current-frame jobs of prep_all, Sobel + candidates -- on any stream; odom_select_bank makes a bank the one the tracker and the
+// init* calls use.
 int odom_enable_banks(hrbf_odometry* o);
 void odom_select_bank(hrbf_odometry* o, int b);
-int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, bool so3, bool has_previous, cudaStream_t s);
+int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, cudaStream_t s);
+// The SO3 pre-alignment of the frame in bank b against the previous camera frame (bank b ^ 1): needs the uploaded RGB8 only, so
+// it can run beside the preprocessing (its <= 10 dependent reductions are latency, not work).
+int odom_stage_so3_dev(hrbf_odometry* o, int b, const unsigned char* rgb8, bool so3, bool has_previous, cudaStream_t s);
 struct OdomFrameEpilogue { float* last_pose_out; float* inv_pose_out; float* weighting_out; float weight_multiplier; float* traj_out; };
 int odom_track_frame_dev(hrbf_odometry* o, float* pose_inout, const OdomFrameEpilogue& ep, bool rgbOnly, float icpWeight, bool pyramid,
                          bool fastOdom, bool so3, bool use_weight, cudaStream_t s);

@@ -791,7 +791,7 @@ int odom_enable_banks(hrbf_odometry* o)
         for (int k = 0; k < 2; ++k) o_pk[k][l] = take(P * sizeof(float4));
         o_ni[l] = take(P); o_nd[l] = take(P * 4); o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cd[l] = take(P);
     }
-    const size_t o_so3 = take(2 * sizeof(So3Pre));
+    const size_t o_so3 = take(2 * sizeof(So3Pre)), o_si0 = take((size_t)o->rows(2) * o->cols(2)), o_si1 = take((size_t)o->rows(2) * o->cols(2));
     if (cudaMalloc(&o->bank1_slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); return HRBF_ERR_CUDA; }
     HRBF_CUDA(cudaMemset(o->bank1_slab, 0, off));
     CurrBank& b1 = o->bank[1];
@@ -802,6 +802,7 @@ int odom_enable_banks(hrbf_odometry* o)
         b1.dIdx[l] = (short*)(o->bank1_slab + o_dx[l]); b1.dIdy[l] = (short*)(o->bank1_slab + o_dy[l]); b1.cand[l] = (unsigned char*)(o->bank1_slab + o_cd[l]);
     }
     o->bank[0].so3 = (So3Pre*)(o->bank1_slab + o_so3); b1.so3 = o->bank[0].so3 + 1;
+    o->bank[0].so3img = (unsigned char*)(o->bank1_slab + o_si0); b1.so3img = (unsigned char*)(o->bank1_slab + o_si1);
     o->banked = true;
     if (o->tmaps_host) {      // tensor maps over bank 1's records
         odom_select_bank(o, 1);
@@ -828,7 +829,24 @@ void odom_select_bank(hrbf_odometry* o, int b)
     o->cur_bank = b;
 }
 static int launch_prep_all(hrbf_odometry* o, const OdomPrepInputs& in, const int* jobs, int njobs, cudaStream_t s);
-int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, bool so3, bool has_previous, cudaStream_t s)
+int odom_stage_so3_dev(hrbf_odometry* o, int b, const unsigned char* rgb8, bool so3, bool has_previous, cudaStream_t s)
+{
+    if (!o->banked) { set_error("odom_stage_so3_dev: banks not enabled"); return HRBF_ERR_INVALID_ARG; }
+    CurrBank& cb = o->bank[b];
+    cb.so3_ready = false;
+    if (!so3) return HRBF_OK;
+    RgbdJob j;
+    memset(&j, 0, sizeof j);
+    j.rgb8 = rgb8; j.img[2] = cb.so3img;
+    HRBF_LAUNCH_PDL(so3_image_kernel, dim3(div_up(o->cols(2), 8), div_up(o->rows(2), 8)), dim3(256), 0, s, j, o->height, o->width);
+    if (has_previous) {
+        HRBF_LAUNCH_PDL(so3_prealign_kernel, dim3(1), dim3(kSo3Threads), 0, s, (const unsigned char*)o->bank[b ^ 1].so3img, (const unsigned char*)cb.so3img,
+                        o->rows(2), o->cols(2), o->intr.fx, o->intr.fy, o->intr.cx, o->intr.cy, cb.so3);
+        cb.so3_ready = true;
+    }
+    return HRBF_OK;
+}
+int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, cudaStream_t s)
 {
     if (!o->banked) { set_error("odom_stage_current_dev: banks not enabled"); return HRBF_ERR_INVALID_ARG; }
     const int before = o->cur_bank;
@@ -838,14 +856,7 @@ int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, bo
     SobelCandArgs sc;
     for (int l = 0; l < 3; ++l) { sc.r[l] = rgbres_args(o, l); sc.cand[l] = o->cand[l]; }
     HRBF_LAUNCH_PDL(sobel_cand_kernel, dim3(div_up(o->width * o->height, 256), 3), dim3(256), 0, s, sc);
-    CurrBank& cb = o->bank[b];
-    cb.cand_ready = true;
-    cb.so3_ready = false;
-    if (so3 && has_previous) {
-        HRBF_LAUNCH_PDL(so3_prealign_kernel, dim3(1), dim3(kSo3Threads), 0, s, (const unsigned char*)o->lastNextImage[2], (const unsigned char*)o->nextImage[2],
-                        o->rows(2), o->cols(2), o->intr.fx, o->intr.fy, o->intr.cx, o->intr.cy, cb.so3);
-        cb.so3_ready = true;
-    }
+    o->bank[b].cand_ready = true;
     o->pack_dirty_curr = false;
     odom_select_bank(o, before);
     return HRBF_OK;

@@ -423,12 +423,14 @@ struct PrepAllArgs {
 
 constexpr int kRgbdL0 = 41, kRgbdL1 = 19;        // tile edge at level 0 / 1 for an 8x8 level-2 tile
 
+// kImageOnly: only the level-2 intensity image is produced (what the SO3 pre-alignment reads), nothing else is loaded or stored
+template <bool kImageOnly = false>
 __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, int cols, float depth_cutoff, bool use_alt, int bx, int by)
 {
     __shared__ unsigned char s_g0[kRgbdL0][kRgbdL0 + 3];
-    __shared__ float s_d0[kRgbdL0][kRgbdL0];
+    __shared__ float s_d0[kImageOnly ? 1 : kRgbdL0][kImageOnly ? 1 : kRgbdL0];
     __shared__ unsigned char s_g1[kRgbdL1][kRgbdL1 + 1];
-    __shared__ float s_d1[kRgbdL1][kRgbdL1];
+    __shared__ float s_d1[kImageOnly ? 1 : kRgbdL1][kImageOnly ? 1 : kRgbdL1];
     const uchar4* rgba = use_alt ? j.rgba_alt : j.rgba;
     const float4* vert = use_alt ? j.vertex_alt : j.vertex;
     const int rows1 = rows / 2, cols1 = cols / 2, rows2 = rows1 / 2, cols2 = cols1 / 2;
@@ -442,10 +444,13 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
         const size_t o = (size_t)gy * cols + gx;
         const unsigned char g = j.rgb8 != nullptr ? bgr_intensity(make_uchar4(__ldg(j.rgb8 + 3 * o), __ldg(j.rgb8 + 3 * o + 1), __ldg(j.rgb8 + 3 * o + 2), 255))
                                                   : bgr_intensity(__ldg(rgba + o));
-        const float z = __ldg(reinterpret_cast<const float*>(vert + o) + 2);
-        const float d = (z > depth_cutoff || z <= 0.f) ? qn : z;
-        s_g0[sy][sx] = g; s_d0[sy][sx] = d;
-        if (sx >= 6 && sx < 38 && sy >= 6 && sy < 38) { j.img[0][o] = g; j.depth[0][o] = d; }
+        s_g0[sy][sx] = g;
+        if (!kImageOnly) {
+            const float z = __ldg(reinterpret_cast<const float*>(vert + o) + 2);
+            const float d = (z > depth_cutoff || z <= 0.f) ? qn : z;
+            s_d0[sy][sx] = d;
+            if (sx >= 6 && sx < 38 && sy >= 6 && sy < 38) { j.img[0][o] = g; j.depth[0][o] = d; }
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < kRgbdL1 * kRgbdL1; t += blockDim.x) {
@@ -453,18 +458,29 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
         const int x1 = X1 + sx, y1 = Y1 + sy;
         if (x1 < 0 || y1 < 0 || x1 >= cols1 || y1 >= rows1) continue;
         const unsigned char g = gauss_down_u8(rows, cols, x1, y1, [&](int cx, int cy) { return s_g0[cy - Y0][cx - X0]; });
-        const float d = gauss_down_f32(rows, cols, x1, y1, [&](int cx, int cy) { return s_d0[cy - Y0][cx - X0]; });
-        s_g1[sy][sx] = g; s_d1[sy][sx] = d;
-        if (sx >= 2 && sx < 18 && sy >= 2 && sy < 18) { j.img[1][(size_t)y1 * cols1 + x1] = g; j.depth[1][(size_t)y1 * cols1 + x1] = d; }
+        s_g1[sy][sx] = g;
+        if (!kImageOnly) {
+            const float d = gauss_down_f32(rows, cols, x1, y1, [&](int cx, int cy) { return s_d0[cy - Y0][cx - X0]; });
+            s_d1[sy][sx] = d;
+            if (sx >= 2 && sx < 18 && sy >= 2 && sy < 18) { j.img[1][(size_t)y1 * cols1 + x1] = g; j.depth[1][(size_t)y1 * cols1 + x1] = d; }
+        }
     }
     __syncthreads();
     if (threadIdx.x < 64) {
         const int x2 = 8 * bx + (threadIdx.x & 7), y2 = 8 * by + (threadIdx.x >> 3);
         if (x2 < cols2 && y2 < rows2) {
             j.img[2][(size_t)y2 * cols2 + x2] = gauss_down_u8(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_g1[cy - Y1][cx - X1]; });
-            j.depth[2][(size_t)y2 * cols2 + x2] = gauss_down_f32(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_d1[cy - Y1][cx - X1]; });
+            if (!kImageOnly) j.depth[2][(size_t)y2 * cols2 + x2] = gauss_down_f32(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_d1[cy - Y1][cx - X1]; });
         }
     }
+}
+
+// the level-2 intensity image of a camera frame alone (the input of the SO3 pre-alignment), straight from the uploaded RGB8:
+// identical values to the image pyramid prep_all_kernel builds later
+__global__ void __launch_bounds__(256) so3_image_kernel(const RgbdJob j, int rows, int cols)
+{
+    pdl_wait();
+    rgbd_pyramid_tile<true>(j, rows, cols, 0.f, false, blockIdx.x, blockIdx.y);
 }
 
 __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)

@@ -594,8 +594,8 @@ __global__ void __launch_bounds__(256) sobel_cand_kernel(const SobelCandArgs a)
 // The SO3 pre-alignment loop (RGBDOdometry.cpp:827-914) on the level-2 images of two consecutive camera frames: ONE CTA (4 800 pixels
 // at 640x480; the loop is a chain of <= 10 dependent reductions, and it runs off the critical path), fp32 per-thread and per-warp
 // sums, fp64 across warps, the same so3_pixel / so3_update as the tracker's in-kernel loop.
-constexpr int kSo3Threads = 1024;
-__global__ void __launch_bounds__(kSo3Threads) so3_prealign_kernel(const unsigned char* __restrict__ lastImage, const unsigned char* __restrict__ nextImage,
+constexpr int kSo3Threads = 256;      // small enough to sit beside a 384-thread tracker (48 K + 16 K registers)
+__global__ void __launch_bounds__(kSo3Threads, 4) so3_prealign_kernel(const unsigned char* __restrict__ lastImage, const unsigned char* __restrict__ nextImage,
                                                                    int rows, int cols, float fx, float fy, float cx, float cy, So3Pre* __restrict__ out)
 {
     pdl_wait();

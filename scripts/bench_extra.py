@@ -6,7 +6,7 @@
   config4 : 1280x960 stream, HRBF K = 16 neighbours, window 3 (bandwidth stress): frames/s of the full pipeline
 
     python scripts/bench_extra.py [--frames3 1000] [--frames4 120] [--only 3|4]      -> one JSON line per configuration
-Frames are rendered on the host (process pool) BEFORE CUDA is touched; inputs are resident in HBM; one live sequence (512-thread
+Frames are rendered on the host (process pool) BEFORE CUDA is touched; inputs are resident in HBM; one live sequence (384-thread
 tracker), reference defaults; device time with CUDA events."""
 import argparse
 import json
@@ -39,6 +39,7 @@ def run(W, H, kind, poses, n_frames, name, capacity, **kw):
     n_in = len(fr)
     del fr
     F = HRBFFusion(W, H, cam, capacity=capacity, **kw)
+    torch.cuda.set_stream(torch.cuda.Stream(priority=-1))   # above the library's staging streams (lowest priority), as in bench.py
     F.stageFrame(rgb[0], depth[0])
     F.processStaged(None)                                   # frame 1 initialises the map
     F.stageFrame(rgb[1 % n_in], depth[1 % n_in])
@@ -74,7 +75,7 @@ def run(W, H, kind, poses, n_frames, name, capacity, **kw):
            "stage_ms_at_final_map": dict(zip(("Initialization (preprocessing runs ahead on the staging stream: not in this span)", "Registration", "Integration", "Prediction"), [float(x) / k for x in acc])),
            "trajectory_ate_rmse_m": ate(tr, [poses[i % len(poses)] for i in range(tr.shape[0])]) if n_frames <= len(poses) else None,
            "overflowed": bool(F.globalModel.overflowed()), "host_render_s": t_render, "params": kw,
-           "timing": "CUDA events around frames 2..%d, inputs resident in HBM, one sequence, 512-thread tracker" % n_frames}
+           "timing": "CUDA events around frames 2..%d, inputs resident in HBM, one sequence, 384-thread tracker" % n_frames}
     print(json.dumps(out), flush=True)
 
 
