@@ -22,6 +22,8 @@ struct hrbf_frame {
     float* weighting = nullptr;      // device scalar (VertexConfidence's uniform)
     float* h_w = nullptr;            // pinned ring of 8
     int slot = 0;
+    float4* fuse_normals = nullptr;  // frame pipeline: fuse_normals_kernel's output for frame number fuse_normals_time (per fuse slot)
+    int fuse_normals_time = -1;
 };
 
 static size_t ft_bytes(int which, size_t P)
@@ -90,11 +92,12 @@ int hrbf_frame_create(hrbf_frame** out, const hrbf_frame_params* p)
     size_t off = 0, o[HRBF_FT_COUNT];
     auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
     for (int t = 0; t < HRBF_FT_COUNT; ++t) o[t] = take(ft_bytes(t, P));
-    const size_t o_w = take(64);
+    const size_t o_w = take(64), o_fn = take((size_t)fuse_slots_x(p->width) * fuse_slots_y(p->height) * sizeof(float4));
     if (cudaMalloc(&f->slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); delete f; return HRBF_ERR_CUDA; }
     cudaMemset(f->slab, 0, off);
     for (int t = 0; t < HRBF_FT_COUNT; ++t) f->tex[t] = f->slab + o[t];
     f->weighting = (float*)(f->slab + o_w);
+    f->fuse_normals = (float4*)(f->slab + o_fn);
     cudaMallocHost(&f->h_w, 8 * sizeof(float));
     {
         float tab[(2 * kBilR + 1) * (2 * kBilR + 1)];
@@ -316,7 +319,7 @@ int model_initialise_dev(hrbf_model* m, const float* vertexMap, const float* nor
 int model_fuse_dev(hrbf_model* m, const float* pose_dev, int time, const unsigned char* rgb8, const float* depthRaw, const float* depthFiltered,
                    const float* curv1, const float* curv2, const float* confidence, const unsigned int* indexMap, const float* vertConf,
                    const float* normRad, float depthCutoff, int indexSubmap, cudaStream_t s, const float* inline_weighting = nullptr,
-                   const float* normal_pca_tex = nullptr)
+                   const float* normal_slot = nullptr)
 {
     ModelArgs a = m->a;
     a.maxDepth = depthCutoff;
@@ -324,7 +327,7 @@ int model_fuse_dev(hrbf_model* m, const float* pose_dev, int time, const unsigne
     f.rgb = rgb8; f.depthRaw = depthRaw; f.depthFiltered = depthFiltered; f.curv1 = (const float4*)curv1; f.curv2 = (const float4*)curv2;
     f.confidence = confidence; f.index = indexMap; f.vertConf = (const float4*)vertConf; f.normRad = (const float4*)normRad;
     f.pose = pose_dev; f.time = time; f.indexSubmap = (float)indexSubmap; f.weighting = inline_weighting;
-    f.normal_pca = (const float4*)normal_pca_tex;
+    f.normal_slot = (const float4*)normal_slot;
     f.staging = m->staging; f.update_id = m->update_id; f.best = m->best; f.winner = m->winner;
     const int nb = div_up(m->n_slots, 128);
     HRBF_LAUNCH_PDL(fuse_associate_kernel, dim3(nb), dim3(128), 0, s, a, m->pa, f, m->count[m->cur]);
@@ -667,6 +670,15 @@ static int stage_current(hrbf_fusion* F, int b, int frame_number, cudaStream_t s
     in.rgba_c = (const unsigned char*)fr->tex[HRBF_FT_RGBA]; in.rgb8_c = (const unsigned char*)fr->tex[HRBF_FT_RGB];
     if (F->ev_bank_free_valid[k]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_bank_free[k], 0));   // frame_number - 2 tracked from this bank
     if (int rc = odom_stage_current_dev(F->odom, k, in, s)) return rc;
+    fr->fuse_normals_time = -1;
+    if (frame_number > 1 && !F->p.rgbOnly && F->model->a.pca) {      // the PCA normals GlobalModel::fuse will ask for (data.vert)
+        ModelArgs a = F->model->a;
+        a.maxDepth = F->p.maxDepthProcessed;
+        HRBF_LAUNCH_PDL(fuse_normals_kernel, dim3(div_up(F->model->n_slots, 128)), dim3(128), 0, s, a, F->model->pa, (const float*)fr->tex[HRBF_FT_DEPTH_METRIC],
+                        (const float*)fr->tex[HRBF_FT_DEPTH_METRIC_FILTERED], (const float4*)fr->tex[HRBF_FT_PRINCIPAL_CURV1], (const float4*)fr->tex[HRBF_FT_PRINCIPAL_CURV2],
+                        frame_number, fr->fuse_normals);
+        fr->fuse_normals_time = frame_number;
+    }
     HRBF_CUDA(cudaEventRecord(F->ev_curr[k], s));
     F->ev_curr_valid[k] = true;
     return HRBF_OK;
@@ -751,7 +763,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
                                         (const float*)FT(HRBF_FT_DEPTH_METRIC_FILTERED), (const float*)FT(HRBF_FT_PRINCIPAL_CURV1), (const float*)FT(HRBF_FT_PRINCIPAL_CURV2),
                                         (const float*)FT(HRBF_FT_CONFIDENCE), (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                         (const float*)IT(HRBF_TEX_NORMRAD), p.maxDepthProcessed, F->indexSubmap, s, inline_w,
-                                        nullptr)) return rc;
+                                        fr->fuse_normals_time == F->tick ? (const float*)fr->fuse_normals : nullptr)) return rc;
             if (int rc = splat(1)) return rc;                  // clean reads index, vertConf, colorTime (copy_unstable.vert)
             if (int rc = model_clean_dev(M, invPose, F->tick, (const unsigned int*)IT(HRBF_TEX_INDEX), (const float*)IT(HRBF_TEX_VERTCONF),
                                          (const float*)IT(HRBF_TEX_COLORTIME), p.confidenceThreshold, p.maxDepthProcessed, s)) return rc;

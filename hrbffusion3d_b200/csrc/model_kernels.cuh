@@ -167,9 +167,8 @@ struct FuseArgs {
     const float* pose;               // device R[9], t[3]
     int time; float indexSubmap;
     const float* weighting;          // frame pipeline: non-null -> confidence evaluated in place (see FillArgs::weighting)
-    const float4* normal_pca;        // frame pipeline: the frame's NORMAL_PCA texture.  data.vert recomputes the PCA normal of the filtered depth
-                                     // at each candidate pixel; depth_vertex_normal_radius.frag already did exactly that (same function, same
-                                     // window, same input) for every pixel, and zeroes it only where fuse rejects the pixel anyway
+    const float4* normal_slot;       // frame pipeline: data.vert's PCA normal of every candidate pixel, per slot, computed ahead of the fuse by
+                                     // fuse_normals_kernel (it depends on the camera frame alone); null: computed here
     float4* staging;                 // [(cols/2+1)*(rows/2+1)][5] : this frame's candidate records
     unsigned char* update_id;        // per slot: 0 none, 1 merge, 2 new
     unsigned int* best;              // per slot: surfel to merge with
@@ -177,6 +176,30 @@ struct FuseArgs {
 };
 __host__ __device__ inline int fuse_slots_x(int cols) { return (cols + 1) / 2; }
 __host__ __device__ inline int fuse_slots_y(int rows) { return (rows + 1) / 2; }
+
+// data.vert:63-110 recomputes the PCA normal of the filtered depth at each candidate pixel (geometry.glsl with the uv VBO's texture
+// coordinates).  That needs the camera frame only, so the frame pipeline runs it ahead of the fuse, on its staging stream: same
+// slots, same rejection tests, same function.
+__global__ void __launch_bounds__(128) fuse_normals_kernel(ModelArgs m, PrepArgs pa, const float* __restrict__ depthRaw, const float* __restrict__ depthFiltered,
+                                                           const float4* __restrict__ curv1, const float4* __restrict__ curv2, int time, float4* __restrict__ out)
+{
+    pdl_wait();
+    const int sxn = fuse_slots_x(m.cols), syn = fuse_slots_y(m.rows);
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= sxn * syn) return;
+    const int par = time % 2;
+    const int px = 2 * (slot / syn) + par, py = 2 * (slot % syn) + par;
+    float3 n = make_float3(0.f, 0.f, 0.f);
+    if (px < m.cols && py < m.rows && m.pca) {
+        const int W = m.cols;
+        const size_t o = (size_t)py * W + px;
+        const float z = __ldg(depthRaw + o), zf = __ldg(depthFiltered + o);
+        const float4 k1 = __ldg(curv1 + o), k2 = __ldg(curv2 + o);
+        if (z > 0.3f && z <= m.maxDepth && k1.w > -300.0f && k1.w < 300.0f && k2.w > -300.0f && k2.w < 300.0f)
+            n = normal_pca(pa, [&](int qx, int qy) { return __ldg(depthFiltered + (size_t)qy * W + qx); }, px, py, zf, /* uv-VBO texcoords */ 1);
+    }
+    out[slot] = make_float4(n.x, n.y, n.z, 0.f);
+}
 
 // One thread per candidate pixel (x%2 == t%2 && y%2 == t%2, data.vert:113).  Slot order = uv order (x outer, y inner).
 __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepArgs pa, FuseArgs f, const unsigned int* __restrict__ count_dev)
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(128) fuse_associate_kernel(ModelArgs m, PrepAr
     if (!(z > 0.3f && z <= m.maxDepth && k1.w > -300.0f && k1.w < 300.0f && k2.w > -300.0f && k2.w < 300.0f)) return;
     float3 n = make_float3(0.f, 0.f, 0.f);
     if (m.pca) {
-        if (f.normal_pca != nullptr) { const float4 t = __ldg(f.normal_pca + o); n = make_float3(t.x, t.y, t.z); }
+        if (f.normal_slot != nullptr) { const float4 t = __ldg(f.normal_slot + slot); n = make_float3(t.x, t.y, t.z); }
         else n = normal_pca(pa, [&](int qx, int qy) { return __ldg(f.depthFiltered + (size_t)qy * W + qx); }, px, py, zf, /* uv-VBO texcoords */ 1);
     }
     const float nlen = norm(n);

@@ -171,8 +171,8 @@ def test_icp_step_search_window(orc, cuda):
     gnames = ("vmap_g_prev", "nmap_g_prev", "ck1_g_prev", "ck2_g_prev", "icpWeight")
     A, b, res, sums, _ = od.icpStep(Rp, tp, *[go.map(k, 0) for k in names], Rpi, tp, cam, *[go.map(k, 0) for k in gnames], use_search=True, search_radius=2)
     Ao, bo, reso, sumso, _ = orc.icpStep(Rp, tp, *[oo.map(k, 0) for k in names], Rpi, tp, cam, *[oo.map(k, 0) for k in gnames], use_search=1, radius=2)
-    assert abs(res[1] - reso[1]) <= 3
-    np.testing.assert_allclose(sums[:27], sumso[:27], rtol=5e-3, atol=1e-3 * np.abs(sumso[:27]).max())
+    assert res[1] == reso[1]                      # the same best candidate in every 5 x 5 window
+    np.testing.assert_allclose(sums[:27], sumso[:27], rtol=2e-4, atol=1e-6 * np.abs(sumso[:27]).max())      # measured: 1.3e-5 / 6e-8
 
 
 def test_rgb_and_so3_steps_match_oracle(orc, cuda):
