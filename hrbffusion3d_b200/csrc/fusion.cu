@@ -684,6 +684,19 @@ static int stage_current(hrbf_fusion* F, int b, int frame_number, cudaStream_t s
     return HRBF_OK;
 }
 
+// Everything of a frame that needs nothing but the uploaded camera frame, on stream s (the staging stream, or the caller's stream for
+// an unstaged frame); the SO3 pre-alignment -- a chain of <= 10 small dependent reductions -- runs beside it on its own stream.
+static int stage_all(hrbf_fusion* F, int b, int frame_number, cudaStream_t s)
+{
+    HRBF_CUDA(cudaEventRecord(F->ev_up, s));
+    HRBF_CUDA(cudaStreamWaitEvent(F->so3_stream, F->ev_up, 0));
+    if (int rc = stage_so3(F, b, frame_number, F->so3_stream)) return rc;
+    if (int rc = hrbf_frame_preprocess(F->frames[b], s)) return rc;
+    if (int rc = stage_current(F, b, frame_number, s)) return rc;
+    HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_so3[frame_number & 1], 0));
+    return HRBF_OK;
+}
+
 // preprocessed = true: frames[cur] was uploaded and preprocessed by hrbf_fusion_stage_frame (on the staging stream)
 static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, bool preprocessed = false)
 {
@@ -702,9 +715,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
 
     mark(0);
     if (!preprocessed) {
-        if (int rc = stage_so3(F, F->cur, F->tick, s)) return rc;
-        if (int rc = hrbf_frame_preprocess(fr, s)) return rc;
-        if (int rc = stage_current(F, F->cur, F->tick, s)) return rc;
+        if (int rc = stage_all(F, F->cur, F->tick, s)) return rc;
     }
     odom_select_bank(F->odom, F->tick & 1);
     mark(1);
@@ -903,12 +914,7 @@ int hrbf_fusion_stage_frame(hrbf_fusion* F, const unsigned char* rgb8, const uns
     if (F->ev_free_valid[b]) HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_free[b], 0));
     if (int rc = frame_upload(F->frames[b], rgb8, depth16, host, first, F->pre_stream)) return rc;
     const int frame_number = F->tick + (b != F->cur ? 1 : 0);
-    HRBF_CUDA(cudaEventRecord(F->ev_up, F->pre_stream));
-    HRBF_CUDA(cudaStreamWaitEvent(F->so3_stream, F->ev_up, 0));
-    if (int rc = stage_so3(F, b, frame_number, F->so3_stream)) return rc;
-    if (int rc = hrbf_frame_preprocess(F->frames[b], F->pre_stream)) return rc;
-    if (int rc = stage_current(F, b, frame_number, F->pre_stream)) return rc;
-    HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_so3[frame_number & 1], 0));
+    if (int rc = stage_all(F, b, frame_number, F->pre_stream)) return rc;
     HRBF_CUDA(cudaEventRecord(F->ev_staged[b], F->pre_stream));
     F->staged[b] = true;
     return HRBF_OK;

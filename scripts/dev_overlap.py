@@ -19,6 +19,7 @@ def timed(fn):
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)
 
+torch.cuda.set_stream(torch.cuda.Stream(priority=-1))      # above the library's staging streams
 for tt in (512, 384, 256):
     F = HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=tt)
     for i in range(8): F.processFrameDev(rgb[i % RING], depth[i % RING])
