@@ -674,7 +674,7 @@ static int stage_current(hrbf_fusion* F, int b, int frame_number, cudaStream_t s
     if (frame_number > 1 && !F->p.rgbOnly && F->model->a.pca) {      // the PCA normals GlobalModel::fuse will ask for (data.vert)
         ModelArgs a = F->model->a;
         a.maxDepth = F->p.maxDepthProcessed;
-        HRBF_LAUNCH_PDL(fuse_normals_kernel, dim3(div_up(F->model->n_slots, 128)), dim3(128), 0, s, a, F->model->pa, (const float*)fr->tex[HRBF_FT_DEPTH_METRIC],
+        HRBF_LAUNCH_PDL(fuse_normals_kernel, dim3(div_up(fuse_slots_x(a.cols), kFnTX), div_up(fuse_slots_y(a.rows), kFnTY)), dim3(kFnTX * kFnTY), 0, s, a, F->model->pa, (const float*)fr->tex[HRBF_FT_DEPTH_METRIC],
                         (const float*)fr->tex[HRBF_FT_DEPTH_METRIC_FILTERED], (const float4*)fr->tex[HRBF_FT_PRINCIPAL_CURV1], (const float4*)fr->tex[HRBF_FT_PRINCIPAL_CURV2],
                         frame_number, fr->fuse_normals);
         fr->fuse_normals_time = frame_number;

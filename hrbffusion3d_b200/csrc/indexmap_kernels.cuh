@@ -174,9 +174,11 @@ inline PredTable make_pred_table()
 // w0 = c0 - c_i:   |p - c_i|^2 / rho_i^2 = a + t (b + t c)      (a = |w0|^2/rho^2, b = 2 w0.r/rho^2, c = |r|^2/rho^2)
 //                  (p - c_i) . s_i        = cs + t ds            (s_i = (200/rho_i^2) n_i, cs = w0.s, ds = r.s)
 // f(p(t)) = -sum_i grad phi_i . (10 n_i) = sum_i (1 - sqrt(u_i))_+^3 (cs_i + t ds_i)   (hrbfbase.glsl:20-34,126-145):
-// 9 instructions per neighbour and evaluation, 5 registers per neighbour (40 for the 8 slots: no spills at 80 registers).
+// 9 operations per neighbour and evaluation, 5 registers per neighbour (40 for the 8 slots: no spills at 80 registers).
 // An empty slot has a = 4 (outside every support) and contributes exactly 0.
-struct NbRay { float a, b, c, cs, ds; };
+// Two neighbours (slots 2k, 2k+1) side by side: the evaluation runs on packed fp32 pairs (fma.rn.f32x2 -- FFMA2 / FMUL2 in SASS), which
+// on sm_100 halves the issue slots of the arithmetic (the kernel is issue-bound: 77 % issue-active, the FMA pipe itself has room).
+struct NbRay2 { float2 a, b, c, cs, ds; };
 
 // Window row r (dy = r - 3) with validity bits m (bit k: dx = k - 3) -> the mask of valid candidates in the shader's scan order.
 // A pixel's 49-candidate mask is the OR of 7 table entries instead of 49 tests.
@@ -194,17 +196,21 @@ inline void make_pred_row_lut(unsigned long long* lut /* [7][128] */)
 
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-__device__ __forceinline__ float hrbf_ray_value(const NbRay (&nb)[kPredSlots], bool upper_half, float t)
+__device__ __forceinline__ float hrbf_ray_value(const NbRay2 (&nb)[kPredSlots / 2], bool upper_half, float t)
 {
-    float value = 0.f;
+    const float2 t2 = make_float2(t, t), one2 = make_float2(1.0f, 1.0f), neg2 = make_float2(-1.0f, -1.0f);
+    float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int s = 0; s < kPredSlots; ++s) {
-        if (s >= kPredSlots / 2 && !upper_half) break;              // warp-uniform
-        const float u = fmaf(t, fmaf(t, nb[s].c, nb[s].b), nb[s].a);
-        const float q = fmaxf(1.0f - sqrt_approx(u), 0.0f);
-        value = fmaf(q * q * q, fmaf(t, nb[s].ds, nb[s].cs), value);
+    for (int k = 0; k < kPredSlots / 2; ++k) {
+        if (k >= kPredSlots / 4 && !upper_half) break;              // warp-uniform
+        const float2 u = __ffma2_rn(t2, __ffma2_rn(t2, nb[k].c, nb[k].b), nb[k].a);
+        const float2 sq = make_float2(sqrt_approx(u.x), sqrt_approx(u.y));
+        float2 q = __ffma2_rn(sq, neg2, one2);                      // 1 - sqrt(u)
+        q.x = fmaxf(q.x, 0.0f); q.y = fmaxf(q.y, 0.0f);
+        const float2 q3 = __fmul2_rn(__fmul2_rn(q, q), q);
+        acc = __ffma2_rn(q3, __ffma2_rn(t2, nb[k].ds, nb[k].cs), acc);
     }
-    return value;
+    return acc.x + acc.y;
 }
 
 // hrbfbase.glsl:147-166 (+ getWeightH :37-69) at point p, over this lane's neighbours (slot s -> s_sel[s * 4 + sub]), summed
@@ -350,11 +356,11 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
     const float c0x = projmin * rx, c0y = projmin * ry, c0z = projmin * rz;
 
     // per-neighbour ray coefficients (registers)
-    NbRay nb[kPredSlots];
+    NbRay2 nb[kPredSlots / 2];
     int cnt0 = 0;                                        // neighbours whose support contains the start point c0 (:152-157)
 #pragma unroll
     for (int sl = 0; sl < kPredSlots; ++sl) {
-        nb[sl].a = 4.0f; nb[sl].b = nb[sl].c = nb[sl].cs = nb[sl].ds = 0.f;
+        float na = 4.0f, nbb = 0.f, nc = 0.f, ncs = 0.f, nds = 0.f;
         if (sl < nslots) {
             float4 v, n;
             nb_at(sl, v, n);
@@ -362,13 +368,16 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
             const float wx = c0x - v.x, wy = c0y - v.y, wz = c0z - v.z;
             const float d2 = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
             const float k = 200.0f * iT2;
-            nb[sl].a = d2 * iT2;
-            nb[sl].b = 2.0f * fmaf(wz, rz, fmaf(wy, ry, wx * rx)) * iT2;
-            nb[sl].c = rr * iT2;
-            nb[sl].cs = k * fmaf(wz, n.z, fmaf(wy, n.y, wx * n.x));
-            nb[sl].ds = k * fmaf(rz, n.z, fmaf(ry, n.y, rx * n.x));
+            na = d2 * iT2;
+            nbb = 2.0f * fmaf(wz, rz, fmaf(wy, ry, wx * rx)) * iT2;
+            nc = rr * iT2;
+            ncs = k * fmaf(wz, n.z, fmaf(wy, n.y, wx * n.x));
+            nds = k * fmaf(rz, n.z, fmaf(ry, n.y, rx * n.x));
             cnt0 += !(T2 < d2) ? 1 : 0;
         }
+        NbRay2& d = nb[sl >> 1];
+        if (sl & 1) { d.a.y = na; d.b.y = nbb; d.c.y = nc; d.cs.y = ncs; d.ds.y = nds; }
+        else { d.a.x = na; d.b.x = nbb; d.c.x = nc; d.cs.x = ncs; d.ds.x = nds; }
     }
 
     // ---- interval search + bisection (:152-270) as ONE warp-convergent state machine over the ray parameter t ----

@@ -180,25 +180,36 @@ __host__ __device__ inline int fuse_slots_y(int rows) { return (rows + 1) / 2; }
 // data.vert:63-110 recomputes the PCA normal of the filtered depth at each candidate pixel (geometry.glsl with the uv VBO's texture
 // coordinates).  That needs the camera frame only, so the frame pipeline runs it ahead of the fuse, on its staging stream: same
 // slots, same rejection tests, same function.
-__global__ void __launch_bounds__(128) fuse_normals_kernel(ModelArgs m, PrepArgs pa, const float* __restrict__ depthRaw, const float* __restrict__ depthFiltered,
-                                                           const float4* __restrict__ curv1, const float4* __restrict__ curv2, int time, float4* __restrict__ out)
+// A CTA covers 16 x 8 candidate pixels (a 32 x 16 pixel patch) and serves the 7 x 7 windows from a shared-memory tile of the filtered depth.
+constexpr int kFnTX = 16, kFnTY = 8, kFnR = 3;
+__global__ void __launch_bounds__(kFnTX * kFnTY) fuse_normals_kernel(ModelArgs m, PrepArgs pa, const float* __restrict__ depthRaw, const float* __restrict__ depthFiltered,
+                                                                     const float4* __restrict__ curv1, const float4* __restrict__ curv2, int time, float4* __restrict__ out)
 {
     pdl_wait();
-    const int sxn = fuse_slots_x(m.cols), syn = fuse_slots_y(m.rows);
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= sxn * syn) return;
+    constexpr int SW = 2 * kFnTX + 2 * kFnR, SH = 2 * kFnTY + 2 * kFnR;
+    __shared__ float s_d[SH][SW + 1];
+    const int W = m.cols, H = m.rows, syn = fuse_slots_y(H), sxn = fuse_slots_x(W);
     const int par = time % 2;
-    const int px = 2 * (slot / syn) + par, py = 2 * (slot % syn) + par;
+    const int x0 = 2 * kFnTX * blockIdx.x + par - kFnR, y0 = 2 * kFnTY * blockIdx.y + par - kFnR;      // pixel of tile cell (0, 0)
+    for (int t = threadIdx.x; t < SH * SW; t += kFnTX * kFnTY) {
+        const int sy = t / SW, sx = t - sy * SW;
+        const int gx = x0 + sx, gy = y0 + sy;
+        s_d[sy][sx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(depthFiltered + (size_t)gy * W + gx) : 0.f;
+    }
+    __syncthreads();
+    const int cx = threadIdx.x % kFnTX, cy = threadIdx.x / kFnTX;
+    const int xs = kFnTX * blockIdx.x + cx, ys = kFnTY * blockIdx.y + cy;          // slot coordinates
+    if (xs >= sxn || ys >= syn) return;
+    const int px = 2 * xs + par, py = 2 * ys + par;
     float3 n = make_float3(0.f, 0.f, 0.f);
-    if (px < m.cols && py < m.rows && m.pca) {
-        const int W = m.cols;
+    if (px < W && py < H && m.pca) {
         const size_t o = (size_t)py * W + px;
-        const float z = __ldg(depthRaw + o), zf = __ldg(depthFiltered + o);
+        const float z = __ldg(depthRaw + o), zf = s_d[py - y0][px - x0];
         const float4 k1 = __ldg(curv1 + o), k2 = __ldg(curv2 + o);
         if (z > 0.3f && z <= m.maxDepth && k1.w > -300.0f && k1.w < 300.0f && k2.w > -300.0f && k2.w < 300.0f)
-            n = normal_pca(pa, [&](int qx, int qy) { return __ldg(depthFiltered + (size_t)qy * W + qx); }, px, py, zf, /* uv-VBO texcoords */ 1);
+            n = normal_pca(pa, [&](int qx, int qy) { return s_d[qy - y0][qx - x0]; }, px, py, zf, /* uv-VBO texcoords */ 1);
     }
-    out[slot] = make_float4(n.x, n.y, n.z, 0.f);
+    out[(size_t)xs * syn + ys] = make_float4(n.x, n.y, n.z, 0.f);
 }
 
 // One thread per candidate pixel (x%2 == t%2 && y%2 == t%2, data.vert:113).  Slot order = uv order (x outer, y inner).
