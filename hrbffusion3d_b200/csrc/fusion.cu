@@ -624,6 +624,8 @@ struct hrbf_fusion {
     cudaStream_t pre_stream = nullptr;              // staging stream (lowest priority)
     cudaStream_t so3_stream = nullptr;              // the staged SO3 pre-alignment, beside the preprocessing (lowest priority)
     cudaEvent_t ev_up = nullptr, ev_so3[2] = {};    // upload done (forks so3_stream) / SO3 pre-alignment of bank k done (joins)
+    cudaEvent_t ev_track = nullptr;                 // the model-side pyramids of the frame being processed are built: its tracker starts
+    bool ev_track_valid = false;
     bool ev_so3_valid[2] = { false, false };
     // tracker-input banks of the odometry (CurrBank): frame number k (1-based) uses bank k & 1, whichever frame buffer it sits in.
     // ev_curr[k]: bank k is built (the next frame's SO3 pre-alignment reads its image); ev_bank_free[k]: the frame that used it is done
@@ -746,6 +748,10 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
             in.dense_thresh = p.denseEnoughThresh; in.pose_dev = currPose;
             in.rgb8_c = (const unsigned char*)FT(HRBF_FT_RGB);
             if (int rc = odom_prep_all_dev(F->odom, in, s)) return rc;
+            // the next frame's staged kernels wait for this point: they fit beside the (latency-bound) tracker, whereas beside the
+            // pyramid kernel they would only delay the tracker's start
+            HRBF_CUDA(cudaEventRecord(F->ev_track, s));
+            F->ev_track_valid = true;
         }
         {
             // the persistent tracker also writes lastPose, the inverse pose, the fusion weight and the trajectory row
@@ -843,6 +849,7 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
             for (auto& e : F->ev) cudaEventCreate(&e);
             for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_curr[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_bank_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_so3[k], cudaEventDisableTiming); }
             cudaEventCreateWithFlags(&F->ev_up, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&F->ev_track, cudaEventDisableTiming);
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             if (cudaStreamCreateWithPriority(&F->pre_stream, cudaStreamNonBlocking, lo) != cudaSuccess ||
@@ -860,6 +867,7 @@ int hrbf_fusion_destroy(hrbf_fusion* F)
     if (F->pre_stream) cudaStreamDestroy(F->pre_stream);
     if (F->so3_stream) cudaStreamDestroy(F->so3_stream);
     if (F->ev_up) cudaEventDestroy(F->ev_up);
+    if (F->ev_track) cudaEventDestroy(F->ev_track);
     for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); if (F->ev_curr[k]) cudaEventDestroy(F->ev_curr[k]); if (F->ev_bank_free[k]) cudaEventDestroy(F->ev_bank_free[k]); if (F->ev_so3[k]) cudaEventDestroy(F->ev_so3[k]); }
     if (F->dev) cudaFree(F->dev);
     if (F->traj) cudaFree(F->traj);
@@ -912,6 +920,7 @@ int hrbf_fusion_stage_frame(hrbf_fusion* F, const unsigned char* rgb8, const uns
     // the first frame ever builds the RGBA texture (initFirstRGB); staged frame index = tick (+1 if it is the one after next)
     const bool first = F->tick + (b != F->cur ? 1 : 0) == 1;
     if (F->ev_free_valid[b]) HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_free[b], 0));
+    if (F->ev_track_valid) HRBF_CUDA(cudaStreamWaitEvent(F->pre_stream, F->ev_track, 0));
     if (int rc = frame_upload(F->frames[b], rgb8, depth16, host, first, F->pre_stream)) return rc;
     const int frame_number = F->tick + (b != F->cur ? 1 : 0);
     if (int rc = stage_all(F, b, frame_number, F->pre_stream)) return rc;
