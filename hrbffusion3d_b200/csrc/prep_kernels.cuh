@@ -67,6 +67,31 @@ __device__ __forceinline__ float exp_bilateral_fast(float x)
     return (x > -87.0f && e >= -125) ? __int_as_float(__float_as_int(p) + (e << 23)) : 0.0f;
 }
 
+// Two taps at once on packed fp32 pairs (fma.rn.f32x2 / mul.rn.f32x2: FFMA2 / FMUL2 in SASS): the weights exp_bilateral_fast gives for the taps
+// t.x and t.y that share the spatial term sp (dx and -dx of a window row).  Every packed operation rounds each half exactly like the
+// scalar sequence (value - tmp as fma(tmp, -1, value); (-a) * log2e as a * (-log2e); t - n as fma(n, -1, t)), so the weights are
+// bit-identical; the kernel is issue-bound and this halves the issue slots of the arithmetic.  x > -87 is implied by e >= -125
+// (x <= -87 gives t <= -125.51 and n = -126).
+__device__ __forceinline__ float2 exp_bilateral_pair(float2 value2, float2 t, float sc, float sp)
+{
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+    const float2 dc = __ffma2_rn(t, neg1, value2);
+    const float2 arg = __ffma2_rn(__fmul2_rn(dc, dc), make_float2(sc, sc), make_float2(sp, sp));
+    const float2 tt = __fmul2_rn(arg, make_float2(-1.44269504088896341f, -1.44269504088896341f));
+    const float2 n = make_float2(rintf(tt.x), rintf(tt.y));
+    const float2 f = __ffma2_rn(n, neg1, tt);
+    float2 p = make_float2(1.54035304e-4f, 1.54035304e-4f);
+    p = __ffma2_rn(p, f, make_float2(1.33335581e-3f, 1.33335581e-3f));
+    p = __ffma2_rn(p, f, make_float2(9.61812911e-3f, 9.61812911e-3f));
+    p = __ffma2_rn(p, f, make_float2(5.55041087e-2f, 5.55041087e-2f));
+    p = __ffma2_rn(p, f, make_float2(2.40226507e-1f, 2.40226507e-1f));
+    p = __ffma2_rn(p, f, make_float2(6.93147181e-1f, 6.93147181e-1f));
+    p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+    const int ex = (int)n.x, ey = (int)n.y;
+    return make_float2(ex >= -125 ? __int_as_float(__float_as_int(p.x) + (ex << 23)) : 0.0f,
+                       ey >= -125 ? __int_as_float(__float_as_int(p.y) + (ey << 23)) : 0.0f);
+}
+
 // ---- depth_bilateral.frag + depth_metric_raw.frag + depth_metric_filtered.frag -------------------------
 constexpr int kBilR = 6, kBilTW = 32, kBilTH = 8;
 // the pose-independent spatial term (dx^2 + dy^2) * 0.024691358f of each of the 13 x 13 taps, rounded like the shader does
@@ -111,19 +136,32 @@ __global__ void __launch_bounds__(256) depth_filter_metric_kernel(PrepArgs a, co
             float sum1 = 0.f, sum2 = 0.f;
             // tiles whose 13 x 13 windows lie inside the image (all but the border tiles) skip the per-tap bounds test
             const bool interior = x0 >= 0 && y0 >= 0 && x0 + kBilTW + 2 * kBilR <= W && y0 + kBilTH + 2 * kBilR <= H;
+            const float2 value2 = make_float2(value, value);
             auto window = [&](auto checked) {
                 for (int dy = -kBilR; dy <= kBilR; ++dy) {
                     const bool iny = (unsigned)(y + dy) < (unsigned)H;
                     const float* row = &s_t[ly + kBilR + dy][lx];
                     const float* sp = c_bil_space + (dy + kBilR) * (2 * kBilR + 1);
+                    constexpr int kTaps = 2 * kBilR + 1;
+                    float tmp[kTaps], w[kTaps];
 #pragma unroll
-                    for (int dx = -kBilR; dx <= kBilR; ++dx) {
-                        const float tmp = row[kBilR + dx];
-                        const float dc = __fsub_rn(value, tmp);
-                        const float color2 = __fmul_rn(dc, dc);
-                        float weight = exp_bilateral_fast(-fmaf(color2, sc, sp[dx + kBilR]));
-                        if (decltype(checked)::value && !(iny && (unsigned)(x + dx) < (unsigned)W)) weight = 0.f;
-                        sum1 = fmaf(tmp, weight, sum1);
+                    for (int k = 0; k < kTaps; ++k) tmp[k] = row[k];
+                    // the weights of a row, two taps (dx, -dx: the same spatial term) per packed operation; the centre tap alone
+#pragma unroll
+                    for (int k = 0; k < kBilR; ++k) {
+                        const float2 w2 = exp_bilateral_pair(value2, make_float2(tmp[k], tmp[kTaps - 1 - k]), sc, sp[k]);
+                        w[k] = w2.x; w[kTaps - 1 - k] = w2.y;
+                    }
+                    {
+                        const float dc = __fsub_rn(value, tmp[kBilR]);
+                        w[kBilR] = exp_bilateral_fast(-fmaf(__fmul_rn(dc, dc), sc, sp[kBilR]));
+                    }
+                    // the sums in the shader's tap order
+#pragma unroll
+                    for (int k = 0; k < kTaps; ++k) {
+                        float weight = w[k];
+                        if (decltype(checked)::value && !(iny && (unsigned)(x + k - kBilR) < (unsigned)W)) weight = 0.f;
+                        sum1 = fmaf(tmp[k], weight, sum1);
                         sum2 = __fadd_rn(sum2, weight);
                     }
                 }
