@@ -383,7 +383,7 @@ __device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& 
         const float j0 = __fsub_rn(uy, __fmul_rn(stepy, wm)), j1 = __fadd_rn(uy, __fmul_rn(stepy, wm));
         auto texel = [](float u, int n) {      // GL_NEAREST with 8 fractional bits of fixed point
             const float fixed = floorf(__fadd_rn(__fmul_rn(__fmul_rn(u, (float)n), 256.0f), 0.5f));
-            return min(max((int)floorf(__fdiv_rn(fixed, 256.0f)), 0), n - 1);
+            return min(max((int)floorf(fixed * 0.00390625f), 0), n - 1);      // / 256: a power of two, the product is the exact quotient
         };
         if (m.cleanWindow == 2) {
             // the reference default: per axis the (4, rarely 5) samples hit at most 3 distinct texels: each DISTINCT texel is fetched once
@@ -401,15 +401,13 @@ __device__ __forceinline__ bool clean_test(const ModelArgs& m, const CleanArgs& 
                 }
             }
             (void)nx; (void)ny;
-            int mx[kS], my[kS];        // multiplicity of sample a if it is the first of a run of equal texels, else 0
+            int mx[kS], my[kS];        // multiplicity of sample a if it is the first of a run of equal texels, else 0 (the samples ascend: runs are contiguous)
 #pragma unroll
             for (int a = 0; a < kS; ++a) {
                 int cx_ = 0, cy_ = 0;
 #pragma unroll
-                for (int b = 0; b < kS; ++b) { cx_ += (tx[b] == tx[a]) ? 1 : 0; cy_ += (ty[b] == ty[a]) ? 1 : 0; }
-                bool fx = tx[a] >= 0, fy = ty[a] >= 0;
-#pragma unroll
-                for (int b = 0; b < kS; ++b) if (b < a) { fx = fx && tx[b] != tx[a]; fy = fy && ty[b] != ty[a]; }
+                for (int b = 0; b < kS; ++b) if (b >= a) { cx_ += (tx[b] == tx[a]) ? 1 : 0; cy_ += (ty[b] == ty[a]) ? 1 : 0; }
+                const bool fx = tx[a] >= 0 && (a == 0 || tx[a] != tx[a > 0 ? a - 1 : 0]), fy = ty[a] >= 0 && (a == 0 || ty[a] != ty[a > 0 ? a - 1 : 0]);
                 mx[a] = fx ? cx_ : 0; my[a] = fy ? cy_ : 0;
             }
 #pragma unroll

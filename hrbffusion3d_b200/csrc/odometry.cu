@@ -855,7 +855,7 @@ int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, cu
     if (int rc = launch_prep_all(o, in, jobs, 3, s)) { odom_select_bank(o, before); return rc; }
     SobelCandArgs sc;
     for (int l = 0; l < 3; ++l) { sc.r[l] = rgbres_args(o, l); sc.cand[l] = o->cand[l]; }
-    HRBF_LAUNCH_PDL(sobel_cand_kernel, dim3(div_up(o->width * o->height, 256), 3), dim3(256), 0, s, sc);
+    HRBF_LAUNCH_PDL(sobel_cand_kernel, dim3(div_up(o->width, 32), div_up(o->height, 8), 3), dim3(256), 0, s, sc);
     o->bank[b].cand_ready = true;
     o->pack_dirty_curr = false;
     odom_select_bank(o, before);

@@ -583,12 +583,36 @@ struct SobelCandArgs { RgbResArgs r[3]; unsigned char* cand[3]; };
 __global__ void __launch_bounds__(256) sobel_cand_kernel(const SobelCandArgs a)
 {
     pdl_wait();
-    const RgbResArgs& r = a.r[blockIdx.y];
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= r.rows * r.cols) return;
-    const int y = k / r.cols, x = k - y * r.cols;
-    sobel_pixel(r.rows, r.cols, r.nextImage, const_cast<short*>(r.dIdx), const_cast<short*>(r.dIdy), x, y);
-    a.cand[blockIdx.y][k] = rgb_static_candidate(r, k, r.dIdx[k], r.dIdy[k]) ? 1 : 0;      // plain loads of this thread's own stores
+    const RgbResArgs& r = a.r[blockIdx.z];
+    const int cols = r.cols, rows = r.rows;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= cols || y >= rows) return;
+    const int k = y * cols + x;
+    short* dIdx = const_cast<short*>(r.dIdx);
+    short* dIdy = const_cast<short*>(r.dIdy);
+    if (x >= 2 && x < cols - 1 && y >= 2 && y < rows - 1) {
+        // interior: the 4 x 4 window of the zero test (rows y-2 .. y+1, columns x-2 .. x+1) contains the 3 x 3 Sobel window; the sums are
+        // small integers, so the float sums of sobel_pixel are exact in any order and the kernel weights fold into two differences
+        int p[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) p[u][v] = (int)__ldg(r.nextImage + (size_t)(y - 2 + u) * cols + (x - 2 + v));
+        const int dx = (p[1][3] + 2 * p[2][3] + p[3][3]) - (p[1][1] + 2 * p[2][1] + p[3][1]);
+        const int dy = (p[3][1] + 2 * p[3][2] + p[3][3]) - (p[1][1] + 2 * p[1][2] + p[1][3]);
+        dIdx[k] = (short)dx; dIdy[k] = (short)dy;
+        bool zero = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) zero = zero || p[u][v] == 0;
+        const short sx = (short)dx, sy = (short)dy;
+        const bool cand = x < cols - 5 && !zero && (float)((sx * sx) + (sy * sy)) >= r.minScale && !isnan(__ldg(r.nextDepth + k));
+        a.cand[blockIdx.z][k] = cand ? 1 : 0;
+        return;
+    }
+    sobel_pixel(rows, cols, r.nextImage, dIdx, dIdy, x, y);
+    a.cand[blockIdx.z][k] = rgb_static_candidate(r, k, dIdx[k], dIdy[k]) ? 1 : 0;      // plain loads of this thread's own stores
 }
 
 // The SO3 pre-alignment loop (RGBDOdometry.cpp:827-914) on the level-2 images of two consecutive camera frames: ONE CTA (4 800 pixels
