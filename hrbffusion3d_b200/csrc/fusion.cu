@@ -721,7 +721,11 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
     }
     odom_select_bank(F->odom, F->tick & 1);
     mark(1);
+    // a staged frame is needed from here on: by the map initialisation (first frame), else by the tracker -- the model-side pyramids
+    // before it read the previous prediction only, so the staging streams get the whole frame period
+    auto wait_staged = [&]() { return preprocessed ? cudaStreamWaitEvent(s, F->ev_staged[F->cur], 0) : cudaSuccess; };
     if (F->tick == 1) {
+        HRBF_CUDA(wait_staged());
         set_identity_pose_kernel<<<1, 32, 0, s>>>(currPose);
         HRBF_KERNEL_CHECK();
         if (int rc = model_initialise_dev(M, (const float*)FT(HRBF_FT_VERTEX_RAW), (const float*)FT(HRBF_FT_NORMAL), (const unsigned char*)FT(HRBF_FT_RGB),
@@ -752,6 +756,7 @@ static int fusion_frame(hrbf_fusion* F, float weightMultiplier, cudaStream_t s, 
             // pyramid kernel they would only delay the tracker's start
             HRBF_CUDA(cudaEventRecord(F->ev_track, s));
             F->ev_track_valid = true;
+            HRBF_CUDA(wait_staged());
         }
         {
             // the persistent tracker also writes lastPose, the inverse pose, the fusion weight and the trajectory row
@@ -934,7 +939,7 @@ int hrbf_fusion_process_staged(hrbf_fusion* F, long long timestamp, float weight
     HRBF_CHECK_ARG(F);
     if (!F->staged[F->cur]) { set_error("process_staged: no staged frame"); return HRBF_ERR_INVALID_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
-    HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_staged[F->cur], 0));
+    // (the staged frame is waited for inside fusion_frame, where it is first read: after the model-side pyramids)
     if (int rc = fusion_frame(F, weightMultiplier, s, true)) return rc;
     F->staged[F->cur] = false;
     F->cur ^= 1;

@@ -355,63 +355,78 @@ __global__ void __launch_bounds__(128) curvature_gradient_kernel(PrepArgs a, con
         (void)win;       // the tables are built for curvWin (hrbf_frame_create)
         const int qx0 = __ldg(a.wx[0].first + px), qx1 = qx0 + __ldg(a.wx[0].count + px) - 1, qy0 = __ldg(a.wy[0].first + py), qy1 = qy0 + __ldg(a.wy[0].count + py) - 1;
         int N = 0;
-        float gx = 0.f, gy = 0.f, gz = 0.f;                               // gradient
-        float h0 = 0.f, h1 = 0.f, h2 = 0.f, h4 = 0.f, h5 = 0.f, h8 = 0.f;   // "Hessian" entries g[0], g[1], g[2], g[4], g[5], g[8]
-        for (int qx = qx0; qx <= qx1; ++qx)
-            for (int qy = qy0; qy <= qy1; ++qy) {
-                const float4 v = s_v[qy - y0][qx - x0];
-                if (!(fabsf(v.z - vf.z) < 0.10f)) continue;
-                ++N;
-                const float4 n = s_n[qy - y0][qx - x0];                    // (sx, sy, sz) = 10 n, iT2 = 1 / rho^2
-                const float iT2 = n.w;
-                const float vx = vf.x - v.x, vy = vf.y - v.y, vz = vf.z - v.z;
-                const float d2 = vx * vx + vy * vy + vz * vz;
-                const float u = d2 * iT2;                                  // (|v| / rho)^2
-                if (u > 1.0f) continue;
-                if (d2 == 0.0f) {            // getWeightH: -20/T2 I ; getWeightT: 0
-                    const float h = -20.0f * iT2;
-                    gx -= n.x * h; gy -= n.y * h; gz -= n.z * h;
-                    continue;
-                }
-                // With s = 10 n, dvs = v.s, r = |v|/rho, q = 1 - r (hrbfbase.glsl:37-69, 72-123, 147-195):
-                //   gradient  -= H s,  H = t1 (3 v v^T + t2 I)          ->  t1 (3 dvs v + t2 s)
-                //   g[ij]     -= sum_k T_ijk s_k  with the shader's T (its 27 entries are restated in the oracle); collecting
-                //   terms:  diagonal ii : A v_i^2 + B + C s_i v_i      off-diagonal ij (i<j) : A v_i v_j + D s_i v_j + E s_j v_i
-                const float ir = rsqrtf(u), r = u * ir, q = 1.0f - r;
-                const float dvs = vx * n.x + vy * n.y + vz * n.z;
-                {
-                    const float t1 = 20.0f * (q * q) * (iT2 * iT2) * ir;
-                    const float t2 = -r * q * d2 * (ir * ir);              // -r q T2  (T2 = d2 / u)
-                    const float c3 = 3.0f * t1 * dvs, ct = t1 * t2;
-                    gx -= c3 * vx + ct * n.x;
-                    gy -= c3 * vy + ct * n.y;
-                    gz -= c3 * vz + ct * n.z;
-                }
-                {
-                    const float s2 = r - 2.0f + ir;
-                    const float s3 = 60.0f * (iT2 * iT2);
-                    const float pi_ = iT2 * ir;                            // 1 / (T2 r)
-                    const float kap = (1.0f - ir * ir) * pi_;
-                    const float tss_pi = q * q * ir;                       // T2 q^2 / (T2 r)
-                    const float A = s3 * kap * dvs, B = s3 * s2 * dvs, Cc = s3 * (tss_pi + s2), D = s3 * tss_pi, E = s3 * s2;
-                    (void)pi_;
-                    h0 -= A * (vx * vx) + B + Cc * (n.x * vx);
-                    h4 -= A * (vy * vy) + B + Cc * (n.y * vy);
-                    h8 -= A * (vz * vz) + B + Cc * (n.z * vz);
-                    h1 -= A * (vx * vy) + D * (n.x * vy) + E * (n.y * vx);
-                    h2 -= A * (vx * vz) + D * (n.x * vz) + E * (n.z * vx);
-                    h5 -= A * (vy * vz) + D * (n.y * vz) + E * (n.z * vy);
-                }
+        // Two neighbours per trip on packed fp32 pairs (FFMA2 / FMUL2 / FADD2: half the issue slots for the same arithmetic; the kernel is
+        // issue-bound).  A rejected neighbour (depth gap, outside the support, the pixel itself) stays in its lane with a harmless u and a
+        // zero mask on everything it adds; the pixel itself (d2 == 0: getWeightH = -20/T2 I, getWeightT = 0) is added on its own below.
+        float2 gx2 = make_float2(0.f, 0.f), gy2 = gx2, gz2 = gx2;                                   // gradient, one partial sum per lane
+        float2 h0 = gx2, h1 = gx2, h2 = gx2, h4 = gx2, h5 = gx2, h8 = gx2;                          // "Hessian" entries g[0], g[1], g[2], g[4], g[5], g[8]
+        const int ny = qy1 - qy0 + 1, ncell = (qx1 - qx0 + 1) * ny;
+        const float2 one2 = make_float2(1.0f, 1.0f), neg2 = make_float2(-1.0f, -1.0f);
+        const float2 pfx = make_float2(vf.x, vf.x), pfy = make_float2(vf.y, vf.y), pfz = make_float2(vf.z, vf.z);
+        auto bc = [](float a) { return make_float2(a, a); };
+        int wx_ = qx0 - x0, wy_ = qy0 - y0;                 // tile cell of the next window cell, in the shader's order (x outer, y inner)
+        const int wy_end = qy0 - y0 + ny;
+        for (int c = 0; c < ncell; c += 2) {
+            const int cax = wx_, cay = wy_;
+            if (++wy_ == wy_end) { wy_ = qy0 - y0; ++wx_; }
+            const bool has_b = c + 1 < ncell;
+            const int cbx = has_b ? wx_ : cax, cby = has_b ? wy_ : cay;
+            if (++wy_ == wy_end) { wy_ = qy0 - y0; ++wx_; }
+            const float4 va = s_v[cay][cax], vb = s_v[cby][cbx];
+            const float4 na = s_n[cay][cax], nb = s_n[cby][cbx];      // (sx, sy, sz) = 10 n, w = 1 / rho^2
+            const bool ina = fabsf(va.z - vf.z) < 0.10f, inb = has_b && fabsf(vb.z - vf.z) < 0.10f;
+            N += (ina ? 1 : 0) + (inb ? 1 : 0);
+            const float2 vx = __ffma2_rn(make_float2(va.x, vb.x), neg2, pfx), vy = __ffma2_rn(make_float2(va.y, vb.y), neg2, pfy), vz = __ffma2_rn(make_float2(va.z, vb.z), neg2, pfz);
+            const float2 sx = make_float2(na.x, nb.x), sy = make_float2(na.y, nb.y), sz = make_float2(na.z, nb.z), iT2 = make_float2(na.w, nb.w);
+            const float2 d2 = __ffma2_rn(vz, vz, __ffma2_rn(vy, vy, __fmul2_rn(vx, vx)));
+            const float2 u = __fmul2_rn(d2, iT2);                                                  // (|v| / rho)^2
+            const bool oka = ina && !(u.x > 1.0f) && d2.x != 0.0f, okb = inb && !(u.y > 1.0f) && d2.y != 0.0f;
+            if (ina && d2.x == 0.0f) { const float h = -20.0f * na.w; gx2.x -= na.x * h; gy2.x -= na.y * h; gz2.x -= na.z * h; }
+            if (inb && d2.y == 0.0f) { const float h = -20.0f * nb.w; gx2.y -= nb.x * h; gy2.y -= nb.y * h; gz2.y -= nb.z * h; }
+            if (!(oka || okb)) continue;
+            // a rejected lane: u = 1/4 and 1 / rho^2 = 0, which zeroes t1 and s3 and with them everything the lane adds
+            const float2 us = make_float2(oka ? u.x : 0.25f, okb ? u.y : 0.25f), iT2m = make_float2(oka ? na.w : 0.0f, okb ? nb.w : 0.0f);
+            // With s = 10 n, dvs = v.s, r = |v|/rho, q = 1 - r (hrbfbase.glsl:37-69, 72-123, 147-195):
+            //   gradient  -= H s,  H = t1 (3 v v^T + t2 I)          ->  t1 (3 dvs v + t2 s)
+            //   g[ij]     -= sum_k T_ijk s_k  with the shader's T (its 27 entries are restated in the oracle); collecting
+            //   terms:  diagonal ii : A v_i^2 + B + C s_i v_i      off-diagonal ij (i<j) : A v_i v_j + D s_i v_j + E s_j v_i
+            const float2 ir = make_float2(rsqrtf(us.x), rsqrtf(us.y)), r = __fmul2_rn(us, ir), q = __ffma2_rn(r, neg2, one2);
+            const float2 dvs = __ffma2_rn(vz, sz, __ffma2_rn(vy, sy, __fmul2_rn(vx, sx)));
+            const float2 iT4 = __fmul2_rn(iT2m, iT2m), qq = __fmul2_rn(q, q);
+            {
+                const float2 t1 = __fmul2_rn(__fmul2_rn(bc(20.0f), qq), __fmul2_rn(iT4, ir));
+                const float2 t2 = __fmul2_rn(__fmul2_rn(__fmul2_rn(r, q), neg2), __fmul2_rn(d2, __fmul2_rn(ir, ir)));      // -r q T2  (T2 = d2 / u)
+                const float2 c3 = __fmul2_rn(__fmul2_rn(bc(3.0f), t1), dvs), ct = __fmul2_rn(t1, t2);
+                gx2 = __ffma2_rn(__ffma2_rn(c3, vx, __fmul2_rn(ct, sx)), neg2, gx2);
+                gy2 = __ffma2_rn(__ffma2_rn(c3, vy, __fmul2_rn(ct, sy)), neg2, gy2);
+                gz2 = __ffma2_rn(__ffma2_rn(c3, vz, __fmul2_rn(ct, sz)), neg2, gz2);
             }
+            {
+                const float2 s2 = __fadd2_rn(__fadd2_rn(r, bc(-2.0f)), ir);
+                const float2 s3 = __fmul2_rn(bc(-60.0f), iT4);                                      // negated: the entries are subtracted
+                const float2 kap = __fmul2_rn(__ffma2_rn(__fmul2_rn(ir, ir), neg2, one2), __fmul2_rn(iT2m, ir));
+                const float2 tss_pi = __fmul2_rn(qq, ir);                                           // T2 q^2 / (T2 r)
+                const float2 A = __fmul2_rn(__fmul2_rn(s3, kap), dvs), B = __fmul2_rn(__fmul2_rn(s3, s2), dvs), Cc = __fmul2_rn(s3, __fadd2_rn(tss_pi, s2)),
+                             D = __fmul2_rn(s3, tss_pi), E = __fmul2_rn(s3, s2);
+                h0 = __fadd2_rn(h0, __ffma2_rn(A, __fmul2_rn(vx, vx), __ffma2_rn(Cc, __fmul2_rn(sx, vx), B)));
+                h4 = __fadd2_rn(h4, __ffma2_rn(A, __fmul2_rn(vy, vy), __ffma2_rn(Cc, __fmul2_rn(sy, vy), B)));
+                h8 = __fadd2_rn(h8, __ffma2_rn(A, __fmul2_rn(vz, vz), __ffma2_rn(Cc, __fmul2_rn(sz, vz), B)));
+                h1 = __fadd2_rn(h1, __ffma2_rn(A, __fmul2_rn(vx, vy), __ffma2_rn(D, __fmul2_rn(sx, vy), __fmul2_rn(E, __fmul2_rn(sy, vx)))));
+                h2 = __fadd2_rn(h2, __ffma2_rn(A, __fmul2_rn(vx, vz), __ffma2_rn(D, __fmul2_rn(sx, vz), __fmul2_rn(E, __fmul2_rn(sz, vx)))));
+                h5 = __fadd2_rn(h5, __ffma2_rn(A, __fmul2_rn(vy, vz), __ffma2_rn(D, __fmul2_rn(sy, vz), __fmul2_rn(E, __fmul2_rn(sz, vy)))));
+            }
+        }
+        const float gx = gx2.x + gx2.y, gy = gy2.x + gy2.y, gz = gz2.x + gz2.y;
+        const float H0 = h0.x + h0.y, H1 = h1.x + h1.y, H2 = h2.x + h2.y, H4 = h4.x + h4.y, H5 = h5.x + h5.y, H8 = h8.x + h8.y;
         if (N > 15) {
             gm = fabsf(gx * vn.x + gy * vn.y + gz * vn.z);
             const float gl = sqrtf(gx * gx + gy * gy + gz * gz);
             nopt = make_float4(gx / gl, gy / gl, gz / gl, vn.w);
             const float h_x = -gx / gz, h_y = -gy / gz;
             const float gz3 = gz * gz * gz;
-            const float h_xx = (2 * gx * gz * h2 - gx * gx * h8 - gz * gz * h0) / gz3;
-            const float h_xy = (gx * gz * h5 + gy * gz * h2 - gx * gy * h8 - gz * gz * h1) / gz3;
-            const float h_yy = (2 * gy * gz * h5 - gy * gy * h8 - gz * gz * h4) / gz3;
+            const float h_xx = (2 * gx * gz * H2 - gx * gx * H8 - gz * gz * H0) / gz3;
+            const float h_xy = (gx * gz * H5 + gy * gz * H2 - gx * gy * H8 - gz * gz * H1) / gz3;
+            const float h_yy = (2 * gy * gz * H5 - gy * gy * H8 - gz * gz * H4) / gz3;
             const float E = 1 + h_x * h_x, F = h_x * h_y, G = 1 + h_y * h_y;
             const float len = sqrtf(h_x * h_x + h_y * h_y + 1);
             const float L = h_xx / len, M = h_xy / len, Nn = h_yy / len;
