@@ -965,6 +965,9 @@ int hrbf_fusion_enable_timings(hrbf_fusion* F, int on) { HRBF_CHECK_ARG(F); F->t
 int hrbf_fusion_last_timings(hrbf_fusion* F, float ms4[4])
 {
     HRBF_CHECK_ARG(F && ms4);
+    if (F->timings && cudaEventQuery(F->ev[4]) == cudaSuccess)       // the last enqueued frame has finished: its spans (else the last ones read)
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&F->last_ms[k], F->ev[k], F->ev[k + 1]);
+    (void)cudaGetLastError();
     for (int k = 0; k < 4; ++k) ms4[k] = F->last_ms[k];
     return HRBF_OK;
 }

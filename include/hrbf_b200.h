@@ -462,7 +462,9 @@ hrbf_model* hrbf_fusion_model(hrbf_fusion*);
 hrbf_frame* hrbf_fusion_frame(hrbf_fusion*);
 hrbf_fillin* hrbf_fusion_fillin(hrbf_fusion*);
 /* CUDA-event timings of the last frame in ms, the reference's Stopwatch spans (HRBFFusion.cpp:1016,1063,1196,1248):
- * [0] Initialization [1] Registration [2] Integration [3] Prediction.  Only recorded when enabled. */
+ * [0] Initialization [1] Registration [2] Integration [3] Prediction.  Only recorded when enabled; the spans of the last enqueued frame
+ * once it has finished (synchronise first), else of the frame before.  With staged frames the Initialization span is empty: that work ran
+ * ahead on the staging streams. */
 int hrbf_fusion_enable_timings(hrbf_fusion*, int on);
 int hrbf_fusion_last_timings(hrbf_fusion*, float ms4_host[4]);
 

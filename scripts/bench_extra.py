@@ -66,8 +66,9 @@ def run(W, H, kind, poses, n_frames, name, capacity, **kw):
     pose_out = np.zeros(16, np.float32)
     for j in range(k):
         i = n_frames + j
-        F.stageFrame(rgb[(i + 1) % n_in], depth[(i + 1) % n_in])       # the next frame is staged first (two in flight): its staged kernels run beside this frame as in the timed loop
-        F.processStaged(pose_out)                            # synchronous: the four stage spans are read back
+        F.processStaged(None)                                # as in the timed loop: this frame, then the next frame's staging beside it ...
+        F.stageFrame(rgb[(i + 1) % n_in], depth[(i + 1) % n_in])
+        torch.cuda.synchronize()                             # ... and only then the read-back of the four stage spans
         acc += np.asarray(list(F.lastTimings().values()), np.float64)
     F.enableTimings(False)
     out = {"config": name, "width": W, "height": H, "frames": n_frames - 1, "frames_per_s": (n_frames - 1) / (ms * 1e-3), "ms_per_frame": ms / (n_frames - 1),

@@ -27,11 +27,12 @@ for tt in (512, 384, 256):
     print(f"TT={tt} serial : {ms / N * 1e3:7.1f} us/frame  {N / ms * 1e3:7.1f} fps")
     F.enableTimings(True)
     acc = np.zeros(4)
-    pose = np.zeros(16, np.float32)
-    for i in range(8 + N, 8 + N + 20):
-        F.stageFrame(rgb[i % RING], depth[i % RING]); F.processStaged(pose)
+    F.stageFrame(rgb[(8 + N) % RING], depth[(8 + N) % RING])
+    for i in range(8 + N, 8 + N + 20):          # pipelined as in the timed loop (this frame, then the next frame's staging beside it), read back after a sync
+        F.processStaged(None); F.stageFrame(rgb[(i + 1) % RING], depth[(i + 1) % RING]); torch.cuda.synchronize()
         acc += np.array(list(F.lastTimings().values()))
-    print("         stage spans of a frame processed alone (us):", np.round(acc / 20 * 1e3, 1), "(Initialization = preprocessing when unstaged, Registration, Integration, Prediction)")
+    F.processStaged(None); torch.cuda.synchronize()
+    print("         stage spans of the dependent chain, next frame's staging beside it (us):", np.round(acc / 20 * 1e3, 1), "(Initialization (staged: empty), Registration, Integration, Prediction)")
     del F
     F = HRBFFusion(W, H, cam, capacity=1 << 22, trackerThreads=tt)
     F.stageFrame(rgb[0], depth[0])
