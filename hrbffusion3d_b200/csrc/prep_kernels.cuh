@@ -54,7 +54,8 @@ __device__ __forceinline__ float exp_bilateral(float x)
 __device__ __forceinline__ float exp_bilateral_fast(float x)
 {
     const float t = __fmul_rn(x, 1.44269504088896341f);
-    const float n = rintf(t);
+    const float tb = __fadd_rn(fmaxf(t, -4194303.0f), 12582912.0f);      // rintf via the 1.5 * 2^23 trick (see exp_bilateral_pair); the clamp keeps it exact for any x
+    const float n = __fadd_rn(tb, -12582912.0f);
     const float f = __fsub_rn(t, n);
     float p = 1.54035304e-4f;
     p = fmaf(p, f, 1.33335581e-3f);
@@ -63,7 +64,7 @@ __device__ __forceinline__ float exp_bilateral_fast(float x)
     p = fmaf(p, f, 2.40226507e-1f);
     p = fmaf(p, f, 6.93147181e-1f);
     p = fmaf(p, f, 1.0f);
-    const int e = (int)n;
+    const int e = __float_as_int(tb) - 0x4B400000;
     return (x > -87.0f && e >= -125) ? __int_as_float(__float_as_int(p) + (e << 23)) : 0.0f;
 }
 
@@ -78,7 +79,11 @@ __device__ __forceinline__ float2 exp_bilateral_pair(float2 value2, float2 t, fl
     const float2 dc = __ffma2_rn(t, neg1, value2);
     const float2 arg = __ffma2_rn(__fmul2_rn(dc, dc), make_float2(sc, sc), make_float2(sp, sp));
     const float2 tt = __fmul2_rn(arg, make_float2(-1.44269504088896341f, -1.44269504088896341f));
-    const float2 n = make_float2(rintf(tt.x), rintf(tt.y));
+    // rintf(t) as (t + 1.5 * 2^23) - 1.5 * 2^23: exact for |t| < 2^22 (round to nearest even in both), and the integer sits in the low mantissa
+    // bits of the first sum -- no FRND / F2I (quarter-rate XU pipe: it was the busiest pipe of the kernel at 68 %)
+    const float2 big = make_float2(12582912.0f, 12582912.0f);
+    const float2 tb = __fadd2_rn(tt, big);
+    const float2 n = __fadd2_rn(tb, make_float2(-12582912.0f, -12582912.0f));
     const float2 f = __ffma2_rn(n, neg1, tt);
     float2 p = make_float2(1.54035304e-4f, 1.54035304e-4f);
     p = __ffma2_rn(p, f, make_float2(1.33335581e-3f, 1.33335581e-3f));
@@ -87,7 +92,7 @@ __device__ __forceinline__ float2 exp_bilateral_pair(float2 value2, float2 t, fl
     p = __ffma2_rn(p, f, make_float2(2.40226507e-1f, 2.40226507e-1f));
     p = __ffma2_rn(p, f, make_float2(6.93147181e-1f, 6.93147181e-1f));
     p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
-    const int ex = (int)n.x, ey = (int)n.y;
+    const int ex = __float_as_int(tb.x) - 0x4B400000, ey = __float_as_int(tb.y) - 0x4B400000;
     return make_float2(ex >= -125 ? __int_as_float(__float_as_int(p.x) + (ex << 23)) : 0.0f,
                        ey >= -125 ? __int_as_float(__float_as_int(p.y) + (ey << 23)) : 0.0f);
 }
