@@ -45,6 +45,8 @@ def lib():
         L.hrbf_odometry_map.restype = C.c_void_p
         L.hrbf_odometry_image.restype = C.c_void_p
         L.hrbf_odometry_depth.restype = C.c_void_p
+        L.hrbf_odometry_gradient.restype = C.c_void_p
+        L.hrbf_odometry_candidates.restype = C.c_void_p
         _lib = L
     return _lib
 

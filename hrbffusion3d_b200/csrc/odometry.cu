@@ -1182,7 +1182,18 @@ const float* hrbf_odometry_map(const hrbf_odometry* o, int which, int level, siz
 const unsigned char* hrbf_odometry_image(const hrbf_odometry* o, int which, int level)
 {
     if (!o || level < 0 || level > 2) return nullptr;
+    if (which == 3) return (o->banked && level == 2) ? o->bank[o->cur_bank].so3img : nullptr;      // what the staged SO3 pre-alignment read as "next"
     return which == 0 ? o->lastImage[level] : which == 1 ? o->nextImage[level] : o->lastNextImage[level];
+}
+const short* hrbf_odometry_gradient(const hrbf_odometry* o, int axis, int level)
+{
+    if (!o || level < 0 || level > 2 || axis < 0 || axis > 1) return nullptr;
+    return axis == 0 ? o->dIdx[level] : o->dIdy[level];
+}
+const unsigned char* hrbf_odometry_candidates(const hrbf_odometry* o, int level)
+{
+    if (!o || level < 0 || level > 2) return nullptr;
+    return o->cand[level];
 }
 const float* hrbf_odometry_depth(const hrbf_odometry* o, int which, int level)
 {

@@ -287,6 +287,11 @@ class HRBFFusion:
         with open(filename, "wb") as f:
             f.write(self.globalModel.exportPly(confThreshold))
 
+    def odometry(self):
+        """the pipeline's RGBDOdometry (borrowed view: pyramids, Sobel images, candidate masks of the frame last tracked)"""
+        from .odometry import RGBDOdometry
+        return RGBDOdometry.borrowed(lib().hrbf_fusion_odometry(self._h), self.width, self.height)
+
     def trajectory(self):
         n = C.c_int(0)
         p = lib().hrbf_fusion_trajectory_dev(self._h, C.byref(n))

@@ -30,10 +30,17 @@ class RGBDOdometry:
                                          C.c_float(distThresh), C.c_float(angleThresh)))
         self.last_stats = None
 
+    @classmethod
+    def borrowed(cls, handle, width, height):
+        """a view of an odometry object somebody else owns (hrbf_fusion_odometry): the accessors work, nothing is destroyed"""
+        o = cls.__new__(cls)
+        o.width, o.height, o._h, o._borrowed, o.last_stats = width, height, C.c_void_p(handle), True, None
+        return o
+
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and not getattr(self, "_borrowed", False):
             lib().hrbf_odometry_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         # at interpreter exit module globals (lib, C) may already be gone: nothing to release then, the process is ending
@@ -130,6 +137,22 @@ class RGBDOdometry:
     def image(self, which, level):
         rows, cols = self.height >> level, self.width >> level
         p = lib().hrbf_odometry_image(self._h, which, level)
+        out = torch.empty(rows * cols, dtype=torch.uint8, device="cuda")
+        _memcpy_d2d(out.data_ptr(), p, rows * cols)
+        return out.view(rows, cols)
+
+    def gradient(self, axis, level):
+        """next-image Sobel derivative (int16), axis 0 = dI/dx, 1 = dI/dy"""
+        rows, cols = self.height >> level, self.width >> level
+        p = lib().hrbf_odometry_gradient(self._h, axis, level)
+        out = torch.empty(rows * cols, dtype=torch.int16, device="cuda")
+        _memcpy_d2d(out.data_ptr(), p, rows * cols * 2)
+        return out.view(rows, cols)
+
+    def candidates(self, level):
+        """pose-independent candidate mask of computeRgbResidual (uint8)"""
+        rows, cols = self.height >> level, self.width >> level
+        p = lib().hrbf_odometry_candidates(self._h, level)
         out = torch.empty(rows * cols, dtype=torch.uint8, device="cuda")
         _memcpy_d2d(out.data_ptr(), p, rows * cols)
         return out.view(rows, cols)

@@ -244,8 +244,12 @@ int hrbf_odometry_icp_step(hrbf_odometry*, int level, const float* Rcurr_host, c
 /* device views of the internal pyramid maps (tests, chaining):
  * which = 0..8 -> vmap_g_prev,nmap_g_prev,ck1_g_prev,ck2_g_prev,vmap_curr,nmap_curr,ck1_curr,ck2_curr,icpWeight */
 const float* hrbf_odometry_map(const hrbf_odometry*, int which, int level, size_t* step_bytes);
-const unsigned char* hrbf_odometry_image(const hrbf_odometry*, int which, int level); /* 0 last, 1 next, 2 lastNext */
+const unsigned char* hrbf_odometry_image(const hrbf_odometry*, int which, int level); /* 0 last, 1 next, 2 lastNext, 3 (level 2, frame pipeline) the staged SO3 pre-alignment's image */
 const float* hrbf_odometry_depth(const hrbf_odometry*, int which, int level);        /* 0 last, 1 next */
+/* next-image Sobel derivatives (computeDerivativeImages, RGBDOdometry.cpp:951-956; short[rows][cols], axis 0 = dI/dx, 1 = dI/dy) and the
+ * pose-independent candidate mask of computeRgbResidual (reduce.cu:1000-1023; bytes) of the bank the tracker last used */
+const short* hrbf_odometry_gradient(const hrbf_odometry*, int axis, int level);
+const unsigned char* hrbf_odometry_candidates(const hrbf_odometry*, int level);
 
 /* ------------------------------------------------------------------------
  * Rows 6-7 : IndexMap  (Core/src/IndexMap.h:36-201)

@@ -318,3 +318,55 @@ def test_concurrent_sequences_on_one_gpu(orc, cuda):
         assert abs(cnt - c512) <= max(5, int(3e-3 * c512))
     with pytest.raises(HrbfError):
         HRBFFusion(W, H, cam, capacity=1 << 16, trackerThreads=320)
+
+
+def test_staged_tracker_inputs_match_their_definitions(orc, cuda):
+    """What the frame pipeline builds one frame ahead for the tracker (odom_stage_current_dev / odom_stage_so3_dev), checked directly on
+    the bank the tracker last read: the Sobel images against the stand-alone computeDerivativeImages kernel on the same next image
+    (bit-exact, including the clamped borders), the candidate mask against the pose-independent tests of computeRgbResidual
+    (reduce.cu:1000-1023) restated in numpy (bit-exact), and the level-2 image of the SO3 pre-alignment against the pyramid's."""
+    torch = cuda
+    import ctypes as C
+    from hrbffusion3d_b200.fusion import HRBFFusion
+    from hrbffusion3d_b200._lib import lib, check, stream_ptr
+    W, H, n = 640, 480, 3
+    cam, poses, fr = _frames(W, H, n)
+    F = HRBFFusion(W, H, cam, capacity=1 << 20)
+    F.stageFrame(torch.from_numpy(fr[0][1]).cuda(), torch.from_numpy(fr[0][0].view(np.int16)).cuda())
+    for i in range(n):
+        if i + 1 < n:
+            F.stageFrame(torch.from_numpy(fr[i + 1][1]).cuda(), torch.from_numpy(fr[i + 1][0].view(np.int16)).cuda())
+        F.processStaged(None)
+    torch.cuda.synchronize()
+    o = F.odometry()
+    assert torch.equal(o.image(3, 2), o.image(1, 2))          # built straight from the upload by so3_image_kernel == the pyramid's level 2
+    assert int((o.image(1, 2) != 0).sum()) > 1000
+    min_grad, sobel_scale = (5.0, 3.0, 1.0), 0.125
+    for lvl in range(3):
+        rows, cols = H >> lvl, W >> lvl
+        img = o.image(1, lvl)
+        dx, dy = torch.empty((rows, cols), dtype=torch.int16, device="cuda"), torch.empty((rows, cols), dtype=torch.int16, device="cuda")
+        check(lib().hrbf_compute_derivative_images(C.c_void_p(img.data_ptr()), C.c_size_t(cols), C.c_void_p(dx.data_ptr()), C.c_size_t(2 * cols),
+                                                  C.c_void_p(dy.data_ptr()), C.c_size_t(2 * cols), rows, cols, stream_ptr()))
+        torch.cuda.synchronize()
+        gx, gy = o.gradient(0, lvl), o.gradient(1, lvl)
+        assert torch.equal(gx, dx) and torch.equal(gy, dy), lvl
+        assert int((gx != 0).sum()) > rows * cols // 10
+        im = img.cpu().numpy()
+        depth = o.depth(1, lvl).cpu().numpy()
+        zero = np.zeros((rows, cols), bool)
+        for du in range(-2, 2):
+            for dv in range(-2, 2):
+                sh = np.zeros((rows, cols), bool)
+                ys, xs = slice(max(0, -du), rows - max(0, du)), slice(max(0, -dv), cols - max(0, dv))
+                yd, xd = slice(max(0, du), rows + min(0, du)), slice(max(0, dv), cols + min(0, dv))
+                sh[ys, xs] = im[yd, xd] == 0
+                zero |= sh
+        gxi, gyi = gx.cpu().numpy().astype(np.int64), gy.cpu().numpy().astype(np.int64)
+        m2 = (gxi * gxi + gyi * gyi).astype(np.float32)
+        min_scale = np.float32((min_grad[lvl] ** 2) / (sobel_scale ** 2))
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        want = (xx < cols - 5) & (yy < rows - 1) & ~zero & (m2 >= min_scale) & ~np.isnan(depth)
+        got = o.candidates(lvl).cpu().numpy().astype(bool)
+        assert want.sum() > 100
+        assert np.array_equal(got, want), (lvl, int((got != want).sum()))
