@@ -269,6 +269,19 @@ def test_staged_pipeline_is_identical_to_process_frame(orc, cuda):
         assert g.globalModel.lastCount() == ref.globalModel.lastCount()
         assert torch.equal(g.trajectory(), ref.trajectory())
         assert g.tick == n + 1
+    # staged and unstaged frames mixed in one sequence, enqueue-only (no host synchronisation between them): the tracker-input banks
+    # follow the frame number, whichever frame buffer and stream built them
+    g = HRBFFusion(W, H, cam, capacity=1 << 20)
+    g.processFrameDev(c_dev[0], d_dev[0])
+    g.processFrameDev(c_dev[1], d_dev[1])
+    g.stageFrame(c_dev[2], d_dev[2]); g.stageFrame(c_dev[3], d_dev[3])
+    g.processStaged(None); g.processStaged(None)
+    g.processFrameDev(c_dev[4], d_dev[4])
+    g.stageFrame(c_dev[5], d_dev[5]); g.processStaged(None)
+    g.processFrameDev(c_dev[6], d_dev[6])
+    torch.cuda.synchronize()
+    assert torch.equal(g.trajectory(), ref.trajectory())
+    assert g.globalModel.lastCount() == ref.globalModel.lastCount()
 
 
 def test_concurrent_sequences_on_one_gpu(orc, cuda):
