@@ -333,6 +333,19 @@ __device__ __forceinline__ float gauss_down_f32(int srows, int scols, int x, int
     const int D = 5;
     const int tx = min(2 * x - D / 2 + D, scols - 1), ty = min(2 * y - D / 2 + D, srows - 1);
     float sum = 0; int count = 0;
+    if (2 * x >= 2 && 2 * y >= 2 && tx == 2 * x + 3 && ty == 2 * y + 3) {
+        // interior: all 25 taps, same order, the (symmetric) kernel as immediates; the weights are integers, so count += g is the reference's
+        // count = (int)((float)count + g)
+        constexpr int G[25] = { 1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1 };
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float s = src_at(2 * x - 2 + i, 2 * y - 2 + j);
+                if (!isnan(s)) { sum = fmaf(s, (float)G[j * 5 + i], sum); count += G[j * 5 + i]; }
+            }
+        return sum / (float)count;
+    }
     for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
         for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
             const float s = src_at(cx, cy);
@@ -351,6 +364,20 @@ __device__ __forceinline__ unsigned char gauss_down_u8(int srows, int scols, int
     const int D = 5;
     const int tx = min(2 * x - D / 2 + D, scols - 1), ty = min(2 * y - D / 2 + D, srows - 1);
     float sum = 0; int count = 0;
+    if (2 * x >= 2 && 2 * y >= 2 && tx == 2 * x + 3 && ty == 2 * y + 3) {
+        // interior: all 25 taps; products and sums are small integers (<= 256 * 255), exact in fp32 in any order: integer arithmetic
+        constexpr int G[25] = { 1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1 };
+        int isum = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int v = (int)src_at(2 * x - 2 + i, 2 * y - 2 + j);
+                isum += v * G[j * 5 + i]; count += v > 0 ? G[j * 5 + i] : 0;
+            }
+        const float r = (float)isum / (float)count;
+        return isnan(r) ? (unsigned char)0 : (unsigned char)(int)r;
+    }
     for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
         for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
             const unsigned char s = src_at(cx, cy);
