@@ -28,6 +28,7 @@ def _scene(W, H, kind, stride):
     (320, 240, "room", 2, {}),                                              # sparse map: min-neighbour rejections
     (320, 240, "room", 1, dict(win=2, minNeighbors=4, maxNeighbors=16, confThreshold=4.5)),
     (640, 480, "room", 1, {}),                                              # BASELINE resolution, reference defaults
+    (1280, 960, "room", 1, dict(maxNeighbors=16)),                          # BASELINE config 4: the float counters of the ring loops (:74-80) at this texture size
 ])
 def test_predict_hrbf_oracle_matches_reference_shader(orc, W, H, kind, stride, kw):
     """row 6: Shaders/predict_hrbf.frag + hrbfbase.glsl + color.glsl + utils.glsl"""
@@ -72,7 +73,7 @@ def literal_windows(orc):
     orc.lib().orc_set_float_loops(default_float_loops())
 
 
-@pytest.mark.parametrize("W,H,kind", [(160, 120, "room"), (320, 240, "plane"), (640, 480, "room")])
+@pytest.mark.parametrize("W,H,kind", [(160, 120, "room"), (320, 240, "plane"), (640, 480, "room"), (1280, 960, "room")])
 def test_preprocess_oracle_matches_reference_shaders(orc, literal_windows, W, H, kind):
     """row 10: depth_bilateral.frag, depth_metric_raw/filtered.frag, depth_vertex_normal_radius.frag (+ geometry.glsl PCA normals,
     surfels.glsl radius / confidence), depth_curvature_gradient.frag (+ hrbfbase.glsl gradient / Hessian).
@@ -156,7 +157,7 @@ def test_vertex_confidence_and_fill_in_oracle_matches_reference_shaders(orc, use
         np.testing.assert_allclose(b["icpw"], a["icpw"], rtol=3e-6, atol=0)
 
 
-@pytest.mark.parametrize("W,H,kind", [(160, 120, "room"), (640, 480, "room"), (640, 480, "plane")])
+@pytest.mark.parametrize("W,H,kind", [(160, 120, "room"), (640, 480, "room"), (640, 480, "plane"), (1280, 960, "room")])
 def test_predict_indices_oracle_matches_reference_vertex_shader(orc, W, H, kind):
     """row 7: Shaders/index_map.vert per surfel (projection, depth / sub-map culling, normal rotation); the point rasterisation and
     the depth test are fixed-function GL, restated in the driver with the rules the oracle states.  The shader goes through
