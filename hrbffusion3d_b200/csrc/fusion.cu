@@ -264,6 +264,7 @@ struct hrbf_model {
     char* slab = nullptr;
     unsigned int* count[2] = {};               // device count of vbo[k]
     unsigned int* overflow = nullptr;
+    unsigned int* scan_ticket = nullptr;      // "last block done" counter of clean_flags_kernel (zero between launches)
     unsigned char* flags = nullptr;
     unsigned int *block_counts = nullptr, *block_offsets = nullptr, *winner = nullptr, *best = nullptr;
     unsigned char* update_id = nullptr;
@@ -351,8 +352,8 @@ int model_clean_dev(hrbf_model* m, const float* inv_pose_dev, int time, const un
     if (nb < 1) nb = 1;
     const int grid = nb < kNumSMs * 8 ? nb : kNumSMs * 8;
     const int nxt = m->cur ^ 1;
-    HRBF_LAUNCH_PDL(clean_flags_kernel, dim3(grid), dim3(kScanBlock), 0, s, a, c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_counts);
-    HRBF_LAUNCH_PDL(scan_blocks_kernel, dim3(1), dim3(1024), 0, s, m->block_counts, m->block_offsets, m->count[m->cur], (unsigned int)c.n_slots, m->capacity, m->count[nxt], m->overflow);
+    const ScanTail tail = { m->scan_ticket, m->block_offsets, m->capacity, m->count[nxt], m->overflow };      // the last block of the flags pass scans the block counts
+    HRBF_LAUNCH_PDL(clean_flags_kernel, dim3(grid), dim3(kScanBlock), 0, s, a, c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_counts, tail);
     HRBF_LAUNCH_PDL(clean_scatter_kernel, dim3(grid), dim3(kScanBlock), 0, s, c, m->vbo[m->cur], m->count[m->cur], m->flags, m->block_offsets, m->capacity, m->vbo[nxt]);
     m->cur = nxt;
     m->bound = n_bound < m->capacity ? n_bound : m->capacity;
@@ -395,7 +396,7 @@ int hrbf_model_create(hrbf_model** out, int width, int height, float cx, float c
     m->winner = (unsigned int*)(m->slab + o_win); m->best = (unsigned int*)(m->slab + o_best); m->update_id = (unsigned char*)(m->slab + o_uid);
     m->staging = (float4*)(m->slab + o_stage); m->pose = (float*)(m->slab + o_pose); m->inv_pose = (float*)(m->slab + o_inv);
     m->active_kf = (float*)(m->slab + o_kf);
-    m->count[0] = (unsigned int*)(m->slab + o_cnt); m->count[1] = m->count[0] + 1; m->overflow = m->count[0] + 2;
+    m->count[0] = (unsigned int*)(m->slab + o_cnt); m->count[1] = m->count[0] + 1; m->overflow = m->count[0] + 2; m->scan_ticket = m->count[0] + 3;
     // only the small control buffers need defined contents (the surfel arrays are written before they are read)
     cudaMemset(m->slab + o_flags, 0, off - o_flags);
     fill_u32_kernel<<<kNumSMs * 4, 256>>>(m->winner, (size_t)capacity, kNoWinner);

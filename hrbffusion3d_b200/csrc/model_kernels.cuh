@@ -58,36 +58,36 @@ __global__ void velocity_weighting_kernel(const float* __restrict__ curr, const 
 
 // ------------------------------------------------------------------ generic order-preserving compaction ---
 // flags (1 byte per item, written by a *_flags_kernel together with block_counts) -> block_offsets, total
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(const unsigned int* __restrict__ block_counts, unsigned int* __restrict__ block_offsets,
-                                                           const unsigned int* __restrict__ n_items_dev, unsigned int n_items_add,
-                                                           unsigned int capacity, unsigned int* __restrict__ total_out, unsigned int* __restrict__ overflow)
+// The exclusive scan of the per-block counts by ONE thread block of kThreads threads (all of them call it), + the total (clamped to the
+// capacity, overflow flagged).
+template <int kThreads>
+__device__ __forceinline__ void scan_blocks_cta(const unsigned int* block_counts, unsigned int* block_offsets, unsigned int n_items,
+                                                unsigned int capacity, unsigned int* total_out, unsigned int* overflow)
 {
-    pdl_wait();
-    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_warp[kThreads / 32];
     __shared__ unsigned int s_carry;
-    const unsigned int n_items = (n_items_dev ? *n_items_dev : 0u) + n_items_add;
     const unsigned int nb = (n_items + kScanBlock - 1) / kScanBlock;
     if (threadIdx.x == 0) s_carry = 0u;
     __syncthreads();
-    for (unsigned int base = 0; base < nb; base += 1024) {
+    for (unsigned int base = 0; base < nb; base += kThreads) {
         const unsigned int b = base + threadIdx.x;
-        const unsigned int v = b < nb ? block_counts[b] : 0u;
+        const unsigned int v = b < nb ? __ldcg(block_counts + b) : 0u;
         unsigned int x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
         if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
         __syncthreads();
         if (threadIdx.x < 32) {
-            unsigned int w = s_warp[threadIdx.x];
+            unsigned int w = threadIdx.x < kThreads / 32 ? s_warp[threadIdx.x] : 0u;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += y; }
-            s_warp[threadIdx.x] = w;
+            if (threadIdx.x < kThreads / 32) s_warp[threadIdx.x] = w;
         }
         __syncthreads();
         const unsigned int incl = x + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u) + s_carry;
         if (b < nb) block_offsets[b] = incl - v;
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = incl;
+        if (threadIdx.x == kThreads - 1) s_carry = incl;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -95,6 +95,13 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const unsigned int* _
         if (tot > capacity) { tot = capacity; *overflow = 1u; }
         *total_out = tot;
     }
+}
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const unsigned int* __restrict__ block_counts, unsigned int* __restrict__ block_offsets,
+                                                           const unsigned int* __restrict__ n_items_dev, unsigned int n_items_add,
+                                                           unsigned int capacity, unsigned int* __restrict__ total_out, unsigned int* __restrict__ overflow)
+{
+    pdl_wait();
+    scan_blocks_cta<1024>(block_counts, block_offsets, (n_items_dev ? *n_items_dev : 0u) + n_items_add, capacity, total_out, overflow);
 }
 
 // exclusive position of a flagged item inside its block (ballot + warp prefix)
@@ -454,8 +461,9 @@ __device__ __forceinline__ bool clean_load(const CleanArgs& c, const float4* __r
     for (int k = 0; k < 5; ++k) rec[k] = src[k];
     return true;
 }
+struct ScanTail { unsigned int* ticket; unsigned int* block_offsets; unsigned int capacity; unsigned int* total_out; unsigned int* overflow; };
 __global__ void __launch_bounds__(kScanBlock) clean_flags_kernel(ModelArgs m, CleanArgs c, const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
-                                                                 unsigned char* __restrict__ flags, unsigned int* __restrict__ block_counts)
+                                                                 unsigned char* __restrict__ flags, unsigned int* __restrict__ block_counts, ScanTail s)
 {
     pdl_wait();
     const unsigned int count = *count_dev, n = count + (unsigned int)c.n_slots;
@@ -473,6 +481,18 @@ __global__ void __launch_bounds__(kScanBlock) clean_flags_kernel(ModelArgs m, Cl
         const int cnt = __syncthreads_count(f);
         if (threadIdx.x == 0) block_counts[blk] = cnt;
     }
+    // the block that finishes last scans the counts (no separate single-block launch between the two passes); the ticket re-arms itself
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(s.ticket, 1u) == gridDim.x - 1;
+        if (s_last) *s.ticket = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    scan_blocks_cta<kScanBlock>(block_counts, s.block_offsets, n, s.capacity, s.total_out, s.overflow);
 }
 __global__ void __launch_bounds__(kScanBlock) clean_scatter_kernel(CleanArgs c, const float4* __restrict__ surfels, const unsigned int* __restrict__ count_dev,
                                                                    const unsigned char* __restrict__ flags, const unsigned int* __restrict__ block_offsets,
