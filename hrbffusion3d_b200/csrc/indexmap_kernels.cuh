@@ -263,9 +263,7 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
     __shared__ float4 s_v[kPredSH][kPredSW];
     __shared__ float4 s_n[kPredSH][kPredSW];
     __shared__ unsigned char s_sel[64][32];              // per pixel: tile cell (row * kPredSW + col) of each selected neighbour
-    __shared__ unsigned long long s_lut[7 * 128];        // make_pred_row_lut
     __shared__ unsigned int s_rowmask[kPredSH];          // per tile row: bit sx = the cell passes the (pixel-independent) neighbour tests
-    for (int t = threadIdx.x; t < 7 * 128; t += blockDim.x) s_lut[t] = __ldg(a.row_lut + t);
     if (threadIdx.x < kPredSH) s_rowmask[threadIdx.x] = 0u;
     __syncthreads();
     __shared__ PredTable s_tab;                          // the candidate tables: per-lane indices would serialise in the constant cache
@@ -301,7 +299,8 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
     // ---- neighbour gather (predict_hrbf.frag:74-113) ----
     const int ncand = s_tab.ring_end[a.win];
     unsigned long long valid = 0ull;
-    for (int r = sub; r < 7; r += kPredLanes) valid |= s_lut[r * 128 + ((s_rowmask[ly + r] >> lx) & 127u)];      // cells outside the image are invalid (z = 0)
+    // (the 7-KB table is read through L1: staging it in shared memory cost every 64-pixel CTA 900 loads + stores, a tenth of the kernel)
+    for (int r = sub; r < 7; r += kPredLanes) valid |= __ldg(a.row_lut + r * 128 + ((s_rowmask[ly + r] >> lx) & 127u));      // cells outside the image are invalid (z = 0)
     valid &= (1ull << ncand) - 1ull;                     // rings beyond `win` are not scanned
     valid |= __shfl_xor_sync(gmask, valid, 1);
     valid |= __shfl_xor_sync(gmask, valid, 2);
@@ -323,8 +322,8 @@ __global__ void __launch_bounds__(256, HRBF_PRED_MINBLOCKS) predict_hrbf_kernel(
     int N = __popcll(sel);
     if (N > 32) N = 32;                                 // cannot happen for maxN <= 16, win <= 3 (host-checked)
     // neighbour of rank j (in scan order) -> lane j & 3, slot j >> 2.  Every lane ranks the candidates it tested itself.
-    for (int c = sub; c < ncand; c += kPredLanes) {
-        if (!((sel >> c) & 1ull)) continue;
+    for (unsigned long long mine = sel & (0x1111111111111111ull << sub); mine != 0ull; mine &= mine - 1ull) {      // only the set bits of this lane's quarter
+        const int c = __ffsll((long long)mine) - 1;
         const int j = __popcll(sel & ((1ull << c) - 1ull));
         if (j < 32) s_sel[grp][j] = (unsigned char)((ly + kPredHalo + s_tab.dy[c]) * kPredSW + lx + kPredHalo + s_tab.dx[c]);
     }
