@@ -45,6 +45,25 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 // the first statement of every such kernel -- blocks until that previous kernel has completed and its writes are visible,
 // so the stream-order semantics are unchanged.  A no-op in a kernel launched the ordinary way.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Packed fp32 pairs, mul.rn.f32x2 / add.rn.f32x2 spelled in PTX.  CAUTION, measured in this repository: neither the CUDA intrinsics
+// __fmul2_rn / __fadd2_rn nor these PTX forms are protected against contraction the way scalar __fmul_rn / __fadd_rn are -- a packed
+// product whose only use is a packed sum comes out of ptxas as ONE FFMA2 (the PCA covariance sums lost their bit-exactness that way).
+// Where the scalar rounding sequence matters, keep the product scalar (or give it a second use), and check the SASS:
+// tests/test_abi.py::test_exact_packed_sequences_are_not_contracted.
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b)
+{
+    float2 r;
+    asm("{ .reg .b64 ma, mb, md; mov.b64 ma, {%2, %3}; mov.b64 mb, {%4, %5}; mul.rn.f32x2 md, ma, mb; mov.b64 {%0, %1}, md; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b)
+{
+    float2 r;
+    asm("{ .reg .b64 ma, mb, md; mov.b64 ma, {%2, %3}; mov.b64 mb, {%4, %5}; add.rn.f32x2 md, ma, mb; mov.b64 {%0, %1}, md; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
 // lets the NEXT kernel of the stream (if launched with programmatic serialization) be scheduled as soon as SM resources free up,
 // instead of after this grid has drained; it still blocks in its own pdl_wait() until this grid has completed
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

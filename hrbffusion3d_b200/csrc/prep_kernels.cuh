@@ -77,13 +77,13 @@ __device__ __forceinline__ float2 exp_bilateral_pair(float2 value2, float2 t, fl
 {
     const float2 neg1 = make_float2(-1.0f, -1.0f);
     const float2 dc = __ffma2_rn(t, neg1, value2);
-    const float2 arg = __ffma2_rn(__fmul2_rn(dc, dc), make_float2(sc, sc), make_float2(sp, sp));
-    const float2 tt = __fmul2_rn(arg, make_float2(-1.44269504088896341f, -1.44269504088896341f));
+    const float2 arg = __ffma2_rn(mul2_rn(dc, dc), make_float2(sc, sc), make_float2(sp, sp));
+    const float2 tt = mul2_rn(arg, make_float2(-1.44269504088896341f, -1.44269504088896341f));      // (must not fuse with the sum below)
     // rintf(t) as (t + 1.5 * 2^23) - 1.5 * 2^23: exact for |t| < 2^22 (round to nearest even in both), and the integer sits in the low mantissa
     // bits of the first sum -- no FRND / F2I (quarter-rate XU pipe: it was the busiest pipe of the kernel at 68 %)
     const float2 big = make_float2(12582912.0f, 12582912.0f);
-    const float2 tb = __fadd2_rn(tt, big);
-    const float2 n = __fadd2_rn(tb, make_float2(-12582912.0f, -12582912.0f));
+    const float2 tb = add2_rn(tt, big);
+    const float2 n = add2_rn(tb, make_float2(-12582912.0f, -12582912.0f));
     const float2 f = __ffma2_rn(n, neg1, tt);
     float2 p = make_float2(1.54035304e-4f, 1.54035304e-4f);
     p = __ffma2_rn(p, f, make_float2(1.33335581e-3f, 1.33335581e-3f));
@@ -243,23 +243,37 @@ __device__ __forceinline__ float3 normal_pca(const PrepArgs& a, DepthAt depth_at
     // The covariance is a difference of nearly equal numbers (E[x^2] - E[x]^2 with |x| ~ 1 m and a spread of
     // centimetres), so the normal inherits ~1e-3 of relative round-off: only a bit-identical evaluation order
     // reproduces the oracle.  Hence explicit _rn arithmetic (no FMA contraction) for the sums and the covariance.
-    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+    // The nine sums as four packed pairs + one scalar (add2_rn, common.cuh: each half rounded like the scalar operation, and every sum
+    // keeps its order): (XX, XY), (Xz, YY), (Yz, zz), (X, Y), z.  The sample coordinates of the window come from the tables once per column
+    // (x) and once per pixel (the <= 7 rows).
+    float2 s01 = make_float2(0.f, 0.f), s23 = s01, s45 = s01, s67 = s01;
+    float a8 = 0.f;
     int N = 0;
     const WinTab tx = a.wx[coord_variant], ty = a.wy[coord_variant];
     const int lx0 = __ldg(tx.first + px), lnx = __ldg(tx.count + px), ly0 = __ldg(ty.first + py), lny = __ldg(ty.count + py);
-    for (int ix = 0; ix < lnx; ++ix)
-        for (int iy = 0; iy < lny; ++iy) {
-            const int qx = lx0 + ix, qy = ly0 + iy;
-            const float z = depth_at(qx, qy);
-            const float fx_ = __ldg(tx.coord + px * kWinMax + ix), fy_ = __ldg(ty.coord + py * kWinMax + iy);
-            const float X = __fmul_rn(__fmul_rn(__fsub_rn(fx_, a.cx), z), a.icx), Y = __fmul_rn(__fmul_rn(__fsub_rn(fy_, a.cy), z), a.icy);
+    float dy[kWinMax - 1];
+#pragma unroll
+    for (int iy = 0; iy < kWinMax - 1; ++iy) dy[iy] = iy < lny ? __fsub_rn(__ldg(ty.coord + py * kWinMax + iy), a.cy) : 0.f;
+    for (int ix = 0; ix < lnx; ++ix) {
+        const float dx = __fsub_rn(__ldg(tx.coord + px * kWinMax + ix), a.cx);
+        const int qx = lx0 + ix;
+#pragma unroll
+        for (int iy = 0; iy < kWinMax - 1; ++iy) {
+            if (iy >= lny) break;
+            const float z = depth_at(qx, ly0 + iy);
             if (z > 0.3f && fabsf(__fsub_rn(z, vz)) < 0.05f) {
-                a0 = __fadd_rn(a0, __fmul_rn(X, X)); a1 = __fadd_rn(a1, __fmul_rn(X, Y)); a2 = __fadd_rn(a2, __fmul_rn(X, z));
-                a3 = __fadd_rn(a3, __fmul_rn(Y, Y)); a4 = __fadd_rn(a4, __fmul_rn(Y, z)); a5 = __fadd_rn(a5, __fmul_rn(z, z));
-                a6 = __fadd_rn(a6, X); a7 = __fadd_rn(a7, Y); a8 = __fadd_rn(a8, z);
+                const float X = __fmul_rn(__fmul_rn(dx, z), a.icx), Y = __fmul_rn(__fmul_rn(dy[iy], z), a.icy);
+                // scalar products: ptxas fuses a packed product that feeds a packed sum into one FFMA2 even when both carry .rn
+                s01 = add2_rn(s01, make_float2(__fmul_rn(X, X), __fmul_rn(X, Y)));
+                s23 = add2_rn(s23, make_float2(__fmul_rn(X, z), __fmul_rn(Y, Y)));
+                s45 = add2_rn(s45, make_float2(__fmul_rn(Y, z), __fmul_rn(z, z)));
+                s67 = add2_rn(s67, make_float2(X, Y));
+                a8 = __fadd_rn(a8, z);
                 ++N;
             }
         }
+    }
+    float a0 = s01.x, a1 = s01.y, a2 = s23.x, a3 = s23.y, a4 = s45.x, a5 = s45.y, a6 = s67.x, a7 = s67.y;
     if (N < 8) return make_float3(0.f, 0.f, 0.f);
     const float fn = (float)N;
     a0 = __fdiv_rn(a0, fn); a1 = __fdiv_rn(a1, fn); a2 = __fdiv_rn(a2, fn); a3 = __fdiv_rn(a3, fn); a4 = __fdiv_rn(a4, fn);

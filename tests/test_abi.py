@@ -178,3 +178,38 @@ def test_class_level_frame_loop_matches_the_fused_pipeline(tmp_path):
             d = float(np.abs(T - poses[i]).max())
             assert d <= tol, (icpWeight, so3, i, d)
         assert not np.allclose(poses[-1], np.eye(4))
+
+
+def test_exact_packed_sequences_are_not_contracted():
+    """The bit-exact kernels use packed fp32 pairs (add.rn.f32x2 / mul.rn.f32x2).  ptxas fuses a packed product whose only use is a packed
+    sum into one FFMA2 even when both carry .rn (measured: the PCA covariance sums lost their bit-exactness that way), so the SASS of
+    those kernels is pinned here: the PCA accumulation has packed sums and NO packed FMA; in the bilateral weights every pair site keeps
+    its two FMUL2 (colour difference squared, argument x -log2 e) and two FADD2 (the 1.5 * 2^23 rounding) next to the nine FFMA2 that
+    are FMAs in the scalar sequence too."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from hrbffusion3d_b200 import LIB_PATH
+    sass = subprocess.run(["cuobjdump", "-sass", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    funcs = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = {"FFMA2": 0, "FMUL2": 0, "FADD2": 0}
+        elif cur:
+            for op in ("FFMA2", "FMUL2", "FADD2"):
+                if re.search(r"\b%s\b" % op, line):
+                    funcs[cur][op] += 1
+    def of(name):
+        hits = [v for k, v in funcs.items() if name in k]
+        assert len(hits) == 1, (name, [k for k in funcs if name in k])
+        return hits[0]
+    for k in ("vertex_normal_radius_kernel", "fuse_normals_kernel", "fuse_associate_kernel"):
+        c = of(k)
+        assert c["FFMA2"] == 0 and c["FMUL2"] == 0 and c["FADD2"] > 0 and c["FADD2"] % 4 == 0, (k, c)
+    c = of("depth_filter_metric_kernel")
+    assert c["FMUL2"] > 0 and c["FMUL2"] == c["FADD2"] and 2 * c["FFMA2"] == 9 * c["FMUL2"], c
