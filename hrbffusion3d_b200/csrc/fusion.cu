@@ -625,6 +625,7 @@ struct hrbf_fusion {
     cudaStream_t pre_stream = nullptr;              // staging stream (lowest priority)
     cudaStream_t so3_stream = nullptr;              // the staged SO3 pre-alignment, beside the preprocessing (lowest priority)
     cudaEvent_t ev_up = nullptr, ev_so3[2] = {};    // upload done (forks so3_stream) / SO3 pre-alignment of bank k done (joins)
+    cudaEvent_t ev_img[2] = {};                     // the intensity pyramid of bank k is written (so3_stream; read by the staging stream)
     cudaEvent_t ev_track = nullptr;                 // the model-side pyramids of the frame being processed are built: its tracker starts
     bool ev_track_valid = false;
     bool ev_so3_valid[2] = { false, false };
@@ -657,7 +658,7 @@ static int stage_so3(hrbf_fusion* F, int b, int frame_number, cudaStream_t s)
     const int k = frame_number & 1;
     if (F->ev_bank_free_valid[k]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_bank_free[k], 0));   // frame_number - 2 read this bank's result
     if (F->ev_so3_valid[k ^ 1]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_so3[k ^ 1], 0));        // the other bank's image: written, and no longer compared with this bank's old one
-    if (int rc = odom_stage_so3_dev(F->odom, k, (const unsigned char*)F->frames[b]->tex[HRBF_FT_RGB], F->p.so3 != 0, frame_number != 1, s)) return rc;
+    if (int rc = odom_stage_so3_dev(F->odom, k, (const unsigned char*)F->frames[b]->tex[HRBF_FT_RGB], F->p.so3 != 0, frame_number != 1, F->ev_img[k], s)) return rc;
     HRBF_CUDA(cudaEventRecord(F->ev_so3[k], s));
     F->ev_so3_valid[k] = true;
     return HRBF_OK;
@@ -672,6 +673,7 @@ static int stage_current(hrbf_fusion* F, int b, int frame_number, cudaStream_t s
     in.k1c = (const float*)fr->tex[HRBF_FT_PRINCIPAL_CURV1]; in.k2c = (const float*)fr->tex[HRBF_FT_PRINCIPAL_CURV2];
     in.rgba_c = (const unsigned char*)fr->tex[HRBF_FT_RGBA]; in.rgb8_c = (const unsigned char*)fr->tex[HRBF_FT_RGB];
     if (F->ev_bank_free_valid[k]) HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_bank_free[k], 0));   // frame_number - 2 tracked from this bank
+    HRBF_CUDA(cudaStreamWaitEvent(s, F->ev_img[k], 0));      // recorded by this frame's stage_so3 (always called first)
     if (int rc = odom_stage_current_dev(F->odom, k, in, s)) return rc;
     fr->fuse_normals_time = -1;
     if (frame_number > 1 && !F->p.rgbOnly && F->model->a.pca) {      // the PCA normals GlobalModel::fuse will ask for (data.vert)
@@ -853,7 +855,7 @@ int hrbf_fusion_create(hrbf_fusion** out, const hrbf_fusion_params* p)
         else {
             cudaMemset(F->dev, 0, 64 * sizeof(float));
             for (auto& e : F->ev) cudaEventCreate(&e);
-            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_curr[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_bank_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_so3[k], cudaEventDisableTiming); }
+            for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&F->ev_staged[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_curr[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_bank_free[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_so3[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&F->ev_img[k], cudaEventDisableTiming); }
             cudaEventCreateWithFlags(&F->ev_up, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&F->ev_track, cudaEventDisableTiming);
             int lo = 0, hi = 0;
@@ -874,7 +876,7 @@ int hrbf_fusion_destroy(hrbf_fusion* F)
     if (F->so3_stream) cudaStreamDestroy(F->so3_stream);
     if (F->ev_up) cudaEventDestroy(F->ev_up);
     if (F->ev_track) cudaEventDestroy(F->ev_track);
-    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); if (F->ev_curr[k]) cudaEventDestroy(F->ev_curr[k]); if (F->ev_bank_free[k]) cudaEventDestroy(F->ev_bank_free[k]); if (F->ev_so3[k]) cudaEventDestroy(F->ev_so3[k]); }
+    for (int k = 0; k < 2; ++k) { if (F->ev_staged[k]) cudaEventDestroy(F->ev_staged[k]); if (F->ev_free[k]) cudaEventDestroy(F->ev_free[k]); if (F->ev_curr[k]) cudaEventDestroy(F->ev_curr[k]); if (F->ev_bank_free[k]) cudaEventDestroy(F->ev_bank_free[k]); if (F->ev_so3[k]) cudaEventDestroy(F->ev_so3[k]); if (F->ev_img[k]) cudaEventDestroy(F->ev_img[k]); }
     if (F->dev) cudaFree(F->dev);
     if (F->traj) cudaFree(F->traj);
     if (F->h_pose) cudaFreeHost(F->h_pose);

@@ -20,10 +20,10 @@ struct CurrBank {
     unsigned char* nextImage[HRBF_NUM_PYRS] = {}; float* nextDepth[HRBF_NUM_PYRS] = {};
     short* dIdx[HRBF_NUM_PYRS] = {}; short* dIdy[HRBF_NUM_PYRS] = {};
     unsigned char* cand[HRBF_NUM_PYRS] = {};
-    unsigned char* so3img = nullptr;             // level-2 intensity image of the camera frame (= nextImage[2]), built straight from the upload
     So3Pre* so3 = nullptr;                       // device: result of the staged SO3 pre-alignment
     void* tmaps = nullptr;                       // host tensor maps over this bank's records
     bool cand_ready = false, so3_ready = false;  // staged for the frame this bank holds
+    bool image_ready = false;                    // nextImage[] was built by so3_image_kernel (odom_stage_so3_dev): the pyramid job only adds the depth
 };
 }
 
@@ -132,7 +132,8 @@ void odom_select_bank(hrbf_odometry* o, int b);
 int odom_stage_current_dev(hrbf_odometry* o, int b, const OdomPrepInputs& in, cudaStream_t s);
 // The SO3 pre-alignment of the frame in bank b against the previous camera frame (bank b ^ 1): needs the uploaded RGB8 only, so
 // it can run beside the preprocessing (its <= 10 dependent reductions are latency, not work).
-int odom_stage_so3_dev(hrbf_odometry* o, int b, const unsigned char* rgb8, bool so3, bool has_previous, cudaStream_t s);
+// image_done (or null) is recorded once the bank's intensity pyramid is written (odom_stage_current_dev reads it).
+int odom_stage_so3_dev(hrbf_odometry* o, int b, const unsigned char* rgb8, bool so3, bool has_previous, cudaEvent_t image_done, cudaStream_t s);
 struct OdomFrameEpilogue { float* last_pose_out; float* inv_pose_out; float* weighting_out; float weight_multiplier; float* traj_out; };
 int odom_track_frame_dev(hrbf_odometry* o, float* pose_inout, const OdomFrameEpilogue& ep, bool rgbOnly, float icpWeight, bool pyramid,
                          bool fastOdom, bool so3, bool use_weight, cudaStream_t s);

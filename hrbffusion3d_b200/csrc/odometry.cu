@@ -791,7 +791,7 @@ int odom_enable_banks(hrbf_odometry* o)
         for (int k = 0; k < 2; ++k) o_pk[k][l] = take(P * sizeof(float4));
         o_ni[l] = take(P); o_nd[l] = take(P * 4); o_dx[l] = take(P * 2); o_dy[l] = take(P * 2); o_cd[l] = take(P);
     }
-    const size_t o_so3 = take(2 * sizeof(So3Pre)), o_si0 = take((size_t)o->rows(2) * o->cols(2)), o_si1 = take((size_t)o->rows(2) * o->cols(2));
+    const size_t o_so3 = take(2 * sizeof(So3Pre));
     if (cudaMalloc(&o->bank1_slab, off) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", off); return HRBF_ERR_CUDA; }
     HRBF_CUDA(cudaMemset(o->bank1_slab, 0, off));
     CurrBank& b1 = o->bank[1];
@@ -802,7 +802,6 @@ int odom_enable_banks(hrbf_odometry* o)
         b1.dIdx[l] = (short*)(o->bank1_slab + o_dx[l]); b1.dIdy[l] = (short*)(o->bank1_slab + o_dy[l]); b1.cand[l] = (unsigned char*)(o->bank1_slab + o_cd[l]);
     }
     o->bank[0].so3 = (So3Pre*)(o->bank1_slab + o_so3); b1.so3 = o->bank[0].so3 + 1;
-    o->bank[0].so3img = (unsigned char*)(o->bank1_slab + o_si0); b1.so3img = (unsigned char*)(o->bank1_slab + o_si1);
     o->banked = true;
     if (o->tmaps_host) {      // tensor maps over bank 1's records
         odom_select_bank(o, 1);
@@ -829,18 +828,23 @@ void odom_select_bank(hrbf_odometry* o, int b)
     o->cur_bank = b;
 }
 static int launch_prep_all(hrbf_odometry* o, const OdomPrepInputs& in, const int* jobs, int njobs, cudaStream_t s);
-int odom_stage_so3_dev(hrbf_odometry* o, int b, const unsigned char* rgb8, bool so3, bool has_previous, cudaStream_t s)
+int odom_stage_so3_dev(hrbf_odometry* o, int b, const unsigned char* rgb8, bool so3, bool has_previous, cudaEvent_t image_done, cudaStream_t s)
 {
     if (!o->banked) { set_error("odom_stage_so3_dev: banks not enabled"); return HRBF_ERR_INVALID_ARG; }
     CurrBank& cb = o->bank[b];
     cb.so3_ready = false;
-    if (!so3) return HRBF_OK;
-    RgbdJob j;
-    memset(&j, 0, sizeof j);
-    j.rgb8 = rgb8; j.img[2] = cb.so3img;
-    HRBF_LAUNCH_PDL(so3_image_kernel, dim3(div_up(o->cols(2), 8), div_up(o->rows(2), 8)), dim3(256), 0, s, j, o->height, o->width);
-    if (has_previous) {
-        HRBF_LAUNCH_PDL(so3_prealign_kernel, dim3(1), dim3(kSo3Threads), 0, s, (const unsigned char*)o->bank[b ^ 1].so3img, (const unsigned char*)cb.so3img,
+    cb.image_ready = false;
+    if (so3) {
+        RgbdJob j;
+        memset(&j, 0, sizeof j);
+        j.rgb8 = rgb8;
+        for (int l = 0; l < 3; ++l) j.img[l] = cb.nextImage[l];
+        HRBF_LAUNCH_PDL(so3_image_kernel, dim3(div_up(o->cols(2), 8), div_up(o->rows(2), 8)), dim3(256), 0, s, j, o->height, o->width);
+        cb.image_ready = true;
+    }
+    if (image_done) HRBF_CUDA(cudaEventRecord(image_done, s));
+    if (so3 && has_previous) {
+        HRBF_LAUNCH_PDL(so3_prealign_kernel, dim3(1), dim3(kSo3Threads), 0, s, (const unsigned char*)o->bank[b ^ 1].nextImage[2], (const unsigned char*)cb.nextImage[2],
                         o->rows(2), o->cols(2), o->intr.fx, o->intr.fy, o->intr.cx, o->intr.cy, cb.so3);
         cb.so3_ready = true;
     }
@@ -872,6 +876,7 @@ static int launch_prep_all(hrbf_odometry* o, const OdomPrepInputs& in, const int
 {
     PrepAllArgs A;
     for (int k = 0; k < 7; ++k) A.jobs[k] = k < njobs ? jobs[k] : 0;
+    A.cur_depth_only = (o->banked && o->bank[o->cur_bank].image_ready) ? 1 : 0;
     A.rows = o->height; A.cols = o->width; A.sel = in.sel; A.pose = in.pose_dev;
     A.dense_count = in.dense_count; A.dense_count_reset = in.dense_count_reset; A.dense_thresh = in.dense_thresh; A.curv_thr = o->curvThr; A.depth_cutoff = o->maxDepthRGB;
     A.vm = (const float4*)in.vm; A.nm = (const float4*)in.nm; A.vm_alt = (const float4*)in.vm_alt; A.nm_alt = (const float4*)in.nm_alt;
@@ -1182,7 +1187,7 @@ const float* hrbf_odometry_map(const hrbf_odometry* o, int which, int level, siz
 const unsigned char* hrbf_odometry_image(const hrbf_odometry* o, int which, int level)
 {
     if (!o || level < 0 || level > 2) return nullptr;
-    if (which == 3) return (o->banked && level == 2) ? o->bank[o->cur_bank].so3img : nullptr;      // what the staged SO3 pre-alignment read as "next"
+    if (which == 3) return (o->banked && level == 2) ? o->bank[o->cur_bank].nextImage[2] : nullptr;      // what the staged SO3 pre-alignment read as "next"
     return which == 0 ? o->lastImage[level] : which == 1 ? o->nextImage[level] : o->lastNextImage[level];
 }
 const short* hrbf_odometry_gradient(const hrbf_odometry* o, int axis, int level)

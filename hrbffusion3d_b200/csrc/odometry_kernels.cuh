@@ -445,19 +445,22 @@ struct PrepAllArgs {
     float* o_w[3]; int w_pitch[3];
     RgbdJob rgbd[2];                             // [0] model ("last"), [1] current ("next")
     int pyr_bx, pyr_by, rgbd_bx, rgbd_by;        // tiles per job
+    int cur_depth_only;                          // job 1: the intensity pyramid of the camera frame exists already (so3_image_kernel)
     int jobs[7];                                 // blockIdx.z -> job (gridDim.z = number of jobs): 0, 1 RGB-D pyramids (model, current), 2..5 map pairs, 6 weight
 };
 
 constexpr int kRgbdL0 = 41, kRgbdL1 = 19;        // tile edge at level 0 / 1 for an 8x8 level-2 tile
 
-// kImageOnly: only the level-2 intensity image is produced (what the SO3 pre-alignment reads), nothing else is loaded or stored
-template <bool kImageOnly = false>
+// kMode 0: intensity + depth pyramids; 1: the three intensity levels only (needs nothing but the RGB upload: the frame pipeline runs it
+// first, for the SO3 pre-alignment); 2: the three depth levels only (the other half of a frame whose intensity pyramid exists already)
+template <int kMode = 0>
 __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, int cols, float depth_cutoff, bool use_alt, int bx, int by)
 {
-    __shared__ unsigned char s_g0[kRgbdL0][kRgbdL0 + 3];
-    __shared__ float s_d0[kImageOnly ? 1 : kRgbdL0][kImageOnly ? 1 : kRgbdL0];
-    __shared__ unsigned char s_g1[kRgbdL1][kRgbdL1 + 1];
-    __shared__ float s_d1[kImageOnly ? 1 : kRgbdL1][kImageOnly ? 1 : kRgbdL1];
+    constexpr bool kImage = kMode != 2, kDepth = kMode != 1;
+    __shared__ unsigned char s_g0[kImage ? kRgbdL0 : 1][kImage ? kRgbdL0 + 3 : 1];
+    __shared__ float s_d0[kDepth ? kRgbdL0 : 1][kDepth ? kRgbdL0 : 1];
+    __shared__ unsigned char s_g1[kImage ? kRgbdL1 : 1][kImage ? kRgbdL1 + 1 : 1];
+    __shared__ float s_d1[kDepth ? kRgbdL1 : 1][kDepth ? kRgbdL1 : 1];
     const uchar4* rgba = use_alt ? j.rgba_alt : j.rgba;
     const float4* vert = use_alt ? j.vertex_alt : j.vertex;
     const int rows1 = rows / 2, cols1 = cols / 2, rows2 = rows1 / 2, cols2 = cols1 / 2;
@@ -469,14 +472,18 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
         const int gx = X0 + sx, gy = Y0 + sy;
         if (gx < 0 || gy < 0 || gx >= cols || gy >= rows) continue;
         const size_t o = (size_t)gy * cols + gx;
-        const unsigned char g = j.rgb8 != nullptr ? bgr_intensity(make_uchar4(__ldg(j.rgb8 + 3 * o), __ldg(j.rgb8 + 3 * o + 1), __ldg(j.rgb8 + 3 * o + 2), 255))
-                                                  : bgr_intensity(__ldg(rgba + o));
-        s_g0[sy][sx] = g;
-        if (!kImageOnly) {
+        const bool own = sx >= 6 && sx < 38 && sy >= 6 && sy < 38;
+        if (kImage) {
+            const unsigned char g = j.rgb8 != nullptr ? bgr_intensity(make_uchar4(__ldg(j.rgb8 + 3 * o), __ldg(j.rgb8 + 3 * o + 1), __ldg(j.rgb8 + 3 * o + 2), 255))
+                                                      : bgr_intensity(__ldg(rgba + o));
+            s_g0[sy][sx] = g;
+            if (own) j.img[0][o] = g;
+        }
+        if (kDepth) {
             const float z = __ldg(reinterpret_cast<const float*>(vert + o) + 2);
             const float d = (z > depth_cutoff || z <= 0.f) ? qn : z;
             s_d0[sy][sx] = d;
-            if (sx >= 6 && sx < 38 && sy >= 6 && sy < 38) { j.img[0][o] = g; j.depth[0][o] = d; }
+            if (own) j.depth[0][o] = d;
         }
     }
     __syncthreads();
@@ -484,30 +491,34 @@ __device__ __forceinline__ void rgbd_pyramid_tile(const RgbdJob& j, int rows, in
         const int sy = t / kRgbdL1, sx = t - sy * kRgbdL1;
         const int x1 = X1 + sx, y1 = Y1 + sy;
         if (x1 < 0 || y1 < 0 || x1 >= cols1 || y1 >= rows1) continue;
-        const unsigned char g = gauss_down_u8(rows, cols, x1, y1, [&](int cx, int cy) { return s_g0[cy - Y0][cx - X0]; });
-        s_g1[sy][sx] = g;
-        if (!kImageOnly) {
+        const bool own = sx >= 2 && sx < 18 && sy >= 2 && sy < 18;
+        if (kImage) {
+            const unsigned char g = gauss_down_u8(rows, cols, x1, y1, [&](int cx, int cy) { return s_g0[cy - Y0][cx - X0]; });
+            s_g1[sy][sx] = g;
+            if (own) j.img[1][(size_t)y1 * cols1 + x1] = g;
+        }
+        if (kDepth) {
             const float d = gauss_down_f32(rows, cols, x1, y1, [&](int cx, int cy) { return s_d0[cy - Y0][cx - X0]; });
             s_d1[sy][sx] = d;
-            if (sx >= 2 && sx < 18 && sy >= 2 && sy < 18) { j.img[1][(size_t)y1 * cols1 + x1] = g; j.depth[1][(size_t)y1 * cols1 + x1] = d; }
+            if (own) j.depth[1][(size_t)y1 * cols1 + x1] = d;
         }
     }
     __syncthreads();
     if (threadIdx.x < 64) {
         const int x2 = 8 * bx + (threadIdx.x & 7), y2 = 8 * by + (threadIdx.x >> 3);
         if (x2 < cols2 && y2 < rows2) {
-            j.img[2][(size_t)y2 * cols2 + x2] = gauss_down_u8(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_g1[cy - Y1][cx - X1]; });
-            if (!kImageOnly) j.depth[2][(size_t)y2 * cols2 + x2] = gauss_down_f32(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_d1[cy - Y1][cx - X1]; });
+            if (kImage) j.img[2][(size_t)y2 * cols2 + x2] = gauss_down_u8(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_g1[cy - Y1][cx - X1]; });
+            if (kDepth) j.depth[2][(size_t)y2 * cols2 + x2] = gauss_down_f32(rows1, cols1, x2, y2, [&](int cx, int cy) { return s_d1[cy - Y1][cx - X1]; });
         }
     }
 }
 
-// the level-2 intensity image of a camera frame alone (the input of the SO3 pre-alignment), straight from the uploaded RGB8:
-// identical values to the image pyramid prep_all_kernel builds later
+// the intensity pyramid of a camera frame alone, straight from the uploaded RGB8: the input of the SO3 pre-alignment (level 2) and of
+// the Sobel images / photometric residual; prep_all_kernel then only adds the depth pyramid (PrepAllArgs::cur_depth_only)
 __global__ void __launch_bounds__(256) so3_image_kernel(const RgbdJob j, int rows, int cols)
 {
     pdl_wait();
-    rgbd_pyramid_tile<true>(j, rows, cols, 0.f, false, blockIdx.x, blockIdx.y);
+    rgbd_pyramid_tile<1>(j, rows, cols, 0.f, false, blockIdx.x, blockIdx.y);
 }
 
 __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
@@ -537,7 +548,8 @@ __global__ void __launch_bounds__(256) prep_all_kernel(const PrepAllArgs A)
     }
     const int job = job_z;
     const bool use_alt = job == 0 && alt;
-    rgbd_pyramid_tile(A.rgbd[job], A.rows, A.cols, A.depth_cutoff, use_alt, bx, by);
+    if (job == 1 && A.cur_depth_only) rgbd_pyramid_tile<2>(A.rgbd[job], A.rows, A.cols, A.depth_cutoff, use_alt, bx, by);
+    else rgbd_pyramid_tile<0>(A.rgbd[job], A.rows, A.cols, A.depth_cutoff, use_alt, bx, by);
 }
 __device__ __forceinline__ void sobel_pixel(int rows, int cols, const unsigned char* __restrict__ src, short* dx, short* dy, int x, int y)
 {
