@@ -13,8 +13,10 @@ A "step" is one frame through the hot path on the workload named in `config.work
              on a bounded sample of the same frames
 Offline throughput (the metric): `--sequences S` (default 3) independent sequences per GPU, each a complete pipeline object on
 its own stream with a 256-thread tracker, so that one sequence's latency-bound Gauss-Newton loop shares the SMs with the
-other sequences' ALU-bound kernels; a step = one frame of every sequence.  `single_sequence` in the same line is the live
-single-camera path (one sequence, 384-thread tracker: the staged preprocessing of frame t+1 runs beside the tracker of frame t), measured the same way in the same run.
+other sequences' ALU-bound kernels; a step = one frame of every sequence.  Every sequence is replayed through the staged API
+(process frame t on a priority -1 stream; stage frame t+1: everything that depends on the camera frame alone runs one frame ahead on
+the library's lowest-priority streams).  `single_sequence` in the same line is ONE such sequence (384-thread tracker: the staged
+kernels of frame t+1 run beside the tracker of frame t), measured the same way in the same run.
 N > 1 : one process per GPU (torchrun), S independent sequences per rank (weak scaling), NCCL only to
 scatter the .klg streams and gather the trajectories; no collective inside the frame loop.
 `--impl reference` times the oracle's CPU path (the reference itself needs OpenGL + Pangolin + Eigen and
